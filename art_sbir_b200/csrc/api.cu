@@ -1,0 +1,320 @@
+// api.cu — the extern "C" boundary declared in include/sbir_b200.h: argument checking,
+// workspace layout, and the launch sequences.  No kernel code lives here.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sbir {
+
+static thread_local int g_last_cuda_error = 0;
+void set_last_cuda_error(int err) { g_last_cuda_error = err; }
+
+namespace {
+
+int num_sms_cached() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+bool dtype_ok(int d) { return d == SBIR_F32 || d == SBIR_BF16; }
+bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
+
+// Workspace of sbir_pairwise_topk / _shard (all offsets 256-byte aligned).
+struct TopkLayout {
+  K1Plan plan;
+  size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert;
+  size_t off_pos_dist, off_lo, off_hi, off_cnt, off_unc_cnt, off_unc_idx, off_rank_tmp;
+  size_t total;
+};
+
+TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int want_rank) {
+  TopkLayout L{};
+  L.plan = make_k1_plan(num_q, num_g, dim, k, dtype, num_sms_cached());
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + (bytes ? bytes : 1), 256); return r; };
+  const size_t nq = (size_t)(num_q > 0 ? num_q : 1);
+  L.off_gvec = take((size_t)L.plan.num_g_tiles * kTileG * sizeof(float));
+  L.off_gmax = take(sizeof(float));
+  L.off_qsq = take(nq * sizeof(float));
+  const size_t cand = (size_t)L.plan.num_units * L.plan.lists_per_row * L.plan.cap * kTileQ;
+  L.off_cand_val = take(cand * sizeof(float));
+  L.off_cand_idx = take(cand * sizeof(int32_t));
+  L.off_flags = take(nq * sizeof(int32_t));
+  L.off_uncert = take(sizeof(int32_t));
+  if (want_rank) {
+    L.off_pos_dist = take(nq * sizeof(double));
+    L.off_lo = take(nq * sizeof(float));
+    L.off_hi = take(nq * sizeof(float));
+    L.off_cnt = take(nq * sizeof(int32_t));
+    L.off_unc_cnt = take(nq * sizeof(int32_t));
+    L.off_unc_idx = take(nq * kUncertainCap * sizeof(int32_t));
+    L.off_rank_tmp = take(nq * sizeof(int64_t));
+  }
+  L.total = o;
+  return L;
+}
+
+// Shared implementation of sbir_pairwise_topk (pos_index given, full rank) and
+// sbir_pairwise_topk_shard (pos_dist given, local count).
+int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+              int metric, int k, int64_t index_offset, const int64_t* pos_index,
+              const double* pos_dist_in, float* out_dist, int64_t* out_index, int64_t* out_rank,
+              int64_t missing_rank, int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
+              cudaStream_t st) {
+  if (!dtype_ok(dtype) || !metric_ok(metric)) return SBIR_ERR_INVALID_ARG;
+  if (num_q < 0 || num_g < 0 || dim <= 0 || k <= 0) return SBIR_ERR_INVALID_ARG;
+  if (k > kMaxK) return SBIR_ERR_UNSUPPORTED;
+  if (num_q > INT32_MAX / 2 || num_g > INT32_MAX / 2 || dim > (1 << 20)) return SBIR_ERR_UNSUPPORTED;
+  if (num_q == 0) return SBIR_OK;
+  if (q == nullptr || out_dist == nullptr || out_index == nullptr) return SBIR_ERR_INVALID_ARG;
+  if (num_g > 0 && g == nullptr) return SBIR_ERR_INVALID_ARG;
+  const bool want_rank = out_rank != nullptr && (pos_index != nullptr || pos_dist_in != nullptr);
+  if (out_rank != nullptr && !want_rank) return SBIR_ERR_INVALID_ARG;
+  if ((dim * (int64_t)elem_size(dtype)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
+
+  const TopkLayout L = topk_layout(num_q, num_g, dim, k, dtype, want_rank ? 1 : 0);
+  if (workspace == nullptr || reinterpret_cast<uintptr_t>(workspace) % 256 != 0 || workspace_bytes < L.total)
+    return SBIR_ERR_WORKSPACE;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* gvec = reinterpret_cast<float*>(ws + L.off_gvec);
+  float* gmax = reinterpret_cast<float*>(ws + L.off_gmax);
+  float* qsq = reinterpret_cast<float*>(ws + L.off_qsq);
+  float* cand_val = reinterpret_cast<float*>(ws + L.off_cand_val);
+  int32_t* cand_idx = reinterpret_cast<int32_t*>(ws + L.off_cand_idx);
+  int32_t* flags = reinterpret_cast<int32_t*>(ws + L.off_flags);
+  int32_t* uncert = out_uncertified ? out_uncertified : reinterpret_cast<int32_t*>(ws + L.off_uncert);
+  SBIR_CUDA_TRY(cudaMemsetAsync(uncert, 0, sizeof(int32_t), st));
+
+  if (num_g == 0) {
+    // Empty gallery: no neighbours; every query's positive is missing.
+    SBIR_TRY(launch_topk_merge(nullptr, nullptr, 0, num_q, k, out_dist, out_index, st));
+    if (want_rank) SBIR_TRY(launch_fill_i64(out_rank, num_q, missing_rank, st));
+    return SBIR_OK;
+  }
+
+  const int64_t padded = (int64_t)L.plan.num_g_tiles * kTileG;
+  SBIR_TRY(launch_row_norm(g, num_g, padded, dim, dtype, metric == SBIR_EUCLIDEAN ? 0 : 1,
+                           metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""), gvec, gmax, st));
+  SBIR_TRY(launch_row_norm(q, num_q, num_q, dim, dtype, 0, 0.f, qsq, nullptr, st));
+
+  RankArgs ra{};
+  if (want_rank) {
+    ra.q = q; ra.g = g; ra.num_q = num_q; ra.num_g = num_g; ra.dim = dim;
+    ra.dtype = dtype; ra.metric = metric;
+    ra.pos_index = pos_index; ra.pos_dist_in = pos_dist_in;
+    ra.qsq = qsq; ra.gsq_max = gmax; ra.kappa = k1_kappa(dtype);
+    ra.pos_dist = reinterpret_cast<double*>(ws + L.off_pos_dist);
+    ra.rank_lo = reinterpret_cast<float*>(ws + L.off_lo);
+    ra.rank_hi = reinterpret_cast<float*>(ws + L.off_hi);
+    ra.cnt_less = reinterpret_cast<int32_t*>(ws + L.off_cnt);
+    ra.unc_cnt = reinterpret_cast<int32_t*>(ws + L.off_unc_cnt);
+    ra.unc_idx = reinterpret_cast<int32_t*>(ws + L.off_unc_idx);
+    ra.out_rank = out_rank;
+    ra.missing_rank = missing_rank;
+    SBIR_CUDA_TRY(cudaMemsetAsync(ra.cnt_less, 0, (size_t)num_q * sizeof(int32_t), st));
+    SBIR_CUDA_TRY(cudaMemsetAsync(ra.unc_cnt, 0, (size_t)num_q * sizeof(int32_t), st));
+    SBIR_TRY(launch_rank_band(ra, st));
+  }
+
+  K1Args ka{};
+  ka.q = q; ka.g = g; ka.num_q = num_q; ka.num_g = num_g; ka.dim = dim;
+  ka.dtype = dtype; ka.metric = metric;
+  ka.mode = want_rank ? kModeTopkRank : kModeTopk;
+  ka.gvec = gvec;
+  ka.cand_val = cand_val; ka.cand_idx = cand_idx;
+  ka.rank_lo = ra.rank_lo; ka.rank_hi = ra.rank_hi;
+  ka.cnt_less = ra.cnt_less; ka.unc_cnt = ra.unc_cnt; ka.unc_idx = ra.unc_idx;
+  SBIR_TRY(launch_k1(ka, L.plan, st));
+
+  FinalizeArgs fa{};
+  fa.q = q; fa.g = g; fa.num_q = num_q; fa.num_g = num_g; fa.dim = dim;
+  fa.dtype = dtype; fa.metric = metric; fa.k = k; fa.index_offset = index_offset;
+  fa.cand_val = cand_val; fa.cand_idx = cand_idx;
+  fa.qsq = qsq; fa.gsq_max = gmax; fa.kappa = k1_kappa(dtype);
+  fa.out_dist = out_dist; fa.out_index = out_index;
+  fa.uncertified = uncert; fa.flags = flags;
+  SBIR_TRY(launch_finalize_topk(fa, L.plan, st));
+  SBIR_TRY(launch_topk_fallback(fa, st));
+  if (want_rank) SBIR_TRY(launch_rank_finalize(ra, st));
+  return SBIR_OK;
+}
+
+}  // namespace
+}  // namespace sbir
+
+using namespace sbir;
+
+extern "C" {
+
+int sbir_abi_version(void) { return SBIR_B200_ABI_VERSION; }
+
+const char* sbir_status_string(int status) {
+  switch (status) {
+    case SBIR_OK: return "ok";
+    case SBIR_ERR_INVALID_ARG: return "invalid argument";
+    case SBIR_ERR_UNSUPPORTED: return "unsupported shape, alignment or k";
+    case SBIR_ERR_CUDA: return "CUDA call failed (see sbir_last_cuda_error)";
+    case SBIR_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
+    case SBIR_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    default: return "unknown status";
+  }
+}
+
+int sbir_last_cuda_error(void) { return g_last_cuda_error; }
+
+int sbir_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int sbir_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype, float eps, void* stream) {
+  if (!dtype_ok(dtype) || rows < 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
+  if (rows == 0) return SBIR_OK;
+  if (x == nullptr || y == nullptr) return SBIR_ERR_INVALID_ARG;
+  return launch_l2_normalize(x, y, rows, dim, dtype, eps, static_cast<cudaStream_t>(stream));
+}
+
+int sbir_row_sqnorm(const void* x, int64_t rows, int64_t dim, int dtype, float* out, void* stream) {
+  if (!dtype_ok(dtype) || rows < 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
+  if (rows == 0) return SBIR_OK;
+  if (x == nullptr || out == nullptr) return SBIR_ERR_INVALID_ARG;
+  return launch_row_norm(x, rows, rows, dim, dtype, 0, 0.f, out, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int sbir_pairwise_distance(const void* x1, int64_t rows1, const void* x2, int64_t rows2, int64_t dim,
+                           int dtype, int metric, float* out, void* stream) {
+  if (!dtype_ok(dtype) || !metric_ok(metric) || rows1 < 0 || rows2 < 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
+  if (rows1 != rows2 && rows1 != 1 && rows2 != 1) return SBIR_ERR_INVALID_ARG;
+  if (rows1 == 0 || rows2 == 0) return SBIR_OK;
+  if (x1 == nullptr || x2 == nullptr || out == nullptr) return SBIR_ERR_INVALID_ARG;
+  return launch_pairwise_distance(x1, rows1, x2, rows2, dim, dtype, metric, out, static_cast<cudaStream_t>(stream));
+}
+
+int sbir_pairwise_distance_bwd(const float* x1, int64_t rows1, const float* x2, int64_t rows2, int64_t dim,
+                               int metric, const float* grad_out, float* grad_x1, float* grad_x2,
+                               void* stream) {
+  if (!metric_ok(metric) || rows1 < 0 || rows2 < 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
+  if (rows1 != rows2 && rows1 != 1 && rows2 != 1) return SBIR_ERR_INVALID_ARG;
+  if (rows1 == 0 || rows2 == 0) return SBIR_OK;
+  if (x1 == nullptr || x2 == nullptr || grad_out == nullptr) return SBIR_ERR_INVALID_ARG;
+  return launch_pairwise_distance_bwd(x1, rows1, x2, rows2, dim, metric, grad_out, grad_x1, grad_x2,
+                                      static_cast<cudaStream_t>(stream));
+}
+
+size_t sbir_pairwise_topk_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
+                                          int metric, int want_rank) {
+  (void)metric;
+  if (num_q < 0 || num_g < 0 || dim <= 0 || k <= 0 || k > kMaxK || !dtype_ok(dtype)) return 0;
+  return topk_layout(num_q, num_g, dim, k, dtype, want_rank).total;
+}
+
+int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+                       int metric, int k, int64_t index_offset, const int64_t* pos_index, float* out_dist,
+                       int64_t* out_index, int64_t* out_rank, int32_t* out_uncertified, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return topk_impl(q, num_q, g, num_g, dim, dtype, metric, k, index_offset, pos_index, nullptr, out_dist,
+                   out_index, out_rank, /*missing_rank=*/num_g, out_uncertified, workspace, workspace_bytes,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int sbir_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+                           int metric, const int64_t* pos_index_local, double* out_pos_dist, void* stream) {
+  if (!dtype_ok(dtype) || !metric_ok(metric) || num_q < 0 || num_g < 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
+  if (num_q == 0) return SBIR_OK;
+  if (q == nullptr || pos_index_local == nullptr || out_pos_dist == nullptr) return SBIR_ERR_INVALID_ARG;
+  return launch_positive_distance(q, num_q, g, num_g, dim, dtype, metric, pos_index_local, out_pos_dist,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
+                             int dtype, int metric, int k, int64_t index_offset, const double* pos_dist,
+                             float* out_dist, int64_t* out_index, int64_t* out_count_less,
+                             int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  // A query without a positive anywhere (NaN pos_dist) contributes a local count of 0.
+  return topk_impl(q, num_q, g, num_g, dim, dtype, metric, k, index_offset, nullptr, pos_dist, out_dist,
+                   out_index, out_count_less, /*missing_rank=*/0, out_uncertified, workspace, workspace_bytes,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int sbir_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
+                    float* out_dist, int64_t* out_index, void* stream) {
+  if (num_lists < 0 || num_q < 0 || k <= 0) return SBIR_ERR_INVALID_ARG;
+  if (num_q == 0) return SBIR_OK;
+  if (out_dist == nullptr || out_index == nullptr) return SBIR_ERR_INVALID_ARG;
+  if (num_lists > 0 && (dist == nullptr || index == nullptr)) return SBIR_ERR_INVALID_ARG;
+  return launch_topk_merge(dist, index, num_lists, num_q, k, out_dist, out_index, static_cast<cudaStream_t>(stream));
+}
+
+int sbir_retrieval_metrics(const int64_t* rank0, int64_t num_q, int k, double* out, void* stream) {
+  if (num_q <= 0 || k <= 0 || k > 1024 || rank0 == nullptr || out == nullptr) return SBIR_ERR_INVALID_ARG;
+  return launch_retrieval_metrics(rank0, num_q, k, out, static_cast<cudaStream_t>(stream));
+}
+
+int sbir_triplet_margin_loss(const float* a, const float* p, const float* n, int64_t batch, int64_t dim,
+                             float margin, int metric, float* out_loss, float* out_per_row, float* grad_a,
+                             float* grad_p, float* grad_n, void* stream) {
+  if (!metric_ok(metric) || batch <= 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
+  if (a == nullptr || p == nullptr || n == nullptr || out_loss == nullptr || out_per_row == nullptr)
+    return SBIR_ERR_INVALID_ARG;
+  return launch_triplet(a, p, n, batch, dim, margin, metric, out_loss, out_per_row, grad_a, grad_p, grad_n,
+                        static_cast<cudaStream_t>(stream));
+}
+
+size_t sbir_batch_hard_workspace_bytes(int64_t batch, int64_t dim) {
+  if (batch <= 0 || dim <= 0) return 0;
+  return batch_hard_workspace_bytes(batch, dim);
+}
+
+int sbir_batch_hard_triplet_loss(const float* a, const float* p, const float* n, int64_t batch, int64_t dim,
+                                 float margin, int metric, const int64_t* anchor_label,
+                                 const int64_t* cand_label, float* out_loss, int64_t* out_hard_index,
+                                 float* grad_a, float* grad_p, float* grad_n, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!metric_ok(metric) || batch <= 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
+  if (a == nullptr || p == nullptr || n == nullptr || out_loss == nullptr) return SBIR_ERR_INVALID_ARG;
+  if ((anchor_label == nullptr) != (cand_label == nullptr)) return SBIR_ERR_INVALID_ARG;
+  if ((dim * 4) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
+  return launch_batch_hard(a, p, n, batch, dim, margin, metric, anchor_label, cand_label, out_loss,
+                           out_hard_index, grad_a, grad_p, grad_n, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+size_t sbir_debug_dist_matrix_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int dtype) {
+  if (num_q <= 0 || num_g <= 0 || dim <= 0 || !dtype_ok(dtype)) return 0;
+  const K1Plan plan = make_k1_plan(num_q, num_g, dim, 1, dtype, num_sms_cached());
+  return align_up((size_t)plan.num_g_tiles * kTileG * sizeof(float), 256);
+}
+
+int sbir_debug_dist_matrix(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+                           int metric, float* out_e, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dtype_ok(dtype) || !metric_ok(metric) || num_q <= 0 || num_g <= 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
+  if (q == nullptr || g == nullptr || out_e == nullptr) return SBIR_ERR_INVALID_ARG;
+  const size_t need = sbir_debug_dist_matrix_workspace_bytes(num_q, num_g, dim, dtype);
+  if (workspace == nullptr || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+    return SBIR_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const K1Plan plan = make_k1_plan(num_q, num_g, dim, 1, dtype, num_sms_cached());
+  float* gvec = static_cast<float*>(workspace);
+  SBIR_TRY(launch_row_norm(g, num_g, (int64_t)plan.num_g_tiles * kTileG, dim, dtype,
+                           metric == SBIR_EUCLIDEAN ? 0 : 1, metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""),
+                           gvec, nullptr, st));
+  K1Args ka{};
+  ka.q = q; ka.g = g; ka.num_q = num_q; ka.num_g = num_g; ka.dim = dim;
+  ka.dtype = dtype; ka.metric = metric; ka.mode = kModeDump;
+  ka.gvec = gvec; ka.dump = out_e;
+  return launch_k1(ka, plan, st);
+}
+
+}  // extern "C"

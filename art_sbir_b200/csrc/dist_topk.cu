@@ -1,0 +1,496 @@
+// dist_topk.cu — K1: pairwise sketch×artwork distance tiles on the 5th-gen tensor cores with
+// the per-query selection fused into the epilogue (the distance matrix never reaches HBM).
+//
+// Replaces the reference's per-query `utils.euclidean_distance(q, G)` / `cosine_distance`
+// followed by `distances.topk(...)` (inference.py:44-49, 62-65) for ALL queries at once.
+//
+// Structure (one persistent CTA per SM, warp-specialised):
+//   warp 0      TMA producer: Q k-slice [128 × 128 B] + G k-slice [256 × 128 B] per stage,
+//               SWIZZLE_128B, mbarrier complete_tx                     (UTMALDG in SASS)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (kind::tf32 for fp32 embeddings,
+//               kind::f16 for bf16) M=128 × N=256 into one of two 256-column TMEM accumulators;
+//               tcgen05.commit releases smem stages and publishes the accumulator (UTC*MMA)
+//   warps 2..   epilogue: tcgen05.ld 32 lanes × 32 columns → e = ‖g‖² − 2·q·g (euclidean) or
+//               e = −q·g/max(‖g‖,eps) (cosine); a thread owns one query row and keeps that
+//               query's running best-`cap` list; only chunks whose minimum beats the
+//               row's current threshold take the insertion path                   (LDTM)
+// e orders gallery rows exactly like the distance does for a fixed query (‖q‖² and the
+// query norm are per-row constants); exact distances are recomputed for the survivors by
+// finalize.cu, so tensor-core rounding never reaches the caller.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace sbir {
+
+namespace {
+
+constexpr int kSwizzleBytes = 128;                    // one k-block = 128 bytes of features per row
+constexpr int kStageBytesQ = kTileQ * kSwizzleBytes;  // 16 KB
+constexpr int kStageBytesG = kTileG * kSwizzleBytes;  // 32 KB
+constexpr int kStageBytes = kStageBytesQ + kStageBytesG;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kTmemCols = 512;  // two 256-column fp32 accumulators
+
+template <int kCap, int kEpiWarps>
+struct K1Config {
+  static constexpr int kListsPerRow = kEpiWarps / 4;
+  static constexpr bool kSmemLists = kCap * kListsPerRow <= 64;
+  static constexpr int kListBytes = kSmemLists ? kCap * kListsPerRow * kTileQ * 8 : 0;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kStagesFit = (kSmemLimit - 1024 - kListBytes - kBarrierBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 4 ? 4 : kStagesFit;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kListBytes + kBarrierBytes;
+  static constexpr int kThreads = 64 + kEpiWarps * 32;
+  static constexpr int kColsPerWarp = kTileG / kListsPerRow;
+  static_assert(kStages >= 2, "operand ring needs at least two stages");
+  static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps must cover the 4 TMEM lane quarters");
+};
+
+struct K1Params {
+  const float* gvec;
+  int num_q, num_g;
+  int num_q_tiles, num_g_tiles, tiles_per_split, num_units, num_k_blocks;
+  int elems_per_kblock;
+  float* cand_val;
+  int32_t* cand_idx;
+  const float* rank_lo;
+  const float* rank_hi;
+  int32_t* cnt_less;
+  int32_t* unc_cnt;
+  int32_t* unc_idx;
+  float* dump;
+  const int64_t* row_label;
+  const int64_t* col_label;
+  float* hard_val;
+  int32_t* hard_idx;
+};
+
+template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps>
+__global__ void __launch_bounds__(K1Config<kCap, kEpiWarps>::kThreads, 1)
+dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                 const __grid_constant__ CUtensorMap tmap_g, const K1Params prm) {
+  using Cfg = K1Config<kCap, kEpiWarps>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr bool kSelect = (kMode == kModeTopk || kMode == kModeTopkRank);
+  constexpr bool kRank = (kMode == kModeTopkRank);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_g = smem + kStages * kStageBytesQ;
+  float* list_val_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+  int32_t* list_idx_s = reinterpret_cast<int32_t*>(list_val_s + (Cfg::kSmemLists ? kCap * Cfg::kListsPerRow * kTileQ : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kListBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* acc_full_bar = bars + 2 * kStages;
+  uint64_t* acc_empty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_g);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full_bar[a], 1);
+      mbar_init(&acc_empty_bar[a], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer ----
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
+        const int q_tile = unit % prm.num_q_tiles;
+        const int split = unit / prm.num_q_tiles;
+        const int t0 = split * prm.tiles_per_split;
+        const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_2d(smem_q + stage * kStageBytesQ, &tmap_q, &full_bar[stage],
+                        kb * prm.elems_per_kblock, q_tile * kTileQ);
+            tma_load_2d(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
+                        kb * prm.elems_per_kblock, t * kTileG);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer ----
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_instr_desc(kTF32 ? 2u : 1u, kTileQ, kTileG);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
+        const int split = unit / prm.num_q_tiles;
+        const int t0 = split * prm.tiles_per_split;
+        const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kTileG;
+          for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_q + stage * kStageBytesQ));
+            const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_g + stage * kStageBytesG));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 4 × 32-byte K steps inside the 128-byte swizzle atom
+              umma_ss<kTF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue ----
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp can read
+    const int half = ew >> 2;      // column half when two warps share a lane quarter
+    const int row = quarter * 32 + lane;
+    const int col_begin = half * Cfg::kColsPerWarp;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+
+    for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
+      const int q_tile = unit % prm.num_q_tiles;
+      const int split = unit / prm.num_q_tiles;
+      const int t0 = split * prm.tiles_per_split;
+      const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
+      const int q = q_tile * kTileQ + row;
+      const bool q_valid = q < prm.num_q;
+
+      // This thread's list: entry p lives at [p * kTileQ + row] (conflict-free / coalesced).
+      float* lv;
+      int32_t* li;
+      const size_t list_slot = (size_t)unit * Cfg::kListsPerRow + half;
+      if constexpr (Cfg::kSmemLists) {
+        lv = list_val_s + half * kCap * kTileQ;
+        li = list_idx_s + half * kCap * kTileQ;
+      } else {
+        lv = prm.cand_val + list_slot * kCap * kTileQ;
+        li = prm.cand_idx + list_slot * kCap * kTileQ;
+      }
+      float thr = INFINITY;
+      int maxpos = 0;
+      float lo = -INFINITY, hi = -INFINITY;
+      int cnt = 0;
+      if constexpr (kSelect) {
+#pragma unroll 4
+        for (int p = 0; p < kCap; ++p) {
+          lv[p * kTileQ + row] = INFINITY;
+          li[p * kTileQ + row] = -1;
+        }
+      }
+      if constexpr (kRank) {
+        if (q_valid) {
+          lo = prm.rank_lo[q];
+          hi = prm.rank_hi[q];
+        }
+      }
+      float hp = -INFINITY, hn = INFINITY;  // batch-hard: hardest positive / negative in e-space
+      int hpi = -1, hni = -1;
+      int64_t my_label = 0;
+      if constexpr (kMode == kModeHard) {
+        if (prm.row_label != nullptr && q_valid) my_label = prm.row_label[q];
+      }
+
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&acc_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const float* gv = prm.gvec + (size_t)t * kTileG + col_begin;
+#pragma unroll 1
+        for (int c = 0; c < Cfg::kColsPerWarp / 32; ++c) {
+          const uint32_t taddr = tmem_base + lane_addr + acc * kTileG + col_begin + c * 32;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr, r);
+          tmem_ld_wait();
+          float e[32];
+          const float4* gv4 = reinterpret_cast<const float4*>(gv + c * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 g4 = __ldg(gv4 + j4);
+            const float gj[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float s = __uint_as_float(r[j4 * 4 + u]);
+              e[j4 * 4 + u] = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, s, gj[u]) : __fmul_rn(s, gj[u]);
+            }
+          }
+          const int gcol0 = t * kTileG + col_begin + c * 32;  // gallery row of e[0]
+
+          if constexpr (kMode == kModeDump) {
+            if (q_valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (gcol0 + j < prm.num_g) prm.dump[(size_t)q * prm.num_g + gcol0 + j] = e[j];
+            }
+          } else if constexpr (kMode == kModeHard) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int gj = gcol0 + j;
+              if (gj < prm.num_g) {
+                const bool is_pos = (prm.row_label == nullptr) ? (gj == q) : (prm.col_label[gj] == my_label);
+                if (is_pos) {
+                  if (e[j] > hp) { hp = e[j]; hpi = gj; }
+                } else {
+                  if (e[j] < hn) { hn = e[j]; hni = gj; }
+                }
+              }
+            }
+          } else {
+            float m = e[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fminf(m, e[j]);
+            if constexpr (kRank) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) cnt += (e[j] < lo) ? 1 : 0;
+            }
+            const float lim = kRank ? fmaxf(thr, hi) : thr;
+            if (__any_sync(kFullMask, m < lim)) {
+              uint32_t mask = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mask |= (e[j] < lim ? 1u : 0u) << j;
+              uint32_t pending = __reduce_or_sync(kFullMask, mask);
+              while (pending) {
+                const int j = __ffs(pending) - 1;
+                pending &= pending - 1;
+                // Re-read column j for every row of this warp (warp-uniform address) and
+                // recompute e with the identical instruction, so it is bit-equal to e[j].
+                const float s = __uint_as_float(tmem_ld_32x32b_x1(taddr + j));
+                tmem_ld_wait();
+                const float gj = __ldg(gv + c * 32 + j);
+                const float ej = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, s, gj) : __fmul_rn(s, gj);
+                if (ej < thr) {
+                  lv[maxpos * kTileQ + row] = ej;
+                  li[maxpos * kTileQ + row] = gcol0 + j;
+                  float mx = -INFINITY;
+                  int mp = 0;
+#pragma unroll 4
+                  for (int p = 0; p < kCap; ++p) {
+                    const float v = lv[p * kTileQ + row];
+                    if (v > mx) { mx = v; mp = p; }
+                  }
+                  thr = mx;
+                  maxpos = mp;
+                }
+                if constexpr (kRank) {
+                  if (ej >= lo && ej < hi) {
+                    const int slot = atomicAdd(prm.unc_cnt + q, 1);
+                    if (slot < kUncertainCap) prm.unc_idx[(size_t)q * kUncertainCap + slot] = gcol0 + j;
+                  }
+                }
+              }
+            }
+          }
+        }
+        // Accumulator fully read: hand it back to the MMA warp.
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+
+      if constexpr (kSelect) {
+        if constexpr (Cfg::kSmemLists) {
+          float* ov = prm.cand_val + list_slot * kCap * kTileQ;
+          int32_t* oi = prm.cand_idx + list_slot * kCap * kTileQ;
+#pragma unroll 4
+          for (int p = 0; p < kCap; ++p) {
+            ov[p * kTileQ + row] = lv[p * kTileQ + row];
+            oi[p * kTileQ + row] = li[p * kTileQ + row];
+          }
+        }
+        if constexpr (kRank) {
+          if (q_valid && cnt) atomicAdd(prm.cnt_less + q, cnt);
+        }
+      }
+      if constexpr (kMode == kModeHard) {
+        // one unit == one gallery tile range; slot [split][q_tile*128+row][half]
+        const size_t o = (((size_t)split * prm.num_q_tiles + q_tile) * kTileQ + row) * Cfg::kListsPerRow + half;
+        prm.hard_val[o * 2 + 0] = hp;
+        prm.hard_val[o * 2 + 1] = hn;
+        prm.hard_idx[o * 2 + 0] = hpi;
+        prm.hard_idx[o * 2 + 1] = hni;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------ host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// [rows, dim] row-major matrix → 2-D tensor map with a (128-byte × box_rows) SWIZZLE_128B box.
+int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int dtype, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return SBIR_ERR_CUDA;
+  const size_t es = elem_size(dtype);
+  const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)dim * es};
+  const cuuint32_t box[2] = {(cuuint32_t)(kSwizzleBytes / es), (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, dtype == SBIR_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                         2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_cuda_error(1000 + (int)r);
+    return SBIR_ERR_CUDA;
+  }
+  return SBIR_OK;
+}
+
+template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps>
+int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm, int grid, cudaStream_t st) {
+  using Cfg = K1Config<kCap, kEpiWarps>;
+  auto kern = dist_topk_kernel<kTF32, kMetric, kMode, kCap, kEpiWarps>;
+  SBIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tg, prm);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+template <bool kTF32, int kMetric, int kEpiWarps>
+int dispatch_mode_cap(int mode, int cap, const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm,
+                      int grid, cudaStream_t st) {
+#define SBIR_K1_CASE(M, C) \
+  if (mode == M && cap == C) return launch_inst<kTF32, kMetric, M, C, kEpiWarps>(tq, tg, prm, grid, st);
+  SBIR_K1_CASE(kModeTopk, 16)
+  SBIR_K1_CASE(kModeTopk, 32)
+  SBIR_K1_CASE(kModeTopk, 64)
+  SBIR_K1_CASE(kModeTopk, 128)
+  SBIR_K1_CASE(kModeTopkRank, 16)
+  SBIR_K1_CASE(kModeTopkRank, 32)
+  SBIR_K1_CASE(kModeTopkRank, 64)
+  SBIR_K1_CASE(kModeTopkRank, 128)
+  SBIR_K1_CASE(kModeDump, 16)
+  SBIR_K1_CASE(kModeHard, 16)
+#undef SBIR_K1_CASE
+  return SBIR_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+// fp32 embeddings → kind::tf32, 4 epilogue warps; bf16 → kind::f16, 8 epilogue warps (the
+// bf16 tiles complete 2-4× sooner, so two warps share each TMEM lane quarter).
+static int epi_warps_for(int dtype) { return dtype == SBIR_BF16 ? 8 : 4; }
+
+K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms) {
+  K1Plan p{};
+  // capacity = k + slack; fp32/tf32 carries a wider error band, so it gets more slack
+  const int want = dtype == SBIR_BF16 ? k + 6 : k + 16;
+  p.cap = want <= 16 ? 16 : want <= 32 ? 32 : want <= 64 ? 64 : 128;
+  if (k + 12 > 128) p.cap = 128;
+  p.lists_per_row = epi_warps_for(dtype) / 4;
+  p.num_q_tiles = (int)((num_q + kTileQ - 1) / kTileQ);
+  p.num_g_tiles = (int)((num_g + kTileG - 1) / kTileG);
+  if (p.num_q_tiles < 1) p.num_q_tiles = 1;
+  if (p.num_g_tiles < 1) p.num_g_tiles = 1;
+  const size_t es = dtype == SBIR_BF16 ? 2 : 4;
+  p.num_k_blocks = (int)((dim * es + kSwizzleBytes - 1) / kSwizzleBytes);
+  // Splits: aim for ~4 waves of units over the SMs, at most one split per gallery tile, and
+  // keep the merged candidate set per query within the finalize kernel's 4096-entry budget.
+  int64_t want_units = (int64_t)num_sms * 4;
+  int64_t splits = (want_units + p.num_q_tiles - 1) / p.num_q_tiles;
+  if (splits > p.num_g_tiles) splits = p.num_g_tiles;
+  const int64_t max_splits = 4096 / (p.cap * p.lists_per_row);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (int)((p.num_g_tiles + splits - 1) / splits);
+  p.num_splits = (p.num_g_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.num_units = p.num_q_tiles * p.num_splits;
+  return p;
+}
+
+int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
+  if ((a.dim * (int64_t)elem_size(a.dtype)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.g)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
+  if (a.num_q <= 0 || a.num_g <= 0) return SBIR_OK;
+  CUtensorMap tq, tg;
+  SBIR_TRY(make_tmap(&tq, a.q, a.num_q, a.dim, a.dtype, kTileQ));
+  SBIR_TRY(make_tmap(&tg, a.g, a.num_g, a.dim, a.dtype, kTileG));
+  K1Params prm{};
+  prm.gvec = a.gvec;
+  prm.num_q = (int)a.num_q;
+  prm.num_g = (int)a.num_g;
+  prm.num_q_tiles = plan.num_q_tiles;
+  prm.num_g_tiles = plan.num_g_tiles;
+  prm.tiles_per_split = plan.tiles_per_split;
+  prm.num_units = plan.num_units;
+  prm.num_k_blocks = plan.num_k_blocks;
+  prm.elems_per_kblock = (int)(kSwizzleBytes / elem_size(a.dtype));
+  prm.cand_val = a.cand_val;
+  prm.cand_idx = a.cand_idx;
+  prm.rank_lo = a.rank_lo;
+  prm.rank_hi = a.rank_hi;
+  prm.cnt_less = a.cnt_less;
+  prm.unc_cnt = a.unc_cnt;
+  prm.unc_idx = a.unc_idx;
+  prm.dump = a.dump;
+  prm.row_label = a.row_label;
+  prm.col_label = a.col_label;
+  prm.hard_val = a.hard_val;
+  prm.hard_idx = a.hard_idx;
+
+  int dev = 0, num_sms = 148;
+  SBIR_CUDA_TRY(cudaGetDevice(&dev));
+  SBIR_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = plan.num_units < num_sms ? plan.num_units : num_sms;
+  const int cap = (a.mode == kModeDump || a.mode == kModeHard) ? 16 : plan.cap;
+
+  if (a.dtype == SBIR_F32) {
+    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<true, SBIR_EUCLIDEAN, 4>(a.mode, cap, tq, tg, prm, grid, st);
+    return dispatch_mode_cap<true, SBIR_COSINE, 4>(a.mode, cap, tq, tg, prm, grid, st);
+  }
+  if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 8>(a.mode, cap, tq, tg, prm, grid, st);
+  return dispatch_mode_cap<false, SBIR_COSINE, 8>(a.mode, cap, tq, tg, prm, grid, st);
+}
+
+}  // namespace sbir

@@ -1,0 +1,586 @@
+// finalize.cu — everything after the tensor-core tiles:
+//   * merge of the per-split candidate lists + EXACT re-scoring with the reference formula
+//     (utils.py:31-42) + certificate that the selection is provably the exact top-k,
+//   * brute-force exact top-k for queries the certificate rejects,
+//   * rank of the positive = count(d < d_pos) (inference.py:49-52) from the fused counters
+//     plus exact resolution of the uncertain band,
+//   * K4 merge of per-shard top-k lists (after the all-gather), retrieval metrics (H5).
+#include <climits>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sbir {
+
+namespace {
+
+template <typename Key>
+__device__ __forceinline__ void bitonic_sort_smem(Key* key, int32_t* idx, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+        const int pos = ((i / stride) * (stride << 1)) + (i % stride);
+        const int par = pos + stride;
+        const bool asc = (pos & size) == 0;
+        const Key ka = key[pos], kb = key[par];
+        const int32_t ia = idx[pos], ib = idx[par];
+        const bool a_first = ka < kb || (ka == kb && ia <= ib);
+        if (a_first != asc) {
+          key[pos] = kb; key[par] = ka;
+          idx[pos] = ib; idx[par] = ia;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// e-space value of an exact distance (what K1's epilogue approximates) and the bound on
+// |approx − exact| for one query.
+__device__ __forceinline__ double e_of_distance(double d, int metric, float qsq) {
+  if (metric == SBIR_EUCLIDEAN) return d * d - (double)qsq;
+  return (d - 1.0) * (double)fmaxf(sqrtf(qsq), kCosineEps);
+}
+__device__ __forceinline__ double e_margin(int metric, float qsq, float gsq_max, float kappa, int dim) {
+  if (metric == SBIR_EUCLIDEAN) {
+    const double s = (double)qsq + (double)gsq_max;
+    // tensor-core rounding of 2·q·g  +  the reference's +1e-6 per component  +  fp32 epilogue rounding
+    return (double)kappa * s + 4e-6 * sqrt((double)dim * s) + 4e-7 * s + 1e-30;
+  }
+  const double nq = sqrt((double)qsq);
+  return (double)kappa * nq + 1e-6 * nq + 1e-30;
+}
+
+constexpr int kFinThreads = 128;
+
+struct FinParams {
+  const void* q;
+  const void* g;
+  int num_q, num_g, dim, metric, k;
+  long long index_offset;
+  const float* cand_val;
+  const int32_t* cand_idx;
+  int cap, lists_per_row, num_q_tiles, num_splits, m_pow2;
+  const float* qsq;
+  const float* gsq_max;
+  float kappa;
+  float* out_dist;
+  long long* out_index;
+  int32_t* uncertified;
+  int32_t* flags;
+};
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinParams p) {
+  extern __shared__ uint8_t fin_smem[];
+  float* sv = reinterpret_cast<float*>(fin_smem);
+  int32_t* si = reinterpret_cast<int32_t*>(sv + p.m_pow2);
+  __shared__ double ex[128];
+  __shared__ int32_t exi[128];
+  __shared__ int s_nfinite;
+
+  const int q = blockIdx.x;
+  const int q_tile = q / kTileQ, row = q % kTileQ;
+  const int m_tot = p.num_splits * p.lists_per_row * p.cap;
+  if (threadIdx.x == 0) s_nfinite = 0;
+  __syncthreads();
+  int local_finite = 0;
+  for (int i = threadIdx.x; i < p.m_pow2; i += kFinThreads) {
+    float v = INFINITY;
+    int32_t ix = INT_MAX;
+    if (i < m_tot) {
+      const int l = i / p.cap, pp = i % p.cap;
+      const int split = l / p.lists_per_row, h = l % p.lists_per_row;
+      const size_t slot = ((size_t)split * p.num_q_tiles + q_tile) * p.lists_per_row + h;
+      const size_t addr = (slot * p.cap + pp) * kTileQ + row;
+      const int32_t cidx = p.cand_idx[addr];
+      if (cidx >= 0) {
+        v = p.cand_val[addr];
+        ix = cidx;
+        ++local_finite;
+      }
+    }
+    sv[i] = v;
+    si[i] = ix;
+  }
+  if (local_finite) atomicAdd(&s_nfinite, local_finite);
+  bitonic_sort_smem<float>(sv, si, p.m_pow2);
+
+  const int nfinite = s_nfinite;
+  const int R = nfinite < p.cap ? nfinite : p.cap;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
+  for (int c = threadIdx.x; c < 128; c += kFinThreads) {
+    ex[c] = INFINITY;
+    exi[c] = INT_MAX;
+  }
+  __syncthreads();
+  for (int c = warp; c < R; c += kFinThreads / 32) {
+    const int32_t gi = si[c];
+    const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)gi * p.dim,
+                                                  p.dim, p.metric, lane);
+    if (lane == 0) {
+      ex[c] = d;
+      exi[c] = gi;
+    }
+  }
+  bitonic_sort_smem<double>(ex, exi, 128);
+
+  for (int i = threadIdx.x; i < p.k; i += kFinThreads) {
+    const bool have = i < R;
+    p.out_dist[(size_t)q * p.k + i] = have ? (float)ex[i] : INFINITY;
+    p.out_index[(size_t)q * p.k + i] = have ? (long long)exi[i] + p.index_offset : -1LL;
+  }
+  if (threadIdx.x == 0 && p.flags != nullptr) {
+    int flag = 0;
+    if (nfinite >= p.cap && p.k <= R) {
+      // Every gallery row that was NOT re-scored has approx e >= tau; it can only belong
+      // to the exact top-k if its exact e is below the k-th exact e, i.e. if
+      // tau - margin < e_k.  Otherwise the selection is proven exact.
+      const double tau = (double)sv[R - 1];
+      const float qsq = p.qsq[q];
+      const double ek = e_of_distance(ex[p.k - 1], p.metric, qsq);
+      const double m = e_margin(p.metric, qsq, p.gsq_max[0], p.kappa, p.dim);
+      if (!(ek + m < tau)) flag = 1;
+    }
+    p.flags[q] = flag;
+    if (flag && p.uncertified != nullptr) atomicAdd(p.uncertified, 1);
+  }
+}
+
+// Exact brute-force top-k for flagged queries: one 256-thread block per query, each warp
+// keeps a sorted best-k list in shared memory, the 8 lists are merged by a bitonic sort.
+constexpr int kFbThreads = 256;
+constexpr int kFbWarps = kFbThreads / 32;
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kFbThreads) topk_fallback_kernel(const FinParams p) {
+  __shared__ double wd[kFbWarps][128];
+  __shared__ int32_t wi[kFbWarps][128];
+  __shared__ double md[1024];
+  __shared__ int32_t mi[1024];
+  const int q = blockIdx.x;
+  if ((p.flags[q] & 1) == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = p.k;
+  for (int i = lane; i < k; i += 32) {
+    wd[warp][i] = INFINITY;
+    wi[warp][i] = INT_MAX;
+  }
+  __syncwarp();
+  const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
+  for (int j = warp; j < p.num_g; j += kFbWarps) {
+    const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)j * p.dim,
+                                                  p.dim, p.metric, lane);
+    // all lanes hold d; the list is sorted ascending, worst at k-1
+    if (ranks_before(d, j, wd[warp][k - 1], wi[warp][k - 1])) {
+      if (lane == 0) {
+        int pos = k - 1;
+        while (pos > 0 && ranks_before(d, j, wd[warp][pos - 1], wi[warp][pos - 1])) {
+          wd[warp][pos] = wd[warp][pos - 1];
+          wi[warp][pos] = wi[warp][pos - 1];
+          --pos;
+        }
+        wd[warp][pos] = d;
+        wi[warp][pos] = j;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += kFbThreads) {
+    const int w = i / 128, pos = i % 128;
+    const bool have = w < kFbWarps && pos < k;
+    md[i] = have ? wd[w][pos] : INFINITY;
+    mi[i] = have ? wi[w][pos] : INT_MAX;
+  }
+  bitonic_sort_smem<double>(md, mi, 1024);
+  for (int i = threadIdx.x; i < k; i += kFbThreads) {
+    const bool have = mi[i] != INT_MAX;
+    p.out_dist[(size_t)q * k + i] = have ? (float)md[i] : INFINITY;
+    p.out_index[(size_t)q * k + i] = have ? (long long)mi[i] + p.index_offset : -1LL;
+  }
+}
+
+// ------------------------------------------------------------------- rank ----
+struct RankParams {
+  const void* q;
+  const void* g;
+  int num_q, num_g, dim, metric;
+  const long long* pos_index;
+  const double* pos_dist_in;
+  const float* qsq;
+  const float* gsq_max;
+  float kappa;
+  double* pos_dist;
+  float* rank_lo;
+  float* rank_hi;
+  int32_t* cnt_less;
+  int32_t* unc_cnt;
+  int32_t* unc_idx;
+  long long* out_rank;
+  long long missing_rank;
+};
+
+constexpr int kRankWarps = 8;
+
+// d_pos (exact) and the e-space band [lo, hi) in which K1's approximate comparison against
+// d_pos cannot be trusted.
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kRankWarps * 32) rank_band_kernel(const RankParams p) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kRankWarps + (threadIdx.x >> 5);
+  if (q >= p.num_q) return;
+  double dpos;
+  if (p.pos_dist_in != nullptr) {
+    dpos = p.pos_dist_in[q];
+  } else {
+    const long long pi = p.pos_index[q];
+    if (pi < 0 || pi >= p.num_g) {
+      dpos = nan("");
+    } else {
+      dpos = warp_exact_distance<T, kVec>(reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim,
+                                          reinterpret_cast<const T*>(p.g) + (size_t)pi * p.dim, p.dim,
+                                          p.metric, lane);
+    }
+  }
+  if (lane == 0) {
+    p.pos_dist[q] = dpos;
+    if (dpos != dpos) {
+      p.rank_lo[q] = -INFINITY;
+      p.rank_hi[q] = -INFINITY;
+    } else {
+      const float qsq = p.qsq[q];
+      const double c = e_of_distance(dpos, p.metric, qsq);
+      const double m = e_margin(p.metric, qsq, p.gsq_max[0], p.kappa, p.dim);
+      p.rank_lo[q] = __double2float_rd(c - m);
+      p.rank_hi[q] = __double2float_ru(c + m);
+    }
+  }
+}
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kRankWarps * 32) rank_finalize_kernel(const RankParams p) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kRankWarps + (threadIdx.x >> 5);
+  if (q >= p.num_q) return;
+  const double dpos = p.pos_dist[q];
+  if (dpos != dpos) {
+    if (lane == 0) p.out_rank[q] = p.missing_rank;
+    return;
+  }
+  const int nu = p.unc_cnt[q];
+  if (nu > kUncertainCap) {
+    if (lane == 0) p.out_rank[q] = -1;  // resolved by rank_fallback_kernel
+    return;
+  }
+  long long r = p.cnt_less[q];
+  const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
+  for (int u = 0; u < nu; ++u) {
+    const int gi = p.unc_idx[(size_t)q * kUncertainCap + u];
+    const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)gi * p.dim,
+                                                  p.dim, p.metric, lane);
+    r += d < dpos ? 1 : 0;
+  }
+  if (lane == 0) p.out_rank[q] = r;
+}
+
+// Exact brute-force count for queries whose uncertain band overflowed.
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kFbThreads) rank_fallback_kernel(const RankParams p) {
+  __shared__ int red[kFbWarps];
+  const int q = blockIdx.x;
+  if (p.out_rank[q] != -1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double dpos = p.pos_dist[q];
+  const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
+  int cnt = 0;
+  for (int j = warp; j < p.num_g; j += kFbWarps) {
+    const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)j * p.dim,
+                                                  p.dim, p.metric, lane);
+    cnt += d < dpos ? 1 : 0;
+  }
+  if (lane == 0) red[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long r = 0;
+    for (int w = 0; w < kFbWarps; ++w) r += red[w];
+    p.out_rank[q] = r;
+  }
+}
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kRankWarps * 32) positive_distance_kernel(
+    const T* __restrict__ q, int num_q, const T* __restrict__ g, int num_g, int dim, int metric,
+    const long long* __restrict__ pos_index, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * kRankWarps + (threadIdx.x >> 5);
+  if (qi >= num_q) return;
+  const long long pi = pos_index[qi];
+  double d = nan("");
+  if (pi >= 0 && pi < num_g)
+    d = warp_exact_distance<T, kVec>(q + (size_t)qi * dim, g + (size_t)pi * dim, dim, metric, lane);
+  if (lane == 0) out[qi] = d;
+}
+
+// ------------------------------------------------------------------ K4 merge ----
+// Rank-by-counting merge of `num_lists` ascending lists of length k per query: element x
+// of list l lands at position Σ_l' #{y ∈ l' : y ranks before x}; positions < k are written.
+// One warp per query; fully parallel and deterministic (ties by index).
+constexpr int kMergeWarps = 4;
+__global__ void __launch_bounds__(kMergeWarps * 32) topk_merge_kernel(
+    const float* __restrict__ dist, const long long* __restrict__ index, int num_lists, int num_q,
+    int k, float* __restrict__ out_dist, long long* __restrict__ out_index) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kMergeWarps + (threadIdx.x >> 5);
+  if (q >= num_q) return;
+  const int total = num_lists * k;
+  for (int x = lane; x < total; x += 32) {
+    const int l = x / k, i = x % k;
+    const size_t base = ((size_t)l * num_q + q) * k;
+    const float dx = dist[base + i];
+    const long long ix = index[base + i];
+    if (ix < 0) continue;  // padding entry of a short list
+    int pos = i;           // elements before x in its own list
+    for (int l2 = 0; l2 < num_lists; ++l2) {
+      if (l2 == l) continue;
+      const size_t b2 = ((size_t)l2 * num_q + q) * k;
+      int lo = 0, hi = k;  // first element of l2 that does NOT rank before x
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float dm = dist[b2 + mid];
+        const long long im = index[b2 + mid];
+        const bool before = im >= 0 && (dm < dx || (dm == dx && im < ix));
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      pos += lo;
+    }
+    if (pos < k) {
+      out_dist[(size_t)q * k + pos] = dx;
+      out_index[(size_t)q * k + pos] = ix;
+    }
+  }
+}
+__global__ void fill_topk_kernel(float* out_dist, long long* out_index, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    out_dist[i] = INFINITY;
+    out_index[i] = -1;
+  }
+}
+
+__global__ void fill_i64_kernel(long long* out, long long n, long long value) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = value;
+}
+
+// ------------------------------------------------------------------ metrics ----
+// Single block: MRR, cumulative top-k accuracy, mean / sample-std / min / max of (rank0+1).
+__global__ void __launch_bounds__(256) retrieval_metrics_kernel(const long long* __restrict__ rank0,
+                                                                long long num_q, int k,
+                                                                double* __restrict__ out) {
+  __shared__ double red[256];
+  __shared__ double s_mean;
+  auto block_sum = [&](double v) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+      __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+  };
+  auto block_minmax = [&](double v, bool want_min) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s)
+        red[threadIdx.x] = want_min ? fmin(red[threadIdx.x], red[threadIdx.x + s]) : fmax(red[threadIdx.x], red[threadIdx.x + s]);
+      __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+  };
+  double mrr = 0.0, sum = 0.0, mn = INFINITY, mx = -INFINITY;
+  for (long long i = threadIdx.x; i < num_q; i += 256) {
+    const double r1 = (double)(rank0[i] + 1);
+    mrr += 1.0 / r1;
+    sum += r1;
+    mn = fmin(mn, r1);
+    mx = fmax(mx, r1);
+  }
+  mrr = block_sum(mrr);
+  sum = block_sum(sum);
+  mn = block_minmax(mn, true);
+  mx = block_minmax(mx, false);
+  if (threadIdx.x == 0) s_mean = sum / (double)num_q;
+  __syncthreads();
+  const double mean = s_mean;
+  double ss = 0.0;
+  for (long long i = threadIdx.x; i < num_q; i += 256) {
+    const double dlt = (double)(rank0[i] + 1) - mean;
+    ss += dlt * dlt;
+  }
+  ss = block_sum(ss);
+  for (int kk = 0; kk < k; ++kk) {
+    double c = 0.0;
+    for (long long i = threadIdx.x; i < num_q; i += 256) c += rank0[i] <= kk ? 1.0 : 0.0;
+    c = block_sum(c);
+    if (threadIdx.x == 0) out[1 + kk] = c / (double)num_q;
+  }
+  if (threadIdx.x == 0) {
+    out[0] = mrr / (double)num_q;
+    out[k + 1] = mean;
+    out[k + 2] = num_q > 1 ? sqrt(ss / (double)(num_q - 1)) : nan("");
+    out[k + 3] = mn;
+    out[k + 4] = mx;
+  }
+}
+
+int next_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+FinParams make_fin_params(const FinalizeArgs& a, const K1Plan* plan) {
+  FinParams p{};
+  p.q = a.q; p.g = a.g;
+  p.num_q = (int)a.num_q; p.num_g = (int)a.num_g; p.dim = (int)a.dim;
+  p.metric = a.metric; p.k = a.k;
+  p.index_offset = a.index_offset;
+  p.cand_val = a.cand_val; p.cand_idx = a.cand_idx;
+  if (plan) {
+    p.cap = plan->cap; p.lists_per_row = plan->lists_per_row;
+    p.num_q_tiles = plan->num_q_tiles; p.num_splits = plan->num_splits;
+    const int m = next_pow2(plan->num_splits * plan->lists_per_row * plan->cap);
+    p.m_pow2 = m < 2 ? 2 : m;
+  }
+  p.qsq = a.qsq; p.gsq_max = a.gsq_max; p.kappa = a.kappa;
+  p.out_dist = a.out_dist; p.out_index = reinterpret_cast<long long*>(a.out_index);
+  p.uncertified = a.uncertified; p.flags = a.flags;
+  return p;
+}
+
+RankParams make_rank_params(const RankArgs& a) {
+  RankParams p{};
+  p.q = a.q; p.g = a.g;
+  p.num_q = (int)a.num_q; p.num_g = (int)a.num_g; p.dim = (int)a.dim; p.metric = a.metric;
+  p.pos_index = reinterpret_cast<const long long*>(a.pos_index);
+  p.pos_dist_in = a.pos_dist_in;
+  p.qsq = a.qsq; p.gsq_max = a.gsq_max; p.kappa = a.kappa;
+  p.pos_dist = a.pos_dist; p.rank_lo = a.rank_lo; p.rank_hi = a.rank_hi;
+  p.cnt_less = a.cnt_less; p.unc_cnt = a.unc_cnt; p.unc_idx = a.unc_idx;
+  p.out_rank = reinterpret_cast<long long*>(a.out_rank);
+  p.missing_rank = a.missing_rank;
+  return p;
+}
+
+// Dispatch on (element type, vectorisable) — KERNEL<T, kVec><<<...>>>(args)
+#define SBIR_DISPATCH_T(dtype, vec, KERNEL, grid, block, smem, st, ...)                       \
+  do {                                                                                        \
+    if ((dtype) == SBIR_F32) {                                                                \
+      if (vec) KERNEL<float, true><<<grid, block, smem, st>>>(__VA_ARGS__);                   \
+      else KERNEL<float, false><<<grid, block, smem, st>>>(__VA_ARGS__);                      \
+    } else {                                                                                  \
+      if (vec) KERNEL<__nv_bfloat16, true><<<grid, block, smem, st>>>(__VA_ARGS__);           \
+      else KERNEL<__nv_bfloat16, false><<<grid, block, smem, st>>>(__VA_ARGS__);              \
+    }                                                                                         \
+  } while (0)
+
+}  // namespace
+
+int launch_finalize_topk(const FinalizeArgs& a, const K1Plan& plan, cudaStream_t st) {
+  if (a.num_q <= 0) return SBIR_OK;
+  const FinParams p = make_fin_params(a, &plan);
+  const size_t smem = (size_t)p.m_pow2 * 8;
+  if (smem > 40 * 1024) return SBIR_ERR_UNSUPPORTED;
+  const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
+  SBIR_DISPATCH_T(a.dtype, vec, finalize_topk_kernel, (unsigned)a.num_q, kFinThreads, smem, st, p);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_topk_fallback(const FinalizeArgs& a, cudaStream_t st) {
+  if (a.num_q <= 0) return SBIR_OK;
+  const FinParams p = make_fin_params(a, nullptr);
+  const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
+  SBIR_DISPATCH_T(a.dtype, vec, topk_fallback_kernel, (unsigned)a.num_q, kFbThreads, 0, st, p);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_rank_band(const RankArgs& a, cudaStream_t st) {
+  if (a.num_q <= 0) return SBIR_OK;
+  const RankParams p = make_rank_params(a);
+  const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
+  const unsigned grid = (unsigned)((a.num_q + kRankWarps - 1) / kRankWarps);
+  SBIR_DISPATCH_T(a.dtype, vec, rank_band_kernel, grid, kRankWarps * 32, 0, st, p);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_rank_finalize(const RankArgs& a, cudaStream_t st) {
+  if (a.num_q <= 0) return SBIR_OK;
+  const RankParams p = make_rank_params(a);
+  const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
+  const unsigned grid = (unsigned)((a.num_q + kRankWarps - 1) / kRankWarps);
+  SBIR_DISPATCH_T(a.dtype, vec, rank_finalize_kernel, grid, kRankWarps * 32, 0, st, p);
+  SBIR_CHECK_LAUNCH();
+  SBIR_DISPATCH_T(a.dtype, vec, rank_fallback_kernel, (unsigned)a.num_q, kFbThreads, 0, st, p);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
+                             int dtype, int metric, const int64_t* pos_index, double* out,
+                             cudaStream_t st) {
+  if (num_q <= 0) return SBIR_OK;
+  const bool vec = rows_vectorizable(q, dim, dtype) && rows_vectorizable(g, dim, dtype);
+  const unsigned grid = (unsigned)((num_q + kRankWarps - 1) / kRankWarps);
+  const long long* pi = reinterpret_cast<const long long*>(pos_index);
+  if (dtype == SBIR_F32) {
+    if (vec) positive_distance_kernel<float, true><<<grid, kRankWarps * 32, 0, st>>>((const float*)q, (int)num_q, (const float*)g, (int)num_g, (int)dim, metric, pi, out);
+    else positive_distance_kernel<float, false><<<grid, kRankWarps * 32, 0, st>>>((const float*)q, (int)num_q, (const float*)g, (int)num_g, (int)dim, metric, pi, out);
+  } else {
+    using B = __nv_bfloat16;
+    if (vec) positive_distance_kernel<B, true><<<grid, kRankWarps * 32, 0, st>>>((const B*)q, (int)num_q, (const B*)g, (int)num_g, (int)dim, metric, pi, out);
+    else positive_distance_kernel<B, false><<<grid, kRankWarps * 32, 0, st>>>((const B*)q, (int)num_q, (const B*)g, (int)num_g, (int)dim, metric, pi, out);
+  }
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
+                      float* out_dist, int64_t* out_index, cudaStream_t st) {
+  if (num_q <= 0 || k <= 0) return SBIR_OK;
+  const size_t n = (size_t)num_q * k;
+  fill_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_dist, reinterpret_cast<long long*>(out_index), n);
+  SBIR_CHECK_LAUNCH();
+  const unsigned grid = (unsigned)((num_q + kMergeWarps - 1) / kMergeWarps);
+  topk_merge_kernel<<<grid, kMergeWarps * 32, 0, st>>>(dist, reinterpret_cast<const long long*>(index), num_lists,
+                                                       (int)num_q, k, out_dist,
+                                                       reinterpret_cast<long long*>(out_index));
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_fill_i64(int64_t* out, int64_t n, int64_t value, cudaStream_t st) {
+  if (n <= 0) return SBIR_OK;
+  fill_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(out), (long long)n,
+                                                              (long long)value);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_retrieval_metrics(const int64_t* rank0, int64_t num_q, int k, double* out, cudaStream_t st) {
+  retrieval_metrics_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(rank0), (long long)num_q, k, out);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+}  // namespace sbir

@@ -1,0 +1,199 @@
+// host_path.cu — sbir_retrieve_host: the same retrieval pass as sbir_pairwise_topk, called
+// with HOST buffers (what a caller holding numpy / torch-CPU embeddings would bind).  The
+// gallery is uploaded in row chunks on a copy stream while earlier chunks are scored on the
+// compute stream (each chunk is a gallery shard: local top-k + local count-less-than, then
+// the K4 merge), so PCIe transfer overlaps the tensor-core work.  Device staging buffers
+// are cached per process and released by sbir_release_host_staging.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sbir {
+namespace {
+
+struct Staging {
+  void* buf = nullptr;
+  size_t bytes = 0;
+  int device = -1;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  std::vector<cudaEvent_t> events;
+};
+Staging g_staging;
+std::mutex g_staging_mu;
+
+int ensure_staging(size_t bytes) {
+  int dev = 0;
+  SBIR_CUDA_TRY(cudaGetDevice(&dev));
+  if (g_staging.device != dev || g_staging.bytes < bytes) {
+    if (g_staging.buf) cudaFree(g_staging.buf);
+    g_staging.buf = nullptr;
+    g_staging.bytes = 0;
+    SBIR_CUDA_TRY(cudaMalloc(&g_staging.buf, bytes));
+    g_staging.bytes = bytes;
+    g_staging.device = dev;
+  }
+  if (!g_staging.compute) SBIR_CUDA_TRY(cudaStreamCreateWithFlags(&g_staging.compute, cudaStreamNonBlocking));
+  if (!g_staging.copy) SBIR_CUDA_TRY(cudaStreamCreateWithFlags(&g_staging.copy, cudaStreamNonBlocking));
+  return SBIR_OK;
+}
+
+__global__ void add_i64_kernel(long long* acc, const long long* x, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] += x[i];
+}
+__global__ void missing_rank_kernel(long long* rank, const double* pos_dist, long long n, long long missing) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && pos_dist[i] != pos_dist[i]) rank[i] = missing;
+}
+
+}  // namespace
+}  // namespace sbir
+
+using namespace sbir;
+
+extern "C" int sbir_release_host_staging(void) {
+  std::lock_guard<std::mutex> lock(g_staging_mu);
+  if (g_staging.buf) cudaFree(g_staging.buf);
+  g_staging.buf = nullptr;
+  g_staging.bytes = 0;
+  for (cudaEvent_t e : g_staging.events) cudaEventDestroy(e);
+  g_staging.events.clear();
+  if (g_staging.compute) cudaStreamDestroy(g_staging.compute);
+  if (g_staging.copy) cudaStreamDestroy(g_staging.copy);
+  g_staging.compute = g_staging.copy = nullptr;
+  g_staging.device = -1;
+  return SBIR_OK;
+}
+
+extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void* g_host, int64_t num_g,
+                                  int64_t dim, int dtype, int metric, int k, const int64_t* pos_index_host,
+                                  float* out_dist_host, int64_t* out_index_host, int64_t* out_rank_host,
+                                  int32_t* out_uncertified_host) {
+  if (num_q <= 0 || num_g <= 0 || dim <= 0 || k <= 0) return SBIR_ERR_INVALID_ARG;
+  if (q_host == nullptr || g_host == nullptr || out_dist_host == nullptr || out_index_host == nullptr)
+    return SBIR_ERR_INVALID_ARG;
+  if (out_rank_host != nullptr && pos_index_host == nullptr) return SBIR_ERR_INVALID_ARG;
+  if (dtype != SBIR_F32 && dtype != SBIR_BF16) return SBIR_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(g_staging_mu);
+  const bool want_rank = out_rank_host != nullptr;
+  const size_t es = elem_size(dtype);
+  const size_t row_bytes = (size_t)dim * es;
+
+  // Chunking: ~1 GiB of gallery rows per chunk (at least 4 chunks when the gallery is large
+  // enough to make overlap worthwhile), chunk rows a multiple of the gallery tile.
+  int64_t chunk_rows = (int64_t)((size_t(1) << 30) / row_bytes);
+  chunk_rows = std::max<int64_t>(kTileG, chunk_rows / kTileG * kTileG);
+  if (chunk_rows > num_g) chunk_rows = num_g;
+  const int num_chunks = (int)((num_g + chunk_rows - 1) / chunk_rows);
+
+  // Device layout: Q | G (whole gallery, chunks land in place) | gathered positives |
+  // per-chunk top-k lists | merged outputs | rank accumulators | workspace.
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + (bytes ? bytes : 1), 256); return r; };
+  const size_t off_q = take((size_t)num_q * row_bytes);
+  const size_t off_g = take((size_t)num_g * row_bytes);
+  const size_t off_lists_d = take((size_t)num_chunks * num_q * k * sizeof(float));
+  const size_t off_lists_i = take((size_t)num_chunks * num_q * k * sizeof(int64_t));
+  const size_t off_out_d = take((size_t)num_q * k * sizeof(float));
+  const size_t off_out_i = take((size_t)num_q * k * sizeof(int64_t));
+  const size_t off_uncert = take(sizeof(int32_t) * (size_t)(num_chunks + 1));
+  size_t off_pos = 0, off_posidx = 0, off_pos_dist = 0, off_rank = 0, off_cnt = 0;
+  if (want_rank) {
+    off_pos = take((size_t)num_q * row_bytes);
+    off_posidx = take((size_t)num_q * sizeof(int64_t));
+    off_pos_dist = take((size_t)num_q * sizeof(double));
+    off_rank = take((size_t)num_q * sizeof(int64_t));
+    off_cnt = take((size_t)num_q * sizeof(int64_t));
+  }
+  const int64_t last_rows = num_g - (int64_t)(num_chunks - 1) * chunk_rows;
+  const size_t ws_bytes = std::max(
+      sbir_pairwise_topk_workspace_bytes(num_q, chunk_rows, dim, k, dtype, metric, want_rank ? 1 : 0),
+      sbir_pairwise_topk_workspace_bytes(num_q, last_rows, dim, k, dtype, metric, want_rank ? 1 : 0));
+  if (ws_bytes == 0) return SBIR_ERR_UNSUPPORTED;
+  const size_t off_ws = take(ws_bytes);
+  SBIR_TRY(ensure_staging(o));
+  uint8_t* base = static_cast<uint8_t*>(g_staging.buf);
+  cudaStream_t cs = g_staging.compute, xs = g_staging.copy;
+  while ((int)g_staging.events.size() < num_chunks + 1) {
+    cudaEvent_t e;
+    SBIR_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_staging.events.push_back(e);
+  }
+
+  uint8_t* d_q = base + off_q;
+  uint8_t* d_g = base + off_g;
+  SBIR_CUDA_TRY(cudaMemcpyAsync(d_q, q_host, (size_t)num_q * row_bytes, cudaMemcpyHostToDevice, xs));
+
+  double* d_pos_dist = nullptr;
+  long long* d_rank = nullptr;
+  if (want_rank) {
+    // The positive's row may sit in any chunk: gather those rows on the host once, upload
+    // them, and evaluate d(q, pos) up front so every chunk can count against it.
+    std::vector<uint8_t> gathered((size_t)num_q * row_bytes);
+    std::vector<int64_t> ident((size_t)num_q);
+    for (int64_t i = 0; i < num_q; ++i) {
+      const int64_t pi = pos_index_host[i];
+      if (pi >= 0 && pi < num_g) {
+        std::memcpy(gathered.data() + (size_t)i * row_bytes, static_cast<const uint8_t*>(g_host) + (size_t)pi * row_bytes, row_bytes);
+        ident[i] = i;
+      } else {
+        std::memset(gathered.data() + (size_t)i * row_bytes, 0, row_bytes);
+        ident[i] = -1;
+      }
+    }
+    SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_pos, gathered.data(), gathered.size(), cudaMemcpyHostToDevice, xs));
+    SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_posidx, ident.data(), ident.size() * sizeof(int64_t), cudaMemcpyHostToDevice, xs));
+    SBIR_CUDA_TRY(cudaStreamSynchronize(xs));  // the two vectors above go out of scope
+    d_pos_dist = reinterpret_cast<double*>(base + off_pos_dist);
+    d_rank = reinterpret_cast<long long*>(base + off_rank);
+    SBIR_TRY(launch_positive_distance(d_q, num_q, base + off_pos, num_q, dim, dtype, metric,
+                                      reinterpret_cast<const int64_t*>(base + off_posidx), d_pos_dist, xs));
+    SBIR_CUDA_TRY(cudaMemsetAsync(d_rank, 0, (size_t)num_q * sizeof(int64_t), xs));
+  }
+  SBIR_CUDA_TRY(cudaEventRecord(g_staging.events[num_chunks], xs));
+  SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, g_staging.events[num_chunks], 0));
+
+  float* d_lists_d = reinterpret_cast<float*>(base + off_lists_d);
+  int64_t* d_lists_i = reinterpret_cast<int64_t*>(base + off_lists_i);
+  int32_t* d_uncert = reinterpret_cast<int32_t*>(base + off_uncert);
+  for (int c = 0; c < num_chunks; ++c) {
+    const int64_t r0 = (int64_t)c * chunk_rows;
+    const int64_t rows = std::min<int64_t>(chunk_rows, num_g - r0);
+    SBIR_CUDA_TRY(cudaMemcpyAsync(d_g + (size_t)r0 * row_bytes, static_cast<const uint8_t*>(g_host) + (size_t)r0 * row_bytes,
+                                  (size_t)rows * row_bytes, cudaMemcpyHostToDevice, xs));
+    SBIR_CUDA_TRY(cudaEventRecord(g_staging.events[c], xs));
+    SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, g_staging.events[c], 0));
+    int64_t* d_cnt = want_rank ? reinterpret_cast<int64_t*>(base + off_cnt) : nullptr;
+    SBIR_TRY(sbir_pairwise_topk_shard(d_q, num_q, d_g + (size_t)r0 * row_bytes, rows, dim, dtype, metric, k, r0,
+                                      d_pos_dist, d_lists_d + (size_t)c * num_q * k,
+                                      d_lists_i + (size_t)c * num_q * k, d_cnt, d_uncert + 1 + c,
+                                      base + off_ws, ws_bytes, cs));
+    if (want_rank) {
+      add_i64_kernel<<<(unsigned)((num_q + 255) / 256), 256, 0, cs>>>(d_rank, reinterpret_cast<long long*>(d_cnt), num_q);
+      SBIR_CHECK_LAUNCH();
+    }
+  }
+  float* d_out_d = reinterpret_cast<float*>(base + off_out_d);
+  int64_t* d_out_i = reinterpret_cast<int64_t*>(base + off_out_i);
+  SBIR_TRY(launch_topk_merge(d_lists_d, d_lists_i, num_chunks, num_q, k, d_out_d, d_out_i, cs));
+  if (want_rank) {
+    missing_rank_kernel<<<(unsigned)((num_q + 255) / 256), 256, 0, cs>>>(d_rank, d_pos_dist, num_q, num_g);
+    SBIR_CHECK_LAUNCH();
+    SBIR_CUDA_TRY(cudaMemcpyAsync(out_rank_host, d_rank, (size_t)num_q * sizeof(int64_t), cudaMemcpyDeviceToHost, cs));
+  }
+  SBIR_CUDA_TRY(cudaMemcpyAsync(out_dist_host, d_out_d, (size_t)num_q * k * sizeof(float), cudaMemcpyDeviceToHost, cs));
+  SBIR_CUDA_TRY(cudaMemcpyAsync(out_index_host, d_out_i, (size_t)num_q * k * sizeof(int64_t), cudaMemcpyDeviceToHost, cs));
+  std::vector<int32_t> unc((size_t)num_chunks + 1, 0);
+  SBIR_CUDA_TRY(cudaMemcpyAsync(unc.data(), d_uncert, unc.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+  SBIR_CUDA_TRY(cudaStreamSynchronize(cs));
+  if (out_uncertified_host) {
+    int32_t total = 0;
+    for (int c = 0; c < num_chunks; ++c) total += unc[1 + c];
+    *out_uncertified_host = total;
+  }
+  return SBIR_OK;
+}

@@ -1,0 +1,127 @@
+// kernels.h — internal launch interface between api.cu and the kernel translation units.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sbir {
+
+// ---- rowops.cu ----------------------------------------------------------------
+// mode 0: ‖x‖² ; mode 1: −1/max(‖x‖,1e-8).  Rows [rows, rows_padded) get pad_value.
+int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int dtype,
+                    int mode, float pad_value, float* out, float* max_sqnorm_out, cudaStream_t st);
+int launch_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype, float eps,
+                        cudaStream_t st);
+int launch_pairwise_distance(const void* x1, int64_t rows1, const void* x2, int64_t rows2,
+                             int64_t dim, int dtype, int metric, float* out, cudaStream_t st);
+int launch_pairwise_distance_bwd(const float* x1, int64_t rows1, const float* x2, int64_t rows2,
+                                 int64_t dim, int metric, const float* grad_out, float* g1,
+                                 float* g2, cudaStream_t st);
+int launch_triplet(const float* a, const float* p, const float* n, int64_t batch, int64_t dim,
+                   float margin, int metric, float* out_loss, float* per_row, float* ga, float* gp,
+                   float* gn, cudaStream_t st);
+
+// ---- dist_topk.cu (K1) ----------------------------------------------------------
+constexpr int kTileQ = 128;        // query rows per tile (UMMA M, TMEM lanes)
+constexpr int kTileG = 256;        // gallery rows per tile (UMMA N, TMEM columns)
+constexpr int kUncertainCap = 64;  // per-query capacity of the rank "uncertain band" list
+constexpr int kMaxK = 116;         // largest supported k (list capacity 128 minus slack)
+
+enum K1Mode { kModeTopk = 0, kModeTopkRank = 1, kModeDump = 2, kModeHard = 3 };
+
+// Work decomposition of one K1 launch.  unit = split * num_q_tiles + q_tile; a unit scans the
+// gallery tiles [split*tiles_per_split, min((split+1)*tiles_per_split, num_g_tiles)).
+struct K1Plan {
+  int cap;            // per-list capacity (16, 32, 64 or 128)
+  int lists_per_row;  // 1 (4 epilogue warps) or 2 (8 epilogue warps: one list per column half)
+  int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks;
+  int lists_per_query() const { return num_splits * lists_per_row; }
+};
+K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms);
+
+struct K1Args {
+  const void* q;
+  const void* g;
+  int64_t num_q, num_g, dim;
+  int dtype, metric, mode;
+  const float* gvec;  // [num_g_tiles * kTileG] epilogue vector (‖g‖² | −1/max(‖g‖,eps)), padded
+  // top-k candidate lists, layout [unit*lists_per_row + l][cap][kTileQ]
+  float* cand_val;
+  int32_t* cand_idx;
+  // rank (mode kModeTopkRank): e-space band per query and its outputs
+  const float* rank_lo;
+  const float* rank_hi;
+  int32_t* cnt_less;  // [num_q], zeroed by the caller
+  int32_t* unc_cnt;   // [num_q], zeroed by the caller
+  int32_t* unc_idx;   // [num_q][kUncertainCap]
+  // debug (mode kModeDump): full epilogue matrix [num_q][num_g]
+  float* dump;
+  // batch-hard mining (mode kModeHard): per query row, the labels and outputs
+  const int64_t* row_label;   // [num_q]  (NULL: positive of row i is column i)
+  const int64_t* col_label;   // [num_g]
+  float* hard_val;            // [num_g_tiles][num_q_tiles*kTileQ][2]  (max pos, min neg) e-space
+  int32_t* hard_idx;          // same shape
+};
+int launch_k1(const K1Args& args, const K1Plan& plan, cudaStream_t st);
+
+// ---- finalize.cu ----------------------------------------------------------------
+struct FinalizeArgs {
+  const void* q;
+  const void* g;
+  int64_t num_q, num_g, dim;
+  int dtype, metric, k;
+  int64_t index_offset;
+  const float* cand_val;
+  const int32_t* cand_idx;
+  const float* qsq;        // [num_q] ‖q‖² (fp32)
+  const float* gsq_max;    // [1] max ‖g‖²
+  float kappa;             // error bound of the tensor-core dot product, relative to ‖q‖·‖g‖
+  float* out_dist;         // [num_q][k]
+  int64_t* out_index;      // [num_q][k]
+  int32_t* uncertified;    // [1] counter (may be NULL)
+  int32_t* flags;          // [num_q] bit0: top-k selection not certified
+};
+int launch_finalize_topk(const FinalizeArgs& a, const K1Plan& plan, cudaStream_t st);
+// Brute-force exact top-k for the queries flagged by finalize (flags[q] & 1).
+int launch_topk_fallback(const FinalizeArgs& a, cudaStream_t st);
+
+struct RankArgs {
+  const void* q;
+  const void* g;
+  int64_t num_q, num_g, dim;
+  int dtype, metric;
+  const int64_t* pos_index;  // [num_q] local gallery row of the positive, <0 = none (may be NULL)
+  const double* pos_dist_in; // [num_q] externally supplied positive distance (NaN = none) or NULL
+  const float* qsq;
+  const float* gsq_max;
+  float kappa;
+  double* pos_dist;          // [num_q] workspace
+  float* rank_lo;            // [num_q]
+  float* rank_hi;            // [num_q]
+  int32_t* cnt_less;
+  int32_t* unc_cnt;
+  int32_t* unc_idx;
+  int64_t* out_rank;         // [num_q]
+  int64_t missing_rank;      // value for queries without a positive (num_g in the reference)
+};
+int launch_rank_band(const RankArgs& a, cudaStream_t st);
+int launch_rank_finalize(const RankArgs& a, cudaStream_t st);
+int launch_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
+                             int dtype, int metric, const int64_t* pos_index, double* out,
+                             cudaStream_t st);
+int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
+                      float* out_dist, int64_t* out_index, cudaStream_t st);
+int launch_fill_i64(int64_t* out, int64_t n, int64_t value, cudaStream_t st);
+int launch_retrieval_metrics(const int64_t* rank0, int64_t num_q, int k, double* out, cudaStream_t st);
+
+// ---- batch_hard.cu (K3) -----------------------------------------------------------
+size_t batch_hard_workspace_bytes(int64_t batch, int64_t dim);
+int launch_batch_hard(const float* a, const float* p, const float* n, int64_t batch, int64_t dim,
+                      float margin, int metric, const int64_t* anchor_label, const int64_t* cand_label,
+                      float* out_loss, int64_t* out_hard_index, float* ga, float* gp, float* gn,
+                      void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+// relative error bound of the tensor-core dot product
+inline float k1_kappa(int dtype) { return dtype == 0 /*F32→tf32*/ ? 1.0f / 512.0f * 1.01f : 1.0f / 16384.0f; }
+
+}  // namespace sbir

@@ -1,0 +1,370 @@
+// rowops.cu — the bandwidth-bound row kernels of the hot path (one warp per embedding row,
+// 16-byte coalesced loads, grid sized in multiples of the SM count):
+//   K5  l2_normalize            (H9; implicit in nn.CosineSimilarity, reference utils.py:34)
+//       row_sqnorm / gallery epilogue vector (‖g‖² or −1/max(‖g‖,eps), padded for K1)
+//   H1/H2 pairwise_distance fwd/bwd  (reference utils.py:31-42; inference.py:44,46,62,64)
+//   K2  triplet margin loss fwd+bwd  (reference train.py:169; utils.py:56,69)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sbir {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kRowThreads = kWarpsPerBlock * 32;
+
+int row_grid(int64_t rows) {
+  // Enough blocks to cover the rows once, capped at 16 waves of 148 SMs × 8 resident blocks;
+  // the kernels grid-stride beyond that.
+  const int64_t want = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int64_t cap = 148LL * 8 * 16;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+// ------------------------------------------------------------ l2_normalize ----
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kRowThreads) l2_normalize_kernel(const T* __restrict__ x,
+                                                                   T* __restrict__ y, int64_t rows,
+                                                                   int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const T* xr = x + r * dim;
+    T* yr = y + r * dim;
+    if constexpr (kVec) {
+      constexpr int E = Vec16<T>::kElems;
+      constexpr int kHeld = 8;  // vectors kept in registers per lane (covers 4 KB rows)
+      const int nvec = dim / E;
+      Vec16<T> held[kHeld];
+      double acc = 0.0;
+#pragma unroll
+      for (int h = 0; h < kHeld; ++h) {
+        const int i = lane + 32 * h;
+        if (i < nvec) {
+          held[h].load(xr + (size_t)i * E);
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc += (double)held[h].v[e] * (double)held[h].v[e];
+        }
+      }
+      for (int i = lane + 32 * kHeld; i < nvec; i += 32) {
+        Vec16<T> a;
+        a.load(xr + (size_t)i * E);
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc += (double)a.v[e] * (double)a.v[e];
+      }
+      const float c = fmaxf((float)sqrt(warp_sum(acc)), eps);
+#pragma unroll
+      for (int h = 0; h < kHeld; ++h) {
+        const int i = lane + 32 * h;
+        if (i < nvec) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) held[h].v[e] = __fdiv_rn(held[h].v[e], c);
+          held[h].store(yr + (size_t)i * E);
+        }
+      }
+      for (int i = lane + 32 * kHeld; i < nvec; i += 32) {
+        Vec16<T> a;
+        a.load(xr + (size_t)i * E);
+#pragma unroll
+        for (int e = 0; e < E; ++e) a.v[e] = __fdiv_rn(a.v[e], c);
+        a.store(yr + (size_t)i * E);
+      }
+    } else {
+      double acc = 0.0;
+      for (int i = lane; i < dim; i += 32) {
+        const float t = to_f32(xr[i]);
+        acc += (double)t * (double)t;
+      }
+      const float c = fmaxf((float)sqrt(warp_sum(acc)), eps);
+      for (int i = lane; i < dim; i += 32) from_f32(yr[i], __fdiv_rn(to_f32(xr[i]), c));
+    }
+  }
+}
+
+// ------------------------------------------------- row_sqnorm / epilogue vector ----
+// mode 0: out[r] = ‖x_r‖²                          (fp32, fp64-accumulated)
+// mode 1: out[r] = −1 / max(‖x_r‖, 1e-8)           (cosine epilogue scale for K1)
+// Rows in [rows, rows_padded) receive `pad_value`.  `max_out` (optional) receives the
+// maximum of ‖x_r‖² via an ordered-int atomicMax (values are non-negative).
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kRowThreads) row_norm_kernel(const T* __restrict__ x,
+                                                               int64_t rows, int64_t rows_padded,
+                                                               int dim, int mode, float pad_value,
+                                                               float* __restrict__ out,
+                                                               float* __restrict__ max_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float local_max = 0.f;
+  for (int64_t r = warp0; r < rows_padded; r += nwarps) {
+    if (r >= rows) {
+      if (lane == 0) out[r] = pad_value;
+      continue;
+    }
+    const double sq = warp_sq_norm<T, kVec>(x + r * dim, dim, lane);
+    const float sqf = (float)sq;
+    local_max = fmaxf(local_max, sqf);
+    if (lane == 0) out[r] = (mode == 0) ? sqf : -1.0f / clamped_norm(sq);
+  }
+  if (max_out != nullptr && lane == 0 && local_max > 0.f)
+    atomicMax(reinterpret_cast<int*>(max_out), __float_as_int(local_max));
+}
+
+// ------------------------------------------------------- pairwise distance ----
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kRowThreads) pairwise_distance_kernel(
+    const T* __restrict__ x1, int64_t stride1, const T* __restrict__ x2, int64_t stride2,
+    int64_t rows, int dim, int metric, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const double d = warp_exact_distance<T, kVec>(x1 + r * stride1, x2 + r * stride2, dim, metric, lane);
+    if (lane == 0) out[r] = (float)d;
+  }
+}
+
+// Backward of the row-wise distance (fp32).  Euclidean: ∂d/∂x1 = (x1−x2+eps)/d (0 where
+// d == 0, as torch's norm backward does).  Cosine with c = max(‖·‖, eps), â = a/ca, b̂ = b/cb,
+// s = â·b̂:  ∂d/∂a = −(b̂ − s·â·[‖a‖>eps]) / ca.   A broadcast side accumulates with atomics.
+__global__ void __launch_bounds__(kRowThreads) pairwise_distance_bwd_kernel(
+    const float* __restrict__ x1, int64_t stride1, const float* __restrict__ x2, int64_t stride2,
+    int64_t rows, int dim, int metric, const float* __restrict__ grad_out,
+    float* __restrict__ g1, float* __restrict__ g2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const float* a = x1 + r * stride1;
+    const float* b = x2 + r * stride2;
+    const float go = grad_out[r];
+    if (metric == SBIR_EUCLIDEAN) {
+      const double d = sqrt(warp_sq_l2_eps<float, false>(a, b, dim, lane));
+      const float inv = d > 0.0 ? (float)((double)go / d) : 0.f;
+      for (int i = lane; i < dim; i += 32) {
+        const float t = __fadd_rn(__fsub_rn(a[i], b[i]), kPairwiseEps) * inv;
+        if (g1) { if (stride1) g1[r * dim + i] = t; else atomicAdd(g1 + i, t); }
+        if (g2) { if (stride2) g2[r * dim + i] = -t; else atomicAdd(g2 + i, -t); }
+      }
+    } else {
+      const double sa = warp_sq_norm<float, false>(a, dim, lane);
+      const double sb = warp_sq_norm<float, false>(b, dim, lane);
+      const float ca = clamped_norm(sa), cb = clamped_norm(sb);
+      const float s = (float)warp_cos_dot<float, false>(a, b, ca, cb, dim, lane);
+      const float ma = (float)sqrt(sa) > kCosineEps ? 1.f : 0.f;
+      const float mb = (float)sqrt(sb) > kCosineEps ? 1.f : 0.f;
+      for (int i = lane; i < dim; i += 32) {
+        const float ah = a[i] / ca, bh = b[i] / cb;
+        const float t1 = -go * (bh - s * ah * ma) / ca;
+        const float t2 = -go * (ah - s * bh * mb) / cb;
+        if (g1) { if (stride1) g1[r * dim + i] = t1; else atomicAdd(g1 + i, t1); }
+        if (g2) { if (stride2) g2[r * dim + i] = t2; else atomicAdd(g2 + i, t2); }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ triplet loss ----
+// One 128-thread block per triplet row: both distances, the hinge, and all three gradient
+// rows in one pass over a, p, n (read once, kept in registers for dim <= 4096).
+constexpr int kTripletThreads = 128;
+
+__device__ __forceinline__ double block_sum_128(double v, double* smem4) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) smem4[w] = v;
+  __syncthreads();
+  return smem4[0] + smem4[1] + smem4[2] + smem4[3];
+}
+
+__global__ void __launch_bounds__(kTripletThreads) triplet_rows_kernel(
+    const float* __restrict__ a, const float* __restrict__ p, const float* __restrict__ n,
+    int dim, float margin, int metric, float inv_batch, float* __restrict__ per_row,
+    float* __restrict__ ga, float* __restrict__ gp, float* __restrict__ gn) {
+  __shared__ double red[4];
+  const int64_t r = blockIdx.x;
+  const float* ar = a + r * dim;
+  const float* pr = p + r * dim;
+  const float* nr = n + r * dim;
+  const int t = threadIdx.x;
+
+  double dap, dan;
+  float sap = 0.f, san = 0.f, ca = 1.f, cp = 1.f, cn = 1.f, ma = 0.f, mp = 0.f, mn = 0.f;
+  if (metric == SBIR_EUCLIDEAN) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = t; i < dim; i += kTripletThreads) {
+      const float av = ar[i];
+      const float u = __fadd_rn(__fsub_rn(av, pr[i]), kPairwiseEps);
+      const float v = __fadd_rn(__fsub_rn(av, nr[i]), kPairwiseEps);
+      s1 += (double)u * (double)u;
+      s2 += (double)v * (double)v;
+    }
+    dap = sqrt(block_sum_128(s1, red));
+    dan = sqrt(block_sum_128(s2, red));
+  } else {
+    double qa = 0.0, qp = 0.0, qn = 0.0;
+    for (int i = t; i < dim; i += kTripletThreads) {
+      const float av = ar[i], pv = pr[i], nv = nr[i];
+      qa += (double)av * (double)av;
+      qp += (double)pv * (double)pv;
+      qn += (double)nv * (double)nv;
+    }
+    qa = block_sum_128(qa, red);
+    qp = block_sum_128(qp, red);
+    qn = block_sum_128(qn, red);
+    ca = clamped_norm(qa); cp = clamped_norm(qp); cn = clamped_norm(qn);
+    ma = (float)sqrt(qa) > kCosineEps ? 1.f : 0.f;
+    mp = (float)sqrt(qp) > kCosineEps ? 1.f : 0.f;
+    mn = (float)sqrt(qn) > kCosineEps ? 1.f : 0.f;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = t; i < dim; i += kTripletThreads) {
+      const float ah = __fdiv_rn(ar[i], ca);
+      s1 += (double)__fmul_rn(ah, __fdiv_rn(pr[i], cp));
+      s2 += (double)__fmul_rn(ah, __fdiv_rn(nr[i], cn));
+    }
+    s1 = block_sum_128(s1, red);
+    s2 = block_sum_128(s2, red);
+    sap = (float)s1; san = (float)s2;
+    dap = 1.0 - s1;
+    dan = 1.0 - s2;
+  }
+  // fp32 like torch: clamp_min(margin + d(a,p) - d(a,n), 0)
+  const float hinge_arg = __fsub_rn(__fadd_rn(margin, (float)dap), (float)dan);
+  const float hinge = fmaxf(hinge_arg, 0.f);
+  if (t == 0) per_row[r] = hinge;
+  if (ga == nullptr && gp == nullptr && gn == nullptr) return;
+  const bool active = hinge_arg >= 0.f;  // torch's clamp_min backward passes grad at equality
+  const float w = active ? inv_batch : 0.f;
+  if (metric == SBIR_EUCLIDEAN) {
+    const float iap = dap > 0.0 ? (float)((double)w / dap) : 0.f;
+    const float ian = dan > 0.0 ? (float)((double)w / dan) : 0.f;
+    for (int i = t; i < dim; i += kTripletThreads) {
+      const float av = ar[i];
+      const float u = __fadd_rn(__fsub_rn(av, pr[i]), kPairwiseEps) * iap;
+      const float v = __fadd_rn(__fsub_rn(av, nr[i]), kPairwiseEps) * ian;
+      if (ga) ga[r * dim + i] = u - v;
+      if (gp) gp[r * dim + i] = -u;
+      if (gn) gn[r * dim + i] = v;
+    }
+  } else {
+    // loss term = (1 - s_ap) - (1 - s_an) → d/da = -∂s_ap/∂a + ∂s_an/∂a
+    for (int i = t; i < dim; i += kTripletThreads) {
+      const float ah = ar[i] / ca, ph = pr[i] / cp, nh = nr[i] / cn;
+      const float ds_ap_da = (ph - sap * ah * ma) / ca;
+      const float ds_an_da = (nh - san * ah * ma) / ca;
+      const float ds_ap_dp = (ah - sap * ph * mp) / cp;
+      const float ds_an_dn = (ah - san * nh * mn) / cn;
+      if (ga) ga[r * dim + i] = w * (ds_an_da - ds_ap_da);
+      if (gp) gp[r * dim + i] = -w * ds_ap_dp;
+      if (gn) gn[r * dim + i] = w * ds_an_dn;
+    }
+  }
+}
+
+// Deterministic mean of the per-row hinge terms (fixed summation order, fp64).
+__global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict__ per_row,
+                                                        int64_t rows, float* __restrict__ out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < rows; i += 256) acc += (double)per_row[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(red[0] / (double)rows);
+}
+
+template <typename T>
+int launch_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int mode,
+                float pad_value, float* out, float* max_out, bool vec, cudaStream_t st) {
+  const int grid = row_grid(rows_padded);
+  if (vec)
+    row_norm_kernel<T, true><<<grid, kRowThreads, 0, st>>>((const T*)x, rows, rows_padded, (int)dim,
+                                                           mode, pad_value, out, max_out);
+  else
+    row_norm_kernel<T, false><<<grid, kRowThreads, 0, st>>>((const T*)x, rows, rows_padded,
+                                                            (int)dim, mode, pad_value, out, max_out);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+}  // namespace
+
+int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int dtype,
+                    int mode, float pad_value, float* out, float* max_out, cudaStream_t st) {
+  if (rows_padded <= 0) return SBIR_OK;
+  const bool vec = rows_vectorizable(x, dim, dtype);
+  if (max_out) SBIR_CUDA_TRY(cudaMemsetAsync(max_out, 0, sizeof(float), st));
+  if (dtype == SBIR_F32)
+    return launch_norm<float>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
+  return launch_norm<__nv_bfloat16>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
+}
+
+int launch_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype, float eps,
+                        cudaStream_t st) {
+  if (rows <= 0) return SBIR_OK;
+  const bool vec = rows_vectorizable(x, dim, dtype) && rows_vectorizable(y, dim, dtype);
+  const int grid = row_grid(rows);
+  if (dtype == SBIR_F32) {
+    if (vec) l2_normalize_kernel<float, true><<<grid, kRowThreads, 0, st>>>((const float*)x, (float*)y, rows, (int)dim, eps);
+    else l2_normalize_kernel<float, false><<<grid, kRowThreads, 0, st>>>((const float*)x, (float*)y, rows, (int)dim, eps);
+  } else {
+    using B = __nv_bfloat16;
+    if (vec) l2_normalize_kernel<B, true><<<grid, kRowThreads, 0, st>>>((const B*)x, (B*)y, rows, (int)dim, eps);
+    else l2_normalize_kernel<B, false><<<grid, kRowThreads, 0, st>>>((const B*)x, (B*)y, rows, (int)dim, eps);
+  }
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_pairwise_distance(const void* x1, int64_t rows1, const void* x2, int64_t rows2,
+                             int64_t dim, int dtype, int metric, float* out, cudaStream_t st) {
+  const int64_t rows = rows1 > rows2 ? rows1 : rows2;
+  if (rows <= 0) return SBIR_OK;
+  const int64_t s1 = rows1 == 1 && rows > 1 ? 0 : dim, s2 = rows2 == 1 && rows > 1 ? 0 : dim;
+  const bool vec = rows_vectorizable(x1, dim, dtype) && rows_vectorizable(x2, dim, dtype);
+  const int grid = row_grid(rows);
+  if (dtype == SBIR_F32) {
+    if (vec) pairwise_distance_kernel<float, true><<<grid, kRowThreads, 0, st>>>((const float*)x1, s1, (const float*)x2, s2, rows, (int)dim, metric, out);
+    else pairwise_distance_kernel<float, false><<<grid, kRowThreads, 0, st>>>((const float*)x1, s1, (const float*)x2, s2, rows, (int)dim, metric, out);
+  } else {
+    using B = __nv_bfloat16;
+    if (vec) pairwise_distance_kernel<B, true><<<grid, kRowThreads, 0, st>>>((const B*)x1, s1, (const B*)x2, s2, rows, (int)dim, metric, out);
+    else pairwise_distance_kernel<B, false><<<grid, kRowThreads, 0, st>>>((const B*)x1, s1, (const B*)x2, s2, rows, (int)dim, metric, out);
+  }
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_pairwise_distance_bwd(const float* x1, int64_t rows1, const float* x2, int64_t rows2,
+                                 int64_t dim, int metric, const float* grad_out, float* g1,
+                                 float* g2, cudaStream_t st) {
+  const int64_t rows = rows1 > rows2 ? rows1 : rows2;
+  if (rows <= 0) return SBIR_OK;
+  const int64_t s1 = rows1 == 1 && rows > 1 ? 0 : dim, s2 = rows2 == 1 && rows > 1 ? 0 : dim;
+  if (g1 && s1 == 0) SBIR_CUDA_TRY(cudaMemsetAsync(g1, 0, sizeof(float) * dim, st));
+  if (g2 && s2 == 0) SBIR_CUDA_TRY(cudaMemsetAsync(g2, 0, sizeof(float) * dim, st));
+  pairwise_distance_bwd_kernel<<<row_grid(rows), kRowThreads, 0, st>>>(x1, s1, x2, s2, rows, (int)dim,
+                                                                       metric, grad_out, g1, g2);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_triplet(const float* a, const float* p, const float* n, int64_t batch, int64_t dim,
+                   float margin, int metric, float* out_loss, float* per_row, float* ga, float* gp,
+                   float* gn, cudaStream_t st) {
+  triplet_rows_kernel<<<(unsigned)batch, kTripletThreads, 0, st>>>(a, p, n, (int)dim, margin, metric,
+                                                                  1.0f / (float)batch, per_row, ga,
+                                                                  gp, gn);
+  SBIR_CHECK_LAUNCH();
+  mean_rows_kernel<<<1, 256, 0, st>>>(per_row, batch, out_loss);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+}  // namespace sbir

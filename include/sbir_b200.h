@@ -1,0 +1,186 @@
+/*
+ * sbir_b200.h — C ABI of the B200-native retrieval / triplet hot path.
+ *
+ * This is the drop-in boundary for the stage of Peer222/art-sbir that follows the
+ * sketch and artwork encoders.  The reference has no FFI of its
+ * own: that stage is a handful of Python callables on torch tensors.  Every entry
+ * point below names the reference call site it replaces (file:line relative to the
+ * reference checkout); INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every buffer (inputs, outputs, workspace) is DEVICE memory owned by the
+ *     caller unless the function name ends in `_host`;
+ *   - row-major, contiguous `[rows, dim]` matrices; `dtype` selects the element
+ *     type of the embedding matrices (SBIR_F32 or SBIR_BF16);
+ *   - enqueue-only on `stream` (a cudaStream_t passed as void*); no device-wide
+ *     synchronisation inside, re-entrant across streams;
+ *   - return value is an sbir_status; 0 = success; nothing throws or aborts.
+ */
+#ifndef SBIR_B200_H_
+#define SBIR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBIR_B200_ABI_VERSION 1
+
+typedef enum sbir_status {
+  SBIR_OK = 0,
+  SBIR_ERR_INVALID_ARG = 1, /* null pointer, negative size, bad enum                */
+  SBIR_ERR_UNSUPPORTED = 2, /* shape outside what the kernels handle (see each fn)  */
+  SBIR_ERR_CUDA = 3,        /* a CUDA runtime/driver call failed; see last_cuda_err */
+  SBIR_ERR_WORKSPACE = 4,   /* workspace pointer null/unaligned or too small        */
+  SBIR_ERR_NO_DEVICE = 5    /* no sm_100 device visible                             */
+} sbir_status;
+
+typedef enum sbir_dtype { SBIR_F32 = 0, SBIR_BF16 = 1 } sbir_dtype;
+
+/* `loss_type` of the reference: 'euclidean' (utils.py:42) or 'cosine' (utils.py:31-40). */
+typedef enum sbir_metric { SBIR_EUCLIDEAN = 0, SBIR_COSINE = 1 } sbir_metric;
+
+/* ---- introspection -------------------------------------------------------- */
+int sbir_abi_version(void);
+const char* sbir_status_string(int status);
+/* cudaError_t of the last failing CUDA call seen by this thread (0 if none). */
+int sbir_last_cuda_error(void);
+/* 1 if the current device is compute capability 10.x, else 0. */
+int sbir_device_supported(void);
+
+/* ---- H9: L2 normalisation (implicit in nn.CosineSimilarity, utils.py:34) ---
+ * y[i,:] = x[i,:] / max(||x[i,:]||_2, eps).  In/out dtype identical.  y may alias x. */
+int sbir_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype,
+                      float eps, void* stream);
+
+/* out[i] = ||x[i,:]||_2^2 (fp32, accumulated in fp64). */
+int sbir_row_sqnorm(const void* x, int64_t rows, int64_t dim, int dtype, float* out,
+                    void* stream);
+
+/* ---- H1 / H2: row-wise distance, the reference's distance modules ----------
+ * utils.euclidean_distance = nn.PairwiseDistance(p=2)  (utils.py:42; called at
+ * inference.py:44,62) and utils.cosine_distance (utils.py:31-40; inference.py:46,64).
+ * x1 is [rows1, dim], x2 is [rows2, dim]; rows1 and rows2 are equal, or one of
+ * them is 1 (torch broadcasting).  out is fp32 [max(rows1, rows2)].
+ *   euclidean: out[i] = || x1[i] - x2[i] + 1e-6 ||_2
+ *   cosine   : out[i] = 1 - sum_d (x1/max(||x1||,1e-8)) * (x2/max(||x2||,1e-8))   */
+int sbir_pairwise_distance(const void* x1, int64_t rows1, const void* x2, int64_t rows2,
+                           int64_t dim, int dtype, int metric, float* out, void* stream);
+
+/* Backward of sbir_pairwise_distance for fp32 inputs: given grad_out [rows],
+ * writes grad_x1 [rows1, dim] and grad_x2 [rows2, dim] (either may be NULL).
+ * A broadcast side (rows == 1) receives the sum over rows. */
+int sbir_pairwise_distance_bwd(const float* x1, int64_t rows1, const float* x2, int64_t rows2,
+                               int64_t dim, int metric, const float* grad_out,
+                               float* grad_x1, float* grad_x2, void* stream);
+
+/* ---- H1+H3+H4 batched: distance + top-K (+ rank of the positive) ------------
+ * Replaces the per-query loop inference.py:109-121 → get_ranking_position
+ * (inference.py:30-57) and get_topk_images (inference.py:60-69):
+ *   for every query row q of Q[num_q, dim] against the gallery G[num_g, dim]
+ *     out_dist[q, 0:k]  = the k smallest distances, ascending (fp32),
+ *     out_index[q, 0:k] = their gallery row indices + index_offset (int64),
+ *                         ties broken by ascending index,
+ *     out_rank[q]       = #{ j : dist(q, j) < dist(q, pos_index[q]) }  (int64) — the
+ *                         0-based position the reference finds with topk(len(G)) at
+ *                         inference.py:49-52 — when pos_index != NULL; entries with
+ *                         pos_index[q] < 0 get num_g (inference.py:39-41).
+ * The distance matrix is never materialised: tcgen05 tiles of Q·Gᵀ feed a fused
+ * per-query selection, the K(+slack) survivors are re-scored with the exact
+ * reference formula, and `out_uncertified[0]` counts queries whose selection could
+ * not be proven exact (they are then recomputed by the brute-force exact kernel, so
+ * results are exact either way; the counter is diagnostic).
+ * k <= 116; dim*sizeof(elem) must be a multiple of 16 bytes; pointers 16-byte aligned.
+ * out_rank, pos_index, out_uncertified may be NULL. */
+size_t sbir_pairwise_topk_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int k,
+                                          int dtype, int metric, int want_rank);
+int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
+                       int dtype, int metric, int k, int64_t index_offset,
+                       const int64_t* pos_index, float* out_dist, int64_t* out_index,
+                       int64_t* out_rank, int32_t* out_uncertified, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* Rank-only partial results for a gallery SHARD (multi-GPU): same
+ * as above but the positive's distance is supplied (pos_dist, fp64 [num_q], from
+ * sbir_positive_distance on the owning shard, all-reduced by the caller) and the
+ * count is local to this shard; the caller sums counts across shards. */
+int sbir_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g,
+                           int64_t dim, int dtype, int metric, const int64_t* pos_index_local,
+                           double* out_pos_dist, void* stream);
+int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, int64_t num_g,
+                             int64_t dim, int dtype, int metric, int k, int64_t index_offset,
+                             const double* pos_dist, float* out_dist, int64_t* out_index, int64_t* out_count_less,
+                             int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* ---- K4: merge of per-shard top-K lists (after the NCCL all-gather) ---------
+ * dist/index are [num_lists, num_q, k], each list ascending; writes the k smallest
+ * of the union per query, ascending, ties by ascending index. */
+int sbir_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
+                    float* out_dist, int64_t* out_index, void* stream);
+
+/* ---- H5: retrieval metrics (inference.py:95-98,113-134) ---------------------
+ * rank0 is the 0-based rank per query.  Writes, as fp64:
+ *   out[0]            = mean reciprocal rank  (sum 1/(rank0+1) / num_q)
+ *   out[1 .. k]       = topk_acc[0..k-1]      (#{rank0 <= i} / num_q)
+ *   out[k+1]          = mean of (rank0+1),  out[k+2] = sample std (ddof=1),
+ *   out[k+3]          = min, out[k+4] = max   (of rank0+1)
+ * (quartiles need a sort; the host mirror computes them from the rank vector). */
+int sbir_retrieval_metrics(const int64_t* rank0, int64_t num_q, int k, double* out, void* stream);
+
+/* ---- H6 / H7: triplet margin loss, forward + backward in one launch ---------
+ * nn.TripletMarginLoss(margin) (train.py:169) and
+ * nn.TripletMarginWithDistanceLoss(margin, distance_function) (utils.py:56,69):
+ *   loss = mean_i max(0, margin + d(a_i,p_i) - d(a_i,n_i)), d per `metric`.
+ * a, p, n are fp32 [batch, dim].  out_loss is one fp32.  grad_* (fp32 [batch, dim],
+ * any may be NULL) receive d loss / d input (i.e. already scaled by 1/batch).
+ * out_per_row (fp32 [batch], may be NULL) receives the un-averaged hinge terms. */
+int sbir_triplet_margin_loss(const float* a, const float* p, const float* n, int64_t batch,
+                             int64_t dim, float margin, int metric, float* out_loss,
+                             float* out_per_row, float* grad_a, float* grad_p, float* grad_n,
+                             void* stream);
+
+/* ---- H8: batch-hard triplet loss (north_star extension) ------
+ * candidates X = cat(p, n) [2*batch, dim]; D_ij = d(a_i, X_j) on tcgen05 tiles;
+ * positives of anchor i: {i} when labels == NULL, else {j : cand_label[j] == anchor_label[i]};
+ * hp_i = max over positives, hn_i = min over the rest;
+ * loss = mean_i max(0, margin + hp_i - hn_i).  Mining runs on the tensor-core
+ * tiles; the selected pairs are re-scored with the exact distance, and gradients
+ * flow through the selected pairs only (deterministic two-pass scatter).
+ * out_hard_index int64 [batch, 2] (positive, negative candidate index; may be NULL). */
+size_t sbir_batch_hard_workspace_bytes(int64_t batch, int64_t dim);
+int sbir_batch_hard_triplet_loss(const float* a, const float* p, const float* n, int64_t batch,
+                                 int64_t dim, float margin, int metric,
+                                 const int64_t* anchor_label, const int64_t* cand_label,
+                                 float* out_loss, int64_t* out_hard_index, float* grad_a,
+                                 float* grad_p, float* grad_n, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
+/* ---- end-to-end with HOST buffers (bench.py `e2e`) ----------
+ * q_host / g_host are host (preferably pinned) matrices; results land in host
+ * buffers.  Gallery chunks are uploaded on a copy stream while earlier chunks are
+ * scored; device staging memory is allocated internally and cached per device.
+ * Synchronous: returns when out_* are valid. */
+int sbir_retrieve_host(const void* q_host, int64_t num_q, const void* g_host, int64_t num_g,
+                       int64_t dim, int dtype, int metric, int k, const int64_t* pos_index_host,
+                       float* out_dist_host, int64_t* out_index_host, int64_t* out_rank_host,
+                       int32_t* out_uncertified_host);
+/* Frees the cached staging memory of sbir_retrieve_host. */
+int sbir_release_host_staging(void);
+
+/* ---- debug / self-test ------------------------------------------------------
+ * Writes the raw epilogue matrix E[num_q, num_g] (euclidean: ||g||²-2qg, cosine:
+ * -q·g/max(||g||,eps)) computed by the tcgen05 tiles; used by tests to validate the
+ * tensor-core path in isolation.  out_e is fp32 [num_q, num_g]. */
+size_t sbir_debug_dist_matrix_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int dtype);
+int sbir_debug_dist_matrix(const void* q, int64_t num_q, const void* g, int64_t num_g,
+                           int64_t dim, int dtype, int metric, float* out_e, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* SBIR_B200_H_ */
