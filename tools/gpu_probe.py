@@ -1,0 +1,250 @@
+"""GPU bring-up probe: runs each check in its own subprocess (a trapped kernel must not take
+the other checks down) and writes gpurun_out/probe.log.  Usage on the GPU box:
+    python tools/gpu_probe.py            # all cases
+    python tools/gpu_probe.py <case>     # one case, in-process
+Not part of the test-suite; torch is used here only as an on-device comparison.
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _data(nq, ng, d, dtype, seed=0):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    q = torch.randn(nq, d, device="cuda", generator=g)
+    x = torch.randn(ng, d, device="cuda", generator=g)
+    c = torch.randn(8, d, device="cuda", generator=g)
+    q = q + c[torch.arange(nq, device="cuda") % 8]
+    x = x + c[torch.arange(ng, device="cuda") % 8]
+    return q.to(dtype).contiguous(), x.to(dtype).contiguous()
+
+
+def case_rowops():
+    import torch
+    from art_sbir_b200 import ops
+    res = {}
+    for dtype in (torch.float32, torch.bfloat16):
+        x, y = _data(1000, 1000, 520 if dtype == torch.float32 else 520, dtype)
+        n = ops.l2_normalize(x)
+        ref = torch.nn.functional.normalize(x.float(), dim=1, eps=1e-8)
+        res[f"l2norm_{dtype}"] = (n.float() - ref).abs().max().item()
+        s = ops.row_sqnorm(x)
+        res[f"sqnorm_rel_{dtype}"] = ((s - (x.double() ** 2).sum(1)).abs() / s).max().item()
+        d = ops.pairwise_distance(x[:1], y, "euclidean")
+        ref = torch.nn.PairwiseDistance(p=2)(x[:1].float(), y.float())
+        res[f"pdist_rel_{dtype}"] = ((d - ref).abs() / ref).max().item()
+        d = ops.pairwise_distance(x, y, "cosine")
+        ref = 1 - torch.nn.CosineSimilarity(dim=1)(x.float(), y.float())
+        res[f"cos_abs_{dtype}"] = (d - ref).abs().max().item()
+    return res
+
+
+def _dump_case(nq, ng, d, dtype_name, metric):
+    import torch
+    from art_sbir_b200 import ops
+    dtype = getattr(torch, dtype_name)
+    q, g = _data(nq, ng, d, dtype)
+    e = ops.debug_dist_matrix(q, g, metric)
+    torch.cuda.synchronize()
+    qd, gd = q.double(), g.double()
+    if metric == "euclidean":
+        ref = (gd ** 2).sum(1)[None, :] - 2 * qd @ gd.T
+        scale = ((qd ** 2).sum(1).max() + (gd ** 2).sum(1).max()).item()
+    else:
+        ref = -(qd @ gd.T) / gd.norm(dim=1).clamp_min(1e-8)[None, :]
+        scale = qd.norm(dim=1).max().item()
+    err = (e.double() - ref).abs()
+    nan_frac = torch.isnan(e).float().mean().item()
+    err = torch.nan_to_num(err, nan=0.0)
+    worst = err.argmax().item()
+    return {"shape": [nq, ng, d, dtype_name, metric], "max_abs_err": err.max().item(), "rel_to_scale": err.max().item() / scale,
+            "mean_abs_err": err.mean().item(), "nan_frac": nan_frac, "worst_rc": [worst // ng, worst % ng],
+            "sample": [e[0, 0].item(), ref[0, 0].item(), e[-1, -1].item(), ref[-1, -1].item()]}
+
+
+def case_dump_small():
+    return [_dump_case(128, 256, 32, "float32", "euclidean"), _dump_case(128, 256, 64, "float32", "euclidean"),
+            _dump_case(128, 256, 64, "bfloat16", "euclidean")]
+
+
+def case_dump_shapes():
+    out = []
+    for args in [(200, 700, 256, "float32", "euclidean"), (130, 1000, 2048, "float32", "euclidean"),
+                 (300, 513, 512, "bfloat16", "euclidean"), (100, 300, 96, "float32", "cosine"),
+                 (257, 2049, 1024, "bfloat16", "cosine"), (1000, 10000, 2048, "float32", "euclidean")]:
+        out.append(_dump_case(*args))
+    return out
+
+
+def _topk_case(nq, ng, d, dtype_name, metric, k, with_rank=True):
+    import torch
+    from art_sbir_b200 import ops
+    dtype = getattr(torch, dtype_name)
+    q, g = _data(nq, ng, d, dtype, seed=1)
+    pos = torch.randint(0, ng, (nq,), device="cuda")
+    pos[::7] = -1
+    t0 = time.time()
+    if with_rank:
+        vals, idx, rank, unc = ops.pairwise_topk(q, g, k, metric, pos_index=pos, return_uncertified=True)
+    else:
+        vals, idx, unc = ops.pairwise_topk(q, g, k, metric, return_uncertified=True)
+        rank = None
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    qd, gd = q.double(), g.double()
+    if metric == "euclidean":
+        dm = ((qd[:, None, :] - gd[None, :, :] + 1e-6) ** 2).sum(-1).sqrt() if nq * ng * d < 2e8 else torch.cdist(qd, gd)
+    else:
+        dm = 1 - (qd / qd.norm(dim=1, keepdim=True).clamp_min(1e-8)) @ (gd / gd.norm(dim=1, keepdim=True).clamp_min(1e-8)).T
+    rv, ri = dm.topk(min(k, ng), dim=1, largest=False)
+    kk = min(k, ng)
+    idx_match = (idx[:, :kk] == ri).float().mean().item()
+    val_err = ((vals[:, :kk].double() - rv).abs() / rv.abs().clamp_min(1e-12)).max().item()
+    res = {"shape": [nq, ng, d, dtype_name, metric, k], "idx_match": idx_match, "val_rel_err": val_err,
+           "uncertified": int(unc.item()), "first_call_s": dt}
+    if with_rank:
+        has = pos >= 0
+        dpos = dm.gather(1, pos.clamp_min(0)[:, None])
+        rr = (dm < dpos).sum(1)
+        rr = torch.where(has, rr, torch.full_like(rr, ng))
+        res["rank_match"] = (rank == rr).float().mean().item()
+        res["rank_maxdiff"] = (rank - rr).abs().max().item()
+    return res
+
+
+def case_topk_small():
+    return [_topk_case(100, 1000, 64, "float32", "euclidean", 10), _topk_case(128, 256, 64, "bfloat16", "euclidean", 10),
+            _topk_case(5, 7, 64, "float32", "euclidean", 10), _topk_case(333, 5000, 512, "bfloat16", "cosine", 10),
+            _topk_case(200, 3000, 128, "float32", "cosine", 5)]
+
+
+def case_topk_mid():
+    return [_topk_case(1000, 10000, 2048, "float32", "euclidean", 10), _topk_case(500, 20000, 1024, "float32", "euclidean", 100),
+            _topk_case(1000, 50000, 512, "bfloat16", "euclidean", 10), _topk_case(300, 9000, 256, "bfloat16", "euclidean", 50)]
+
+
+def case_triplet():
+    import torch
+    from art_sbir_b200 import ops
+    res = {}
+    for metric in ("euclidean", "cosine"):
+        torch.manual_seed(0)
+        a, p, n = (torch.randn(256, 2048, device="cuda", requires_grad=True) for _ in range(3))
+        loss = ops.triplet_margin_loss(a, p, n, 0.2, metric)
+        loss.backward()
+        ga, gp, gn = a.grad.clone(), p.grad.clone(), n.grad.clone()
+        a.grad = p.grad = n.grad = None
+        if metric == "euclidean":
+            ref = torch.nn.TripletMarginLoss(margin=0.2)(a, p, n)
+        else:
+            cosd = lambda x, y: 1 - torch.nn.CosineSimilarity(dim=1)(x, y)
+            ref = torch.nn.TripletMarginWithDistanceLoss(margin=0.2, distance_function=cosd)(a, p, n)
+        ref.backward()
+        res[metric] = {"loss": loss.item(), "ref": ref.item(),
+                       "grad_rel": max(((x - y.grad).abs().max() / y.grad.abs().max()).item() for x, y in ((ga, a), (gp, p), (gn, n)))}
+    return res
+
+
+def case_batch_hard():
+    import torch
+    from art_sbir_b200 import ops
+    res = {}
+    for metric in ("euclidean", "cosine"):
+        torch.manual_seed(1)
+        a, p, n = (torch.randn(256, 2048, device="cuda", requires_grad=True) for _ in range(3))
+        loss, hard = ops.batch_hard_triplet_loss(a, p, n, 0.2, metric, return_indices=True)
+        loss.backward()
+        ga, gp, gn = a.grad.clone(), p.grad.clone(), n.grad.clone()
+        a.grad = p.grad = n.grad = None
+        x = torch.cat([p, n])
+        if metric == "euclidean":
+            dm = torch.cdist(a, x)
+        else:
+            dm = 1 - torch.nn.functional.normalize(a, dim=1, eps=1e-8) @ torch.nn.functional.normalize(x, dim=1, eps=1e-8).T
+        posmask = torch.zeros_like(dm, dtype=torch.bool)
+        posmask[torch.arange(256), torch.arange(256)] = True
+        hp = dm.masked_fill(~posmask, -1e30).max(1)
+        hn = dm.masked_fill(posmask, 1e30).min(1)
+        ref = (0.2 + hp.values - hn.values).clamp_min(0).mean()
+        ref.backward()
+        res[metric] = {"loss": loss.item(), "ref": ref.item(), "hp_match": (hard[:, 0] == hp.indices).float().mean().item(),
+                       "hn_match": (hard[:, 1] == hn.indices).float().mean().item(),
+                       "grad_rel": max(((x_ - y.grad).abs().max() / y.grad.abs().max().clamp_min(1e-30)).item()
+                                       for x_, y in ((ga, a), (gp, p), (gn, n)))}
+    return res
+
+
+def _time_topk(nq, ng, d, dtype_name, k, iters=3, rank=False):
+    import torch
+    from art_sbir_b200 import ops
+    dtype = getattr(torch, dtype_name)
+    q = torch.randn(nq, d, device="cuda").to(dtype)
+    g = torch.randn(ng, d, device="cuda").to(dtype)
+    pos = torch.randint(0, ng, (nq,), device="cuda") if rank else None
+    ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = min(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    pairs = nq * ng
+    return {"shape": [nq, ng, d, dtype_name, k, rank], "ms": ms, "pairs_per_s": pairs / ms * 1e3,
+            "tflops": 2 * d * pairs / ms * 1e3 / 1e12}
+
+
+def case_time():
+    return [_time_topk(1000, 10000, 2048, "float32", 10), _time_topk(12500, 75000, 2048, "float32", 100),
+            _time_topk(12500, 75000, 2048, "float32", 10), _time_topk(12500, 75000, 2048, "float32", 10, rank=True),
+            _time_topk(20000, 1000000, 512, "bfloat16", 10), _time_topk(20000, 1000000, 512, "bfloat16", 10, rank=True),
+            _time_topk(12500, 75000, 2048, "bfloat16", 10)]
+
+
+def case_host():
+    import torch
+    import ctypes
+    from art_sbir_b200 import _binding as B, ops
+    nq, ng, d, k = 500, 20000, 512, 10
+    q = torch.randn(nq, d).bfloat16().pin_memory()
+    g = torch.randn(ng, d).bfloat16().pin_memory()
+    pos = torch.randint(0, ng, (nq,), dtype=torch.int64)
+    od = torch.empty(nq, k).pin_memory()
+    oi = torch.empty(nq, k, dtype=torch.int64).pin_memory()
+    orank = torch.empty(nq, dtype=torch.int64).pin_memory()
+    unc = ctypes.c_int32(0)
+    lib = B.load()
+    B.check(lib.sbir_retrieve_host(q.data_ptr(), nq, g.data_ptr(), ng, d, B.SBIR_BF16, 0, k, pos.data_ptr(),
+                                   od.data_ptr(), oi.data_ptr(), orank.data_ptr(), ctypes.byref(unc)), "retrieve_host")
+    v, i, r = ops.pairwise_topk(q.cuda(), g.cuda(), k, "euclidean", pos_index=pos.cuda())
+    return {"idx_equal": bool((i.cpu() == oi).all()), "val_equal": bool((v.cpu() == od).all()),
+            "rank_equal": bool((r.cpu() == orank).all()), "unc": unc.value}
+
+
+CASES = ["rowops", "dump_small", "dump_shapes", "topk_small", "topk_mid", "triplet", "batch_hard", "host", "time"]
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        out = globals()["case_" + sys.argv[1]]()
+        print("RESULT " + json.dumps(out))
+        sys.exit(0)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/probe.log", "w") as log:
+        for c in CASES:
+            t0 = time.time()
+            try:
+                r = subprocess.run([sys.executable, __file__, c], capture_output=True, text=True, timeout=400)
+                tail = (r.stdout[-6000:] + "\n--stderr--\n" + r.stderr[-3000:]) if r.returncode else \
+                    "\n".join(l for l in r.stdout.splitlines() if l.startswith("RESULT"))
+                msg = f"=== {c} rc={r.returncode} {time.time() - t0:.1f}s\n{tail}\n"
+            except subprocess.TimeoutExpired:
+                msg = f"=== {c} TIMEOUT\n"
+            log.write(msg)
+            log.flush()
+            print(msg)
