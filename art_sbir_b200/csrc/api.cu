@@ -30,8 +30,9 @@ bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 // Workspace of sbir_pairwise_topk / _shard (all offsets 256-byte aligned).
 struct TopkLayout {
   K1Plan plan;
-  size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert;
-  size_t off_pos_dist, off_lo, off_hi, off_cnt, off_unc_cnt, off_unc_idx, off_rank_tmp;
+  size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert, off_shared_thr;
+  size_t off_pos_dist, off_lo, off_hi, off_cnt, off_dropped, off_pool_count, off_pool_q, off_pool_idx;
+  uint32_t pool_cap;
   size_t total;
 };
 
@@ -49,14 +50,18 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   L.off_cand_idx = take(cand * sizeof(int32_t));
   L.off_flags = take(nq * sizeof(int32_t));
   L.off_uncert = take(sizeof(int32_t));
+  L.off_shared_thr = take((size_t)L.plan.num_q_tiles * kTileQ * sizeof(int32_t));
   if (want_rank) {
     L.off_pos_dist = take(nq * sizeof(double));
     L.off_lo = take(nq * sizeof(float));
     L.off_hi = take(nq * sizeof(float));
     L.off_cnt = take(nq * sizeof(int32_t));
-    L.off_unc_cnt = take(nq * sizeof(int32_t));
-    L.off_unc_idx = take(nq * kUncertainCap * sizeof(int32_t));
-    L.off_rank_tmp = take(nq * sizeof(int64_t));
+    L.off_dropped = take(nq * sizeof(int32_t));
+    L.off_pool_count = take(sizeof(uint32_t));
+    const size_t cap = nq * kUncertainPerQuery < 65536 ? 65536 : nq * kUncertainPerQuery;
+    L.pool_cap = (uint32_t)(cap > 0x7fffffffu ? 0x7fffffffu : cap);
+    L.off_pool_q = take((size_t)L.pool_cap * sizeof(int32_t));
+    L.off_pool_idx = take((size_t)L.pool_cap * sizeof(int32_t));
   }
   L.total = o;
   return L;
@@ -116,12 +121,16 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
     ra.rank_lo = reinterpret_cast<float*>(ws + L.off_lo);
     ra.rank_hi = reinterpret_cast<float*>(ws + L.off_hi);
     ra.cnt_less = reinterpret_cast<int32_t*>(ws + L.off_cnt);
-    ra.unc_cnt = reinterpret_cast<int32_t*>(ws + L.off_unc_cnt);
-    ra.unc_idx = reinterpret_cast<int32_t*>(ws + L.off_unc_idx);
+    ra.dropped = reinterpret_cast<int32_t*>(ws + L.off_dropped);
+    ra.pool_count = reinterpret_cast<uint32_t*>(ws + L.off_pool_count);
+    ra.pool_cap = L.pool_cap;
+    ra.pool_q = reinterpret_cast<int32_t*>(ws + L.off_pool_q);
+    ra.pool_idx = reinterpret_cast<int32_t*>(ws + L.off_pool_idx);
     ra.out_rank = out_rank;
     ra.missing_rank = missing_rank;
     SBIR_CUDA_TRY(cudaMemsetAsync(ra.cnt_less, 0, (size_t)num_q * sizeof(int32_t), st));
-    SBIR_CUDA_TRY(cudaMemsetAsync(ra.unc_cnt, 0, (size_t)num_q * sizeof(int32_t), st));
+    SBIR_CUDA_TRY(cudaMemsetAsync(ra.dropped, 0, (size_t)num_q * sizeof(int32_t), st));
+    SBIR_CUDA_TRY(cudaMemsetAsync(ra.pool_count, 0, sizeof(uint32_t), st));
     SBIR_TRY(launch_rank_band(ra, st));
   }
 
@@ -132,7 +141,11 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   ka.gvec = gvec;
   ka.cand_val = cand_val; ka.cand_idx = cand_idx;
   ka.rank_lo = ra.rank_lo; ka.rank_hi = ra.rank_hi;
-  ka.cnt_less = ra.cnt_less; ka.unc_cnt = ra.unc_cnt; ka.unc_idx = ra.unc_idx;
+  ka.cnt_less = ra.cnt_less;
+  ka.pool_count = ra.pool_count; ka.pool_cap = ra.pool_cap; ka.pool_q = ra.pool_q; ka.pool_idx = ra.pool_idx;
+  ka.dropped = ra.dropped;
+  ka.shared_thr = reinterpret_cast<int32_t*>(ws + L.off_shared_thr);
+  SBIR_TRY(launch_fill_i32(ka.shared_thr, (int64_t)L.plan.num_q_tiles * kTileQ, 0x7f800000, st));
   SBIR_TRY(launch_k1(ka, L.plan, st));
 
   FinalizeArgs fa{};

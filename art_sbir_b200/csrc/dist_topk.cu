@@ -34,11 +34,29 @@ constexpr int kStageBytes = kStageBytesQ + kStageBytesG;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kTmemCols = 512;  // two 256-column fp32 accumulators
 
+// Monotone float <-> int32 map so a float minimum can be taken with an integer atomicMin.
+__device__ __forceinline__ int32_t float_to_ordered_int(float f) {
+  const int32_t b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_int_to_float(int32_t i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+__device__ __forceinline__ int32_t ld_relaxed(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int kCap, int kEpiWarps>
 struct K1Config {
   static constexpr int kListsPerRow = kEpiWarps / 4;
-  static constexpr bool kSmemLists = kCap * kListsPerRow <= 64;
-  static constexpr int kListBytes = kSmemLists ? kCap * kListsPerRow * kTileQ * 8 : 0;
+  // distance keys of the running lists always live in shared memory (they are re-scanned on
+  // every insertion); the gallery indices are write-only until the end and go straight to
+  // the global candidate buffer when they do not fit beside the operand ring.
+  static constexpr bool kIdxInSmem = kCap * kListsPerRow <= 64;
+  static constexpr int kValBytes = kCap * kListsPerRow * kTileQ * 4;
+  static constexpr int kListBytes = kValBytes + (kIdxInSmem ? kValBytes : 0);
   static constexpr int kBarrierBytes = 256;
   static constexpr int kStagesFit = (kSmemLimit - 1024 - kListBytes - kBarrierBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 4 ? 4 : kStagesFit;
@@ -59,8 +77,12 @@ struct K1Params {
   const float* rank_lo;
   const float* rank_hi;
   int32_t* cnt_less;
-  int32_t* unc_cnt;
-  int32_t* unc_idx;
+  uint32_t* pool_count;
+  uint32_t pool_cap;
+  int32_t* pool_q;
+  int32_t* pool_idx;
+  int32_t* dropped;
+  int32_t* shared_thr;
   float* dump;
   const int64_t* row_label;
   const int64_t* col_label;
@@ -82,7 +104,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint8_t* smem_q = smem;
   uint8_t* smem_g = smem + kStages * kStageBytesQ;
   float* list_val_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);
-  int32_t* list_idx_s = reinterpret_cast<int32_t*>(list_val_s + (Cfg::kSmemLists ? kCap * Cfg::kListsPerRow * kTileQ : 0));
+  int32_t* list_idx_s = reinterpret_cast<int32_t*>(list_val_s + kCap * Cfg::kListsPerRow * kTileQ);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kListBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
@@ -188,26 +210,20 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const bool q_valid = q < prm.num_q;
 
       // This thread's list: entry p lives at [p * kTileQ + row] (conflict-free / coalesced).
-      float* lv;
-      int32_t* li;
       const size_t list_slot = (size_t)unit * Cfg::kListsPerRow + half;
-      if constexpr (Cfg::kSmemLists) {
-        lv = list_val_s + half * kCap * kTileQ;
-        li = list_idx_s + half * kCap * kTileQ;
-      } else {
-        lv = prm.cand_val + list_slot * kCap * kTileQ;
-        li = prm.cand_idx + list_slot * kCap * kTileQ;
-      }
-      float thr = INFINITY;
+      float* lv = list_val_s + half * kCap * kTileQ;
+      int32_t* li;
+      if constexpr (Cfg::kIdxInSmem) li = list_idx_s + half * kCap * kTileQ;
+      else li = prm.cand_idx + list_slot * kCap * kTileQ;
+      float thr = INFINITY;      // insertion threshold = min(own list maximum, shared threshold)
+      float own_max = INFINITY;  // maximum of this thread's list (+inf until it is full)
+      float published = INFINITY;
       int maxpos = 0;
       float lo = -INFINITY, hi = -INFINITY;
       int cnt = 0;
       if constexpr (kSelect) {
 #pragma unroll 4
-        for (int p = 0; p < kCap; ++p) {
-          lv[p * kTileQ + row] = INFINITY;
-          li[p * kTileQ + row] = -1;
-        }
+        for (int p = 0; p < kCap; ++p) lv[p * kTileQ + row] = INFINITY;
       }
       if constexpr (kRank) {
         if (q_valid) {
@@ -223,6 +239,13 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
 
       for (int t = t0; t < t1; ++t) {
+        if constexpr (kSelect) {
+          // Another split (or the other column half) scanning the same query may already hold
+          // `cap` candidates below some value: nothing at or above it can reach the final
+          // best-`cap`, so adopt it as an upper bound on this list's threshold.
+          const float shared = ordered_int_to_float(ld_relaxed(prm.shared_thr + q_tile * kTileQ + row));
+          thr = fminf(thr, shared);
+        }
         mbar_wait(&acc_full_bar[acc], acc_phase);
         tc_fence_after();
         const float* gv = prm.gvec + (size_t)t * kTileG + col_begin;
@@ -298,17 +321,32 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const float v = lv[p * kTileQ + row];
                     if (v > mx) { mx = v; mp = p; }
                   }
-                  thr = mx;
+                  own_max = mx;
+                  thr = fminf(thr, mx);
                   maxpos = mp;
                 }
                 if constexpr (kRank) {
                   if (ej >= lo && ej < hi) {
-                    const int slot = atomicAdd(prm.unc_cnt + q, 1);
-                    if (slot < kUncertainCap) prm.unc_idx[(size_t)q * kUncertainCap + slot] = gcol0 + j;
+                    // approximate comparison against d_pos is not trustworthy: queue the
+                    // pair for exact evaluation (finalize.cu: rank_resolve_kernel)
+                    const uint32_t slot = atomicAdd(prm.pool_count, 1u);
+                    if (slot < prm.pool_cap) {
+                      prm.pool_q[slot] = q;
+                      prm.pool_idx[slot] = gcol0 + j;
+                    } else {
+                      atomicAdd(prm.dropped + q, 1);
+                    }
                   }
                 }
+                __syncwarp();
               }
             }
+          }
+        }
+        if constexpr (kSelect) {
+          if (own_max < published) {  // list is full and its maximum dropped: share it
+            atomicMin(prm.shared_thr + q_tile * kTileQ + row, float_to_ordered_int(own_max));
+            published = own_max;
           }
         }
         // Accumulator fully read: hand it back to the MMA warp.
@@ -320,14 +358,12 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
 
       if constexpr (kSelect) {
-        if constexpr (Cfg::kSmemLists) {
-          float* ov = prm.cand_val + list_slot * kCap * kTileQ;
-          int32_t* oi = prm.cand_idx + list_slot * kCap * kTileQ;
+        float* ov = prm.cand_val + list_slot * kCap * kTileQ;
+        int32_t* oi = prm.cand_idx + list_slot * kCap * kTileQ;
 #pragma unroll 4
-          for (int p = 0; p < kCap; ++p) {
-            ov[p * kTileQ + row] = lv[p * kTileQ + row];
-            oi[p * kTileQ + row] = li[p * kTileQ + row];
-          }
+        for (int p = 0; p < kCap; ++p) {
+          ov[p * kTileQ + row] = lv[p * kTileQ + row];
+          if constexpr (Cfg::kIdxInSmem) oi[p * kTileQ + row] = li[p * kTileQ + row];
         }
         if constexpr (kRank) {
           if (q_valid && cnt) atomicAdd(prm.cnt_less + q, cnt);
@@ -420,7 +456,7 @@ int dispatch_mode_cap(int mode, int cap, const CUtensorMap& tq, const CUtensorMa
 
 // fp32 embeddings → kind::tf32, 4 epilogue warps; bf16 → kind::f16, 8 epilogue warps (the
 // bf16 tiles complete 2-4× sooner, so two warps share each TMEM lane quarter).
-static int epi_warps_for(int dtype) { return dtype == SBIR_BF16 ? 8 : 4; }
+static int epi_warps_for(int dtype, int cap) { return (dtype == SBIR_BF16 && cap <= 32) ? 8 : 4; }
 
 K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms) {
   K1Plan p{};
@@ -428,7 +464,7 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   const int want = dtype == SBIR_BF16 ? k + 6 : k + 16;
   p.cap = want <= 16 ? 16 : want <= 32 ? 32 : want <= 64 ? 64 : 128;
   if (k + 12 > 128) p.cap = 128;
-  p.lists_per_row = epi_warps_for(dtype) / 4;
+  p.lists_per_row = epi_warps_for(dtype, p.cap) / 4;
   p.num_q_tiles = (int)((num_q + kTileQ - 1) / kTileQ);
   p.num_g_tiles = (int)((num_g + kTileG - 1) / kTileG);
   if (p.num_q_tiles < 1) p.num_q_tiles = 1;
@@ -471,8 +507,12 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.rank_lo = a.rank_lo;
   prm.rank_hi = a.rank_hi;
   prm.cnt_less = a.cnt_less;
-  prm.unc_cnt = a.unc_cnt;
-  prm.unc_idx = a.unc_idx;
+  prm.pool_count = a.pool_count;
+  prm.pool_cap = a.pool_cap;
+  prm.pool_q = a.pool_q;
+  prm.pool_idx = a.pool_idx;
+  prm.dropped = a.dropped;
+  prm.shared_thr = a.shared_thr;
   prm.dump = a.dump;
   prm.row_label = a.row_label;
   prm.col_label = a.col_label;
@@ -489,8 +529,12 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
     if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<true, SBIR_EUCLIDEAN, 4>(a.mode, cap, tq, tg, prm, grid, st);
     return dispatch_mode_cap<true, SBIR_COSINE, 4>(a.mode, cap, tq, tg, prm, grid, st);
   }
-  if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 8>(a.mode, cap, tq, tg, prm, grid, st);
-  return dispatch_mode_cap<false, SBIR_COSINE, 8>(a.mode, cap, tq, tg, prm, grid, st);
+  if (plan.lists_per_row == 2) {
+    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 8>(a.mode, cap, tq, tg, prm, grid, st);
+    return dispatch_mode_cap<false, SBIR_COSINE, 8>(a.mode, cap, tq, tg, prm, grid, st);
+  }
+  if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 4>(a.mode, cap, tq, tg, prm, grid, st);
+  return dispatch_mode_cap<false, SBIR_COSINE, 4>(a.mode, cap, tq, tg, prm, grid, st);
 }
 
 }  // namespace sbir

@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinPar
       const int split = l / p.lists_per_row, h = l % p.lists_per_row;
       const size_t slot = ((size_t)split * p.num_q_tiles + q_tile) * p.lists_per_row + h;
       const size_t addr = (slot * p.cap + pp) * kTileQ + row;
-      const int32_t cidx = p.cand_idx[addr];
-      if (cidx >= 0) {
-        v = p.cand_val[addr];
-        ix = cidx;
+      const float cv = p.cand_val[addr];
+      if (cv < INFINITY) {  // slots never filled keep +inf (their index is unspecified)
+        v = cv;
+        ix = p.cand_idx[addr];
         ++local_finite;
       }
     }
@@ -217,8 +217,11 @@ struct RankParams {
   float* rank_lo;
   float* rank_hi;
   int32_t* cnt_less;
-  int32_t* unc_cnt;
-  int32_t* unc_idx;
+  uint32_t* pool_count;
+  uint32_t pool_cap;
+  int32_t* pool_q;
+  int32_t* pool_idx;
+  int32_t* dropped;
   long long* out_rank;
   long long missing_rank;
 };
@@ -260,30 +263,30 @@ __global__ void __launch_bounds__(kRankWarps * 32) rank_band_kernel(const RankPa
   }
 }
 
+// One warp per pooled (query, gallery row) pair: exact distance, exact comparison with d_pos.
 template <typename T, bool kVec>
-__global__ void __launch_bounds__(kRankWarps * 32) rank_finalize_kernel(const RankParams p) {
+__global__ void __launch_bounds__(kRankWarps * 32) rank_resolve_kernel(const RankParams p) {
   const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * kRankWarps + (threadIdx.x >> 5);
+  const uint32_t claimed = *p.pool_count;
+  const uint32_t n = claimed < p.pool_cap ? claimed : p.pool_cap;
+  const uint32_t stride = gridDim.x * kRankWarps;
+  for (uint32_t e = blockIdx.x * kRankWarps + (threadIdx.x >> 5); e < n; e += stride) {
+    const int q = p.pool_q[e];
+    const int gi = p.pool_idx[e];
+    const double d = warp_exact_distance<T, kVec>(reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim,
+                                                  reinterpret_cast<const T*>(p.g) + (size_t)gi * p.dim,
+                                                  p.dim, p.metric, lane);
+    if (lane == 0 && d < p.pos_dist[q]) atomicAdd(p.cnt_less + q, 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) rank_finalize_kernel(const RankParams p) {
+  const int q = blockIdx.x * 256 + threadIdx.x;
   if (q >= p.num_q) return;
   const double dpos = p.pos_dist[q];
-  if (dpos != dpos) {
-    if (lane == 0) p.out_rank[q] = p.missing_rank;
-    return;
-  }
-  const int nu = p.unc_cnt[q];
-  if (nu > kUncertainCap) {
-    if (lane == 0) p.out_rank[q] = -1;  // resolved by rank_fallback_kernel
-    return;
-  }
-  long long r = p.cnt_less[q];
-  const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
-  for (int u = 0; u < nu; ++u) {
-    const int gi = p.unc_idx[(size_t)q * kUncertainCap + u];
-    const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)gi * p.dim,
-                                                  p.dim, p.metric, lane);
-    r += d < dpos ? 1 : 0;
-  }
-  if (lane == 0) p.out_rank[q] = r;
+  if (dpos != dpos) p.out_rank[q] = p.missing_rank;
+  else if (p.dropped[q] > 0) p.out_rank[q] = -1;  // resolved by rank_fallback_kernel
+  else p.out_rank[q] = p.cnt_less[q];
 }
 
 // Exact brute-force count for queries whose uncertain band overflowed.
@@ -370,6 +373,10 @@ __global__ void fill_topk_kernel(float* out_dist, long long* out_index, size_t n
   }
 }
 
+__global__ void fill_i32_kernel(int32_t* out, long long n, int32_t value) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = value;
+}
 __global__ void fill_i64_kernel(long long* out, long long n, long long value) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = value;
@@ -474,7 +481,9 @@ RankParams make_rank_params(const RankArgs& a) {
   p.pos_dist_in = a.pos_dist_in;
   p.qsq = a.qsq; p.gsq_max = a.gsq_max; p.kappa = a.kappa;
   p.pos_dist = a.pos_dist; p.rank_lo = a.rank_lo; p.rank_hi = a.rank_hi;
-  p.cnt_less = a.cnt_less; p.unc_cnt = a.unc_cnt; p.unc_idx = a.unc_idx;
+  p.cnt_less = a.cnt_less;
+  p.pool_count = a.pool_count; p.pool_cap = a.pool_cap; p.pool_q = a.pool_q; p.pool_idx = a.pool_idx;
+  p.dropped = a.dropped;
   p.out_rank = reinterpret_cast<long long*>(a.out_rank);
   p.missing_rank = a.missing_rank;
   return p;
@@ -528,8 +537,9 @@ int launch_rank_finalize(const RankArgs& a, cudaStream_t st) {
   if (a.num_q <= 0) return SBIR_OK;
   const RankParams p = make_rank_params(a);
   const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
-  const unsigned grid = (unsigned)((a.num_q + kRankWarps - 1) / kRankWarps);
-  SBIR_DISPATCH_T(a.dtype, vec, rank_finalize_kernel, grid, kRankWarps * 32, 0, st, p);
+  SBIR_DISPATCH_T(a.dtype, vec, rank_resolve_kernel, 148 * 8, kRankWarps * 32, 0, st, p);
+  SBIR_CHECK_LAUNCH();
+  rank_finalize_kernel<<<(unsigned)((a.num_q + 255) / 256), 256, 0, st>>>(p);
   SBIR_CHECK_LAUNCH();
   SBIR_DISPATCH_T(a.dtype, vec, rank_fallback_kernel, (unsigned)a.num_q, kFbThreads, 0, st, p);
   SBIR_CHECK_LAUNCH();
@@ -565,6 +575,13 @@ int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, in
   topk_merge_kernel<<<grid, kMergeWarps * 32, 0, st>>>(dist, reinterpret_cast<const long long*>(index), num_lists,
                                                        (int)num_q, k, out_dist,
                                                        reinterpret_cast<long long*>(out_index));
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_fill_i32(int32_t* out, int64_t n, int32_t value, cudaStream_t st) {
+  if (n <= 0) return SBIR_OK;
+  fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, (long long)n, value);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }

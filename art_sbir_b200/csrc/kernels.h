@@ -24,7 +24,7 @@ int launch_triplet(const float* a, const float* p, const float* n, int64_t batch
 // ---- dist_topk.cu (K1) ----------------------------------------------------------
 constexpr int kTileQ = 128;        // query rows per tile (UMMA M, TMEM lanes)
 constexpr int kTileG = 256;        // gallery rows per tile (UMMA N, TMEM columns)
-constexpr int kUncertainCap = 64;  // per-query capacity of the rank "uncertain band" list
+constexpr int kUncertainPerQuery = 64;  // uncertain-pool capacity = this × num_q (min 65536)
 constexpr int kMaxK = 116;         // largest supported k (list capacity 128 minus slack)
 
 enum K1Mode { kModeTopk = 0, kModeTopkRank = 1, kModeDump = 2, kModeHard = 3 };
@@ -51,9 +51,15 @@ struct K1Args {
   // rank (mode kModeTopkRank): e-space band per query and its outputs
   const float* rank_lo;
   const float* rank_hi;
-  int32_t* cnt_less;  // [num_q], zeroed by the caller
-  int32_t* unc_cnt;   // [num_q], zeroed by the caller
-  int32_t* unc_idx;   // [num_q][kUncertainCap]
+  int32_t* cnt_less;     // [num_q], zeroed by the caller
+  uint32_t* pool_count;  // [1] zeroed by the caller: entries claimed in the uncertain pool
+  uint32_t pool_cap;     // capacity of the pool
+  int32_t* pool_q;       // [pool_cap] query of each uncertain (query, gallery row) pair
+  int32_t* pool_idx;     // [pool_cap] gallery row of each pair
+  int32_t* dropped;      // [num_q] zeroed by the caller: pairs that did not fit in the pool
+  // cross-split shared threshold per query row, ordered-int encoded, [num_q_tiles*kTileQ],
+  // initialised to +inf (0x7f800000) by the caller (select modes)
+  int32_t* shared_thr;
   // debug (mode kModeDump): full epilogue matrix [num_q][num_g]
   float* dump;
   // batch-hard mining (mode kModeHard): per query row, the labels and outputs
@@ -99,8 +105,11 @@ struct RankArgs {
   float* rank_lo;            // [num_q]
   float* rank_hi;            // [num_q]
   int32_t* cnt_less;
-  int32_t* unc_cnt;
-  int32_t* unc_idx;
+  uint32_t* pool_count;
+  uint32_t pool_cap;
+  int32_t* pool_q;
+  int32_t* pool_idx;
+  int32_t* dropped;
   int64_t* out_rank;         // [num_q]
   int64_t missing_rank;      // value for queries without a positive (num_g in the reference)
 };
@@ -111,6 +120,7 @@ int launch_positive_distance(const void* q, int64_t num_q, const void* g, int64_
                              cudaStream_t st);
 int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
                       float* out_dist, int64_t* out_index, cudaStream_t st);
+int launch_fill_i32(int32_t* out, int64_t n, int32_t value, cudaStream_t st);
 int launch_fill_i64(int64_t* out, int64_t n, int64_t value, cudaStream_t st);
 int launch_retrieval_metrics(const int64_t* rank0, int64_t num_q, int k, double* out, cudaStream_t st);
 
@@ -122,6 +132,6 @@ int launch_batch_hard(const float* a, const float* p, const float* n, int64_t ba
                       void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 // relative error bound of the tensor-core dot product
-inline float k1_kappa(int dtype) { return dtype == 0 /*F32→tf32*/ ? 1.0f / 512.0f * 1.01f : 1.0f / 16384.0f; }
+inline float k1_kappa(int dtype) { return dtype == 0 /*F32→tf32*/ ? 1.0f / 512.0f * 1.01f : 1.0f / 262144.0f; }
 
 }  // namespace sbir

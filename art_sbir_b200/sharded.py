@@ -1,0 +1,88 @@
+"""Gallery-sharded retrieval across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Rank r holds the contiguous
+gallery rows [offset_r, offset_r + n_r); queries are replicated.  The path has exactly one
+exchange step:
+
+    d(q, pos)      owner shard computes it, all-reduce(sum) of (value, has) pairs  [Q] fp64
+    local K1       per-shard top-k with global indices + local count(d < d_pos)
+    all-gather     [Q, k] (dist, index) per shard            — Q·k·12 bytes per rank
+    all-reduce     int64 [Q] counts (sum)
+    K4 merge       k best of the P·k gathered candidates, ties by global index
+
+so the result is identical to the single-GPU result for any number of shards.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def shard_bounds(num_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of `rank`: the first (num_rows % world_size) ranks get one extra row."""
+    base, rem = divmod(num_rows, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def _cuda_local(queries, shard, k, loss_type, offset, pos_dist):
+    vals, idx, cnt, unc = ops.pairwise_topk_shard(queries, shard, k, loss_type, offset, pos_dist)
+    return vals, idx, cnt
+
+
+def _cuda_pos_dist(queries, shard, pos_local, loss_type):
+    return ops.positive_distance(queries, shard, pos_local, loss_type)
+
+
+def sharded_pairwise_topk(queries: torch.Tensor, gallery_shard: torch.Tensor, k: int, loss_type: str = "euclidean",
+                          pos_index: Optional[torch.Tensor] = None, shard_offset: Optional[int] = None,
+                          num_gallery_total: Optional[int] = None, group=None,
+                          local_fn: Callable = _cuda_local, pos_dist_fn: Callable = _cuda_pos_dist,
+                          merge_fn: Callable = ops.topk_merge):
+    """Top-k (and rank of the positive) of `queries` against a gallery sharded over `group`.
+
+    pos_index holds GLOBAL gallery rows (<0 = no positive).  Returns (values [Q,k] fp32,
+    indices [Q,k] int64 global, rank int64 [Q] or None) — the same on every rank.
+    `local_fn` / `pos_dist_fn` / `merge_fn` exist so the collective plumbing can be exercised
+    on CPU (gloo) with a stand-in scorer in tests; the defaults are the CUDA kernels."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_local = gallery_shard.shape[0]
+    dev = queries.device
+    if shard_offset is None or num_gallery_total is None:
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        sizes[rank] = n_local
+        if world > 1:
+            dist.all_reduce(sizes, group=group)
+        shard_offset = int(sizes[:rank].sum().item())
+        num_gallery_total = int(sizes.sum().item())
+
+    pos_dist = None
+    if pos_index is not None:
+        pos_index = pos_index.to(device=dev, dtype=torch.int64)
+        mine = (pos_index >= shard_offset) & (pos_index < shard_offset + n_local)
+        pos_local = torch.where(mine, pos_index - shard_offset, torch.full_like(pos_index, -1))
+        d_local = pos_dist_fn(queries, gallery_shard, pos_local, loss_type).to(torch.float64)
+        pair = torch.stack([torch.where(mine, d_local, torch.zeros_like(d_local)), mine.to(torch.float64)])
+        if world > 1:
+            dist.all_reduce(pair, group=group)  # exactly one owner per query: the sum is exact
+        pos_dist = torch.where(pair[1] > 0, pair[0], torch.full_like(pair[0], float("nan")))
+
+    vals, idx, cnt = local_fn(queries, gallery_shard, k, loss_type, shard_offset, pos_dist)
+
+    if world > 1:
+        all_vals = [torch.empty_like(vals) for _ in range(world)]
+        all_idx = [torch.empty_like(idx) for _ in range(world)]
+        dist.all_gather(all_vals, vals.contiguous(), group=group)
+        dist.all_gather(all_idx, idx.contiguous(), group=group)
+        vals, idx = merge_fn(torch.stack(all_vals), torch.stack(all_idx))
+        if cnt is not None:
+            dist.all_reduce(cnt, group=group)
+    rank_out = None
+    if pos_index is not None:
+        rank_out = torch.where(pos_dist != pos_dist, torch.full_like(cnt, num_gallery_total), cnt)
+    return vals, idx, rank_out

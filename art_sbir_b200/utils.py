@@ -1,0 +1,216 @@
+"""Host-side mirror of the reference's `utils` module for the retrieval / triplet path.
+
+Same names, constructor arguments, attributes and error behaviour as the reference
+(utils.py:22-77, 258-284 of Peer222/art-sbir), so `inference.py` / `train.py` call sites keep
+working; the arithmetic runs in libsbir_b200.so (CUDA tensors only — no CPU fallback).
+"""
+from __future__ import annotations
+
+import csv
+from datetime import datetime
+from pathlib import Path
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+
+MARGIN = 0.2  # utils.py:77 ("Sketching without Worrying"); train.py:133 overwrites it from --loss_margin
+
+
+# ---------------------------------------------------------------------------- N3 ----
+class _StemIndex:
+    """stem → first gallery index, built once per gallery list (the reference scans the list
+    linearly for every query, utils.py:22-25)."""
+
+    def __init__(self) -> None:
+        self._key = None
+        self._map: Dict[str, int] = {}
+
+    def lookup(self, image_paths: Sequence[Path], name: str) -> int:
+        key = (id(image_paths), len(image_paths))
+        if key != self._key:
+            m: Dict[str, int] = {}
+            for idx, path in enumerate(image_paths):
+                m.setdefault(Path(path).stem, idx)
+            self._map, self._key = m, key
+        return self._map.get(name, -1)
+
+
+_stem_index = _StemIndex()
+
+
+def find_image_index(image_paths: List[Path], sketch_name: str) -> int:
+    """utils.py:22-25: index of the first path whose stem equals `sketch_name`, else -1."""
+    return _stem_index.lookup(image_paths, sketch_name)
+
+
+# ------------------------------------------------------------------------ H1 / H2 ----
+class PairwiseDistance(nn.Module):
+    """Stands in for `nn.PairwiseDistance(p=2, keepdim=False)` (utils.py:42): ‖x1 − x2 + eps‖₂
+    with torch's single-row broadcasting; exposes the same attributes."""
+
+    def __init__(self, p: float = 2.0, eps: float = 1e-6, keepdim: bool = False) -> None:
+        super().__init__()
+        if float(p) != 2.0 or keepdim or abs(eps - 1e-6) > 1e-12:
+            raise NotImplementedError("the sbir_b200 path implements p=2, eps=1e-6, keepdim=False (the reference's use)")
+        self.norm = float(p)
+        self.eps = eps
+        self.keepdim = keepdim
+
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+        return ops.pairwise_distance(x1, x2, "euclidean")
+
+
+class CosineLoss(nn.Module):
+    """utils.py:31-38: 1 − cosine similarity along dim 1 (per-operand norm clamp 1e-8)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+
+    def forward(self, sketch_tensor: torch.Tensor, image_tensor: torch.Tensor) -> torch.Tensor:
+        return ops.pairwise_distance(sketch_tensor, image_tensor, "cosine")
+
+
+cosine_distance = CosineLoss()            # utils.py:40
+euclidean_distance = PairwiseDistance()   # utils.py:42
+
+
+def _loss_type_of(distance_f) -> str:
+    if isinstance(distance_f, PairwiseDistance) or isinstance(distance_f, nn.PairwiseDistance):
+        return "euclidean"
+    if isinstance(distance_f, CosineLoss) or type(distance_f).__name__ == "CosineLoss":
+        return "cosine"
+    raise TypeError("distance_f must be utils.euclidean_distance or utils.cosine_distance "
+                    "(arbitrary distance callables have no fused kernel)")
+
+
+# ------------------------------------------------------------------------ H6 / H7 ----
+class TripletMarginLoss(nn.Module):
+    """Replaces `nn.TripletMarginLoss(margin=utils.MARGIN)` (train.py:169)."""
+
+    def __init__(self, margin: float = 1.0) -> None:
+        super().__init__()
+        self.margin = margin
+
+    def forward(self, anchor, positive, negative):
+        return ops.triplet_margin_loss(anchor, positive, negative, self.margin, "euclidean")
+
+
+class TripletMarginWithDistanceLoss(nn.Module):
+    """Replaces `nn.TripletMarginWithDistanceLoss(margin, distance_function)` (train.py:175,
+    utils.py:56,69) for the two distance modules of the reference."""
+
+    def __init__(self, *, distance_function=None, margin: float = 1.0) -> None:
+        super().__init__()
+        self.margin = margin
+        self.distance_function = distance_function if distance_function is not None else euclidean_distance
+        self._loss_type = _loss_type_of(self.distance_function)
+
+    def forward(self, anchor, positive, negative):
+        return ops.triplet_margin_loss(anchor, positive, negative, self.margin, self._loss_type)
+
+
+class TripletMarginLoss_with_classification(nn.Module):
+    """utils.py:49-60: triplet term (fused kernel) + weight·(CE(cs,l) + CE(cp,l)); the
+    cross-entropy terms stay in torch."""
+
+    def __init__(self, margin, classification_weight=0.5, distance_f=euclidean_distance):
+        super().__init__()
+        self.classification_weight = classification_weight
+        self.classification_weight2 = 0
+        self.margin = margin
+        self.triplet_loss = TripletMarginWithDistanceLoss(margin=self.margin, distance_function=distance_f)
+        self.classification_loss = nn.CrossEntropyLoss()
+
+    def forward(self, s_logits, p_logits, n_logits, cs_logits, cp_logits, labels):
+        return self.triplet_loss(s_logits, p_logits, n_logits) + self.classification_weight * (
+            self.classification_loss(cs_logits, labels) + self.classification_loss(cp_logits, labels))
+
+
+class TripletMarginLoss_with_classification2(nn.Module):
+    """utils.py:62-75 (styles + genres heads)."""
+
+    def __init__(self, margin, classification_weight=0.25, classification_weight2=0.5, distance_f=euclidean_distance):
+        super().__init__()
+        self.classification_weight = classification_weight
+        self.classification_weight2 = classification_weight2
+        self.margin = margin
+        self.triplet_loss = TripletMarginWithDistanceLoss(margin=self.margin, distance_function=distance_f)
+        self.classification_loss = nn.CrossEntropyLoss()
+
+    def forward(self, s_logits, p_logits, n_logits, cs_logits, cp_logits, cs_logits2, cp_logits2, labels, labels2):
+        classification_loss = self.classification_loss(cs_logits, labels) + self.classification_loss(cp_logits, labels)
+        classification_loss2 = self.classification_loss(cs_logits2, labels2) + self.classification_loss(cp_logits2, labels2)
+        return (self.triplet_loss(s_logits, p_logits, n_logits) + self.classification_weight * classification_loss
+                + self.classification_weight2 * classification_loss2)
+
+
+# -------------------------------------------------------------------------------- H8 ----
+class BatchHardTripletLoss(nn.Module):
+    """north_star extension: same call shape as the triplet losses above,
+    but the hardest positive / negative are mined over cat(positive, negative) on the tensor
+    cores.  `labels` (optional, int64 [batch]) widens the positive set to same-label candidates."""
+
+    def __init__(self, margin: float = MARGIN, distance_f=euclidean_distance) -> None:
+        super().__init__()
+        self.margin = margin
+        self._loss_type = _loss_type_of(distance_f)
+
+    def forward(self, anchor, positive, negative, labels=None):
+        return ops.batch_hard_triplet_loss(anchor, positive, negative, self.margin, self._loss_type, labels)
+
+
+def make_loss_fn(loss_type: str, with_classification: bool, dataset_name: str = "", margin: float = MARGIN):
+    """The dispatch of train.py:164-175 with the fused modules."""
+    if loss_type not in ("euclidean", "cosine"):
+        raise Exception(f"loss type not correct {loss_type}")
+    dist = euclidean_distance if loss_type == "euclidean" else cosine_distance
+    if with_classification:
+        if "Sketchy" in dataset_name:
+            return TripletMarginLoss_with_classification(margin=margin, distance_f=dist)
+        if "Mixed" in dataset_name:
+            w = {"classification_weight": 0.01} if loss_type == "euclidean" else {}
+            return TripletMarginLoss_with_classification(margin=margin, distance_f=dist, **w)
+        if "Kaggle" in dataset_name:
+            w = {"classification_weight": 0, "classification_weight2": 0.2} if loss_type == "euclidean" else {}
+            return TripletMarginLoss_with_classification2(margin=margin, distance_f=dist, **w)
+    if loss_type == "euclidean":
+        return TripletMarginLoss(margin=margin)
+    return TripletMarginWithDistanceLoss(margin=margin, distance_function=cosine_distance)
+
+
+# ---------------------------------------------------------------------------- N2 ----
+def load_image_features(folder_name: str, root: Path = Path("data/image_features")) -> Tuple[list, torch.Tensor]:
+    """utils.py:258-263.  Reads the reference's CSV pair; if the binary sidecar written by
+    save_image_features is present it is used instead (fp32, no text parsing).  The CSV route
+    returns float64 exactly like the reference (pandas → torch.from_numpy)."""
+    import pandas as pd
+    path = Path(root) / folder_name
+    image_paths = [Path(p[0]) for p in pd.read_csv(path / "image_paths.csv", header=None).values]
+    sidecar = path / "image_features.f32.npy"
+    if sidecar.is_file():
+        return image_paths, torch.from_numpy(np.load(sidecar))
+    image_features = pd.read_csv(path / "image_features.csv", header=None).values
+    return image_paths, torch.from_numpy(image_features)
+
+
+def save_image_features(model_name: str, dataset_name: str, inference_dataset, image_features: torch.Tensor,
+                        root: Path = Path("data/image_features"), write_csv: bool = True) -> str:
+    """utils.py:265-284: same folder naming and CSV files; additionally writes
+    image_features.f32.npy so reloading is exact fp32 and O(bytes) instead of text parsing."""
+    feature_path = Path(root)
+    feature_path.mkdir(parents=True, exist_ok=True)
+    date_time = datetime.now().strftime("%Y-%m-%d_%H-%M")
+    feature_path = feature_path / f"{model_name}_{dataset_name}_{date_time}"
+    feature_path.mkdir(parents=True, exist_ok=True)
+    with open(feature_path / "image_paths.csv", "w") as f:
+        csv.writer(f).writerows([[str(p)] for p in inference_dataset.image_paths])
+    feats = image_features.detach().float().cpu().numpy()
+    np.save(feature_path / "image_features.f32.npy", feats)
+    if write_csv:
+        with open(feature_path / "image_features.csv", "w") as f:
+            csv.writer(f).writerows(feats)
+    return feature_path.name

@@ -1,0 +1,81 @@
+"""CPU suite, part 2: the C-ABI boundary — the library builds for sm_100a, loads, exports every
+symbol include/sbir_b200.h declares, the ctypes prototypes cover the header one to one, and the
+argument checks that return before touching the device behave (no compute without a GPU)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "sbir_b200.h"
+
+
+def _declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(sbir_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(sbir_lib):
+    from art_sbir_b200 import _binding
+    names = _declared_symbols()
+    assert len(names) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_binding.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (sbir_[a-z0-9_]+)", out))
+    assert set(names) <= exported, sorted(set(names) - exported)
+    # nothing torch-typed or C++-mangled is part of the contract
+    assert all(hasattr(sbir_lib, n) for n in names)
+
+
+def test_binding_covers_header_exactly(sbir_lib):
+    from art_sbir_b200 import _binding
+    assert sorted(_binding.PROTOTYPES) == _declared_symbols()
+    assert sbir_lib.sbir_abi_version() == 1
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "sbir_b200.h"\nint main(void){return SBIR_OK + SBIR_F32 + SBIR_EUCLIDEAN;}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o",
+                    str(tmp_path / "t.o")], check=True)
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(sbir_lib):
+    from art_sbir_b200 import _binding
+    elf = subprocess.run(["cuobjdump", "-lelf", str(_binding.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run(["cuobjdump", "-sass", str(_binding.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCQMMA" in sass      # tcgen05.mma
+    assert "UTMALDG" in sass                            # TMA tensor loads
+    assert "LDTM" in sass                               # tcgen05.ld
+
+
+def test_status_strings_and_argument_checks(sbir_lib):
+    lib = sbir_lib
+    assert lib.sbir_status_string(0) == b"ok"
+    assert b"invalid" in lib.sbir_status_string(1)
+    assert b"workspace" in lib.sbir_status_string(4)
+    # bad enum / sizes are rejected before any CUDA call
+    assert lib.sbir_l2_normalize(None, None, 4, 8, 7, 1e-8, None) == 1
+    assert lib.sbir_pairwise_distance(None, 3, None, 2, 8, 0, 0, None, None) == 1      # 3 vs 2 rows do not broadcast
+    assert lib.sbir_pairwise_topk(None, 4, None, 4, 8, 0, 0, 0, 0, None, None, None, None, None, None, 0, None) == 1  # k = 0
+    assert lib.sbir_pairwise_topk(None, 4, None, 4, 8, 0, 0, 500, 0, None, None, None, None, None, None, 0, None) == 2  # k too large
+    assert lib.sbir_pairwise_topk(None, 4, None, 4, 8, 0, 5, 10, 0, None, None, None, None, None, None, 0, None) == 1  # bad metric
+    assert lib.sbir_triplet_margin_loss(None, None, None, 4, 8, 0.2, 0, None, None, None, None, None, None) == 1
+    assert lib.sbir_pairwise_topk_workspace_bytes(1000, 10000, 2048, 10, 0, 0, 1) > 0
+    assert lib.sbir_pairwise_topk_workspace_bytes(1000, 10000, 2048, 1000, 0, 0, 1) == 0
+    # empty problems are a no-op success
+    assert lib.sbir_l2_normalize(None, None, 0, 8, 0, 1e-8, None) == 0
+    assert lib.sbir_pairwise_topk(None, 0, None, 4, 8, 0, 0, 10, 0, None, None, None, None, None, None, 0, None) == 0
+
+
+def test_product_refuses_cpu_tensors_and_never_imports_the_oracle():
+    import torch
+    from art_sbir_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.pairwise_topk(torch.randn(4, 8), torch.randn(9, 8), 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.triplet_margin_loss(torch.randn(4, 8), torch.randn(4, 8), torch.randn(4, 8))
+    for py in (ROOT / "art_sbir_b200").glob("*.py"):
+        assert "oracle" not in py.read_text().replace("oracle.synthetic_embeddings", ""), py

@@ -1,0 +1,373 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (art_sbir_b200.ops → ctypes →
+libsbir_b200.so), against (1) the golden fixtures minted from the reference, (2) the oracle on
+seeded inputs at sizes the oracle finishes in seconds, (3) size-independent properties at the
+BASELINE.json sizes.  Tolerances are north_star's: recall@K / ranks bit-exact, ranked indices
+identical except at distance ties within 1e-4 relative, distances and losses within 1e-3
+relative in fp32 (bf16 inputs: oracle = fp32 math on the bf16-rounded inputs)."""
+import ctypes
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sbir_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DIST_RTOL = 1e-3   # north_star: distances / loss within 1e-3 relative (fp32)
+TIE_RTOL = 1e-4    # north_star: index swaps allowed only between distances closer than this
+
+
+@pytest.fixture(scope="module")
+def ops(sbir_lib):
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    assert sbir_lib.sbir_device_supported() == 1, "not an sm_100 device"
+    from art_sbir_b200 import ops as _ops
+    return _ops
+
+
+def assert_topk_matches(vals, idx, ref_vals, ref_idx, dist_rows):
+    """dist_rows[i] = oracle distances of query i to every gallery row (for tie analysis)."""
+    vals, idx = vals.cpu(), idx.cpu()
+    assert vals.shape == ref_vals.shape and idx.shape == ref_idx.shape
+    assert torch.allclose(vals, ref_vals.float(), rtol=DIST_RTOL, atol=1e-6)
+    bad = (idx != ref_idx).nonzero()
+    for i, j in bad.tolist():
+        ours = dist_rows[i][idx[i, j]].item()
+        theirs = ref_vals[i, j].item()
+        assert abs(ours - theirs) <= TIE_RTOL * max(abs(theirs), 1e-6), (i, j, ours, theirs)
+    return len(bad)
+
+
+# --------------------------------------------------------------------- golden fixtures ----
+def test_golden_ranks_and_topk(ops, retrieval_golden):
+    g = retrieval_golden
+    lt = g["loss_type"]
+    Q, G = torch.from_numpy(g["Q"]), torch.from_numpy(g["G"])
+    from art_sbir_b200 import inference as inf
+    image_paths = [Path(str(p)) for p in g["image_paths"]]
+    sketch_paths = [Path(str(p)) for p in g["sketch_paths"]]
+    pos = inf.positive_indices(sketch_paths, image_paths, verbose=False)
+    vals, idx, rank, unc = ops.pairwise_topk(Q.cuda(), G.cuda(), 10, lt, pos_index=pos.cuda(), return_uncertified=True)
+    assert rank.cpu().tolist() == g["ranks"].tolist()                       # bit-exact ranks → recall@K
+    dist_rows = [O.distances(Q[i:i + 1], G, lt) for i in range(len(Q))]
+    swaps = assert_topk_matches(vals, idx, torch.from_numpy(g["top_val"]), torch.from_numpy(g["top_idx"]), dist_rows)
+    assert swaps == 0                                                        # this fixture is tie-free
+    # the per-query drop-in functions (inference.py:30-69) give the same answers
+    for i in (0, 5, 17):
+        assert inf.get_ranking_position(sketch_paths[i], image_paths, Q[i:i + 1], G, lt) == int(g["ranks"][i])
+    tk = inf.get_topk_images(10, image_paths, Q[2:3], G, lt)
+    assert [p for p, _ in tk] == [str(image_paths[j]) for j in g["top_idx"][2]]
+    assert np.allclose([v for _, v in tk], g["top_val"][2], rtol=DIST_RTOL)
+
+
+@pytest.mark.parametrize("loss_type", ["euclidean", "cosine"])
+def test_golden_process_inference(ops, golden_dir, loss_type):
+    from art_sbir_b200 import inference as inf
+    z = np.load(golden_dir / f"retrieval_{loss_type}.npz")
+    ref = json.load(open(golden_dir / f"process_inference_{loss_type}.json"))
+    Q, G = torch.from_numpy(z["Q"]), torch.from_numpy(z["G"])
+
+    class DS:
+        sketch_paths = [Path(str(p)) for p in z["sketch_paths"]]
+
+        def __len__(self):
+            return len(self.sketch_paths)
+
+    class InfDS:
+        image_paths = [Path(str(p)) for p in z["image_paths"]]
+
+        def __len__(self):
+            return len(self.image_paths)
+
+    loader = [(Q[i:i + 16],) for i in range(0, len(Q), 16)]     # batched queries (N4)
+    from timeit import default_timer as timer
+    got = inf.process_inference(torch.nn.Identity(), DS(), InfDS(), loader, G, timer(), False, loss_type)
+    assert set(got) == set(ref) | {"inference_time"}
+    for key in ("size", "count", "min", "25%", "50%", "75%", "max"):
+        assert got[key] == ref[key], key
+    assert got["topk_acc"] == ref["topk_acc"]                                   # recall@1..10 bit-exact
+    assert got["mean_reciprocal_rank"] == pytest.approx(ref["mean_reciprocal_rank"], rel=1e-12)
+    assert got["mean"] == pytest.approx(ref["mean"], rel=1e-12) and got["std"] == pytest.approx(ref["std"], rel=1e-12)
+    assert len(got["retrieval_samples"]) == len(ref["retrieval_samples"])
+    for a, b in zip(got["retrieval_samples"], ref["retrieval_samples"]):
+        assert list(a) == list(b)
+        (ka, va), (kb, vb) = next(iter(a.items())), next(iter(b.items()))
+        assert [p for p, _ in va] == [p for p, _ in vb]
+        assert np.allclose([d for _, d in va], [d for _, d in vb], rtol=DIST_RTOL)
+    json.dumps(got)                                                             # JSON-serialisable like the reference's
+
+
+def test_golden_triplet_losses(ops, triplet_golden):
+    from art_sbir_b200 import utils as U
+    t = triplet_golden
+    m = O.MARGIN
+    dev = "cuda"
+    cs, cp, cs2, cp2 = (torch.from_numpy(t[k]).to(dev) for k in ("cs", "cp", "cs2", "cp2"))
+    l1, l2 = torch.from_numpy(t["l1"]).to(dev), torch.from_numpy(t["l2"]).to(dev)
+    cases = {
+        "tml_euclid": lambda A, P, N: U.TripletMarginLoss(margin=m)(A, P, N),
+        "tmdl_cosine": lambda A, P, N: U.TripletMarginWithDistanceLoss(margin=m, distance_function=U.cosine_distance)(A, P, N),
+        "tmdl_euclid": lambda A, P, N: U.TripletMarginWithDistanceLoss(margin=m, distance_function=U.euclidean_distance)(A, P, N),
+        "wc_euclid": lambda A, P, N: U.TripletMarginLoss_with_classification(margin=m)(A, P, N, cs, cp, l1),
+        "wc_cosine": lambda A, P, N: U.TripletMarginLoss_with_classification(margin=m, distance_f=U.cosine_distance)(A, P, N, cs, cp, l1),
+        "wc2_euclid": lambda A, P, N: U.TripletMarginLoss_with_classification2(margin=m, classification_weight=0, classification_weight2=0.2)(A, P, N, cs, cp, cs2, cp2, l1, l2),
+    }
+    for name, fn in cases.items():
+        A, P, N = (torch.from_numpy(t[k]).to(dev).requires_grad_(True) for k in ("a", "p", "n"))
+        loss = fn(A, P, N)
+        loss.backward()
+        assert loss.item() == pytest.approx(float(t[name + "_loss"]), rel=DIST_RTOL), name
+        for got, key in ((A.grad, "_ga"), (P.grad, "_gp"), (N.grad, "_gn")):
+            ref = torch.from_numpy(t[name + key])
+            assert torch.allclose(got.cpu(), ref, rtol=DIST_RTOL, atol=1e-6 * ref.abs().max().item()), name + key
+
+
+# ------------------------------------------------------------- oracle on seeded inputs ----
+SHAPES = [  # (Q, N, D, dtype, loss, k) — Q, N not multiples of the 128×256 tile; D in {64..2048}; k in {1,10,100}
+    (37, 300, 64, "float32", "euclidean", 10),
+    (130, 1000, 512, "float32", "euclidean", 1),
+    (200, 2500, 1024, "float32", "cosine", 10),
+    (64, 1500, 2048, "float32", "euclidean", 100),
+    (257, 3001, 512, "bfloat16", "euclidean", 10),
+    (100, 777, 256, "bfloat16", "cosine", 100),
+    (1, 513, 1024, "float32", "euclidean", 10),
+    (300, 5000, 96, "float32", "euclidean", 30),
+]
+
+
+@pytest.mark.parametrize("nq,ng,d,dtype,lt,k", SHAPES)
+def test_topk_and_rank_match_oracle(ops, nq, ng, d, dtype, lt, k):
+    Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=nq + ng, beta=0.3 if d < 512 else None, num_classes=max(4, ng // 80))
+    pos[::9] = -1
+    tdt = getattr(torch, dtype)
+    Qd, Gd = Q.to(tdt), G.to(tdt)
+    Qo, Go = Qd.float(), Gd.float()            # oracle = fp32 math on the (possibly bf16-rounded) inputs
+    vals, idx, rank, unc = ops.pairwise_topk(Qd.cuda(), Gd.cuda(), k, lt, pos_index=pos.cuda(), return_uncertified=True)
+    ref_v, ref_i = O.pairwise_topk_batched(Qo, Go, k, lt)
+    dist_rows = [O.distances(Qo[i:i + 1], Go, lt) for i in range(nq)]
+    assert_topk_matches(vals, idx, ref_v, ref_i, dist_rows)
+    ref_r64 = O.rank_of_positive_batched(Qo, Go, pos, lt, fp64=True)
+    ref_r32 = O.rank_of_positive_batched(Qo, Go, pos, lt)
+    got = rank.cpu()
+    # exact wherever the oracle itself is unambiguous (fp32 and fp64 evaluation agree)
+    same = ref_r64 == ref_r32
+    assert torch.equal(got[same], ref_r32[same])
+    assert ((got == ref_r64) | (got == ref_r32)).all()
+    assert (got[pos < 0] == ng).all()
+
+
+def test_edge_cases(ops):
+    dev = "cuda"
+    torch.manual_seed(0)
+    G = torch.randn(5, 64)
+    Q = torch.randn(3, 64)
+    # fewer gallery rows than k: tail padded with (+inf, -1)
+    vals, idx = ops.pairwise_topk(Q.to(dev), G.to(dev), 10, "euclidean")
+    rv, ri = O.pairwise_topk_batched(Q, G, 10, "euclidean")
+    assert torch.equal(idx[:, :5].cpu(), ri) and torch.allclose(vals[:, :5].cpu(), rv, rtol=DIST_RTOL)
+    assert (idx[:, 5:] == -1).all() and torch.isinf(vals[:, 5:]).all()
+    # empty gallery / empty queries
+    vals, idx, rank = ops.pairwise_topk(Q.to(dev), torch.empty(0, 64, device=dev), 3, "euclidean",
+                                        pos_index=torch.tensor([-1, -1, -1], device=dev))
+    assert (idx == -1).all() and (rank == 0).all()
+    vals, idx = ops.pairwise_topk(torch.empty(0, 64, device=dev), G.to(dev), 3, "euclidean")
+    assert vals.shape == (0, 3)
+    # exact duplicates: ties resolved by ascending index; rank = count of strictly closer rows
+    G2 = torch.cat([G, G[1:2], G[1:2]])            # rows 5, 6 duplicate row 1
+    q = G[1:2] + 0.01
+    vals, idx, rank = ops.pairwise_topk(q.to(dev), G2.to(dev), 3, "euclidean", pos_index=torch.tensor([6], device=dev))
+    assert idx[0].tolist() == [1, 5, 6] and rank.item() == 0
+    assert O.ranking_position(q, G2, 6, "euclidean") in (0, 1, 2)   # the reference lands on one of the tied slots
+    # zero vectors under cosine: distance 1 to everything (per-operand clamp, utils.py:34)
+    Gz = torch.cat([torch.zeros(1, 64), G])
+    vals, idx = ops.pairwise_topk(torch.zeros(1, 64, device=dev), Gz.to(dev), 6, "cosine")
+    assert torch.allclose(vals.cpu(), torch.ones(1, 6)) and idx[0].tolist() == [0, 1, 2, 3, 4, 5]
+    ref = O.cosine_distance(Q[:1], Gz)
+    vals, idx = ops.pairwise_topk(Q[:1].to(dev), Gz.to(dev), 6, "cosine")
+    assert torch.allclose(vals.cpu()[0], ref.topk(6, largest=False).values, rtol=DIST_RTOL, atol=1e-6)
+    with pytest.raises(Exception, match="loss type not correct"):
+        ops.pairwise_topk(Q.to(dev), G.to(dev), 3, "manhattan")
+    with pytest.raises(ValueError):
+        ops.pairwise_topk(Q.to(dev), G.to(dev), 500, "euclidean")
+    with pytest.raises(RuntimeError, match="unsupported"):
+        ops.pairwise_topk(torch.randn(3, 66, device=dev), torch.randn(5, 66, device=dev), 3)   # rows not 16-byte multiples
+
+
+def test_fp64_gallery_like_csv_features(ops):
+    """F8: CSV-loaded galleries are float64 in the reference; ranks must still agree."""
+    from art_sbir_b200 import inference as inf
+    Q, G, pos = O.synthetic_embeddings(20, 400, 128, seed=3, beta=0.3, num_classes=5)
+    G64 = G.double()
+    paths = [Path(f"p/n{i:05d}.jpg") for i in range(400)]
+    for i in range(0, 20, 7):
+        sk = Path(f"s/n{int(pos[i]):05d}-1.png")
+        assert inf.get_ranking_position(sk, paths, Q[i:i + 1], G64, "euclidean") == \
+            O.get_ranking_position(sk, paths, Q[i:i + 1], G64, "euclidean")
+
+
+def test_rowwise_distance_modules(ops):
+    from art_sbir_b200 import utils as U
+    torch.manual_seed(1)
+    q, G = torch.randn(1, 777), torch.randn(300, 777)         # 777: scalar (unvectorised) row path
+    for mod, ref in ((U.euclidean_distance, O.euclidean_distance), (U.cosine_distance, O.cosine_distance)):
+        got = mod(q.cuda(), G.cuda()).cpu()
+        assert torch.allclose(got, ref(q, G), rtol=1e-5, atol=1e-6)
+        a, b = torch.randn(40, 512), torch.randn(40, 512)
+        assert torch.allclose(mod(a.cuda(), b.cuda()).cpu(), ref(a, b), rtol=1e-5, atol=1e-6)
+        # autograd through the drop-in distance module, broadcast and same-shape
+        for x1, x2 in ((q[:, :64], G[:50, :64]), (a[:, :64], b[:, :64])):
+            X1, X2 = x1.clone().cuda().requires_grad_(True), x2.clone().cuda().requires_grad_(True)
+            mod(X1, X2).pow(2).sum().backward()
+            Y1, Y2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+            ref(Y1, Y2).pow(2).sum().backward()
+            assert torch.allclose(X1.grad.cpu(), Y1.grad, rtol=1e-3, atol=1e-5 * Y1.grad.abs().max().item())
+            assert torch.allclose(X2.grad.cpu(), Y2.grad, rtol=1e-3, atol=1e-5 * Y2.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_l2_normalize(ops, dtype):
+    tdt = getattr(torch, dtype)
+    x = torch.randn(1000, 520).to(tdt)
+    x[7] = 0
+    got = ops.l2_normalize(x.cuda()).cpu()
+    ref = O.l2_normalize(x.float())
+    tol = 1e-6 if dtype == "float32" else 4e-3
+    assert torch.allclose(got.float(), ref, atol=tol, rtol=tol)
+    assert (got[7] == 0).all()
+    big = torch.randn(64, 4100)          # rows longer than the register-held part
+    assert torch.allclose(ops.l2_normalize(big.cuda()).cpu(), O.l2_normalize(big), atol=1e-6)
+
+
+@pytest.mark.parametrize("lt", ["euclidean", "cosine"])
+def test_triplet_and_batch_hard_cfg2(ops, lt):
+    """BASELINE config 2: a/p/n [256, 2048] fp32, margin 0.2."""
+    g = torch.Generator().manual_seed(11)
+    a, p, n = (torch.randn(256, 2048, generator=g) for _ in range(3))
+    p = a + 0.9 * p
+    A, P, N = (t.clone().cuda().requires_grad_(True) for t in (a, p, n))
+    loss = ops.triplet_margin_loss(A, P, N, 0.2, lt)
+    loss.backward()
+    Ar, Pr, Nr = (t.clone().requires_grad_(True) for t in (a, p, n))
+    ref = O.triplet_margin_loss(Ar, Pr, Nr, 0.2, lt)
+    ref.backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=DIST_RTOL)
+    for got, want in ((A.grad, Ar.grad), (P.grad, Pr.grad), (N.grad, Nr.grad)):
+        assert torch.allclose(got.cpu(), want, rtol=DIST_RTOL, atol=1e-6 * want.abs().max().item())
+
+    for labels in (None, torch.arange(256) // 4):
+        A, P, N = (t.clone().cuda().requires_grad_(True) for t in (a, p, n))
+        loss, hard = ops.batch_hard_triplet_loss(A, P, N, 0.2, lt, labels=None if labels is None else labels.cuda(),
+                                                 return_indices=True)
+        loss.backward()
+        Ar, Pr, Nr = (t.clone().requires_grad_(True) for t in (a, p, n))
+        ref, hpi, hni = O.batch_hard_triplet_loss(Ar, Pr, Nr, 0.2, lt, labels)
+        ref.backward()
+        assert loss.item() == pytest.approx(ref.item(), rel=DIST_RTOL)
+        assert (hard[:, 0].cpu() == hpi).float().mean() > 0.99 and (hard[:, 1].cpu() == hni).float().mean() > 0.99
+        if torch.equal(hard[:, 0].cpu(), hpi) and torch.equal(hard[:, 1].cpu(), hni):
+            for got, want in ((A.grad, Ar.grad), (P.grad, Pr.grad), (N.grad, Nr.grad)):
+                assert torch.allclose(got.cpu(), want, rtol=DIST_RTOL, atol=2e-6 * want.abs().max().item())
+
+
+def test_tensor_core_error_stays_inside_the_certified_bound(ops):
+    """The selection certificate and the rank band rely on |e_tc − e_exact| <= kappa·(‖q‖²+‖g‖²):
+    kappa = 2^-9 for kind::tf32 (operand truncation), 2^-18 for bf16 inputs (fp32 accumulation)."""
+    for dtype, kappa in ((torch.float32, 2.0 ** -9), (torch.bfloat16, 2.0 ** -18)):
+        Q, G, _ = O.synthetic_embeddings(300, 2000, 1024, seed=9)
+        Q, G = Q.to(dtype).cuda(), G.to(dtype).cuda()
+        e = ops.debug_dist_matrix(Q, G, "euclidean").double()
+        qd, gd = Q.double(), G.double()
+        ref = (gd ** 2).sum(1)[None, :] - 2 * qd @ gd.T
+        bound = kappa * ((qd ** 2).sum(1)[:, None] + (gd ** 2).sum(1)[None, :])
+        assert not torch.isnan(e).any()
+        assert ((e - ref).abs() <= bound).all(), ((e - ref).abs() / bound).max().item()
+
+
+# --------------------------------------------------- shard / merge / host-buffer identities ----
+def test_sharded_merge_equals_single_pass(ops):
+    Q, G, pos = O.synthetic_embeddings(300, 9001, 512, seed=21)
+    Qc, Gc, pc = Q.cuda(), G.cuda(), pos.cuda()
+    v1, i1, r1 = ops.pairwise_topk(Qc, Gc, 10, "euclidean", pos_index=pc)
+    from art_sbir_b200 import sharded
+    for world in (2, 3, 8):
+        vs, is_, cnt = [], [], torch.zeros_like(r1)
+        own = torch.full((300,), float("nan"), dtype=torch.float64, device="cuda")
+        for r in range(world):
+            a, b = sharded.shard_bounds(9001, world, r)
+            mine = (pc >= a) & (pc < b)
+            d = ops.positive_distance(Qc, Gc[a:b], torch.where(mine, pc - a, torch.full_like(pc, -1)))
+            own = torch.where(mine, d, own)
+        for r in range(world):
+            a, b = sharded.shard_bounds(9001, world, r)
+            v, i, c, _ = ops.pairwise_topk_shard(Qc, Gc[a:b].contiguous(), 10, "euclidean", a, own)
+            vs.append(v); is_.append(i); cnt += c
+        vm, im = ops.topk_merge(torch.stack(vs), torch.stack(is_))
+        assert torch.equal(im, i1) and torch.equal(vm, v1) and torch.equal(cnt, r1)
+
+
+def test_retrieve_host_equals_device_path(ops, sbir_lib):
+    from art_sbir_b200 import _binding as B
+    nq, ng, d, k = 300, 20000, 512, 10
+    Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=8)
+    q, g = Q.bfloat16().pin_memory(), G.bfloat16().pin_memory()
+    od = torch.empty(nq, k).pin_memory()
+    oi = torch.empty(nq, k, dtype=torch.int64).pin_memory()
+    orank = torch.empty(nq, dtype=torch.int64).pin_memory()
+    unc = ctypes.c_int32(-1)
+    B.check(sbir_lib.sbir_retrieve_host(q.data_ptr(), nq, g.data_ptr(), ng, d, B.SBIR_BF16, B.SBIR_EUCLIDEAN, k,
+                                        pos.data_ptr(), od.data_ptr(), oi.data_ptr(), orank.data_ptr(), ctypes.byref(unc)),
+            "sbir_retrieve_host")
+    v, i, r = ops.pairwise_topk(q.cuda(), g.cuda(), k, "euclidean", pos_index=pos.cuda())
+    assert torch.equal(i.cpu(), oi) and torch.equal(v.cpu(), od) and torch.equal(r.cpu(), orank) and unc.value == 0
+    sbir_lib.sbir_release_host_staging()
+
+
+# ------------------------------------------------------------ BASELINE-size property checks ----
+def _device_clustered(nq, ng, d, dtype, seed=1234):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    C = max(125, ng // 80)
+    beta = 0.06 if d >= 2048 else 0.12
+    cent = torch.randn(C, d, device="cuda", generator=gen)
+    noise = torch.randn(ng, d, device="cuda", generator=gen)
+    cls = torch.arange(ng, device="cuda") % C
+    G = (cent[cls] + noise).to(dtype)
+    pos = torch.randperm(ng, device="cuda", generator=gen)[:nq]
+    Q = (cent[cls[pos]] + beta * noise[pos] + torch.randn(nq, d, device="cuda", generator=gen)).to(dtype)
+    return Q.contiguous(), G.contiguous(), pos
+
+
+@pytest.mark.parametrize("nq,ng,d,dtype,k", [(1000, 10000, 2048, torch.float32, 10),      # BASELINE cfg1
+                                              (12500, 75000, 2048, torch.float32, 100),    # BASELINE cfg3
+                                              (4096, 400000, 512, torch.bfloat16, 10)])    # cfg4-shaped slice
+def test_full_size_properties(ops, nq, ng, d, dtype, k):
+    Q, G, pos = _device_clustered(nq, ng, d, dtype)
+    vals, idx, rank, unc = ops.pairwise_topk(Q, G, k, "euclidean", pos_index=pos, return_uncertified=True)
+    # (1) returned distances are the exact reference distances of the returned rows
+    sub = torch.arange(0, nq, max(1, nq // 64), device="cuda")
+    exact = ((Q[sub].double()[:, None, :] - G[idx[sub]].double() + 1e-6) ** 2).sum(-1).sqrt()
+    assert torch.allclose(vals[sub].double(), exact, rtol=1e-5)
+    # (2) ascending, unique indices
+    assert (vals[:, 1:] >= vals[:, :-1]).all()
+    assert (torch.sort(idx, dim=1).values[:, 1:] != torch.sort(idx, dim=1).values[:, :-1]).all()
+    # (3) rank consistent with the top-k: positive inside top-k ⇔ rank < k, at the right slot
+    inside = (idx == pos[:, None])
+    assert torch.equal(inside.any(1), rank < k)
+    assert torch.equal(inside.float().argmax(1)[rank < k], rank[rank < k])
+    # (4) brute-force check of a query subsample against torch on the same device (fp64)
+    sub = sub[:16]
+    dm = ((Q[sub].double()[:, None, :] - G.double()[None, :, :] + 1e-6) ** 2).sum(-1).sqrt() if ng * d <= 2.1e8 else \
+        torch.cdist(Q[sub].double(), G.double())
+    ref_v, ref_i = dm.topk(k, dim=1, largest=False)
+    mism = (ref_i != idx[sub])
+    assert mism.float().mean() < 0.01
+    assert torch.allclose(ref_v, vals[sub].double(), rtol=1e-5)
+    dpos = dm.gather(1, pos[sub][:, None])
+    assert ((dm < dpos).sum(1) - rank[sub]).abs().max() <= 1
+    # (5) gallery-permutation invariance of the set of distances
+    perm = torch.randperm(ng, device="cuda")
+    v2, i2 = ops.pairwise_topk(Q[:256], G[perm].contiguous(), k, "euclidean")
+    assert torch.equal(v2, vals[:256]) and torch.equal(perm[i2], idx[:256])

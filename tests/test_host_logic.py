@@ -1,0 +1,82 @@
+"""CPU suite, part 3: host-side mirror of the reference interface (names, attributes, error
+behaviour, file-name conventions, feature store) — everything that does not need a kernel."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from art_sbir_b200 import inference as inf
+from art_sbir_b200 import sharded, utils as U
+from oracle import sbir_oracle as O
+
+
+def test_loss_module_surface_matches_reference():
+    assert U.MARGIN == O.MARGIN == 0.2
+    assert (U.euclidean_distance.norm, U.euclidean_distance.eps, U.euclidean_distance.keepdim) == (2.0, 1e-6, False)
+    wc = U.TripletMarginLoss_with_classification(margin=0.2)
+    assert (wc.margin, wc.classification_weight, wc.classification_weight2) == (0.2, 0.5, 0)
+    wc2 = U.TripletMarginLoss_with_classification2(margin=0.3, classification_weight=0, classification_weight2=0.2)
+    assert (wc2.margin, wc2.classification_weight, wc2.classification_weight2) == (0.3, 0, 0.2)
+    # train.py:164-175 dispatch
+    assert isinstance(U.make_loss_fn("euclidean", False), U.TripletMarginLoss)
+    assert isinstance(U.make_loss_fn("cosine", False), U.TripletMarginWithDistanceLoss)
+    assert U.make_loss_fn("euclidean", True, "MixedDatasetV2").classification_weight == 0.01
+    assert U.make_loss_fn("cosine", True, "MixedDatasetV2").classification_weight == 0.5
+    k = U.make_loss_fn("euclidean", True, "KaggleDatasetV2")
+    assert isinstance(k, U.TripletMarginLoss_with_classification2) and (k.classification_weight, k.classification_weight2) == (0, 0.2)
+    assert U.make_loss_fn("euclidean", True, "SketchyV2").margin == 0.2       # param_dict reads loss_fn.margin (train.py:178)
+    with pytest.raises(Exception, match="loss type not correct"):
+        U.make_loss_fn("manhattan", False)
+    with pytest.raises(TypeError):
+        U.TripletMarginLoss_with_classification(margin=0.2, distance_f=lambda a, b: (a - b).abs().sum(1))
+
+
+def test_name_parsing_and_positive_lookup_match_oracle():
+    photos = sorted(Path(f"data/sketchy/photos/n{i:04d}.jpg") for i in range(50))
+    sketches = ["s/n0007-3.png", "s/n0049.png", "s/12-n0003-99887.png", "s/n9999-1.png"]
+    got = inf.positive_indices(sketches, photos, verbose=False).tolist()
+    want = [O.find_image_index(photos, O.sketch_name_to_key(s, photos)) for s in sketches]
+    assert got == want == [7, 49, 3, -1]
+    art = [Path("data/artworks/a-b.jpg"), Path("data/artworks/c.jpg")]
+    assert inf.sketch_key("s/a-b.png", art) == O.sketch_name_to_key("s/a-b.png", art) == "a-b"
+    # first match wins, like the reference's linear scan (utils.py:22-25)
+    dup = [Path("x/a.jpg"), Path("y/a.jpg")]
+    assert U.find_image_index(dup, "a") == 0
+
+
+def test_inference_dataset_dedups_and_sorts():
+    ds = inf.InferenceDataset([Path("b.jpg"), Path("a.jpg"), Path("b.jpg")])
+    assert ds.image_paths == [Path("a.jpg"), Path("b.jpg")] and len(ds) == 2
+
+
+def test_bad_loss_type_raises_like_reference():
+    with pytest.raises(Exception, match="loss type not correct"):
+        inf.get_ranking_position("s/n0001-1.png", [Path("p/n0001.jpg")], torch.zeros(1, 8), torch.zeros(1, 8), "manhattan")
+
+
+def test_missing_positive_short_circuits_without_gpu(capsys):
+    # inference.py:39-41: returns len(image_paths) and prints, before any distance is computed
+    r = inf.get_ranking_position("s/zzz-1.png", [Path("p/n0001.jpg"), Path("p/n0002.jpg")], torch.zeros(1, 8), torch.zeros(2, 8), "euclidean")
+    assert r == 2 and "No image found" in capsys.readouterr().out
+
+
+def test_feature_store_roundtrip(tmp_path):
+    class DS:
+        image_paths = [Path("p/a.jpg"), Path("p/b.jpg"), Path("p/c.jpg")]
+    feats = torch.randn(3, 16)
+    name = U.save_image_features("ModifiedResNet", "SketchyV1", DS(), feats, root=tmp_path)
+    assert name.startswith("ModifiedResNet_SketchyV1_")
+    paths, loaded = U.load_image_features(name, root=tmp_path)
+    assert paths == DS.image_paths and torch.equal(loaded, feats)           # sidecar: exact fp32
+    (tmp_path / name / "image_features.f32.npy").unlink()
+    paths, loaded = U.load_image_features(name, root=tmp_path)              # reference CSV route → float64 (F8)
+    assert loaded.dtype == torch.float64 and torch.allclose(loaded.float(), feats, rtol=1e-6)
+
+
+def test_shard_bounds_partition_the_gallery():
+    for n, w in ((10, 3), (75000, 8), (7, 8), (0, 2)):
+        spans = [sharded.shard_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1

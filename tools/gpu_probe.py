@@ -179,14 +179,41 @@ def case_batch_hard():
     return res
 
 
-def _time_topk(nq, ng, d, dtype_name, k, iters=3, rank=False):
+def _clustered(nq, ng, d, dtype, seed=1234):
+    """Device-side version of oracle.synthetic_embeddings (same construction, CUDA RNG)."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    C = max(125, ng // 80)
+    beta = 0.06 if d >= 2048 else 0.12
+    cent = torch.randn(C, d, device="cuda", generator=g)
+    G = torch.empty(ng, d, device="cuda", dtype=dtype)
+    pos = torch.randint(0, ng, (nq,), device="cuda", generator=g)
+    Q = torch.randn(nq, d, device="cuda", generator=g)
+    step = 1 << 18
+    for s0 in range(0, ng, step):
+        n = min(step, ng - s0)
+        cls = torch.arange(s0, s0 + n, device="cuda") % C
+        noise = torch.randn(n, d, device="cuda", generator=g)
+        G[s0:s0 + n] = (cent[cls] + noise).to(dtype)
+        sel = (pos >= s0) & (pos < s0 + n)
+        if sel.any():
+            pi = pos[sel] - s0
+            Q[sel] += cent[cls[pi]] + beta * noise[pi]
+    return Q.to(dtype).contiguous(), G, pos
+
+
+def _time_topk(nq, ng, d, dtype_name, k, iters=3, rank=False, clustered=True):
     import torch
     from art_sbir_b200 import ops
     dtype = getattr(torch, dtype_name)
-    q = torch.randn(nq, d, device="cuda").to(dtype)
-    g = torch.randn(ng, d, device="cuda").to(dtype)
-    pos = torch.randint(0, ng, (nq,), device="cuda") if rank else None
-    ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
+    if clustered:
+        q, g, pos = _clustered(nq, ng, d, dtype)
+    else:
+        q = torch.randn(nq, d, device="cuda").to(dtype)
+        g = torch.randn(ng, d, device="cuda").to(dtype)
+        pos = torch.randint(0, ng, (nq,), device="cuda")
+    pos = pos if rank else None
+    out = ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos, return_uncertified=True)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
     ev[0].record()
@@ -196,15 +223,60 @@ def _time_topk(nq, ng, d, dtype_name, k, iters=3, rank=False):
     torch.cuda.synchronize()
     ms = min(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
     pairs = nq * ng
-    return {"shape": [nq, ng, d, dtype_name, k, rank], "ms": ms, "pairs_per_s": pairs / ms * 1e3,
-            "tflops": 2 * d * pairs / ms * 1e3 / 1e12}
+    res = {"shape": [nq, ng, d, dtype_name, k, rank, clustered], "ms": ms, "pairs_per_s": pairs / ms * 1e3,
+           "tflops": 2 * d * pairs / ms * 1e3 / 1e12, "uncertified": int(out[-1].item())}
+    if rank:
+        r = out[2]
+        res["recall@1,10"] = [(r < 1).float().mean().item(), (r < 10).float().mean().item()]
+        res["rank_max"] = int(r.max().item())
+    return res
 
 
 def case_time():
-    return [_time_topk(1000, 10000, 2048, "float32", 10), _time_topk(12500, 75000, 2048, "float32", 100),
-            _time_topk(12500, 75000, 2048, "float32", 10), _time_topk(12500, 75000, 2048, "float32", 10, rank=True),
-            _time_topk(20000, 1000000, 512, "bfloat16", 10), _time_topk(20000, 1000000, 512, "bfloat16", 10, rank=True),
-            _time_topk(12500, 75000, 2048, "bfloat16", 10)]
+    return [_time_topk(1000, 10000, 2048, "float32", 10, rank=True),
+            _time_topk(12500, 75000, 2048, "float32", 100),
+            _time_topk(12500, 75000, 2048, "float32", 100, rank=True),
+            _time_topk(12500, 75000, 2048, "float32", 10),
+            _time_topk(12500, 75000, 2048, "float32", 10, rank=True),
+            _time_topk(12500, 75000, 2048, "float32", 10, rank=True, clustered=False),
+            _time_topk(20000, 1000000, 512, "bfloat16", 10),
+            _time_topk(20000, 1000000, 512, "bfloat16", 10, rank=True),
+            _time_topk(20000, 1000000, 512, "bfloat16", 100),
+            _time_topk(12500, 75000, 2048, "bfloat16", 10, rank=True)]
+
+
+def case_peaks():
+    import torch
+    res = {}
+    for name, dtype, tf32 in (("bf16", torch.bfloat16, False), ("tf32", torch.float32, True), ("fp32", torch.float32, False)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        n = 8192
+        a = torch.randn(n, n, device="cuda", dtype=dtype)
+        b = torch.randn(n, n, device="cuda", dtype=dtype)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        res[name + "_tflops"] = 2 * n ** 3 / best * 1e3 / 1e12
+    x = torch.empty(1 << 30, device="cuda", dtype=torch.bfloat16)
+    y = torch.empty_like(x)
+    best = 1e9
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y.copy_(x)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    res["copy_gbs"] = 2 * x.numel() * 2 / best * 1e3 / 1e9
+    return res
 
 
 def case_host():
@@ -227,7 +299,7 @@ def case_host():
             "rank_equal": bool((r.cpu() == orank).all()), "unc": unc.value}
 
 
-CASES = ["rowops", "dump_small", "dump_shapes", "topk_small", "topk_mid", "triplet", "batch_hard", "host", "time"]
+CASES = ["rowops", "dump_small", "dump_shapes", "topk_small", "topk_mid", "triplet", "batch_hard", "host", "peaks", "time"]
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
