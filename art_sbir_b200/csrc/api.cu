@@ -1,7 +1,11 @@
 // api.cu — the extern "C" boundary declared in include/sbir_b200.h: argument checking,
 // workspace layout, and the launch sequences.  No kernel code lives here.
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -10,6 +14,33 @@ namespace sbir {
 
 static thread_local int g_last_cuda_error = 0;
 void set_last_cuda_error(int err) { g_last_cuda_error = err; }
+
+// ---- profiling state (process-wide; bench.py only) ----
+static std::atomic<long long> g_kernel_launches{0};
+static std::atomic<int> g_profile_on{0};
+static std::mutex g_profile_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_k1_events;
+static cudaEvent_t g_k1_open = nullptr;
+
+void count_kernel_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+void profile_k1_begin(cudaStream_t st) {
+  if (!g_profile_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  cudaEvent_t e0 = nullptr;
+  if (cudaEventCreate(&e0) != cudaSuccess) return;
+  cudaEventRecord(e0, st);
+  g_k1_open = e0;
+}
+void profile_k1_end(cudaStream_t st) {
+  if (!g_profile_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  if (g_k1_open == nullptr) return;
+  cudaEvent_t e1 = nullptr;
+  if (cudaEventCreate(&e1) != cudaSuccess) return;
+  cudaEventRecord(e1, st);
+  g_k1_events.emplace_back(g_k1_open, e1);
+  g_k1_open = nullptr;
+}
 
 namespace {
 
@@ -189,6 +220,31 @@ int sbir_device_supported(void) {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
   return major == 10 ? 1 : 0;
+}
+
+int sbir_profile_enable(int on) {
+  g_profile_on.store(on ? 1 : 0);
+  return SBIR_OK;
+}
+
+int sbir_profile_collect(double* k1_ms_sum, int64_t* k1_launches, int64_t* kernel_launches) {
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  double sum = 0.0;
+  int64_t n = 0;
+  for (auto& ev : g_k1_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+      sum += ms;
+      ++n;
+    }
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  g_k1_events.clear();
+  if (k1_ms_sum) *k1_ms_sum = sum;
+  if (k1_launches) *k1_launches = n;
+  if (kernel_launches) *kernel_launches = g_kernel_launches.exchange(0);
+  return SBIR_OK;
 }
 
 int sbir_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype, float eps, void* stream) {

@@ -30,8 +30,17 @@ void set_last_cuda_error(int err);
     int _s = (expr);                    \
     if (_s != SBIR_OK) return _s;       \
   } while (0)
-// Kernel launches: catch configuration errors immediately (no device sync).
-#define SBIR_CHECK_LAUNCH() SBIR_CUDA_TRY(cudaGetLastError())
+// Kernel launches: catch configuration errors immediately (no device sync) and count them
+// (sbir_profile_collect reports the count; bench.py's `gpu_launches`).
+void count_kernel_launch();
+#define SBIR_CHECK_LAUNCH()              \
+  do {                                   \
+    ::sbir::count_kernel_launch();       \
+    SBIR_CUDA_TRY(cudaGetLastError());   \
+  } while (0)
+// Profiling hooks around the K1 launch (no-ops unless sbir_profile_enable(1) was called).
+void profile_k1_begin(cudaStream_t st);
+void profile_k1_end(cudaStream_t st);
 
 inline size_t elem_size(int dtype) { return dtype == SBIR_BF16 ? 2 : 4; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

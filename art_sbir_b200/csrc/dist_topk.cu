@@ -428,7 +428,9 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& pr
   using Cfg = K1Config<kCap, kEpiWarps>;
   auto kern = dist_topk_kernel<kTF32, kMetric, kMode, kCap, kEpiWarps>;
   SBIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  profile_k1_begin(st);
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tg, prm);
+  profile_k1_end(st);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }

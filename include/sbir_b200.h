@@ -171,6 +171,14 @@ int sbir_retrieve_host(const void* q_host, int64_t num_q, const void* g_host, in
 /* Frees the cached staging memory of sbir_retrieve_host. */
 int sbir_release_host_staging(void);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------
+ * With profiling enabled every launch of the distance/top-k kernel (K1) is bracketed by
+ * CUDA events on its own stream.  sbir_profile_collect waits for them, returns the summed
+ * K1 device time in milliseconds, the number of K1 launches, and the number of kernels
+ * this library launched since the previous collect, and resets all three. */
+int sbir_profile_enable(int on);
+int sbir_profile_collect(double* k1_ms_sum, int64_t* k1_launches, int64_t* kernel_launches);
+
 /* ---- debug / self-test ------------------------------------------------------
  * Writes the raw epilogue matrix E[num_q, num_g] (euclidean: ||g||²-2qg, cosine:
  * -q·g/max(||g||,eps)) computed by the tcgen05 tiles; used by tests to validate the
