@@ -102,7 +102,7 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
 // sbir_pairwise_topk_shard (pos_dist given, local count).
 int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
               int metric, int k, int64_t index_offset, const int64_t* pos_index,
-              const double* pos_dist_in, float* out_dist, int64_t* out_index, int64_t* out_rank,
+              const double* pos_dist_in, const int64_t* pos_tie, int64_t tie_offset, float* out_dist, int64_t* out_index, int64_t* out_rank,
               int64_t missing_rank, int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
               cudaStream_t st) {
   if (!dtype_ok(dtype) || !metric_ok(metric)) return SBIR_ERR_INVALID_ARG;
@@ -147,6 +147,7 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
     ra.q = q; ra.g = g; ra.num_q = num_q; ra.num_g = num_g; ra.dim = dim;
     ra.dtype = dtype; ra.metric = metric;
     ra.pos_index = pos_index; ra.pos_dist_in = pos_dist_in;
+    ra.pos_tie = pos_tie; ra.tie_offset = tie_offset;
     ra.qsq = qsq; ra.gsq_max = gmax; ra.kappa = k1_kappa(dtype);
     ra.pos_dist = reinterpret_cast<double*>(ws + L.off_pos_dist);
     ra.rank_lo = reinterpret_cast<float*>(ws + L.off_lo);
@@ -292,7 +293,7 @@ int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, int64_t num_
                        int metric, int k, int64_t index_offset, const int64_t* pos_index, float* out_dist,
                        int64_t* out_index, int64_t* out_rank, int32_t* out_uncertified, void* workspace,
                        size_t workspace_bytes, void* stream) {
-  return topk_impl(q, num_q, g, num_g, dim, dtype, metric, k, index_offset, pos_index, nullptr, out_dist,
+  return topk_impl(q, num_q, g, num_g, dim, dtype, metric, k, index_offset, pos_index, nullptr, pos_index, 0, out_dist,
                    out_index, out_rank, /*missing_rank=*/num_g, out_uncertified, workspace, workspace_bytes,
                    static_cast<cudaStream_t>(stream));
 }
@@ -308,11 +309,12 @@ int sbir_positive_distance(const void* q, int64_t num_q, const void* g, int64_t 
 
 int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
                              int dtype, int metric, int k, int64_t index_offset, const double* pos_dist,
-                             float* out_dist, int64_t* out_index, int64_t* out_count_less,
+                             const int64_t* pos_index_global, float* out_dist, int64_t* out_index, int64_t* out_count_less,
                              int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
                              void* stream) {
   // A query without a positive anywhere (NaN pos_dist) contributes a local count of 0.
-  return topk_impl(q, num_q, g, num_g, dim, dtype, metric, k, index_offset, nullptr, pos_dist, out_dist,
+  return topk_impl(q, num_q, g, num_g, dim, dtype, metric, k, index_offset, nullptr, pos_dist, pos_index_global,
+                   index_offset, out_dist,
                    out_index, out_count_less, /*missing_rank=*/0, out_uncertified, workspace, workspace_bytes,
                    static_cast<cudaStream_t>(stream));
 }

@@ -298,25 +298,14 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
             const float lim = kRank ? fmaxf(thr, hi) : thr;
             if (__any_sync(kFullMask, m < lim)) {
-              uint32_t mask = 0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) mask |= (e[j] < lim ? 1u : 0u) << j;
-              uint32_t pending = __reduce_or_sync(kFullMask, mask);
-              while (pending) {
-                const int j = __ffs(pending) - 1;
-                pending &= pending - 1;
-                // Re-read column j for every row of this warp (warp-uniform address) and
-                // recompute e with the identical instruction, so it is bit-equal to e[j].
-                const float s = __uint_as_float(tmem_ld_32x32b_x1(taddr + j));
-                tmem_ld_wait();
-                const float gj = __ldg(gv + c * 32 + j);
-                const float ej = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, s, gj) : __fmul_rn(s, gj);
+              // One candidate of this row: maybe enters the list, maybe sits in the rank band.
+              auto consume = [&](float ej, int gidx) {
                 if (ej < thr) {
                   lv[maxpos * kTileQ + row] = ej;
-                  li[maxpos * kTileQ + row] = gcol0 + j;
+                  li[maxpos * kTileQ + row] = gidx;
                   float mx = -INFINITY;
                   int mp = 0;
-#pragma unroll 4
+#pragma unroll 8
                   for (int p = 0; p < kCap; ++p) {
                     const float v = lv[p * kTileQ + row];
                     if (v > mx) { mx = v; mp = p; }
@@ -332,13 +321,61 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const uint32_t slot = atomicAdd(prm.pool_count, 1u);
                     if (slot < prm.pool_cap) {
                       prm.pool_q[slot] = q;
-                      prm.pool_idx[slot] = gcol0 + j;
+                      prm.pool_idx[slot] = gidx;
                     } else {
                       atomicAdd(prm.dropped + q, 1);
                     }
                   }
                 }
+              };
+              // Each lane queues its own hits of this chunk (up to 4, in registers) so that the
+              // lanes' insertions run side by side instead of one gallery column at a time.
+              float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+              int c0 = 0, c1 = 0, c2 = 0, c3 = 0, nh = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (e[j] < lim) {
+                  h3 = h2; c3 = c2;
+                  h2 = h1; c2 = c1;
+                  h1 = h0; c1 = c0;
+                  h0 = e[j]; c0 = j;
+                  ++nh;
+                }
+              }
+              const int maxh = __reduce_max_sync(kFullMask, nh);
+              if (maxh <= 4) {
+                if (nh > 0) consume(h0, gcol0 + c0);
                 __syncwarp();
+                if (maxh > 1) {
+                  if (nh > 1) consume(h1, gcol0 + c1);
+                  __syncwarp();
+                }
+                if (maxh > 2) {
+                  if (nh > 2) consume(h2, gcol0 + c2);
+                  __syncwarp();
+                }
+                if (maxh > 3) {
+                  if (nh > 3) consume(h3, gcol0 + c3);
+                  __syncwarp();
+                }
+              } else {
+                // Dense chunk (list warm-up): walk the hit columns of the whole warp.  Column j is
+                // re-read for every row (warp-uniform TMEM address) and e recomputed with the
+                // identical instruction, so it is bit-equal to e[j].
+                uint32_t mask = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mask |= (e[j] < lim ? 1u : 0u) << j;
+                uint32_t pending = __reduce_or_sync(kFullMask, mask);
+                while (pending) {
+                  const int j = __ffs(pending) - 1;
+                  pending &= pending - 1;
+                  const float s = __uint_as_float(tmem_ld_32x32b_x1(taddr + j));
+                  tmem_ld_wait();
+                  const float gj = __ldg(gv + c * 32 + j);
+                  const float ej = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, s, gj) : __fmul_rn(s, gj);
+                  consume(ej, gcol0 + j);
+                  __syncwarp();
+                }
               }
             }
           }

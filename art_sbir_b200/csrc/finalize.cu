@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinPar
     const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)gi * p.dim,
                                                   p.dim, p.metric, lane);
     if (lane == 0) {
-      ex[c] = d;
+      ex[c] = (double)(float)d;  // canonical order = (fp32 distance, index): shard-count invariant
       exi[c] = gi;
     }
   }
@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(kFbThreads) topk_fallback_kernel(const FinPara
   __syncwarp();
   const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
   for (int j = warp; j < p.num_g; j += kFbWarps) {
-    const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)j * p.dim,
-                                                  p.dim, p.metric, lane);
+    const double d = (double)(float)warp_exact_distance<T, kVec>(
+        qrow, reinterpret_cast<const T*>(p.g) + (size_t)j * p.dim, p.dim, p.metric, lane);
     // all lanes hold d; the list is sorted ascending, worst at k-1
     if (ranks_before(d, j, wd[warp][k - 1], wi[warp][k - 1])) {
       if (lane == 0) {
@@ -210,6 +210,8 @@ struct RankParams {
   int num_q, num_g, dim, metric;
   const long long* pos_index;
   const double* pos_dist_in;
+  const long long* pos_tie;  // index of the positive in the space (local row + tie_offset), or NULL
+  long long tie_offset;
   const float* qsq;
   const float* gsq_max;
   float kappa;
@@ -227,6 +229,18 @@ struct RankParams {
 };
 
 constexpr int kRankWarps = 8;
+
+// Canonical order of the ranked list: (fp32-rounded exact distance, gallery index).  Row j of
+// this gallery (shard) precedes the positive of query q iff its distance is smaller, or equal
+// with a smaller global index (pos_tie == NULL: equal distances never precede).
+__device__ __forceinline__ bool ranks_before_positive(double d_exact, int j_local, const RankParams& p, int q) {
+  const float d = (float)d_exact;
+  const float dp = (float)p.pos_dist[q];
+  if (d < dp) return true;
+  if (d > dp || p.pos_tie == nullptr) return false;
+  const long long pt = p.pos_tie[q];
+  return pt >= 0 && (long long)j_local + p.tie_offset < pt;
+}
 
 // d_pos (exact) and the e-space band [lo, hi) in which K1's approximate comparison against
 // d_pos cannot be trusted.
@@ -276,7 +290,7 @@ __global__ void __launch_bounds__(kRankWarps * 32) rank_resolve_kernel(const Ran
     const double d = warp_exact_distance<T, kVec>(reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim,
                                                   reinterpret_cast<const T*>(p.g) + (size_t)gi * p.dim,
                                                   p.dim, p.metric, lane);
-    if (lane == 0 && d < p.pos_dist[q]) atomicAdd(p.cnt_less + q, 1);
+    if (lane == 0 && ranks_before_positive(d, gi, p, q)) atomicAdd(p.cnt_less + q, 1);
   }
 }
 
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(kFbThreads) rank_fallback_kernel(const RankPar
   for (int j = warp; j < p.num_g; j += kFbWarps) {
     const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)j * p.dim,
                                                   p.dim, p.metric, lane);
-    cnt += d < dpos ? 1 : 0;
+    cnt += ranks_before_positive(d, j, p, q) ? 1 : 0;
   }
   if (lane == 0) red[warp] = cnt;
   __syncthreads();
@@ -479,6 +493,8 @@ RankParams make_rank_params(const RankArgs& a) {
   p.num_q = (int)a.num_q; p.num_g = (int)a.num_g; p.dim = (int)a.dim; p.metric = a.metric;
   p.pos_index = reinterpret_cast<const long long*>(a.pos_index);
   p.pos_dist_in = a.pos_dist_in;
+  p.pos_tie = reinterpret_cast<const long long*>(a.pos_tie);
+  p.tie_offset = a.tie_offset;
   p.qsq = a.qsq; p.gsq_max = a.gsq_max; p.kappa = a.kappa;
   p.pos_dist = a.pos_dist; p.rank_lo = a.rank_lo; p.rank_hi = a.rank_hi;
   p.cnt_less = a.cnt_less;

@@ -5,6 +5,7 @@
 // the K4 merge), so PCIe transfer overlaps the tensor-core work.  Device staging buffers
 // are cached per process and released by sbir_release_host_staging.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -86,6 +87,10 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   // Chunking: ~1 GiB of gallery rows per chunk (at least 4 chunks when the gallery is large
   // enough to make overlap worthwhile), chunk rows a multiple of the gallery tile.
   int64_t chunk_rows = (int64_t)((size_t(1) << 30) / row_bytes);
+  if (const char* env = std::getenv("SBIR_HOST_CHUNK_ROWS")) {  // test hook: force small chunks
+    const long long v = std::atoll(env);
+    if (v > 0) chunk_rows = v;
+  }
   chunk_rows = std::max<int64_t>(kTileG, chunk_rows / kTileG * kTileG);
   if (chunk_rows > num_g) chunk_rows = num_g;
   const int num_chunks = (int)((num_g + chunk_rows - 1) / chunk_rows);
@@ -101,10 +106,11 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   const size_t off_out_d = take((size_t)num_q * k * sizeof(float));
   const size_t off_out_i = take((size_t)num_q * k * sizeof(int64_t));
   const size_t off_uncert = take(sizeof(int32_t) * (size_t)(num_chunks + 1));
-  size_t off_pos = 0, off_posidx = 0, off_pos_dist = 0, off_rank = 0, off_cnt = 0;
+  size_t off_pos = 0, off_posidx = 0, off_posglobal = 0, off_pos_dist = 0, off_rank = 0, off_cnt = 0;
   if (want_rank) {
     off_pos = take((size_t)num_q * row_bytes);
     off_posidx = take((size_t)num_q * sizeof(int64_t));
+    off_posglobal = take((size_t)num_q * sizeof(int64_t));
     off_pos_dist = take((size_t)num_q * sizeof(double));
     off_rank = take((size_t)num_q * sizeof(int64_t));
     off_cnt = take((size_t)num_q * sizeof(int64_t));
@@ -130,6 +136,7 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
 
   double* d_pos_dist = nullptr;
   long long* d_rank = nullptr;
+  const int64_t* d_pos_global = nullptr;
   if (want_rank) {
     // The positive's row may sit in any chunk: gather those rows on the host once, upload
     // them, and evaluate d(q, pos) up front so every chunk can count against it.
@@ -147,6 +154,8 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
     }
     SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_pos, gathered.data(), gathered.size(), cudaMemcpyHostToDevice, xs));
     SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_posidx, ident.data(), ident.size() * sizeof(int64_t), cudaMemcpyHostToDevice, xs));
+    SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_posglobal, pos_index_host, (size_t)num_q * sizeof(int64_t), cudaMemcpyHostToDevice, xs));
+    d_pos_global = reinterpret_cast<const int64_t*>(base + off_posglobal);
     SBIR_CUDA_TRY(cudaStreamSynchronize(xs));  // the two vectors above go out of scope
     d_pos_dist = reinterpret_cast<double*>(base + off_pos_dist);
     d_rank = reinterpret_cast<long long*>(base + off_rank);
@@ -169,7 +178,7 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
     SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, g_staging.events[c], 0));
     int64_t* d_cnt = want_rank ? reinterpret_cast<int64_t*>(base + off_cnt) : nullptr;
     SBIR_TRY(sbir_pairwise_topk_shard(d_q, num_q, d_g + (size_t)r0 * row_bytes, rows, dim, dtype, metric, k, r0,
-                                      d_pos_dist, d_lists_d + (size_t)c * num_q * k,
+                                      d_pos_dist, d_pos_global, d_lists_d + (size_t)c * num_q * k,
                                       d_lists_i + (size_t)c * num_q * k, d_cnt, d_uncert + 1 + c,
                                       base + off_ws, ws_bytes, cs));
     if (want_rank) {

@@ -98,6 +98,8 @@ struct RankArgs {
   int dtype, metric;
   const int64_t* pos_index;  // [num_q] local gallery row of the positive, <0 = none (may be NULL)
   const double* pos_dist_in; // [num_q] externally supplied positive distance (NaN = none) or NULL
+  const int64_t* pos_tie;    // [num_q] positive's index in the (local row + tie_offset) space, or NULL
+  int64_t tie_offset;
   const float* qsq;
   const float* gsq_max;
   float kappa;

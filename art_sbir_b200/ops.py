@@ -176,7 +176,7 @@ def positive_distance(queries, gallery_shard, pos_index_local, loss_type="euclid
     return out
 
 
-def pairwise_topk_shard(queries, gallery_shard, k, loss_type, index_offset, pos_dist=None):
+def pairwise_topk_shard(queries, gallery_shard, k, loss_type, index_offset, pos_dist=None, pos_index_global=None):
     """One gallery shard's contribution: local top-k with global indices and, if pos_dist
     (fp64 [Q], NaN = no positive) is given, the local count of rows closer than it."""
     q, g = _dev(queries, "queries"), _dev(gallery_shard, "gallery")
@@ -188,12 +188,13 @@ def pairwise_topk_shard(queries, gallery_shard, k, loss_type, index_offset, pos_
     want = pos_dist is not None
     cnt = torch.zeros(nq, dtype=torch.int64, device=dev) if want else None
     pd = _dev(pos_dist.to(torch.float64), "pos_dist") if want else None
+    pg = _dev(pos_index_global.to(torch.int64), "pos_index_global") if (want and pos_index_global is not None) else None
     unc = torch.zeros(1, dtype=torch.int32, device=dev)
     lib = B.load()
     with torch.cuda.device(dev):
         ws = _workspace(lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, _dtype_id(q), metric, int(want)), dev)
         B.check(lib.sbir_pairwise_topk_shard(q.data_ptr(), nq, _ptr(g) if ng else None, ng, d, _dtype_id(q), metric,
-                                             k, int(index_offset), _ptr(pd), vals.data_ptr(), idx.data_ptr(),
+                                             k, int(index_offset), _ptr(pd), _ptr(pg), vals.data_ptr(), idx.data_ptr(),
                                              _ptr(cnt), unc.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                 "sbir_pairwise_topk_shard")
     return vals, idx, cnt, unc

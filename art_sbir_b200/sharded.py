@@ -29,8 +29,8 @@ def shard_bounds(num_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def _cuda_local(queries, shard, k, loss_type, offset, pos_dist):
-    vals, idx, cnt, unc = ops.pairwise_topk_shard(queries, shard, k, loss_type, offset, pos_dist)
+def _cuda_local(queries, shard, k, loss_type, offset, pos_dist, pos_index_global=None):
+    vals, idx, cnt, unc = ops.pairwise_topk_shard(queries, shard, k, loss_type, offset, pos_dist, pos_index_global)
     return vals, idx, cnt
 
 
@@ -72,7 +72,7 @@ def sharded_pairwise_topk(queries: torch.Tensor, gallery_shard: torch.Tensor, k:
             dist.all_reduce(pair, group=group)  # exactly one owner per query: the sum is exact
         pos_dist = torch.where(pair[1] > 0, pair[0], torch.full_like(pair[0], float("nan")))
 
-    vals, idx, cnt = local_fn(queries, gallery_shard, k, loss_type, shard_offset, pos_dist)
+    vals, idx, cnt = local_fn(queries, gallery_shard, k, loss_type, shard_offset, pos_dist, pos_index)
 
     if world > 1:
         all_vals = [torch.empty_like(vals) for _ in range(world)]

@@ -84,10 +84,12 @@ int sbir_pairwise_distance_bwd(const float* x1, int64_t rows1, const float* x2, 
  *     out_dist[q, 0:k]  = the k smallest distances, ascending (fp32),
  *     out_index[q, 0:k] = their gallery row indices + index_offset (int64),
  *                         ties broken by ascending index,
- *     out_rank[q]       = #{ j : dist(q, j) < dist(q, pos_index[q]) }  (int64) — the
- *                         0-based position the reference finds with topk(len(G)) at
- *                         inference.py:49-52 — when pos_index != NULL; entries with
- *                         pos_index[q] < 0 get num_g (inference.py:39-41).
+ *     out_rank[q]       = 0-based position of gallery row pos_index[q] in that same
+ *                         (distance, index) order over the WHOLE gallery (int64) — what the
+ *                         reference finds with topk(len(G)) + nonzero at inference.py:49-52 —
+ *                         when pos_index != NULL; pos_index[q] < 0 gives num_g (inference.py:39-41).
+ * "distance" in the order is the exact reference distance rounded to fp32, so the order (and
+ * therefore top-k, rank and recall@K) does not depend on how the gallery is split into shards.
  * The distance matrix is never materialised: tcgen05 tiles of Q·Gᵀ feed a fused
  * per-query selection, the K(+slack) survivors are re-scored with the exact
  * reference formula, and `out_uncertified[0]` counts queries whose selection could
@@ -106,13 +108,16 @@ int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, int64_t num_
 /* Rank-only partial results for a gallery SHARD (multi-GPU): same
  * as above but the positive's distance is supplied (pos_dist, fp64 [num_q], from
  * sbir_positive_distance on the owning shard, all-reduced by the caller) and the
- * count is local to this shard; the caller sums counts across shards. */
+ * count is local to this shard; the caller sums counts across shards.  pos_index_global
+ * (int64 [num_q], may be NULL) is the positive's GLOBAL row, used only to break exact
+ * fp32 distance ties by index so that shard counts add up to the single-pass rank. */
 int sbir_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g,
                            int64_t dim, int dtype, int metric, const int64_t* pos_index_local,
                            double* out_pos_dist, void* stream);
 int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, int64_t num_g,
                              int64_t dim, int dtype, int metric, int k, int64_t index_offset,
-                             const double* pos_dist, float* out_dist, int64_t* out_index, int64_t* out_count_less,
+                             const double* pos_dist, const int64_t* pos_index_global, float* out_dist,
+                             int64_t* out_index, int64_t* out_count_less,
                              int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
                              void* stream);
 

@@ -180,7 +180,8 @@ def test_edge_cases(ops):
     G2 = torch.cat([G, G[1:2], G[1:2]])            # rows 5, 6 duplicate row 1
     q = G[1:2] + 0.01
     vals, idx, rank = ops.pairwise_topk(q.to(dev), G2.to(dev), 3, "euclidean", pos_index=torch.tensor([6], device=dev))
-    assert idx[0].tolist() == [1, 5, 6] and rank.item() == 0
+    # canonical order (distance, index): row 6 sits behind its duplicates 1 and 5
+    assert idx[0].tolist() == [1, 5, 6] and rank.item() == 2
     assert O.ranking_position(q, G2, 6, "euclidean") in (0, 1, 2)   # the reference lands on one of the tied slots
     # zero vectors under cosine: distance 1 to everything (per-operand clamp, utils.py:34)
     Gz = torch.cat([torch.zeros(1, 64), G])
@@ -303,14 +304,19 @@ def test_sharded_merge_equals_single_pass(ops):
             own = torch.where(mine, d, own)
         for r in range(world):
             a, b = sharded.shard_bounds(9001, world, r)
-            v, i, c, _ = ops.pairwise_topk_shard(Qc, Gc[a:b].contiguous(), 10, "euclidean", a, own)
+            v, i, c, _ = ops.pairwise_topk_shard(Qc, Gc[a:b].contiguous(), 10, "euclidean", a, own, pc)
             vs.append(v); is_.append(i); cnt += c
         vm, im = ops.topk_merge(torch.stack(vs), torch.stack(is_))
         assert torch.equal(im, i1) and torch.equal(vm, v1) and torch.equal(cnt, r1)
 
 
-def test_retrieve_host_equals_device_path(ops, sbir_lib):
+@pytest.mark.parametrize("chunk_rows", [0, 4096])
+def test_retrieve_host_equals_device_path(ops, sbir_lib, chunk_rows, monkeypatch):
+    """Host-buffer entry point == device path, also when the gallery is uploaded and scored in
+    several chunks (SBIR_HOST_CHUNK_ROWS forces 5 chunks here; production chunks are 1 GiB)."""
     from art_sbir_b200 import _binding as B
+    if chunk_rows:
+        monkeypatch.setenv("SBIR_HOST_CHUNK_ROWS", str(chunk_rows))
     nq, ng, d, k = 300, 20000, 512, 10
     Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=8)
     q, g = Q.bfloat16().pin_memory(), G.bfloat16().pin_memory()

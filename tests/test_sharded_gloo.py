@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 from oracle import sbir_oracle as O
 
 
-def _oracle_local(queries, shard, k, loss_type, offset, pos_dist):
+def _oracle_local(queries, shard, k, loss_type, offset, pos_dist, pos_index_global=None):
     n = shard.shape[0]
     kk = min(k, n)
     vals = torch.full((queries.shape[0], k), float("inf"))
