@@ -48,6 +48,23 @@ __device__ __forceinline__ int32_t ld_relaxed(const int32_t* p) {
   return v;
 }
 
+// Unit → (query tile, gallery split).  Units are numbered band by band: a band is `band_q`
+// consecutive query tiles whose operand rows stay L2-resident together; inside a band the
+// query tile varies fastest, so the CTAs running at the same time share gallery tiles (one
+// HBM read serves the whole band) while re-reading only a small set of query tiles.
+struct UnitCoord { int q_tile, split; };
+__device__ __forceinline__ UnitCoord decode_unit(int unit, int num_q_tiles, int num_splits, int band_q) {
+  const int band_units = band_q * num_splits;
+  const int band = unit / band_units;
+  const int r = unit - band * band_units;
+  const int q0 = band * band_q;
+  const int bq = min(band_q, num_q_tiles - q0);
+  UnitCoord c;
+  c.split = r / bq;
+  c.q_tile = q0 + r - c.split * bq;
+  return c;
+}
+
 template <int kCap, int kEpiWarps>
 struct K1Config {
   static constexpr int kListsPerRow = kEpiWarps / 4;
@@ -70,7 +87,7 @@ struct K1Config {
 struct K1Params {
   const float* gvec;
   int num_q, num_g;
-  int num_q_tiles, num_g_tiles, tiles_per_split, num_units, num_k_blocks;
+  int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks, band_q;
   int elems_per_kblock;
   float* cand_val;
   int32_t* cand_idx;
@@ -140,9 +157,9 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
-        const int q_tile = unit % prm.num_q_tiles;
-        const int split = unit / prm.num_q_tiles;
-        const int t0 = split * prm.tiles_per_split;
+        const UnitCoord uc = decode_unit(unit, prm.num_q_tiles, prm.num_splits, prm.band_q);
+        const int q_tile = uc.q_tile;
+        const int t0 = uc.split * prm.tiles_per_split;
         const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
@@ -166,8 +183,8 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
-        const int split = unit / prm.num_q_tiles;
-        const int t0 = split * prm.tiles_per_split;
+        const UnitCoord uc = decode_unit(unit, prm.num_q_tiles, prm.num_splits, prm.band_q);
+        const int t0 = uc.split * prm.tiles_per_split;
         const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
@@ -202,15 +219,17 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     uint32_t acc_phase = 0;
 
     for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
-      const int q_tile = unit % prm.num_q_tiles;
-      const int split = unit / prm.num_q_tiles;
+      const UnitCoord uc = decode_unit(unit, prm.num_q_tiles, prm.num_splits, prm.band_q);
+      const int q_tile = uc.q_tile;
+      const int split = uc.split;
       const int t0 = split * prm.tiles_per_split;
       const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
       const int q = q_tile * kTileQ + row;
       const bool q_valid = q < prm.num_q;
 
       // This thread's list: entry p lives at [p * kTileQ + row] (conflict-free / coalesced).
-      const size_t list_slot = (size_t)unit * Cfg::kListsPerRow + half;
+      // candidate slot is keyed by (split, query tile), independent of the unit numbering
+      const size_t list_slot = ((size_t)split * prm.num_q_tiles + q_tile) * Cfg::kListsPerRow + half;
       float* lv = list_val_s + half * kCap * kTileQ;
       int32_t* li;
       if constexpr (Cfg::kIdxInSmem) li = list_idx_s + half * kCap * kTileQ;
@@ -510,16 +529,35 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   if (p.num_g_tiles < 1) p.num_g_tiles = 1;
   const size_t es = dtype == SBIR_BF16 ? 2 : 4;
   p.num_k_blocks = (int)((dim * es + kSwizzleBytes - 1) / kSwizzleBytes);
-  // Splits: aim for ~4 waves of units over the SMs, at most one split per gallery tile, and
-  // keep the merged candidate set per query within the finalize kernel's 4096-entry budget.
-  int64_t want_units = (int64_t)num_sms * 4;
-  int64_t splits = (want_units + p.num_q_tiles - 1) / p.num_q_tiles;
-  if (splits > p.num_g_tiles) splits = p.num_g_tiles;
-  const int64_t max_splits = 4096 / (p.cap * p.lists_per_row);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  p.tiles_per_split = (int)((p.num_g_tiles + splits - 1) / splits);
+  // Splits: all units cost the same (tiles_per_split tiles + a fixed start-up/write-out of about
+  // one tile), CTAs take units round-robin, so the makespan is ceil(units / SMs) rounds.  Pick
+  // the split count with the smallest makespan (ties: fewer splits), at most one split per
+  // gallery tile, keeping the merged candidate set per query within finalize's 4096 entries.
+  int64_t max_splits = 4096 / (p.cap * p.lists_per_row);
+  if (max_splits > p.num_g_tiles) max_splits = p.num_g_tiles;
+  if (max_splits > 64) max_splits = 64;
+  if (max_splits < 1) max_splits = 1;
+  double best_cost = 0.0;
+  int best_tps = p.num_g_tiles;
+  for (int64_t s = 1; s <= max_splits; ++s) {
+    const int64_t tps = (p.num_g_tiles + s - 1) / s;
+    const int64_t splits = (p.num_g_tiles + tps - 1) / tps;
+    const int64_t units = splits * p.num_q_tiles;
+    const double cost = (double)((units + num_sms - 1) / num_sms) * ((double)tps + 1.0);
+    if (s == 1 || cost < best_cost * 0.995) {
+      best_cost = cost;
+      best_tps = (int)tps;
+    }
+  }
+  p.tiles_per_split = best_tps;
   p.num_splits = (p.num_g_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  // Band: as many query tiles as keep their rows (tile × dim × elem bytes each) within ~32 MB
+  // of L2 next to the streaming gallery tiles.
+  const int64_t q_tile_bytes = (int64_t)kTileQ * dim * (int64_t)es;
+  int64_t band = (32LL << 20) / (q_tile_bytes > 0 ? q_tile_bytes : 1);
+  if (band < 1) band = 1;
+  if (band > p.num_q_tiles) band = p.num_q_tiles;
+  p.band_q = (int)band;
   p.num_units = p.num_q_tiles * p.num_splits;
   return p;
 }
@@ -537,6 +575,8 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.num_g = (int)a.num_g;
   prm.num_q_tiles = plan.num_q_tiles;
   prm.num_g_tiles = plan.num_g_tiles;
+  prm.num_splits = plan.num_splits;
+  prm.band_q = plan.band_q > 0 ? plan.band_q : plan.num_q_tiles;
   prm.tiles_per_split = plan.tiles_per_split;
   prm.num_units = plan.num_units;
   prm.num_k_blocks = plan.num_k_blocks;
