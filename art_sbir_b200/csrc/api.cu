@@ -76,12 +76,12 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   L.off_gvec = take((size_t)L.plan.num_g_tiles * kTileG * sizeof(float));
   L.off_gmax = take(sizeof(float));
   L.off_qsq = take(nq * sizeof(float));
-  const size_t cand = (size_t)L.plan.num_units * L.plan.lists_per_row * L.plan.cap * kTileQ;
+  const size_t cand = (size_t)L.plan.num_splits * L.plan.q_tile_stride * L.plan.lists_per_row * L.plan.cap * kTileQ;
   L.off_cand_val = take(cand * sizeof(float));
   L.off_cand_idx = take(cand * sizeof(int32_t));
   L.off_flags = take(nq * sizeof(int32_t));
   L.off_uncert = take(sizeof(int32_t));
-  L.off_shared_thr = take((size_t)L.plan.num_q_tiles * kTileQ * sizeof(int32_t));
+  L.off_shared_thr = take((size_t)L.plan.q_tile_stride * kTileQ * sizeof(int32_t));
   if (want_rank) {
     L.off_pos_dist = take(nq * sizeof(double));
     L.off_lo = take(nq * sizeof(float));
@@ -177,7 +177,7 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   ka.pool_count = ra.pool_count; ka.pool_cap = ra.pool_cap; ka.pool_q = ra.pool_q; ka.pool_idx = ra.pool_idx;
   ka.dropped = ra.dropped;
   ka.shared_thr = reinterpret_cast<int32_t*>(ws + L.off_shared_thr);
-  SBIR_TRY(launch_fill_i32(ka.shared_thr, (int64_t)L.plan.num_q_tiles * kTileQ, 0x7f800000, st));
+  SBIR_TRY(launch_fill_i32(ka.shared_thr, (int64_t)L.plan.q_tile_stride * kTileQ, 0x7f800000, st));
   SBIR_TRY(launch_k1(ka, L.plan, st));
 
   FinalizeArgs fa{};

@@ -192,15 +192,17 @@ struct BhLayout {
 BhLayout bh_layout(int64_t batch, int64_t dim) {
   BhLayout L{};
   L.plan = make_k1_plan(batch, 2 * batch, dim, 1, SBIR_F32, 148);
-  // one unit per gallery tile keeps the epilogue state per (tile, row)
+  // single-CTA tiles, one unit per gallery tile: the epilogue state is per (tile, row)
+  L.plan.pair = 1;
   L.plan.tiles_per_split = 1;
   L.plan.num_splits = L.plan.num_g_tiles;
+  L.plan.band_q = L.plan.num_q_tiles;
   L.plan.num_units = L.plan.num_q_tiles * L.plan.num_splits;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + bytes, 256); return r; };
   L.off_x = take((size_t)2 * batch * dim * sizeof(float));
   L.off_gvec = take((size_t)L.plan.num_g_tiles * kTileG * sizeof(float));
-  const size_t hard_elems = (size_t)L.plan.num_splits * L.plan.num_q_tiles * kTileQ * L.plan.lists_per_row * 2;
+  const size_t hard_elems = (size_t)L.plan.num_splits * L.plan.q_tile_stride * kTileQ * L.plan.lists_per_row * 2;
   L.off_hard_val = take(hard_elems * sizeof(float));
   L.off_hard_idx = take(hard_elems * sizeof(int32_t));
   L.off_per_row = take((size_t)batch * sizeof(float));
@@ -247,7 +249,7 @@ int launch_batch_hard(const float* a, const float* p, const float* n, int64_t ba
 
   bh_select_kernel<<<(unsigned)batch, kBhThreads, 0, st>>>(
       a, x, (int)batch, (int)dim, metric, margin, hard_val, hard_idx, L.plan.num_splits,
-      L.plan.num_q_tiles * kTileQ, L.plan.lists_per_row, 1.0f / (float)batch, per_row, weight, sel,
+      L.plan.q_tile_stride * kTileQ, L.plan.lists_per_row, 1.0f / (float)batch, per_row, weight, sel,
       reinterpret_cast<long long*>(out_hard_index));
   SBIR_CHECK_LAUNCH();
   bh_mean_kernel<<<1, 256, 0, st>>>(per_row, (int)batch, out_loss);

@@ -17,6 +17,8 @@
 // e orders gallery rows exactly like the distance does for a fixed query (‖q‖² and the
 // query norm are per-row constants); exact distances are recomputed for the survivors by
 // finalize.cu, so tensor-core rounding never reaches the caller.
+#include <cstdlib>
+
 #include <cuda.h>
 
 #include "common.cuh"
@@ -29,8 +31,7 @@ namespace {
 
 constexpr int kSwizzleBytes = 128;                    // one k-block = 128 bytes of features per row
 constexpr int kStageBytesQ = kTileQ * kSwizzleBytes;  // 16 KB
-constexpr int kStageBytesG = kTileG * kSwizzleBytes;  // 32 KB
-constexpr int kStageBytes = kStageBytesQ + kStageBytesG;
+constexpr int kStageBytesGFull = kTileG * kSwizzleBytes;  // 32 KB (halved per CTA in pair mode)
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kTmemCols = 512;  // two 256-column fp32 accumulators
 
@@ -65,8 +66,15 @@ __device__ __forceinline__ UnitCoord decode_unit(int unit, int num_q_tiles, int 
   return c;
 }
 
-template <int kCap, int kEpiWarps>
+// kPair = 1: one CTA computes a 128×256 tile (cta_group::1).  kPair = 2: a 2-CTA cluster computes
+// a 256×256 tile with one M=256 tcgen05.mma (cta_group::2): each CTA loads its own 128 query rows
+// and only HALF of the gallery tile, so the TMA/L2 traffic and the shared-memory operand reads per
+// FLOP drop by a third and the smaller stages allow a deeper ring.
+template <int kCap, int kEpiWarps, int kPair>
 struct K1Config {
+  static constexpr int kStageBytesG = kStageBytesGFull / kPair;
+  static constexpr int kStageBytes = kStageBytesQ + kStageBytesG;
+  static constexpr int kMaxStages = kPair == 2 ? 6 : 4;
   static constexpr int kListsPerRow = kEpiWarps / 4;
   // distance keys of the running lists always live in shared memory (they are re-scanned on
   // every insertion); the gallery indices are write-only until the end and go straight to
@@ -76,7 +84,7 @@ struct K1Config {
   static constexpr int kListBytes = kValBytes + (kIdxInSmem ? kValBytes : 0);
   static constexpr int kBarrierBytes = 256;
   static constexpr int kStagesFit = (kSmemLimit - 1024 - kListBytes - kBarrierBytes) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 4 ? 4 : kStagesFit;
+  static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : kStagesFit;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kListBytes + kBarrierBytes;
   static constexpr int kThreads = 64 + kEpiWarps * 32;
   static constexpr int kColsPerWarp = kTileG / kListsPerRow;
@@ -88,6 +96,8 @@ struct K1Params {
   const float* gvec;
   int num_q, num_g;
   int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks, band_q;
+  int num_row_tiles;   // query tiles (kPair = 1) or query-tile pairs (kPair = 2) — the unit grid's rows
+  int q_tile_stride;   // query-tile stride of the candidate slots (num_q_tiles rounded up to even)
   int elems_per_kblock;
   float* cand_val;
   int32_t* cand_idx;
@@ -107,12 +117,20 @@ struct K1Params {
   int32_t* hard_idx;
 };
 
-template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps>
-__global__ void __launch_bounds__(K1Config<kCap, kEpiWarps>::kThreads, 1)
+template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps, int kPair>
+__global__ void __launch_bounds__(K1Config<kCap, kEpiWarps, kPair>::kThreads, 1)
 dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                  const __grid_constant__ CUtensorMap tmap_g, const K1Params prm) {
-  using Cfg = K1Config<kCap, kEpiWarps>;
+  using Cfg = K1Config<kCap, kEpiWarps, kPair>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kStageBytesG = Cfg::kStageBytesG;
+  constexpr int kStageBytes = Cfg::kStageBytes;
+  // Pair mode: `cta_rank` 0 is the leader (issues the MMAs, owns the full/acc_empty barriers);
+  // a "unit" is then (PAIR of query tiles, gallery split) and this CTA works on query tile
+  // 2·pair + cta_rank and on gallery rows [rank·128, +128) of every 256-row tile.
+  const int cta_rank = kPair == 2 ? (int)cluster_ctarank() : 0;
+  const int worker = kPair == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = kPair == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr bool kSelect = (kMode == kModeTopk || kMode == kModeTopkRank);
   constexpr bool kRank = (kMode == kModeTopkRank);
 
@@ -141,13 +159,17 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full_bar[a], 1);
-      mbar_init(&acc_empty_bar[a], kEpiWarps);
+      mbar_init(&acc_empty_bar[a], kEpiWarps * kPair);  // epilogue warps of both CTAs of a pair
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) {
+    if constexpr (kPair == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -156,34 +178,44 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
-        const UnitCoord uc = decode_unit(unit, prm.num_q_tiles, prm.num_splits, prm.band_q);
-        const int q_tile = uc.q_tile;
+      for (int unit = worker; unit < prm.num_units; unit += num_workers) {
+        const UnitCoord uc = decode_unit(unit, prm.num_row_tiles, prm.num_splits, prm.band_q);
+        const int q_tile = uc.q_tile * kPair + cta_rank;
         const int t0 = uc.split * prm.tiles_per_split;
         const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_2d(smem_q + stage * kStageBytesQ, &tmap_q, &full_bar[stage],
-                        kb * prm.elems_per_kblock, q_tile * kTileQ);
-            tma_load_2d(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
-                        kb * prm.elems_per_kblock, t * kTileG);
+            if constexpr (kPair == 2) {
+              // the leader's barrier collects the bytes of both CTAs' loads
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+              tma_load_2d_pair(smem_q + stage * kStageBytesQ, &tmap_q, &full_bar[stage],
+                               kb * prm.elems_per_kblock, q_tile * kTileQ);
+              tma_load_2d_pair(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
+                               kb * prm.elems_per_kblock, t * kTileG + cta_rank * (kTileG / 2));
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+              tma_load_2d(smem_q + stage * kStageBytesQ, &tmap_q, &full_bar[stage],
+                          kb * prm.elems_per_kblock, q_tile * kTileQ);
+              tma_load_2d(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
+                          kb * prm.elems_per_kblock, t * kTileG);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
+    __syncwarp();  // reconverge before the (warp-aligned) teardown barriers
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer ----
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_instr_desc(kTF32 ? 2u : 1u, kTileQ, kTileG);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_instr_desc(kTF32 ? 2u : 1u, kTileQ * kPair, kTileG);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
-        const UnitCoord uc = decode_unit(unit, prm.num_q_tiles, prm.num_splits, prm.band_q);
+      for (int unit = worker; unit < prm.num_units; unit += num_workers) {
+        const UnitCoord uc = decode_unit(unit, prm.num_row_tiles, prm.num_splits, prm.band_q);
         const int t0 = uc.split * prm.tiles_per_split;
         const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
         for (int t = t0; t < t1; ++t) {
@@ -196,17 +228,22 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_q + stage * kStageBytesQ));
             const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_g + stage * kStageBytesG));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // 4 × 32-byte K steps inside the 128-byte swizzle atom
-              umma_ss<kTF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(&empty_bar[stage]);
+            for (int k = 0; k < 4; ++k) {  // 4 × 32-byte K steps inside the 128-byte swizzle atom
+              if constexpr (kPair == 2) umma_ss_pair<kTF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              else umma_ss<kTF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
+            if constexpr (kPair == 2) umma_commit_pair(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&acc_full_bar[acc]);
+          if constexpr (kPair == 2) umma_commit_pair(&acc_full_bar[acc]);
+          else umma_commit(&acc_full_bar[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
       }
     }
+    __syncwarp();
   } else {
     // ---------------------------------------------------------------- epilogue ----
     const int ew = warp - 2;
@@ -218,9 +255,9 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int acc = 0;
     uint32_t acc_phase = 0;
 
-    for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
-      const UnitCoord uc = decode_unit(unit, prm.num_q_tiles, prm.num_splits, prm.band_q);
-      const int q_tile = uc.q_tile;
+    for (int unit = worker; unit < prm.num_units; unit += num_workers) {
+      const UnitCoord uc = decode_unit(unit, prm.num_row_tiles, prm.num_splits, prm.band_q);
+      const int q_tile = uc.q_tile * kPair + cta_rank;
       const int split = uc.split;
       const int t0 = split * prm.tiles_per_split;
       const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
@@ -229,7 +266,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
       // This thread's list: entry p lives at [p * kTileQ + row] (conflict-free / coalesced).
       // candidate slot is keyed by (split, query tile), independent of the unit numbering
-      const size_t list_slot = ((size_t)split * prm.num_q_tiles + q_tile) * Cfg::kListsPerRow + half;
+      const size_t list_slot = ((size_t)split * prm.q_tile_stride + q_tile) * Cfg::kListsPerRow + half;
       float* lv = list_val_s + half * kCap * kTileQ;
       int32_t* li;
       if constexpr (Cfg::kIdxInSmem) li = list_idx_s + half * kCap * kTileQ;
@@ -408,7 +445,10 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // Accumulator fully read: hand it back to the MMA warp.
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
+        if (lane == 0) {
+          if constexpr (kPair == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty_bar[acc]), 0));
+          else mbar_arrive(&acc_empty_bar[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -427,7 +467,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       if constexpr (kMode == kModeHard) {
         // one unit == one gallery tile range; slot [split][q_tile*128+row][half]
-        const size_t o = (((size_t)split * prm.num_q_tiles + q_tile) * kTileQ + row) * Cfg::kListsPerRow + half;
+        const size_t o = (((size_t)split * prm.q_tile_stride + q_tile) * kTileQ + row) * Cfg::kListsPerRow + half;
         prm.hard_val[o * 2 + 0] = hp;
         prm.hard_val[o * 2 + 1] = hn;
         prm.hard_idx[o * 2 + 0] = hpi;
@@ -437,8 +477,13 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if constexpr (kPair == 2) {
+    cluster_sync_all();  // the peer may still be arriving on / reading this CTA's shared memory
+    if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------ host side ----
@@ -479,23 +524,46 @@ int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int
   return SBIR_OK;
 }
 
-template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps>
-int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm, int grid, cudaStream_t st) {
-  using Cfg = K1Config<kCap, kEpiWarps>;
-  auto kern = dist_topk_kernel<kTF32, kMetric, kMode, kCap, kEpiWarps>;
+template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps, int kPair>
+int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm, int num_sms, cudaStream_t st) {
+  using Cfg = K1Config<kCap, kEpiWarps, kPair>;
+  auto kern = dist_topk_kernel<kTF32, kMetric, kMode, kCap, kEpiWarps, kPair>;
   SBIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  int workers = num_sms / kPair;
+  if (workers > prm.num_units) workers = prm.num_units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(workers * kPair));
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kPair == 2 ? 1 : 0;
   profile_k1_begin(st);
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tg, prm);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tq, tg, prm);
   profile_k1_end(st);
+  if (e != cudaSuccess) {
+    set_last_cuda_error((int)e);
+    return SBIR_ERR_CUDA;
+  }
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }
 
 template <bool kTF32, int kMetric, int kEpiWarps>
-int dispatch_mode_cap(int mode, int cap, const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm,
-                      int grid, cudaStream_t st) {
-#define SBIR_K1_CASE(M, C) \
-  if (mode == M && cap == C) return launch_inst<kTF32, kMetric, M, C, kEpiWarps>(tq, tg, prm, grid, st);
+int dispatch_mode_cap(int mode, int cap, int pair, const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm,
+                      int num_sms, cudaStream_t st) {
+#define SBIR_K1_CASE(M, C)                                                                              \
+  if (mode == M && cap == C) {                                                                          \
+    if (pair == 2) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 2>(tq, tg, prm, num_sms, st);    \
+    return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 1>(tq, tg, prm, num_sms, st);                   \
+  }
+#define SBIR_K1_CASE1(M, C) \
+  if (mode == M && cap == C) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 1>(tq, tg, prm, num_sms, st);
   SBIR_K1_CASE(kModeTopk, 16)
   SBIR_K1_CASE(kModeTopk, 32)
   SBIR_K1_CASE(kModeTopk, 64)
@@ -505,8 +573,9 @@ int dispatch_mode_cap(int mode, int cap, const CUtensorMap& tq, const CUtensorMa
   SBIR_K1_CASE(kModeTopkRank, 64)
   SBIR_K1_CASE(kModeTopkRank, 128)
   SBIR_K1_CASE(kModeDump, 16)
-  SBIR_K1_CASE(kModeHard, 16)
+  SBIR_K1_CASE1(kModeHard, 16)
 #undef SBIR_K1_CASE
+#undef SBIR_K1_CASE1
   return SBIR_ERR_UNSUPPORTED;
 }
 
@@ -515,6 +584,16 @@ int dispatch_mode_cap(int mode, int cap, const CUtensorMap& tq, const CUtensorMa
 // fp32 embeddings → kind::tf32, 4 epilogue warps; bf16 → kind::f16, 8 epilogue warps (the
 // bf16 tiles complete 2-4× sooner, so two warps share each TMEM lane quarter).
 static int epi_warps_for(int dtype, int cap) { return (dtype == SBIR_BF16 && cap <= 32) ? 8 : 4; }
+
+// CTA-pair mode (cta_group::2) is the default; SBIR_K1_PAIR=0 selects the single-CTA kernel (A/B runs).
+static int k1_pair_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SBIR_K1_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 1 : 2;
+  }
+  return v;
+}
 
 K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms) {
   K1Plan p{};
@@ -527,11 +606,15 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   p.num_g_tiles = (int)((num_g + kTileG - 1) / kTileG);
   if (p.num_q_tiles < 1) p.num_q_tiles = 1;
   if (p.num_g_tiles < 1) p.num_g_tiles = 1;
+  p.q_tile_stride = (p.num_q_tiles + 1) & ~1;
+  p.pair = (p.num_q_tiles >= 2 && num_sms >= 2) ? k1_pair_default() : 1;
+  const int row_tiles = (p.num_q_tiles + p.pair - 1) / p.pair;  // rows of the unit grid
+  const int workers = num_sms / p.pair;                           // CTAs or CTA pairs
   const size_t es = dtype == SBIR_BF16 ? 2 : 4;
   p.num_k_blocks = (int)((dim * es + kSwizzleBytes - 1) / kSwizzleBytes);
   // Splits: all units cost the same (tiles_per_split tiles + a fixed start-up/write-out of about
-  // one tile), CTAs take units round-robin, so the makespan is ceil(units / SMs) rounds.  Pick
-  // the split count with the smallest makespan (ties: fewer splits), at most one split per
+  // one tile), workers take units round-robin, so the makespan is ceil(units / workers) rounds.
+  // Pick the split count with the smallest makespan (ties: fewer splits), at most one split per
   // gallery tile, keeping the merged candidate set per query within finalize's 4096 entries.
   int64_t max_splits = 4096 / (p.cap * p.lists_per_row);
   if (max_splits > p.num_g_tiles) max_splits = p.num_g_tiles;
@@ -542,8 +625,8 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   for (int64_t s = 1; s <= max_splits; ++s) {
     const int64_t tps = (p.num_g_tiles + s - 1) / s;
     const int64_t splits = (p.num_g_tiles + tps - 1) / tps;
-    const int64_t units = splits * p.num_q_tiles;
-    const double cost = (double)((units + num_sms - 1) / num_sms) * ((double)tps + 1.0);
+    const int64_t units = splits * row_tiles;
+    const double cost = (double)((units + workers - 1) / workers) * ((double)tps + 1.0);
     if (s == 1 || cost < best_cost * 0.995) {
       best_cost = cost;
       best_tps = (int)tps;
@@ -551,14 +634,14 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   }
   p.tiles_per_split = best_tps;
   p.num_splits = (p.num_g_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  // Band: as many query tiles as keep their rows (tile × dim × elem bytes each) within ~32 MB
-  // of L2 next to the streaming gallery tiles.
-  const int64_t q_tile_bytes = (int64_t)kTileQ * dim * (int64_t)es;
-  int64_t band = (32LL << 20) / (q_tile_bytes > 0 ? q_tile_bytes : 1);
+  // Band: as many unit-grid rows as keep their query rows within ~32 MB of L2 next to the
+  // streaming gallery tiles.
+  const int64_t row_bytes = (int64_t)kTileQ * p.pair * dim * (int64_t)es;
+  int64_t band = (32LL << 20) / (row_bytes > 0 ? row_bytes : 1);
   if (band < 1) band = 1;
-  if (band > p.num_q_tiles) band = p.num_q_tiles;
+  if (band > row_tiles) band = row_tiles;
   p.band_q = (int)band;
-  p.num_units = p.num_q_tiles * p.num_splits;
+  p.num_units = row_tiles * p.num_splits;
   return p;
 }
 
@@ -568,7 +651,8 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   if (a.num_q <= 0 || a.num_g <= 0) return SBIR_OK;
   CUtensorMap tq, tg;
   SBIR_TRY(make_tmap(&tq, a.q, a.num_q, a.dim, a.dtype, kTileQ));
-  SBIR_TRY(make_tmap(&tg, a.g, a.num_g, a.dim, a.dtype, kTileG));
+  // pair mode: each CTA of the pair loads half of the 256-row gallery tile
+  SBIR_TRY(make_tmap(&tg, a.g, a.num_g, a.dim, a.dtype, plan.pair == 2 ? kTileG / 2 : kTileG));
   K1Params prm{};
   prm.gvec = a.gvec;
   prm.num_q = (int)a.num_q;
@@ -576,7 +660,10 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.num_q_tiles = plan.num_q_tiles;
   prm.num_g_tiles = plan.num_g_tiles;
   prm.num_splits = plan.num_splits;
-  prm.band_q = plan.band_q > 0 ? plan.band_q : plan.num_q_tiles;
+  const int pair = plan.pair == 2 ? 2 : 1;
+  prm.num_row_tiles = (plan.num_q_tiles + pair - 1) / pair;
+  prm.q_tile_stride = plan.q_tile_stride;
+  prm.band_q = plan.band_q > 0 ? plan.band_q : prm.num_row_tiles;
   prm.tiles_per_split = plan.tiles_per_split;
   prm.num_units = plan.num_units;
   prm.num_k_blocks = plan.num_k_blocks;
@@ -601,19 +688,18 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   int dev = 0, num_sms = 148;
   SBIR_CUDA_TRY(cudaGetDevice(&dev));
   SBIR_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = plan.num_units < num_sms ? plan.num_units : num_sms;
   const int cap = (a.mode == kModeDump || a.mode == kModeHard) ? 16 : plan.cap;
 
   if (a.dtype == SBIR_F32) {
-    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<true, SBIR_EUCLIDEAN, 4>(a.mode, cap, tq, tg, prm, grid, st);
-    return dispatch_mode_cap<true, SBIR_COSINE, 4>(a.mode, cap, tq, tg, prm, grid, st);
+    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<true, SBIR_EUCLIDEAN, 4>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
+    return dispatch_mode_cap<true, SBIR_COSINE, 4>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
   }
   if (plan.lists_per_row == 2) {
-    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 8>(a.mode, cap, tq, tg, prm, grid, st);
-    return dispatch_mode_cap<false, SBIR_COSINE, 8>(a.mode, cap, tq, tg, prm, grid, st);
+    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 8>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
+    return dispatch_mode_cap<false, SBIR_COSINE, 8>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
   }
-  if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 4>(a.mode, cap, tq, tg, prm, grid, st);
-  return dispatch_mode_cap<false, SBIR_COSINE, 4>(a.mode, cap, tq, tg, prm, grid, st);
+  if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 4>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
+  return dispatch_mode_cap<false, SBIR_COSINE, 4>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
 }
 
 }  // namespace sbir

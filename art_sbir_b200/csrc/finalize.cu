@@ -61,7 +61,7 @@ struct FinParams {
   long long index_offset;
   const float* cand_val;
   const int32_t* cand_idx;
-  int cap, lists_per_row, num_q_tiles, num_splits, m_pow2;
+  int cap, lists_per_row, q_tile_stride, num_splits, m_pow2;
   const float* qsq;
   const float* gsq_max;
   float kappa;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinPar
     if (i < m_tot) {
       const int l = i / p.cap, pp = i % p.cap;
       const int split = l / p.lists_per_row, h = l % p.lists_per_row;
-      const size_t slot = ((size_t)split * p.num_q_tiles + q_tile) * p.lists_per_row + h;
+      const size_t slot = ((size_t)split * p.q_tile_stride + q_tile) * p.lists_per_row + h;
       const size_t addr = (slot * p.cap + pp) * kTileQ + row;
       const float cv = p.cand_val[addr];
       if (cv < INFINITY) {  // slots never filled keep +inf (their index is unspecified)
@@ -477,7 +477,7 @@ FinParams make_fin_params(const FinalizeArgs& a, const K1Plan* plan) {
   p.cand_val = a.cand_val; p.cand_idx = a.cand_idx;
   if (plan) {
     p.cap = plan->cap; p.lists_per_row = plan->lists_per_row;
-    p.num_q_tiles = plan->num_q_tiles; p.num_splits = plan->num_splits;
+    p.q_tile_stride = plan->q_tile_stride; p.num_splits = plan->num_splits;
     const int m = next_pow2(plan->num_splits * plan->lists_per_row * plan->cap);
     p.m_pow2 = m < 2 ? 2 : m;
   }

@@ -35,7 +35,9 @@ struct K1Plan {
   int cap;            // per-list capacity (16, 32, 64 or 128)
   int lists_per_row;  // 1 (4 epilogue warps) or 2 (8 epilogue warps: one list per column half)
   int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks;
-  int band_q;         // query tiles per L2 band (unit numbering, see decode_unit in dist_topk.cu)
+  int band_q;         // unit-grid rows per L2 band (unit numbering, see decode_unit in dist_topk.cu)
+  int pair;           // 1: single-CTA tiles (cta_group::1); 2: CTA-pair tiles (cta_group::2, M = 256)
+  int q_tile_stride;  // query-tile stride of candidate slots / shared thresholds (num_q_tiles rounded up to even)
   int lists_per_query() const { return num_splits * lists_per_row; }
 };
 K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms);

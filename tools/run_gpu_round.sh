@@ -1,3 +1,4 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-python tools/gpu_probe.py time > gpurun_out/time.log 2>&1
-python bench.py --steps 3 --no-cpu > gpurun_out/bench_cfg4.json 2> gpurun_out/bench_cfg4.err
+SBIR_K1_PAIR=1 timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_cfg4_pair.json 2> gpurun_out/bench_cfg4_pair.err
+SBIR_K1_PAIR=0 timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_cfg4_single.json 2> gpurun_out/bench_cfg4_single.err
+SBIR_K1_PAIR=1 timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_cfg4_pair2.json 2> gpurun_out/bench_cfg4_pair2.err
+SBIR_K1_PAIR=0 timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_cfg4_single2.json 2> gpurun_out/bench_cfg4_single2.err
