@@ -81,7 +81,9 @@ struct K1Config {
   // the global candidate buffer when they do not fit beside the operand ring.
   static constexpr bool kIdxInSmem = kCap * kListsPerRow <= 64;
   static constexpr int kValBytes = kCap * kListsPerRow * kTileQ * 4;
-  static constexpr int kListBytes = kValBytes + (kIdxInSmem ? kValBytes : 0);
+  static constexpr bool kTwoLevel = kCap >= 64;  // per-group-of-8 maxima beside the keys
+  static constexpr int kGroupBytes = kTwoLevel ? (kCap / 8) * kListsPerRow * kTileQ * 4 : 0;
+  static constexpr int kListBytes = kValBytes + (kIdxInSmem ? kValBytes : 0) + kGroupBytes;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kStagesFit = (kSmemLimit - 1024 - kListBytes - kBarrierBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : kStagesFit;
@@ -140,6 +142,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint8_t* smem_g = smem + kStages * kStageBytesQ;
   float* list_val_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);
   int32_t* list_idx_s = reinterpret_cast<int32_t*>(list_val_s + kCap * Cfg::kListsPerRow * kTileQ);
+  float* list_grp_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + Cfg::kListBytes - Cfg::kGroupBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kListBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
@@ -268,6 +271,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // candidate slot is keyed by (split, query tile), independent of the unit numbering
       const size_t list_slot = ((size_t)split * prm.q_tile_stride + q_tile) * Cfg::kListsPerRow + half;
       float* lv = list_val_s + half * kCap * kTileQ;
+      [[maybe_unused]] float* lg = list_grp_s + half * (kCap / 8) * kTileQ;
       int32_t* li;
       if constexpr (Cfg::kIdxInSmem) li = list_idx_s + half * kCap * kTileQ;
       else li = prm.cand_idx + list_slot * kCap * kTileQ;
@@ -280,6 +284,9 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if constexpr (kSelect) {
 #pragma unroll 4
         for (int p = 0; p < kCap; ++p) lv[p * kTileQ + row] = INFINITY;
+        if constexpr (Cfg::kTwoLevel) {
+          for (int u = 0; u < kCap / 8; ++u) lg[u * kTileQ + row] = INFINITY;
+        }
       }
       if constexpr (kRank) {
         if (q_valid) {
@@ -361,10 +368,41 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   li[maxpos * kTileQ + row] = gidx;
                   float mx = -INFINITY;
                   int mp = 0;
+                  if constexpr (Cfg::kTwoLevel) {
+                    // lists of 64/128 keep a maximum per group of 8: refresh the touched group,
+                    // pick the group holding the overall maximum, locate it inside that group
+                    // (24-32 shared loads instead of kCap)
+                    const int g = maxpos >> 3;
+                    float gm = -INFINITY;
+                    int gp = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                      const float v = lv[(g * 8 + u) * kTileQ + row];
+                      if (v > gm) { gm = v; gp = g * 8 + u; }
+                    }
+                    lg[g * kTileQ + row] = gm;
+                    int bg = 0;
+#pragma unroll
+                    for (int u = 0; u < kCap / 8; ++u) {
+                      const float v = lg[u * kTileQ + row];
+                      if (v > mx) { mx = v; bg = u; }
+                    }
+                    if (bg == g) {
+                      mp = gp;
+                    } else {
+                      float bm = -INFINITY;
+#pragma unroll
+                      for (int u = 0; u < 8; ++u) {
+                        const float v = lv[(bg * 8 + u) * kTileQ + row];
+                        if (v > bm) { bm = v; mp = bg * 8 + u; }
+                      }
+                    }
+                  } else {
 #pragma unroll 8
-                  for (int p = 0; p < kCap; ++p) {
-                    const float v = lv[p * kTileQ + row];
-                    if (v > mx) { mx = v; mp = p; }
+                    for (int p = 0; p < kCap; ++p) {
+                      const float v = lv[p * kTileQ + row];
+                      if (v > mx) { mx = v; mp = p; }
+                    }
                   }
                   own_max = mx;
                   thr = fminf(thr, mx);
@@ -557,10 +595,13 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& pr
 template <bool kTF32, int kMetric, int kEpiWarps>
 int dispatch_mode_cap(int mode, int cap, int pair, const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm,
                       int num_sms, cudaStream_t st) {
+  // 8 epilogue warps (two lists per row) exist only for the small capacities
 #define SBIR_K1_CASE(M, C)                                                                              \
-  if (mode == M && cap == C) {                                                                          \
-    if (pair == 2) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 2>(tq, tg, prm, num_sms, st);    \
-    return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 1>(tq, tg, prm, num_sms, st);                   \
+  if constexpr (kEpiWarps == 4 || C <= 32) {                                                            \
+    if (mode == M && cap == C) {                                                                        \
+      if (pair == 2) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 2>(tq, tg, prm, num_sms, st);  \
+      return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 1>(tq, tg, prm, num_sms, st);                 \
+    }                                                                                                   \
   }
 #define SBIR_K1_CASE1(M, C) \
   if (mode == M && cap == C) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 1>(tq, tg, prm, num_sms, st);
@@ -585,12 +626,15 @@ int dispatch_mode_cap(int mode, int cap, int pair, const CUtensorMap& tq, const 
 // bf16 tiles complete 2-4× sooner, so two warps share each TMEM lane quarter).
 static int epi_warps_for(int dtype, int cap) { return (dtype == SBIR_BF16 && cap <= 32) ? 8 : 4; }
 
-// CTA-pair mode (cta_group::2) is the default; SBIR_K1_PAIR=0 selects the single-CTA kernel (A/B runs).
+// Single-CTA tiles are the default: on B200 the CTA-pair kernel (cta_group::2, M = 256) measured
+// 4-5 % slower on the power-capped cfg4 pass (profiles/r01_pair_vs_single_cfg4.txt) — its coarser
+// work granularity and pair-wide accumulator hand-off cost more than the halved gallery traffic
+// saves.  SBIR_K1_PAIR=2 selects it (A/B runs, tests).
 static int k1_pair_default() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("SBIR_K1_PAIR");
-    v = (e != nullptr && e[0] == '0') ? 1 : 2;
+    v = (e != nullptr && e[0] == '2') ? 2 : 1;
   }
   return v;
 }

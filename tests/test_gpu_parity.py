@@ -376,4 +376,13 @@ def test_full_size_properties(ops, nq, ng, d, dtype, k):
     # (5) gallery-permutation invariance of the set of distances
     perm = torch.randperm(ng, device="cuda")
     v2, i2 = ops.pairwise_topk(Q[:256], G[perm].contiguous(), k, "euclidean")
-    assert torch.equal(v2, vals[:256]) and torch.equal(perm[i2], idx[:256])
+    assert torch.equal(v2, vals[:256])
+
+    def canon(v, i):   # exact fp32 ties are ordered by index, which the permutation changes
+        o = torch.argsort(i, dim=1, stable=True)
+        v, i = v.gather(1, o), i.gather(1, o)
+        o = torch.argsort(v, dim=1, stable=True)
+        return i.gather(1, o)
+    same = canon(v2, perm[i2]) == canon(vals[:256], idx[:256])
+    # a tie exactly at the k-th place may legitimately swap which of the tied rows is kept
+    assert same[:, :-1].all() or (~same).sum() <= 2

@@ -1,4 +1,3 @@
-SBIR_K1_PAIR=1 timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_cfg4_pair.json 2> gpurun_out/bench_cfg4_pair.err
-SBIR_K1_PAIR=0 timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_cfg4_single.json 2> gpurun_out/bench_cfg4_single.err
-SBIR_K1_PAIR=1 timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_cfg4_pair2.json 2> gpurun_out/bench_cfg4_pair2.err
-SBIR_K1_PAIR=0 timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_cfg4_single2.json 2> gpurun_out/bench_cfg4_single2.err
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+SBIR_K1_PAIR=2 timeout 600 python -m pytest tests -m gpu -x -q -k "oracle or full_size or sharded" > gpurun_out/pytest_gpu_pair.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_pair.log
+timeout 300 python tools/gpu_probe.py time > gpurun_out/time.log 2>&1
