@@ -71,9 +71,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken in [t_begin, t_end] (wall clock); if the timed region was
+        too short to catch one, of all samples since start() (warm-up included; flagged)."""
         if self.proc:
             self.proc.terminate()
             try:
@@ -82,7 +84,11 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if t_begin is None or (t_begin <= ts <= t_end + 0.15)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than the sampling period)"
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -93,7 +99,7 @@ class ClockSampler:
                 continue
         busy = [s for s in sm if s > 0]
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------ data ----
@@ -232,20 +238,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     for _ in range(args.warmup):
         out = step()
     barrier()
     lib.sbir_profile_enable(1)
     k1_ms, k1_n, launches = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
     lib.sbir_profile_collect(ctypes.byref(k1_ms), ctypes.byref(k1_n), ctypes.byref(launches))  # reset counters
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # inputs smaller than L2 are evicted between timed steps by writing a 512 MiB buffer (untimed)
     in_bytes = (Q.numel() + Gs.numel()) * Q.element_size()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if in_bytes < 400e6 else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_begin = time.time()
     for a, b in evs:
         if flush is not None:
             flush.fill_(1)
@@ -253,7 +261,7 @@ def main():
         out = step()
         b.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     ms_total = sum(a.elapsed_time(b) for a, b in evs)
     lib.sbir_profile_collect(ctypes.byref(k1_ms), ctypes.byref(k1_n), ctypes.byref(launches))
     lib.sbir_profile_enable(0)
@@ -344,7 +352,7 @@ def main():
     cpu = None
     if not args.no_cpu:
         ng_s = min(num_g, 500_000 if dim <= 512 else 75_000)
-        v, done, dt, threads = cpu_reference_sample(ng_s, dim, 16, seconds_hint=20.0)
+        v, done, dt, threads = cpu_reference_sample(ng_s, dim, 4096, seconds_hint=12.0)
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                "sample": f"{done} queries x {ng_s} gallery rows, {dim}-d fp32, reference per-query loop "
                          f"(PairwiseDistance + topk(N), inference.py:44,49,52), {dt:.1f} s"}

@@ -245,6 +245,62 @@ def case_time():
             _time_topk(12500, 75000, 2048, "bfloat16", 10, rank=True)]
 
 
+def _bench(fn, iters=20, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def case_bw():
+    """Bandwidth kernels (K5 normalise, norms, K4 merge) and the cfg2 triplet step."""
+    import torch
+    from art_sbir_b200 import ops
+    res = {}
+    x = torch.randn(10_000_000, 512, device="cuda", dtype=torch.bfloat16)
+    ms = _bench(lambda: ops.l2_normalize(x), 10)
+    res["l2_normalize 10Mx512 bf16"] = {"ms": ms, "GB/s": 2 * x.numel() * 2 / ms / 1e6}
+    ms = _bench(lambda: ops.row_sqnorm(x), 10)
+    res["row_sqnorm 10Mx512 bf16"] = {"ms": ms, "GB/s": x.numel() * 2 / ms / 1e6}
+    del x
+    y = torch.randn(2_000_000, 1024, device="cuda")
+    ms = _bench(lambda: ops.l2_normalize(y), 10)
+    res["l2_normalize 2Mx1024 fp32"] = {"ms": ms, "GB/s": 2 * y.numel() * 4 / ms / 1e6}
+    ms = _bench(lambda: torch.nn.functional.normalize(y, dim=1, eps=1e-8), 10)
+    res["torch normalize 2Mx1024 fp32 (library, for reference)"] = {"ms": ms, "GB/s": 2 * y.numel() * 4 / ms / 1e6}
+    del y
+    d = torch.sort(torch.rand(8, 100_000, 10, device="cuda"), dim=2).values
+    i = torch.randint(0, 10_000_000, (8, 100_000, 10), device="cuda")
+    ms = _bench(lambda: ops.topk_merge(d, i), 20)
+    res["topk_merge 8x100kx10"] = {"ms": ms, "GB/s": (d.numel() * 12 + 100_000 * 10 * 12) / ms / 1e6}
+    a, p, n = (torch.randn(256, 2048, device="cuda", requires_grad=True) for _ in range(3))
+
+    def ours():
+        loss = ops.triplet_margin_loss(a, p, n, 0.2, "euclidean")
+        loss.backward()
+
+    def lib():
+        loss = torch.nn.TripletMarginLoss(margin=0.2)(a, p, n)
+        loss.backward()
+
+    def bh():
+        loss = ops.batch_hard_triplet_loss(a, p, n, 0.2, "euclidean")
+        loss.backward()
+    res["cfg2 triplet fwd+bwd 256x2048 (ours, us)"] = _bench(ours, 50) * 1e3
+    res["cfg2 triplet fwd+bwd 256x2048 (torch library on the same GPU, us)"] = _bench(lib, 50) * 1e3
+    res["cfg2 batch-hard fwd+bwd 256x(512)x2048 (ours, us)"] = _bench(bh, 50) * 1e3
+    return res
+
+
 def case_peaks():
     import torch
     res = {}
