@@ -62,6 +62,7 @@ bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 struct TopkLayout {
   K1Plan plan;
   size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert, off_shared_thr;
+  size_t off_row_max, off_row_maxpos, off_sched, sched_bytes;  // off_sched: unit counter + chunk_done (zeroed together)
   size_t off_pos_dist, off_lo, off_hi, off_cnt, off_dropped, off_pool_count, off_pool_q, off_pool_idx;
   uint32_t pool_cap;
   size_t total;
@@ -82,6 +83,11 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   L.off_flags = take(nq * sizeof(int32_t));
   L.off_uncert = take(sizeof(int32_t));
   L.off_shared_thr = take((size_t)L.plan.q_tile_stride * kTileQ * sizeof(int32_t));
+  const size_t rows = (size_t)L.plan.num_splits * L.plan.q_tile_stride * L.plan.lists_per_row * kTileQ;
+  L.off_row_max = take(rows * sizeof(float));
+  L.off_row_maxpos = take(rows * sizeof(int32_t));
+  L.sched_bytes = 256 + (size_t)L.plan.num_splits * L.plan.q_tile_stride * sizeof(int32_t);
+  L.off_sched = take(L.sched_bytes);
   if (want_rank) {
     L.off_pos_dist = take(nq * sizeof(double));
     L.off_lo = take(nq * sizeof(float));
@@ -172,6 +178,11 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   ka.mode = want_rank ? kModeTopkRank : kModeTopk;
   ka.gvec = gvec;
   ka.cand_val = cand_val; ka.cand_idx = cand_idx;
+  ka.row_max = reinterpret_cast<float*>(ws + L.off_row_max);
+  ka.row_maxpos = reinterpret_cast<int32_t*>(ws + L.off_row_maxpos);
+  ka.unit_counter = reinterpret_cast<uint32_t*>(ws + L.off_sched);
+  ka.chunk_done = reinterpret_cast<int32_t*>(ws + L.off_sched + 256);
+  SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_sched, 0, L.sched_bytes, st));
   ka.rank_lo = ra.rank_lo; ka.rank_hi = ra.rank_hi;
   ka.cnt_less = ra.cnt_less;
   ka.pool_count = ra.pool_count; ka.pool_cap = ra.pool_cap; ka.pool_q = ra.pool_q; ka.pool_idx = ra.pool_idx;
@@ -365,7 +376,7 @@ int sbir_batch_hard_triplet_loss(const float* a, const float* p, const float* n,
 size_t sbir_debug_dist_matrix_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int dtype) {
   if (num_q <= 0 || num_g <= 0 || dim <= 0 || !dtype_ok(dtype)) return 0;
   const K1Plan plan = make_k1_plan(num_q, num_g, dim, 1, dtype, num_sms_cached());
-  return align_up((size_t)plan.num_g_tiles * kTileG * sizeof(float), 256);
+  return align_up((size_t)plan.num_g_tiles * kTileG * sizeof(float), 256) + 256;
 }
 
 int sbir_debug_dist_matrix(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
@@ -378,13 +389,15 @@ int sbir_debug_dist_matrix(const void* q, int64_t num_q, const void* g, int64_t 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const K1Plan plan = make_k1_plan(num_q, num_g, dim, 1, dtype, num_sms_cached());
   float* gvec = static_cast<float*>(workspace);
+  uint32_t* counter = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + need - 256);
+  SBIR_CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
   SBIR_TRY(launch_row_norm(g, num_g, (int64_t)plan.num_g_tiles * kTileG, dim, dtype,
                            metric == SBIR_EUCLIDEAN ? 0 : 1, metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""),
                            gvec, nullptr, st));
   K1Args ka{};
   ka.q = q; ka.g = g; ka.num_q = num_q; ka.num_g = num_g; ka.dim = dim;
   ka.dtype = dtype; ka.metric = metric; ka.mode = kModeDump;
-  ka.gvec = gvec; ka.dump = out_e;
+  ka.gvec = gvec; ka.dump = out_e; ka.unit_counter = counter;
   return launch_k1(ka, plan, st);
 }
 

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) bh_mean_kernel(const float* __restrict__ 
 
 struct BhLayout {
   K1Plan plan;
-  size_t off_x, off_gvec, off_hard_val, off_hard_idx, off_per_row, off_weight, off_sel, total;
+  size_t off_x, off_gvec, off_hard_val, off_hard_idx, off_per_row, off_weight, off_sel, off_counter, total;
 };
 
 BhLayout bh_layout(int64_t batch, int64_t dim) {
@@ -197,6 +197,9 @@ BhLayout bh_layout(int64_t batch, int64_t dim) {
   L.plan.tiles_per_split = 1;
   L.plan.num_splits = L.plan.num_g_tiles;
   L.plan.band_q = L.plan.num_q_tiles;
+  L.plan.num_chunks = 1;
+  L.plan.tiles_per_chunk = 1;
+  L.plan.part_fastest = 0;
   L.plan.num_units = L.plan.num_q_tiles * L.plan.num_splits;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + bytes, 256); return r; };
@@ -208,6 +211,7 @@ BhLayout bh_layout(int64_t batch, int64_t dim) {
   L.off_per_row = take((size_t)batch * sizeof(float));
   L.off_weight = take((size_t)batch * sizeof(float));
   L.off_sel = take((size_t)batch * 2 * sizeof(long long));
+  L.off_counter = take(256);
   L.total = o;
   return L;
 }
@@ -245,6 +249,8 @@ int launch_batch_hard(const float* a, const float* p, const float* n, int64_t ba
   ka.gvec = gvec;
   ka.row_label = anchor_label; ka.col_label = cand_label;
   ka.hard_val = hard_val; ka.hard_idx = hard_idx;
+  ka.unit_counter = reinterpret_cast<uint32_t*>(ws + L.off_counter);
+  SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_counter, 0, 256, st));
   SBIR_TRY(launch_k1(ka, L.plan, st));
 
   bh_select_kernel<<<(unsigned)batch, kBhThreads, 0, st>>>(

@@ -5,18 +5,30 @@
 // followed by `distances.topk(...)` (inference.py:44-49, 62-65) for ALL queries at once.
 //
 // Structure (one persistent CTA per SM, warp-specialised):
-//   warp 0      TMA producer: Q k-slice [128 × 128 B] + G k-slice [256 × 128 B] per stage,
-//               SWIZZLE_128B, mbarrier complete_tx                     (UTMALDG in SASS)
+//   warp 0      scheduler + TMA producer: claims work units from a global counter, publishes
+//               them to the other warps through a small shared-memory ring, and streams
+//               Q k-slices [128 × 128 B] + G k-slices [256 × 128 B] (SWIZZLE_128B, mbarrier
+//               complete_tx) through a 4-stage ring                        (UTMALDG in SASS)
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (kind::tf32 for fp32 embeddings,
 //               kind::f16 for bf16) M=128 × N=256 into one of two 256-column TMEM accumulators;
-//               tcgen05.commit releases smem stages and publishes the accumulator (UTC*MMA)
+//               tcgen05.commit releases smem stages and publishes the accumulator   (UTC*MMA)
 //   warps 2..   epilogue: tcgen05.ld 32 lanes × 32 columns → e = ‖g‖² − 2·q·g (euclidean) or
 //               e = −q·g/max(‖g‖,eps) (cosine); a thread owns one query row and keeps that
-//               query's running best-`cap` list; only chunks whose minimum beats the
-//               row's current threshold take the insertion path                   (LDTM)
+//               query's running best-`cap` list; only chunks whose minimum beats the row's
+//               current threshold take the insertion path                             (LDTM)
 // e orders gallery rows exactly like the distance does for a fixed query (‖q‖² and the
 // query norm are per-row constants); exact distances are recomputed for the survivors by
 // finalize.cu, so tensor-core rounding never reaches the caller.
+//
+// Work decomposition (make_k1_plan).  The gallery is cut into `num_splits` PARTITIONS (scanned
+// independently, each with its own candidate lists — parallelism when there are few query
+// tiles) and every partition into CHUNKS of a few MB that are scanned one after the other; a
+// unit is (query tile, partition, chunk).  Units are numbered chunk-major and handed out
+// dynamically, so at any moment all CTAs work on the same one or two chunk steps: the chunk's
+// gallery rows are read from HBM once and served to everyone else from L2 (with long units the
+// CTAs drift apart and L2 sharing collapses — ncu measured 1.73 TB of DRAM reads per cfg4 pass,
+// profiles/r01_ncu_k1_cfg4_full.txt).  The candidate list of a (query tile, partition) is
+// carried from chunk to chunk through global memory, ordered by a completion counter.
 #include <cstdlib>
 
 #include <cuda.h>
@@ -29,11 +41,12 @@ namespace sbir {
 
 namespace {
 
-constexpr int kSwizzleBytes = 128;                    // one k-block = 128 bytes of features per row
-constexpr int kStageBytesQ = kTileQ * kSwizzleBytes;  // 16 KB
+constexpr int kSwizzleBytes = 128;                        // one k-block = 128 bytes of features per row
+constexpr int kStageBytesQ = kTileQ * kSwizzleBytes;      // 16 KB
 constexpr int kStageBytesGFull = kTileG * kSwizzleBytes;  // 32 KB (halved per CTA in pair mode)
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kTmemCols = 512;  // two 256-column fp32 accumulators
+constexpr int kSchedDepth = 4;  // unit ring between the scheduler and the other warps
 
 // Monotone float <-> int32 map so a float minimum can be taken with an integer atomicMin.
 __device__ __forceinline__ int32_t float_to_ordered_int(float f) {
@@ -48,28 +61,18 @@ __device__ __forceinline__ int32_t ld_relaxed(const int32_t* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-
-// Unit → (query tile, gallery split).  Units are numbered band by band: a band is `band_q`
-// consecutive query tiles whose operand rows stay L2-resident together; inside a band the
-// query tile varies fastest, so the CTAs running at the same time share gallery tiles (one
-// HBM read serves the whole band) while re-reading only a small set of query tiles.
-struct UnitCoord { int q_tile, split; };
-__device__ __forceinline__ UnitCoord decode_unit(int unit, int num_q_tiles, int num_splits, int band_q) {
-  const int band_units = band_q * num_splits;
-  const int band = unit / band_units;
-  const int r = unit - band * band_units;
-  const int q0 = band * band_q;
-  const int bq = min(band_q, num_q_tiles - q0);
-  UnitCoord c;
-  c.split = r / bq;
-  c.q_tile = q0 + r - c.split * bq;
-  return c;
+__device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int32_t* p, int32_t v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // kPair = 1: one CTA computes a 128×256 tile (cta_group::1).  kPair = 2: a 2-CTA cluster computes
 // a 256×256 tile with one M=256 tcgen05.mma (cta_group::2): each CTA loads its own 128 query rows
-// and only HALF of the gallery tile, so the TMA/L2 traffic and the shared-memory operand reads per
-// FLOP drop by a third and the smaller stages allow a deeper ring.
+// and only HALF of the gallery tile.
 template <int kCap, int kEpiWarps, int kPair>
 struct K1Config {
   static constexpr int kStageBytesG = kStageBytesGFull / kPair;
@@ -77,14 +80,14 @@ struct K1Config {
   static constexpr int kMaxStages = kPair == 2 ? 6 : 4;
   static constexpr int kListsPerRow = kEpiWarps / 4;
   // distance keys of the running lists always live in shared memory (they are re-scanned on
-  // every insertion); the gallery indices are write-only until the end and go straight to
+  // every insertion); the gallery indices are write-only inside the kernel and go straight to
   // the global candidate buffer when they do not fit beside the operand ring.
   static constexpr bool kIdxInSmem = kCap * kListsPerRow <= 64;
   static constexpr int kValBytes = kCap * kListsPerRow * kTileQ * 4;
   static constexpr bool kTwoLevel = kCap >= 64;  // per-group-of-8 maxima beside the keys
   static constexpr int kGroupBytes = kTwoLevel ? (kCap / 8) * kListsPerRow * kTileQ * 4 : 0;
   static constexpr int kListBytes = kValBytes + (kIdxInSmem ? kValBytes : 0) + kGroupBytes;
-  static constexpr int kBarrierBytes = 256;
+  static constexpr int kBarrierBytes = 384;
   static constexpr int kStagesFit = (kSmemLimit - 1024 - kListBytes - kBarrierBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : kStagesFit;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kListBytes + kBarrierBytes;
@@ -97,12 +100,17 @@ struct K1Config {
 struct K1Params {
   const float* gvec;
   int num_q, num_g;
-  int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks, band_q;
-  int num_row_tiles;   // query tiles (kPair = 1) or query-tile pairs (kPair = 2) — the unit grid's rows
-  int q_tile_stride;   // query-tile stride of the candidate slots (num_q_tiles rounded up to even)
+  int num_q_tiles, num_g_tiles, num_k_blocks;
+  int num_row_tiles;   // query tiles (kPair = 1) or query-tile pairs (kPair = 2): rows of the unit grid
+  int num_parts, tiles_per_part, num_chunks, tiles_per_chunk, num_units, part_fastest;
+  int q_tile_stride;   // query-tile stride of candidate slots (num_q_tiles rounded up to even)
   int elems_per_kblock;
-  float* cand_val;
+  uint32_t* unit_counter;  // [1] zeroed by the caller: next unit to hand out (kPair = 1)
+  int32_t* chunk_done;     // [num_parts][q_tile_stride] zeroed: chunks finished per (partition, query tile)
+  float* cand_val;         // [part][q_tile_stride][lists][cap][128]
   int32_t* cand_idx;
+  float* row_max;          // [part][q_tile_stride][lists][128] list maximum carried between chunks
+  int32_t* row_maxpos;
   const float* rank_lo;
   const float* rank_hi;
   int32_t* cnt_less;
@@ -119,6 +127,32 @@ struct K1Params {
   int32_t* hard_idx;
 };
 
+// Unit → (row of the unit grid, partition, chunk) and the gallery tiles it covers.  Chunk-major;
+// inside a chunk step either the query row or the partition varies fastest (plan.part_fastest:
+// wide fp32 rows keep fewer query tiles live in L2 when partitions of one query tile run together).
+struct UnitCoord {
+  int row_tile, part, chunk, t_begin, t_end;
+};
+__device__ __forceinline__ UnitCoord decode_unit(int unit, const K1Params& p) {
+  const int per_step = p.num_parts * p.num_row_tiles;
+  UnitCoord c;
+  c.chunk = unit / per_step;
+  const int r = unit - c.chunk * per_step;
+  if (p.part_fastest) {
+    c.row_tile = r / p.num_parts;
+    c.part = r - c.row_tile * p.num_parts;
+  } else {
+    c.part = r / p.num_row_tiles;
+    c.row_tile = r - c.part * p.num_row_tiles;
+  }
+  const int part_begin = c.part * p.tiles_per_part;
+  const int part_end = min(part_begin + p.tiles_per_part, p.num_g_tiles);
+  c.t_begin = part_begin + c.chunk * p.tiles_per_chunk;
+  c.t_end = min(c.t_begin + p.tiles_per_chunk, part_end);
+  if (c.t_begin > c.t_end) c.t_begin = c.t_end;  // empty unit (short last partition)
+  return c;
+}
+
 template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps, int kPair>
 __global__ void __launch_bounds__(K1Config<kCap, kEpiWarps, kPair>::kThreads, 1)
 dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -127,14 +161,15 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytesG = Cfg::kStageBytesG;
   constexpr int kStageBytes = Cfg::kStageBytes;
+  constexpr bool kSelect = (kMode == kModeTopk || kMode == kModeTopkRank);
+  constexpr bool kRank = (kMode == kModeTopkRank);
+  constexpr bool kDynamic = (kPair == 1);  // dynamic unit hand-out (pairs walk a static stride)
   // Pair mode: `cta_rank` 0 is the leader (issues the MMAs, owns the full/acc_empty barriers);
-  // a "unit" is then (PAIR of query tiles, gallery split) and this CTA works on query tile
-  // 2·pair + cta_rank and on gallery rows [rank·128, +128) of every 256-row tile.
+  // a unit's query "row" is then a PAIR of query tiles and this CTA works on query tile
+  // 2·row + cta_rank and on gallery rows [rank·128, +128) of every 256-row tile.
   const int cta_rank = kPair == 2 ? (int)cluster_ctarank() : 0;
   const int worker = kPair == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int num_workers = kPair == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  constexpr bool kSelect = (kMode == kModeTopk || kMode == kModeTopkRank);
-  constexpr bool kRank = (kMode == kModeTopkRank);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -144,11 +179,14 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   int32_t* list_idx_s = reinterpret_cast<int32_t*>(list_val_s + kCap * Cfg::kListsPerRow * kTileQ);
   float* list_grp_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + Cfg::kListBytes - Cfg::kGroupBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kListBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* acc_full_bar = bars + 2 * kStages;
-  uint64_t* acc_empty_bar = bars + 2 * kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* full_bar = bars;                         // [kStages]
+  uint64_t* empty_bar = bars + kStages;              // [kStages]
+  uint64_t* acc_full_bar = bars + 2 * kStages;       // [2]
+  uint64_t* acc_empty_bar = bars + 2 * kStages + 2;  // [2]
+  uint64_t* sched_full_bar = bars + 2 * kStages + 4;                 // [kSchedDepth]
+  uint64_t* sched_empty_bar = bars + 2 * kStages + 4 + kSchedDepth;  // [kSchedDepth]
+  int32_t* sched_unit = reinterpret_cast<int32_t*>(bars + 2 * kStages + 4 + 2 * kSchedDepth);  // [kSchedDepth]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_unit + kSchedDepth);
 
   const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -164,6 +202,10 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(&acc_full_bar[a], 1);
       mbar_init(&acc_empty_bar[a], kEpiWarps * kPair);  // epilogue warps of both CTAs of a pair
     }
+    for (int s = 0; s < kSchedDepth; ++s) {
+      mbar_init(&sched_full_bar[s], 1);
+      mbar_init(&sched_empty_bar[s], 1 + kEpiWarps);  // MMA issuer + every epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -176,17 +218,44 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Consumers (MMA issuer, epilogue warps) take their next unit from the scheduler ring.
+  // Returns -1 when the work is exhausted.  `it` counts units taken by this role.
+  auto next_unit_consumer = [&](int it) -> int {
+    if constexpr (kDynamic) {
+      const int slot = it % kSchedDepth;
+      mbar_wait(&sched_full_bar[slot], (uint32_t)(it / kSchedDepth) & 1u);
+      return *reinterpret_cast<volatile int32_t*>(&sched_unit[slot]);
+    } else {
+      const int u = worker + it * num_workers;
+      return u < prm.num_units ? u : -1;
+    }
+  };
+  auto release_unit_slot = [&](int it) {
+    if constexpr (kDynamic) mbar_arrive(&sched_empty_bar[it % kSchedDepth]);
+  };
+
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer ----
+    // ------------------------------------------------- scheduler + TMA producer ----
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = worker; unit < prm.num_units; unit += num_workers) {
-        const UnitCoord uc = decode_unit(unit, prm.num_row_tiles, prm.num_splits, prm.band_q);
-        const int q_tile = uc.q_tile * kPair + cta_rank;
-        const int t0 = uc.split * prm.tiles_per_split;
-        const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
-        for (int t = t0; t < t1; ++t) {
+      for (int it = 0;; ++it) {
+        int unit;
+        if constexpr (kDynamic) {
+          const int slot = it % kSchedDepth;
+          mbar_wait(&sched_empty_bar[slot], ((uint32_t)(it / kSchedDepth) & 1u) ^ 1u);
+          const uint32_t u = atomicAdd(prm.unit_counter, 1u);
+          unit = u < (uint32_t)prm.num_units ? (int)u : -1;
+          *reinterpret_cast<volatile int32_t*>(&sched_unit[slot]) = unit;
+          mbar_arrive(&sched_full_bar[slot]);  // release semantics: the store above is visible to waiters
+        } else {
+          unit = worker + it * num_workers;
+          if (unit >= prm.num_units) unit = -1;
+        }
+        if (unit < 0) break;
+        const UnitCoord uc = decode_unit(unit, prm);
+        const int q_tile = uc.row_tile * kPair + cta_rank;
+        for (int t = uc.t_begin; t < uc.t_end; ++t) {
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if constexpr (kPair == 2) {
@@ -217,11 +286,12 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = worker; unit < prm.num_units; unit += num_workers) {
-        const UnitCoord uc = decode_unit(unit, prm.num_row_tiles, prm.num_splits, prm.band_q);
-        const int t0 = uc.split * prm.tiles_per_split;
-        const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
-        for (int t = t0; t < t1; ++t) {
+      for (int it = 0;; ++it) {
+        const int unit = next_unit_consumer(it);
+        release_unit_slot(it);
+        if (unit < 0) break;
+        const UnitCoord uc = decode_unit(unit, prm);
+        for (int t = uc.t_begin; t < uc.t_end; ++t) {
           mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kTileG;
@@ -258,23 +328,27 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int acc = 0;
     uint32_t acc_phase = 0;
 
-    for (int unit = worker; unit < prm.num_units; unit += num_workers) {
-      const UnitCoord uc = decode_unit(unit, prm.num_row_tiles, prm.num_splits, prm.band_q);
-      const int q_tile = uc.q_tile * kPair + cta_rank;
-      const int split = uc.split;
-      const int t0 = split * prm.tiles_per_split;
-      const int t1 = min(t0 + prm.tiles_per_split, prm.num_g_tiles);
+    for (int it = 0;; ++it) {
+      const int unit = next_unit_consumer(it);
+      __syncwarp();  // every lane has read the ring slot
+      if (lane == 0) release_unit_slot(it);
+      if (unit < 0) break;
+      const UnitCoord uc = decode_unit(unit, prm);
+      const int q_tile = uc.row_tile * kPair + cta_rank;
       const int q = q_tile * kTileQ + row;
       const bool q_valid = q < prm.num_q;
 
       // This thread's list: entry p lives at [p * kTileQ + row] (conflict-free / coalesced).
-      // candidate slot is keyed by (split, query tile), independent of the unit numbering
-      const size_t list_slot = ((size_t)split * prm.q_tile_stride + q_tile) * Cfg::kListsPerRow + half;
+      // Global slot of the list: keyed by (partition, query tile), shared by all its chunks.
+      const size_t list_slot = ((size_t)uc.part * prm.q_tile_stride + q_tile) * Cfg::kListsPerRow + half;
       float* lv = list_val_s + half * kCap * kTileQ;
       [[maybe_unused]] float* lg = list_grp_s + half * (kCap / 8) * kTileQ;
+      float* gval = prm.cand_val + list_slot * kCap * kTileQ;
+      int32_t* gidx = prm.cand_idx + list_slot * kCap * kTileQ;
       int32_t* li;
       if constexpr (Cfg::kIdxInSmem) li = list_idx_s + half * kCap * kTileQ;
-      else li = prm.cand_idx + list_slot * kCap * kTileQ;
+      else li = gidx;
+      int32_t* done_flag = prm.chunk_done + (size_t)uc.part * prm.q_tile_stride + q_tile;
       float thr = INFINITY;      // insertion threshold = min(own list maximum, shared threshold)
       float own_max = INFINITY;  // maximum of this thread's list (+inf until it is full)
       float published = INFINITY;
@@ -282,10 +356,41 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       float lo = -INFINITY, hi = -INFINITY;
       int cnt = 0;
       if constexpr (kSelect) {
+        if (uc.chunk == 0) {
 #pragma unroll 4
-        for (int p = 0; p < kCap; ++p) lv[p * kTileQ + row] = INFINITY;
-        if constexpr (Cfg::kTwoLevel) {
-          for (int u = 0; u < kCap / 8; ++u) lg[u * kTileQ + row] = INFINITY;
+          for (int p = 0; p < kCap; ++p) lv[p * kTileQ + row] = INFINITY;
+          if constexpr (Cfg::kTwoLevel) {
+            for (int u = 0; u < kCap / 8; ++u) lg[u * kTileQ + row] = INFINITY;
+          }
+        } else {
+          // continue the list the previous chunk of this (partition, query tile) left behind
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire(done_flag) < uc.chunk) {
+              if (clock64() - t0 > 4000000000LL) {
+                printf("sbir: chunk hand-over timed out (unit %d)\n", unit);
+                __trap();
+              }
+            }
+          }
+          __syncwarp();
+          (void)ld_acquire(done_flag);
+#pragma unroll 4
+          for (int p = 0; p < kCap; ++p) {
+            lv[p * kTileQ + row] = __ldcg(gval + p * kTileQ + row);
+            if constexpr (Cfg::kIdxInSmem) li[p * kTileQ + row] = __ldcg(gidx + p * kTileQ + row);
+          }
+          if constexpr (Cfg::kTwoLevel) {
+            for (int u = 0; u < kCap / 8; ++u) {
+              float gm = -INFINITY;
+#pragma unroll
+              for (int v = 0; v < 8; ++v) gm = fmaxf(gm, lv[(u * 8 + v) * kTileQ + row]);
+              lg[u * kTileQ + row] = gm;
+            }
+          }
+          own_max = __ldcg(prm.row_max + list_slot * kTileQ + row);
+          maxpos = __ldcg(prm.row_maxpos + list_slot * kTileQ + row);
+          thr = own_max;
         }
       }
       if constexpr (kRank) {
@@ -294,6 +399,8 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           hi = prm.rank_hi[q];
         }
       }
+      int32_t shared_next = 0x7f800000;  // +inf in the ordered-int encoding
+      if constexpr (kSelect) shared_next = ld_relaxed(prm.shared_thr + q_tile * kTileQ + row);
       float hp = -INFINITY, hn = INFINITY;  // batch-hard: hardest positive / negative in e-space
       int hpi = -1, hni = -1;
       int64_t my_label = 0;
@@ -301,16 +408,16 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (prm.row_label != nullptr && q_valid) my_label = prm.row_label[q];
       }
 
-      for (int t = t0; t < t1; ++t) {
-        if constexpr (kSelect) {
-          // Another split (or the other column half) scanning the same query may already hold
-          // `cap` candidates below some value: nothing at or above it can reach the final
-          // best-`cap`, so adopt it as an upper bound on this list's threshold.
-          const float shared = ordered_int_to_float(ld_relaxed(prm.shared_thr + q_tile * kTileQ + row));
-          thr = fminf(thr, shared);
-        }
+      for (int t = uc.t_begin; t < uc.t_end; ++t) {
         mbar_wait(&acc_full_bar[acc], acc_phase);
         tc_fence_after();
+        if constexpr (kSelect) {
+          // Another partition (or the other column half) scanning the same query may already
+          // hold `cap` candidates below some value: nothing at or above it can reach the final
+          // best-`cap`, so adopt it as an upper bound on this list's threshold.  The value was
+          // requested before waiting for the accumulator (L2 round trip off the critical path).
+          thr = fminf(thr, ordered_int_to_float(shared_next));
+        }
         const float* gv = prm.gvec + (size_t)t * kTileG + col_begin;
 #pragma unroll 1
         for (int c = 0; c < Cfg::kColsPerWarp / 32; ++c) {
@@ -355,17 +462,15 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             float m = e[0];
 #pragma unroll
             for (int j = 1; j < 32; ++j) m = fminf(m, e[j]);
-            if constexpr (kRank) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) cnt += (e[j] < lo) ? 1 : 0;
-            }
+            // rank: rows closer than the band (e < lo <= hi <= lim) are counted inside the gated
+            // path below — a chunk whose minimum is not below lim has none of them
             const float lim = kRank ? fmaxf(thr, hi) : thr;
             if (__any_sync(kFullMask, m < lim)) {
               // One candidate of this row: maybe enters the list, maybe sits in the rank band.
-              auto consume = [&](float ej, int gidx) {
+              auto consume = [&](float ej, int gidx_e) {
                 if (ej < thr) {
                   lv[maxpos * kTileQ + row] = ej;
-                  li[maxpos * kTileQ + row] = gidx;
+                  li[maxpos * kTileQ + row] = gidx_e;
                   float mx = -INFINITY;
                   int mp = 0;
                   if constexpr (Cfg::kTwoLevel) {
@@ -415,7 +520,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const uint32_t slot = atomicAdd(prm.pool_count, 1u);
                     if (slot < prm.pool_cap) {
                       prm.pool_q[slot] = q;
-                      prm.pool_idx[slot] = gidx;
+                      prm.pool_idx[slot] = gidx_e;
                     } else {
                       atomicAdd(prm.dropped + q, 1);
                     }
@@ -428,6 +533,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               int c0 = 0, c1 = 0, c2 = 0, c3 = 0, nh = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
+                if constexpr (kRank) cnt += (e[j] < lo) ? 1 : 0;
                 if (e[j] < lim) {
                   h3 = h2; c3 = c2;
                   h2 = h1; c2 = c1;
@@ -479,6 +585,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             atomicMin(prm.shared_thr + q_tile * kTileQ + row, float_to_ordered_int(own_max));
             published = own_max;
           }
+          shared_next = ld_relaxed(prm.shared_thr + q_tile * kTileQ + row);
         }
         // Accumulator fully read: hand it back to the MMA warp.
         tc_fence_before();
@@ -492,20 +599,25 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
 
       if constexpr (kSelect) {
-        float* ov = prm.cand_val + list_slot * kCap * kTileQ;
-        int32_t* oi = prm.cand_idx + list_slot * kCap * kTileQ;
+        // Park the list in global memory: the next chunk of this (partition, query tile) — on
+        // whichever SM it lands — or finalize.cu picks it up from there.
 #pragma unroll 4
         for (int p = 0; p < kCap; ++p) {
-          ov[p * kTileQ + row] = lv[p * kTileQ + row];
-          if constexpr (Cfg::kIdxInSmem) oi[p * kTileQ + row] = li[p * kTileQ + row];
+          gval[p * kTileQ + row] = lv[p * kTileQ + row];
+          if constexpr (Cfg::kIdxInSmem) gidx[p * kTileQ + row] = li[p * kTileQ + row];
         }
+        prm.row_max[list_slot * kTileQ + row] = own_max;
+        prm.row_maxpos[list_slot * kTileQ + row] = maxpos;
         if constexpr (kRank) {
           if (q_valid && cnt) atomicAdd(prm.cnt_less + q, cnt);
         }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");  // all epilogue warps parked their lists
+        if (ew == 0 && lane == 0) st_release(done_flag, uc.chunk + 1);
       }
       if constexpr (kMode == kModeHard) {
-        // one unit == one gallery tile range; slot [split][q_tile*128+row][half]
-        const size_t o = (((size_t)split * prm.q_tile_stride + q_tile) * kTileQ + row) * Cfg::kListsPerRow + half;
+        // one unit == one gallery tile; slot [part][q_tile*128+row][half]
+        const size_t o = (((size_t)uc.part * prm.q_tile_stride + q_tile) * kTileQ + row) * Cfg::kListsPerRow + half;
         prm.hard_val[o * 2 + 0] = hp;
         prm.hard_val[o * 2 + 1] = hn;
         prm.hard_idx[o * 2 + 0] = hpi;
@@ -622,8 +734,8 @@ int dispatch_mode_cap(int mode, int cap, int pair, const CUtensorMap& tq, const 
 
 }  // namespace
 
-// fp32 embeddings → kind::tf32, 4 epilogue warps; bf16 → kind::f16, 8 epilogue warps (the
-// bf16 tiles complete 2-4× sooner, so two warps share each TMEM lane quarter).
+// fp32 embeddings → kind::tf32, 4 epilogue warps; bf16 → kind::f16, 8 epilogue warps when the
+// lists are small (the bf16 tiles complete 2-4× sooner, so two warps share each TMEM lane quarter).
 static int epi_warps_for(int dtype, int cap) { return (dtype == SBIR_BF16 && cap <= 32) ? 8 : 4; }
 
 // Single-CTA tiles are the default: on B200 the CTA-pair kernel (cta_group::2, M = 256) measured
@@ -656,36 +768,32 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   const int workers = num_sms / p.pair;                           // CTAs or CTA pairs
   const size_t es = dtype == SBIR_BF16 ? 2 : 4;
   p.num_k_blocks = (int)((dim * es + kSwizzleBytes - 1) / kSwizzleBytes);
-  // Splits: all units cost the same (tiles_per_split tiles + a fixed start-up/write-out of about
-  // one tile), workers take units round-robin, so the makespan is ceil(units / workers) rounds.
-  // Pick the split count with the smallest makespan (ties: fewer splits), at most one split per
-  // gallery tile, keeping the merged candidate set per query within finalize's 4096 entries.
-  int64_t max_splits = 4096 / (p.cap * p.lists_per_row);
-  if (max_splits > p.num_g_tiles) max_splits = p.num_g_tiles;
-  if (max_splits > 64) max_splits = 64;
-  if (max_splits < 1) max_splits = 1;
-  double best_cost = 0.0;
-  int best_tps = p.num_g_tiles;
-  for (int64_t s = 1; s <= max_splits; ++s) {
-    const int64_t tps = (p.num_g_tiles + s - 1) / s;
-    const int64_t splits = (p.num_g_tiles + tps - 1) / tps;
-    const int64_t units = splits * row_tiles;
-    const double cost = (double)((units + workers - 1) / workers) * ((double)tps + 1.0);
-    if (s == 1 || cost < best_cost * 0.995) {
-      best_cost = cost;
-      best_tps = (int)tps;
-    }
-  }
-  p.tiles_per_split = best_tps;
+
+  // Partitions (independent candidate lists; finalize merges them): only as many as it takes to
+  // give every chunk step about two waves of units, at most one per gallery tile and within
+  // finalize's 4096 candidate entries per query.
+  int64_t parts = (2LL * workers + row_tiles - 1) / row_tiles;
+  const int64_t max_parts = 4096 / (p.cap * p.lists_per_row);
+  if (parts > max_parts) parts = max_parts;
+  if (parts > p.num_g_tiles) parts = p.num_g_tiles;
+  if (parts < 1) parts = 1;
+  p.tiles_per_split = (int)((p.num_g_tiles + parts - 1) / parts);
   p.num_splits = (p.num_g_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  // Band: as many unit-grid rows as keep their query rows within ~32 MB of L2 next to the
-  // streaming gallery tiles.
-  const int64_t row_bytes = (int64_t)kTileQ * p.pair * dim * (int64_t)es;
-  int64_t band = (32LL << 20) / (row_bytes > 0 ? row_bytes : 1);
-  if (band < 1) band = 1;
-  if (band > row_tiles) band = row_tiles;
-  p.band_q = (int)band;
-  p.num_units = row_tiles * p.num_splits;
+  // Chunks: ~12 MB of gallery rows per (partition, chunk) so that the rows every CTA of a chunk
+  // step streams stay in L2 together with the live query tiles.
+  const int64_t tile_bytes = (int64_t)kTileG * dim * (int64_t)es;
+  int64_t tpc = (12LL << 20) / (tile_bytes > 0 ? tile_bytes : 1);
+  if (tpc < 1) tpc = 1;
+  if (tpc > p.tiles_per_split) tpc = p.tiles_per_split;
+  p.num_chunks = (int)((p.tiles_per_split + tpc - 1) / tpc);
+  p.tiles_per_chunk = (p.tiles_per_split + p.num_chunks - 1) / p.num_chunks;
+  // Wide rows: the query tiles of all concurrently running units must stay L2-resident (each is
+  // re-read for every gallery tile); when one tile per worker would not (> 24 MB), run the
+  // partitions of the same query tile next to each other instead.
+  const int64_t q_tile_bytes = (int64_t)kTileQ * p.pair * dim * (int64_t)es;
+  p.part_fastest = (p.num_splits > 1 && q_tile_bytes * workers > (24LL << 20)) ? 1 : 0;
+  p.num_units = p.num_chunks * p.num_splits * row_tiles;
+  p.band_q = row_tiles;
   return p;
 }
 
@@ -693,27 +801,33 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   if ((a.dim * (int64_t)elem_size(a.dtype)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.g)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
   if (a.num_q <= 0 || a.num_g <= 0) return SBIR_OK;
+  const int pair = plan.pair == 2 ? 2 : 1;
   CUtensorMap tq, tg;
   SBIR_TRY(make_tmap(&tq, a.q, a.num_q, a.dim, a.dtype, kTileQ));
   // pair mode: each CTA of the pair loads half of the 256-row gallery tile
-  SBIR_TRY(make_tmap(&tg, a.g, a.num_g, a.dim, a.dtype, plan.pair == 2 ? kTileG / 2 : kTileG));
+  SBIR_TRY(make_tmap(&tg, a.g, a.num_g, a.dim, a.dtype, pair == 2 ? kTileG / 2 : kTileG));
   K1Params prm{};
   prm.gvec = a.gvec;
   prm.num_q = (int)a.num_q;
   prm.num_g = (int)a.num_g;
   prm.num_q_tiles = plan.num_q_tiles;
   prm.num_g_tiles = plan.num_g_tiles;
-  prm.num_splits = plan.num_splits;
-  const int pair = plan.pair == 2 ? 2 : 1;
-  prm.num_row_tiles = (plan.num_q_tiles + pair - 1) / pair;
-  prm.q_tile_stride = plan.q_tile_stride;
-  prm.band_q = plan.band_q > 0 ? plan.band_q : prm.num_row_tiles;
-  prm.tiles_per_split = plan.tiles_per_split;
-  prm.num_units = plan.num_units;
   prm.num_k_blocks = plan.num_k_blocks;
+  prm.num_row_tiles = (plan.num_q_tiles + pair - 1) / pair;
+  prm.num_parts = plan.num_splits;
+  prm.tiles_per_part = plan.tiles_per_split;
+  prm.num_chunks = plan.num_chunks > 0 ? plan.num_chunks : 1;
+  prm.tiles_per_chunk = plan.tiles_per_chunk > 0 ? plan.tiles_per_chunk : plan.tiles_per_split;
+  prm.num_units = plan.num_units;
+  prm.part_fastest = plan.part_fastest;
+  prm.q_tile_stride = plan.q_tile_stride;
   prm.elems_per_kblock = (int)(kSwizzleBytes / elem_size(a.dtype));
+  prm.unit_counter = a.unit_counter;
+  prm.chunk_done = a.chunk_done;
   prm.cand_val = a.cand_val;
   prm.cand_idx = a.cand_idx;
+  prm.row_max = a.row_max;
+  prm.row_maxpos = a.row_maxpos;
   prm.rank_lo = a.rank_lo;
   prm.rank_hi = a.rank_hi;
   prm.cnt_less = a.cnt_less;
@@ -728,6 +842,10 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.col_label = a.col_label;
   prm.hard_val = a.hard_val;
   prm.hard_idx = a.hard_idx;
+  if (pair == 1 && prm.unit_counter == nullptr) return SBIR_ERR_INVALID_ARG;
+  const bool select = a.mode == kModeTopk || a.mode == kModeTopkRank;
+  if (select && (prm.chunk_done == nullptr || prm.row_max == nullptr || prm.row_maxpos == nullptr))
+    return SBIR_ERR_INVALID_ARG;
 
   int dev = 0, num_sms = 148;
   SBIR_CUDA_TRY(cudaGetDevice(&dev));

@@ -29,13 +29,16 @@ constexpr int kMaxK = 116;         // largest supported k (list capacity 128 min
 
 enum K1Mode { kModeTopk = 0, kModeTopkRank = 1, kModeDump = 2, kModeHard = 3 };
 
-// Work decomposition of one K1 launch.  unit = split * num_q_tiles + q_tile; a unit scans the
-// gallery tiles [split*tiles_per_split, min((split+1)*tiles_per_split, num_g_tiles)).
+// Work decomposition of one K1 launch: `num_splits` gallery partitions of `tiles_per_split` tiles
+// (independent candidate lists), each scanned in `num_chunks` serial chunks; a unit is
+// (query tile, partition, chunk) — see make_k1_plan / decode_unit in dist_topk.cu.
 struct K1Plan {
   int cap;            // per-list capacity (16, 32, 64 or 128)
   int lists_per_row;  // 1 (4 epilogue warps) or 2 (8 epilogue warps: one list per column half)
   int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks;
   int band_q;         // unit-grid rows per L2 band (unit numbering, see decode_unit in dist_topk.cu)
+  int num_chunks, tiles_per_chunk;  // every partition is scanned in `num_chunks` serial chunks
+  int part_fastest;   // unit numbering inside a chunk step: partitions (1) or query tiles (0) vary fastest
   int pair;           // 1: single-CTA tiles (cta_group::1); 2: CTA-pair tiles (cta_group::2, M = 256)
   int q_tile_stride;  // query-tile stride of candidate slots / shared thresholds (num_q_tiles rounded up to even)
   int lists_per_query() const { return num_splits * lists_per_row; }
@@ -48,9 +51,13 @@ struct K1Args {
   int64_t num_q, num_g, dim;
   int dtype, metric, mode;
   const float* gvec;  // [num_g_tiles * kTileG] epilogue vector (‖g‖² | −1/max(‖g‖,eps)), padded
-  // top-k candidate lists, layout [unit*lists_per_row + l][cap][kTileQ]
+  // top-k candidate lists, layout [partition][q_tile_stride][lists_per_row][cap][kTileQ]
   float* cand_val;
   int32_t* cand_idx;
+  float* row_max;          // [partition][q_tile_stride][lists_per_row][kTileQ] carried list maximum
+  int32_t* row_maxpos;     // ... and its position
+  int32_t* chunk_done;     // [partition][q_tile_stride], zeroed by the caller
+  uint32_t* unit_counter;  // [1], zeroed by the caller (dynamic unit hand-out)
   // rank (mode kModeTopkRank): e-space band per query and its outputs
   const float* rank_lo;
   const float* rank_hi;

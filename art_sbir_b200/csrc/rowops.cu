@@ -55,12 +55,17 @@ __global__ void __launch_bounds__(kRowThreads) l2_normalize_kernel(const T* __re
         for (int e = 0; e < E; ++e) acc += (double)a.v[e] * (double)a.v[e];
       }
       const float c = fmaxf((float)sqrt(warp_sum(acc)), eps);
+      // fp32 output: true division, bit-compatible with torch's x / norm.  bf16 output: the
+      // quotient is rounded to 8 mantissa bits anyway, so one reciprocal + multiplies (the
+      // IEEE division sequence would make the 2-byte path instruction-bound, not HBM-bound).
+      const float inv = 1.0f / c;
+      auto scale = [&](float v) { return sizeof(T) == 2 ? v * inv : __fdiv_rn(v, c); };
 #pragma unroll
       for (int h = 0; h < kHeld; ++h) {
         const int i = lane + 32 * h;
         if (i < nvec) {
 #pragma unroll
-          for (int e = 0; e < E; ++e) held[h].v[e] = __fdiv_rn(held[h].v[e], c);
+          for (int e = 0; e < E; ++e) held[h].v[e] = scale(held[h].v[e]);
           held[h].store(yr + (size_t)i * E);
         }
       }
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(kRowThreads) l2_normalize_kernel(const T* __re
         Vec16<T> a;
         a.load(xr + (size_t)i * E);
 #pragma unroll
-        for (int e = 0; e < E; ++e) a.v[e] = __fdiv_rn(a.v[e], c);
+        for (int e = 0; e < E; ++e) a.v[e] = scale(a.v[e]);
         a.store(yr + (size_t)i * E);
       }
     } else {
