@@ -88,6 +88,54 @@ __global__ void __launch_bounds__(kRowThreads) l2_normalize_kernel(const T* __re
   }
 }
 
+// Rows of at most 1 KB (64 vectors): one row per warp leaves too few bytes in flight to cover
+// the HBM latency, so a warp takes FOUR rows per iteration and issues all their loads first.
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads) l2_normalize_short_kernel(const T* __restrict__ x,
+                                                                         T* __restrict__ y, int64_t rows,
+                                                                         int dim, float eps) {
+  constexpr int E = Vec16<T>::kElems;
+  constexpr int kRows = 4;
+  const int lane = threadIdx.x & 31;
+  const int nvec = dim / E;  // <= 64
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t r0 = warp0 * kRows; r0 < rows; r0 += nwarps * kRows) {
+    Vec16<T> v[kRows][2];
+    bool have[kRows][2];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        have[k][h] = (r0 + k < rows) && (i < nvec);
+        if (have[k][h]) v[k][h].load(x + (r0 + k) * dim + (size_t)i * E);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      double acc = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (have[k][h]) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc += (double)v[k][h].v[e] * (double)v[k][h].v[e];
+        }
+      }
+      const float c = fmaxf((float)sqrt(warp_sum(acc)), eps);
+      const float inv = 1.0f / c;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (have[k][h]) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) v[k][h].v[e] = sizeof(T) == 2 ? v[k][h].v[e] * inv : __fdiv_rn(v[k][h].v[e], c);
+          v[k][h].store(y + (r0 + k) * dim + (size_t)(lane + 32 * h) * E);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------- row_sqnorm / epilogue vector ----
 // mode 0: out[r] = ‖x_r‖²                          (fp32, fp64-accumulated)
 // mode 1: out[r] = −1 / max(‖x_r‖, 1e-8)           (cosine epilogue scale for K1)
@@ -315,6 +363,13 @@ int launch_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int d
   if (rows <= 0) return SBIR_OK;
   const bool vec = rows_vectorizable(x, dim, dtype) && rows_vectorizable(y, dim, dtype);
   const int grid = row_grid(rows);
+  if (vec && dim * (int64_t)elem_size(dtype) <= 1024) {
+    const int g4 = row_grid((rows + 3) / 4);
+    if (dtype == SBIR_F32) l2_normalize_short_kernel<float><<<g4, kRowThreads, 0, st>>>((const float*)x, (float*)y, rows, (int)dim, eps);
+    else l2_normalize_short_kernel<__nv_bfloat16><<<g4, kRowThreads, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, rows, (int)dim, eps);
+    SBIR_CHECK_LAUNCH();
+    return SBIR_OK;
+  }
   if (dtype == SBIR_F32) {
     if (vec) l2_normalize_kernel<float, true><<<grid, kRowThreads, 0, st>>>((const float*)x, (float*)y, rows, (int)dim, eps);
     else l2_normalize_kernel<float, false><<<grid, kRowThreads, 0, st>>>((const float*)x, (float*)y, rows, (int)dim, eps);

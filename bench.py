@@ -344,7 +344,9 @@ def main():
         peak = 746.8  # cuBLAS TF32 8192^3 measured on this pool (profiles/r01_probe2_shared_thr_pool.log), MEASURED_PEAKS has no tf32 entry
         peak_note = "tf32 dense, cuBLAS 8192^3 measured in round 1 (kind::tf32 runs at half the bf16 rate)"
     traffic_file = ROOT / "profiles" / f"k1_traffic_{args.workload}.json"
-    traffic = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch") if traffic_file.is_file() else None
+    # ncu capture of the single-GPU launch of this workload (profiles/); per-rank launches at N > 1
+    # cover a shard and were not captured separately
+    traffic = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch") if (traffic_file.is_file() and world == 1) else None
     roofline = {"bound": "tensor", "kernel": "dist_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_note": peak_note,
                 "k1_ms_per_launch": k1_ms_per_launch, "k1_share_of_step": k1_ms_per_launch / ms_per_step}

@@ -241,6 +241,12 @@ def test_l2_normalize(ops, dtype):
     assert (got[7] == 0).all()
     big = torch.randn(64, 4100)          # rows longer than the register-held part
     assert torch.allclose(ops.l2_normalize(big.cuda()).cpu(), O.l2_normalize(big), atol=1e-6)
+    for rows, dim in ((1001, 512), (7, 64), (4099, 256)):   # rows <= 1 KB: four rows per warp
+        s = torch.randn(rows, dim).to(tdt)
+        s[rows // 2] = 0
+        got = ops.l2_normalize(s.cuda()).cpu()
+        assert torch.allclose(got.float(), O.l2_normalize(s.float()), atol=tol, rtol=tol)
+        assert (got[rows // 2] == 0).all()
 
 
 @pytest.mark.parametrize("lt", ["euclidean", "cosine"])

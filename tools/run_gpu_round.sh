@@ -1,5 +1,6 @@
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-SBIR_K1_PAIR=2 timeout 600 python -m pytest tests -m gpu -x -q -k "oracle or full_size or sharded" > gpurun_out/pytest_gpu_pair.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_pair.log
-timeout 300 python tools/gpu_probe.py time > gpurun_out/time.log 2>&1
-timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err && \
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct,lts__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:dist_topk -s 3 -c 1 --csv --log-file gpurun_out/k1_cfg4_traffic.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_cfg4.log 2>&1
+timeout 300 python tools/gpu_probe.py bw > gpurun_out/bw.log 2>&1 && \
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:"l2_normalize|row_norm|topk_merge|triplet_rows" -c 40 --csv --log-file gpurun_out/bw_kernels_ncu.csv python tools/gpu_probe.py bw > gpurun_out/ncu_bw.log 2>&1
+timeout 300 python bench.py --workload cfg3 --steps 5 --no-cpu > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err
+timeout 300 python bench.py --workload cfg3k10 --steps 5 --no-cpu > gpurun_out/bench_cfg3k10.json 2> gpurun_out/bench_cfg3k10.err
+timeout 300 python bench.py --workload cfg1 --steps 10 --no-cpu > gpurun_out/bench_cfg1.json 2> gpurun_out/bench_cfg1.err
