@@ -62,7 +62,7 @@ bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 struct TopkLayout {
   K1Plan plan;
   size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert, off_shared_thr;
-  size_t off_row_max, off_row_maxpos, off_sched, sched_bytes;  // off_sched: unit counter + chunk_done (zeroed together)
+  size_t off_row_max, off_row_maxpos, off_sched, sched_bytes, off_gmin;  // off_sched: unit counter + chunk_done (zeroed together)
   size_t off_pos_dist, off_lo, off_hi, off_cnt, off_dropped, off_pool_count, off_pool_q, off_pool_idx;
   uint32_t pool_cap;
   size_t total;
@@ -76,6 +76,7 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   const size_t nq = (size_t)(num_q > 0 ? num_q : 1);
   L.off_gvec = take((size_t)L.plan.num_g_tiles * kTileG * sizeof(float));
   L.off_gmax = take(sizeof(float));
+  L.off_gmin = take((size_t)L.plan.num_g_tiles * (kTileG / 32) * sizeof(float));
   L.off_qsq = take(nq * sizeof(float));
   const size_t cand = (size_t)L.plan.num_splits * L.plan.q_tile_stride * L.plan.lists_per_row * L.plan.cap * kTileQ;
   L.off_cand_val = take(cand * sizeof(float));
@@ -147,6 +148,8 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   SBIR_TRY(launch_row_norm(g, num_g, padded, dim, dtype, metric == SBIR_EUCLIDEAN ? 0 : 1,
                            metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""), gvec, gmax, st));
   SBIR_TRY(launch_row_norm(q, num_q, num_q, dim, dtype, 0, 0.f, qsq, nullptr, st));
+  float* gmin = reinterpret_cast<float*>(ws + L.off_gmin);
+  SBIR_TRY(launch_chunk_min(gvec, padded / 32, gmin, st));
 
   RankArgs ra{};
   if (want_rank) {
@@ -177,6 +180,7 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   ka.dtype = dtype; ka.metric = metric;
   ka.mode = want_rank ? kModeTopkRank : kModeTopk;
   ka.gvec = gvec;
+  ka.gmin = gmin;
   ka.cand_val = cand_val; ka.cand_idx = cand_idx;
   ka.row_max = reinterpret_cast<float*>(ws + L.off_row_max);
   ka.row_maxpos = reinterpret_cast<int32_t*>(ws + L.off_row_maxpos);

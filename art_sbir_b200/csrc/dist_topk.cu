@@ -99,12 +99,14 @@ struct K1Config {
 
 struct K1Params {
   const float* gvec;
+  const float* gmin;   // per 32 gallery rows: min of gvec (euclidean) / min of gvec = -1/min-norm (cosine)
   int num_q, num_g;
   int num_q_tiles, num_g_tiles, num_k_blocks;
   int num_row_tiles;   // query tiles (kPair = 1) or query-tile pairs (kPair = 2): rows of the unit grid
   int num_parts, tiles_per_part, num_chunks, tiles_per_chunk, num_units, part_fastest;
   int q_tile_stride;   // query-tile stride of candidate slots (num_q_tiles rounded up to even)
   int elems_per_kblock;
+  int flags;               // diagnostics (SBIR_K1_FLAGS): 8 = epilogue skips the accumulator (mainloop alone), 16 = no chunk screen
   uint32_t* unit_counter;  // [1] zeroed by the caller: next unit to hand out (kPair = 1)
   int32_t* chunk_done;     // [num_parts][q_tile_stride] zeroed: chunks finished per (partition, query tile)
   float* cand_val;         // [part][q_tile_stride][lists][cap][128]
@@ -420,11 +422,23 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         const float* gv = prm.gvec + (size_t)t * kTileG + col_begin;
 #pragma unroll 1
-        for (int c = 0; c < Cfg::kColsPerWarp / 32; ++c) {
+        for (int c = 0; c < ((prm.flags & 8) ? 0 : Cfg::kColsPerWarp / 32); ++c) {
           const uint32_t taddr = tmem_base + lane_addr + acc * kTileG + col_begin + c * 32;
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
+          if constexpr (kSelect) {
+            // Cheap conservative screen before any per-element work: every e of this chunk is
+            // >= bound (rounding is monotone, so this holds for the computed values too);
+            // when no row of the warp can beat its threshold the chunk costs 31 FMNMX + 1 FFMA.
+            float smax = __uint_as_float(r[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) smax = fmaxf(smax, __uint_as_float(r[j]));
+            const float gmin = __ldg(prm.gmin + ((size_t)t * kTileG + col_begin) / 32 + c);
+            const float bound = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, smax, gmin) : fminf(0.f, __fmul_rn(smax, gmin));
+            const float lim0 = kRank ? fmaxf(thr, hi) : thr;
+            if (!(prm.flags & 16) && !__any_sync(kFullMask, bound < lim0)) continue;
+          }
           float e[32];
           const float4* gv4 = reinterpret_cast<const float4*>(gv + c * 32);
 #pragma unroll
@@ -808,6 +822,7 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   SBIR_TRY(make_tmap(&tg, a.g, a.num_g, a.dim, a.dtype, pair == 2 ? kTileG / 2 : kTileG));
   K1Params prm{};
   prm.gvec = a.gvec;
+  prm.gmin = a.gmin;
   prm.num_q = (int)a.num_q;
   prm.num_g = (int)a.num_g;
   prm.num_q_tiles = plan.num_q_tiles;
@@ -822,6 +837,10 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.part_fastest = plan.part_fastest;
   prm.q_tile_stride = plan.q_tile_stride;
   prm.elems_per_kblock = (int)(kSwizzleBytes / elem_size(a.dtype));
+  {
+    const char* fe = std::getenv("SBIR_K1_FLAGS");
+    prm.flags = fe ? std::atoi(fe) : 0;
+  }
   prm.unit_counter = a.unit_counter;
   prm.chunk_done = a.chunk_done;
   prm.cand_val = a.cand_val;
@@ -844,7 +863,7 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.hard_idx = a.hard_idx;
   if (pair == 1 && prm.unit_counter == nullptr) return SBIR_ERR_INVALID_ARG;
   const bool select = a.mode == kModeTopk || a.mode == kModeTopkRank;
-  if (select && (prm.chunk_done == nullptr || prm.row_max == nullptr || prm.row_maxpos == nullptr))
+  if (select && (prm.chunk_done == nullptr || prm.row_max == nullptr || prm.row_maxpos == nullptr || prm.gmin == nullptr))
     return SBIR_ERR_INVALID_ARG;
 
   int dev = 0, num_sms = 148;

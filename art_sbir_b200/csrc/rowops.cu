@@ -332,6 +332,17 @@ __global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict_
   if (threadIdx.x == 0) out[0] = (float)(red[0] / (double)rows);
 }
 
+__global__ void __launch_bounds__(256) chunk_min_kernel(const float* __restrict__ gvec, long long num_chunks,
+                                                        float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= num_chunks) return;
+  float v = gvec[w * 32 + lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFullMask, v, o));
+  if (lane == 0) out[w] = v;
+}
+
 template <typename T>
 int launch_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int mode,
                 float pad_value, float* out, float* max_out, bool vec, cudaStream_t st) {
@@ -356,6 +367,13 @@ int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t di
   if (dtype == SBIR_F32)
     return launch_norm<float>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
   return launch_norm<__nv_bfloat16>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
+}
+
+int launch_chunk_min(const float* gvec, int64_t num_chunks, float* out, cudaStream_t st) {
+  if (num_chunks <= 0) return SBIR_OK;
+  chunk_min_kernel<<<(unsigned)((num_chunks * 32 + 255) / 256), 256, 0, st>>>(gvec, (long long)num_chunks, out);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
 }
 
 int launch_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype, float eps,

@@ -301,6 +301,70 @@ def case_bw():
     return res
 
 
+def case_mainloop():
+    """K1 with the epilogue switched off (SBIR_K1_FLAGS=8, results meaningless) vs the full kernel:
+    how much of the pass is the TMA+MMA mainloop alone."""
+    import ctypes
+    import torch
+    from art_sbir_b200 import _binding as B, ops
+    lib = B.load()
+    out = {}
+    for nq, ng, d, dt, k in [(20000, 1000000, 512, "bfloat16", 10), (12500, 75000, 2048, "float32", 10),
+                             (12500, 75000, 2048, "bfloat16", 10), (20000, 500000, 1024, "bfloat16", 10)]:
+        q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
+        res = {}
+        for rep in range(2):
+            for flags in (0, 8):
+                os.environ["SBIR_K1_FLAGS"] = str(flags)
+                ops.pairwise_topk(q, g, k, "euclidean")
+                torch.cuda.synchronize()
+                lib.sbir_profile_enable(1)
+                ms, n, l = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+                lib.sbir_profile_collect(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(l))
+                for _ in range(5):
+                    ops.pairwise_topk(q, g, k, "euclidean")
+                torch.cuda.synchronize()
+                lib.sbir_profile_collect(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(l))
+                lib.sbir_profile_enable(0)
+                k1 = ms.value / max(1, n.value)
+                res.setdefault("full" if flags == 0 else "mainloop_only", []).append(
+                    {"k1_ms": round(k1, 3), "tflops": round(2 * d * nq * ng / k1 / 1e9, 1)})
+        out[f"{nq}x{ng}x{d} {dt}"] = res
+    os.environ.pop("SBIR_K1_FLAGS", None)
+    return out
+
+
+def case_ab():
+    """Same-process A/B of K1 switches (SBIR_K1_FLAGS is read at every launch): 16 = no chunk screen."""
+    import ctypes
+    import torch
+    from art_sbir_b200 import _binding as B, ops
+    lib = B.load()
+    out = {}
+    for nq, ng, d, dt, k, rank in [(20000, 1000000, 512, "bfloat16", 10, True), (20000, 1000000, 512, "bfloat16", 10, False),
+                                   (12500, 75000, 2048, "float32", 10, True), (12500, 75000, 2048, "float32", 100, True)]:
+        q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
+        p = pos if rank else None
+        res = {}
+        for rep in range(3):
+            for flags in (0, 16):
+                os.environ["SBIR_K1_FLAGS"] = str(flags)
+                ops.pairwise_topk(q, g, k, "euclidean", pos_index=p)
+                torch.cuda.synchronize()
+                lib.sbir_profile_enable(1)
+                ms, n, l = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+                lib.sbir_profile_collect(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(l))
+                for _ in range(5):
+                    ops.pairwise_topk(q, g, k, "euclidean", pos_index=p)
+                torch.cuda.synchronize()
+                lib.sbir_profile_collect(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(l))
+                lib.sbir_profile_enable(0)
+                res.setdefault(flags, []).append(round(ms.value / max(1, n.value), 3))
+        out[f"{nq}x{ng}x{d} {dt} k={k} rank={rank}"] = res
+    os.environ.pop("SBIR_K1_FLAGS", None)
+    return out
+
+
 def case_peaks():
     import torch
     res = {}
