@@ -62,7 +62,10 @@ bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 struct TopkLayout {
   K1Plan plan;
   size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert, off_shared_thr;
-  size_t off_row_max, off_row_maxpos, off_sched, sched_bytes, off_gmin;  // off_sched: unit counter + chunk_done (zeroed together)
+  size_t off_row_max, off_row_maxpos, off_sched, sched_bytes, off_gmin;
+  bool precise;        // fp32 inputs small enough for the 3xTF32 escalation workspace
+  K1Plan plan3;        // plan of the escalation pass (dim' = 3·dim), same partitions / lists as `plan`
+  size_t off_gate, off_q3, off_g3;  // off_sched: unit counter + chunk_done (zeroed together)
   size_t off_pos_dist, off_lo, off_hi, off_cnt, off_dropped, off_pool_count, off_pool_q, off_pool_idx;
   uint32_t pool_cap;
   size_t total;
@@ -89,6 +92,20 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   L.off_row_maxpos = take(rows * sizeof(int32_t));
   L.sched_bytes = 256 + (size_t)L.plan.num_splits * L.plan.q_tile_stride * sizeof(int32_t);
   L.off_sched = take(L.sched_bytes);
+  // 3xTF32 escalation copies ([rows, 3·dim] fp32) — only when they stay below 12 GiB
+  const size_t split_bytes = ((size_t)num_q + (size_t)num_g) * (size_t)dim * 3 * sizeof(float);
+  L.precise = dtype == SBIR_F32 && num_g > 0 && split_bytes <= (size_t(12) << 30);
+  if (L.precise) {
+    L.plan3 = make_k1_plan(num_q, num_g, 3 * dim, k, dtype, num_sms_cached());
+    // identical list geometry (it depends on the query/gallery tile counts, k and dtype only)
+    L.precise = L.plan3.num_splits == L.plan.num_splits && L.plan3.cap == L.plan.cap &&
+                L.plan3.lists_per_row == L.plan.lists_per_row && L.plan3.tiles_per_split == L.plan.tiles_per_split;
+  }
+  if (L.precise) {
+    L.off_gate = take(256);
+    L.off_q3 = take((size_t)num_q * dim * 3 * sizeof(float));
+    L.off_g3 = take((size_t)num_g * dim * 3 * sizeof(float));
+  }
   if (want_rank) {
     L.off_pos_dist = take(nq * sizeof(double));
     L.off_lo = take(nq * sizeof(float));
@@ -157,7 +174,7 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
     ra.dtype = dtype; ra.metric = metric;
     ra.pos_index = pos_index; ra.pos_dist_in = pos_dist_in;
     ra.pos_tie = pos_tie; ra.tie_offset = tie_offset;
-    ra.qsq = qsq; ra.gsq_max = gmax; ra.kappa = k1_kappa(dtype);
+    ra.qsq = qsq; ra.gsq_max = gmax;
     ra.pos_dist = reinterpret_cast<double*>(ws + L.off_pos_dist);
     ra.rank_lo = reinterpret_cast<float*>(ws + L.off_lo);
     ra.rank_hi = reinterpret_cast<float*>(ws + L.off_hi);
@@ -169,14 +186,9 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
     ra.pool_idx = reinterpret_cast<int32_t*>(ws + L.off_pool_idx);
     ra.out_rank = out_rank;
     ra.missing_rank = missing_rank;
-    SBIR_CUDA_TRY(cudaMemsetAsync(ra.cnt_less, 0, (size_t)num_q * sizeof(int32_t), st));
-    SBIR_CUDA_TRY(cudaMemsetAsync(ra.dropped, 0, (size_t)num_q * sizeof(int32_t), st));
-    SBIR_CUDA_TRY(cudaMemsetAsync(ra.pool_count, 0, sizeof(uint32_t), st));
-    SBIR_TRY(launch_rank_band(ra, st));
   }
-
   K1Args ka{};
-  ka.q = q; ka.g = g; ka.num_q = num_q; ka.num_g = num_g; ka.dim = dim;
+  ka.num_q = num_q; ka.num_g = num_g;
   ka.dtype = dtype; ka.metric = metric;
   ka.mode = want_rank ? kModeTopkRank : kModeTopk;
   ka.gvec = gvec;
@@ -186,25 +198,64 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   ka.row_maxpos = reinterpret_cast<int32_t*>(ws + L.off_row_maxpos);
   ka.unit_counter = reinterpret_cast<uint32_t*>(ws + L.off_sched);
   ka.chunk_done = reinterpret_cast<int32_t*>(ws + L.off_sched + 256);
-  SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_sched, 0, L.sched_bytes, st));
   ka.rank_lo = ra.rank_lo; ka.rank_hi = ra.rank_hi;
   ka.cnt_less = ra.cnt_less;
   ka.pool_count = ra.pool_count; ka.pool_cap = ra.pool_cap; ka.pool_q = ra.pool_q; ka.pool_idx = ra.pool_idx;
   ka.dropped = ra.dropped;
   ka.shared_thr = reinterpret_cast<int32_t*>(ws + L.off_shared_thr);
-  SBIR_TRY(launch_fill_i32(ka.shared_thr, (int64_t)L.plan.q_tile_stride * kTileQ, 0x7f800000, st));
-  SBIR_TRY(launch_k1(ka, L.plan, st));
-
   FinalizeArgs fa{};
   fa.q = q; fa.g = g; fa.num_q = num_q; fa.num_g = num_g; fa.dim = dim;
   fa.dtype = dtype; fa.metric = metric; fa.k = k; fa.index_offset = index_offset;
   fa.cand_val = cand_val; fa.cand_idx = cand_idx;
-  fa.qsq = qsq; fa.gsq_max = gmax; fa.kappa = k1_kappa(dtype);
+  fa.qsq = qsq; fa.gsq_max = gmax;
   fa.out_dist = out_dist; fa.out_index = out_index;
   fa.uncertified = uncert; fa.flags = flags;
-  SBIR_TRY(launch_finalize_topk(fa, L.plan, st));
+
+  // One scoring pass: (rank band) -> K1 -> finalize (+ rank pool resolution).  `gate` makes every
+  // kernel of the pass a no-op unless the device flag is set.
+  auto run_pass = [&](const void* kq, const void* kg, int64_t kdim, const K1Plan& plan, float kappa,
+                      const int32_t* gate) -> int {
+    ra.kappa = kappa; ra.gate = gate;
+    fa.kappa = kappa; fa.gate = gate;
+    ka.q = kq; ka.g = kg; ka.dim = kdim; ka.gate = gate;
+    if (want_rank) {
+      SBIR_CUDA_TRY(cudaMemsetAsync(ra.cnt_less, 0, (size_t)num_q * sizeof(int32_t), st));
+      SBIR_CUDA_TRY(cudaMemsetAsync(ra.dropped, 0, (size_t)num_q * sizeof(int32_t), st));
+      SBIR_CUDA_TRY(cudaMemsetAsync(ra.pool_count, 0, sizeof(uint32_t), st));
+      SBIR_TRY(launch_rank_band(ra, st));
+    }
+    SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_sched, 0, L.sched_bytes, st));
+    SBIR_TRY(launch_fill_i32(ka.shared_thr, (int64_t)L.plan.q_tile_stride * kTileQ, 0x7f800000, st));
+    SBIR_TRY(launch_k1(ka, plan, st));
+    SBIR_TRY(launch_finalize_topk(fa, plan, st));
+    if (want_rank) SBIR_TRY(launch_rank_finalize(ra, st));
+    return SBIR_OK;
+  };
+
+  // Pass 1: tensor-core tiles on the embeddings as they are (fp32 -> kind::tf32, bf16 -> kind::f16).
+  SBIR_TRY(run_pass(q, g, dim, L.plan, k1_kappa(dtype, dim), nullptr));
+
+  // Pass 2 (fp32 only, device-gated): when more than 2 % of the queries could not be certified or
+  // overflowed the rank pool — embeddings whose norms dwarf their distances, positives deep in an
+  // unstructured distribution — the TF32 error band is the problem, so redo the pass with the
+  // operands split into TF32 hi/lo parts concatenated along K ([qh|qh|ql]·[gh|gl|gh] = 3xTF32,
+  // error ~2^-20): same kernel, 3x the MMA work, far cheaper than brute-forcing every query.
+  if (L.precise) {
+    int32_t* gate = reinterpret_cast<int32_t*>(ws + L.off_gate);
+    float* q3 = reinterpret_cast<float*>(ws + L.off_q3);
+    float* g3 = reinterpret_cast<float*>(ws + L.off_g3);
+    int64_t max_bad = num_q / 50;
+    if (max_bad < 4) max_bad = 4;
+    SBIR_TRY(launch_escalate_decide(flags, want_rank ? ra.dropped : nullptr, num_q, max_bad, gate, uncert, st));
+    SBIR_TRY(launch_split_tf32(static_cast<const float*>(q), num_q, dim, 0, q3, gate, st));
+    SBIR_TRY(launch_split_tf32(static_cast<const float*>(g), num_g, dim, 1, g3, gate, st));
+    SBIR_TRY(run_pass(q3, g3, 3 * dim, L.plan3, k1_kappa_precise(dim), gate));
+  }
+  // Whatever is still unresolved is recomputed exactly by brute force.
+  fa.gate = nullptr;
+  ra.gate = nullptr;
   SBIR_TRY(launch_topk_fallback(fa, st));
-  if (want_rank) SBIR_TRY(launch_rank_finalize(ra, st));
+  if (want_rank) SBIR_TRY(launch_rank_fallback(ra, st));
   return SBIR_OK;
 }
 

@@ -129,6 +129,7 @@ struct K1Params {
   int num_parts, tiles_per_part, num_chunks, tiles_per_chunk, num_units, part_fastest;
   int q_tile_stride;   // query-tile stride of candidate slots (num_q_tiles rounded up to even)
   int elems_per_kblock;
+  const int32_t* gate;     // optional: the kernel is a no-op unless *gate != 0 (escalation pass)
   int flags;               // diagnostics (SBIR_K1_FLAGS): 8 = epilogue skips the accumulator (mainloop alone), 16 = no chunk screen
   uint32_t* unit_counter;  // [1] zeroed by the caller: next unit to hand out (kPair = 1)
   int32_t* chunk_done;     // [num_parts][q_tile_stride] zeroed: chunks finished per (partition, query tile)
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(K1Config<kCap, kEpiWarps, kPair>::kThreads, 1)
 dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                  const __grid_constant__ CUtensorMap tmap_g, const K1Params prm) {
   using Cfg = K1Config<kCap, kEpiWarps, kPair>;
+  if (prm.gate != nullptr && *prm.gate == 0) return;  // uniform across the grid: nothing was set up yet
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytesG = Cfg::kStageBytesG;
   constexpr int kStageBytes = Cfg::kStageBytes;
@@ -803,9 +805,10 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   p.num_k_blocks = (int)((dim * es + kSwizzleBytes - 1) / kSwizzleBytes);
 
   // Partitions (independent candidate lists; finalize merges them): only as many as it takes to
-  // give every chunk step about two waves of units, at most one per gallery tile and within
+  // give every chunk step a bit more than one wave of units (every extra partition repeats the
+  // list warm-up, ~cap·ln(rows/cap) insertions per query), at most one per gallery tile and within
   // finalize's 4096 candidate entries per query.
-  int64_t parts = (2LL * workers + row_tiles - 1) / row_tiles;
+  int64_t parts = (5LL * workers / 4 + row_tiles - 1) / row_tiles;
   const int64_t max_parts = 4096 / (p.cap * p.lists_per_row);
   if (parts > max_parts) parts = max_parts;
   if (parts > p.num_g_tiles) parts = p.num_g_tiles;
@@ -842,6 +845,7 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   K1Params prm{};
   prm.gvec = a.gvec;
   prm.gmin = a.gmin;
+  prm.gate = a.gate;
   prm.num_q = (int)a.num_q;
   prm.num_g = (int)a.num_g;
   prm.num_q_tiles = plan.num_q_tiles;

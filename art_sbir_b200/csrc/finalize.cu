@@ -69,10 +69,12 @@ struct FinParams {
   long long* out_index;
   int32_t* uncertified;
   int32_t* flags;
+  const int32_t* gate;
 };
 
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinParams p) {
+  if (p.gate != nullptr && *p.gate == 0) return;
   extern __shared__ uint8_t fin_smem[];
   float* sv = reinterpret_cast<float*>(fin_smem);
   int32_t* si = reinterpret_cast<int32_t*>(sv + p.m_pow2);
@@ -226,6 +228,7 @@ struct RankParams {
   int32_t* dropped;
   long long* out_rank;
   long long missing_rank;
+  const int32_t* gate;
 };
 
 constexpr int kRankWarps = 8;
@@ -246,6 +249,7 @@ __device__ __forceinline__ bool ranks_before_positive(double d_exact, int j_loca
 // d_pos cannot be trusted.
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kRankWarps * 32) rank_band_kernel(const RankParams p) {
+  if (p.gate != nullptr && *p.gate == 0) return;
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * kRankWarps + (threadIdx.x >> 5);
   if (q >= p.num_q) return;
@@ -280,6 +284,7 @@ __global__ void __launch_bounds__(kRankWarps * 32) rank_band_kernel(const RankPa
 // One warp per pooled (query, gallery row) pair: exact distance, exact comparison with d_pos.
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kRankWarps * 32) rank_resolve_kernel(const RankParams p) {
+  if (p.gate != nullptr && *p.gate == 0) return;
   const int lane = threadIdx.x & 31;
   const uint32_t claimed = *p.pool_count;
   const uint32_t n = claimed < p.pool_cap ? claimed : p.pool_cap;
@@ -295,6 +300,7 @@ __global__ void __launch_bounds__(kRankWarps * 32) rank_resolve_kernel(const Ran
 }
 
 __global__ void __launch_bounds__(256) rank_finalize_kernel(const RankParams p) {
+  if (p.gate != nullptr && *p.gate == 0) return;
   const int q = blockIdx.x * 256 + threadIdx.x;
   if (q >= p.num_q) return;
   const double dpos = p.pos_dist[q];
@@ -384,6 +390,51 @@ __global__ void fill_topk_kernel(float* out_dist, long long* out_index, size_t n
   if (i < n) {
     out_dist[i] = INFINITY;
     out_index[i] = -1;
+  }
+}
+
+// gate[0] = 1 iff more than max_bad queries are unresolved after the TF32 pass (top-k certificate
+// failed, or rank pool entries dropped).  One block; when escalating, the diagnostic counter
+// restarts for the second pass.
+__global__ void __launch_bounds__(1024) escalate_decide_kernel(const int32_t* __restrict__ flags,
+                                                               const int32_t* __restrict__ dropped, long long num_q,
+                                                               long long max_bad, int32_t* __restrict__ gate,
+                                                               int32_t* __restrict__ uncertified) {
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  int bad = 0;
+  for (long long i = threadIdx.x; i < num_q; i += 1024)
+    bad += ((flags != nullptr && (flags[i] & 1)) || (dropped != nullptr && dropped[i] > 0)) ? 1 : 0;
+  if (bad) atomicAdd(&s_bad, bad);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int esc = (long long)s_bad > max_bad ? 1 : 0;
+    gate[0] = esc;
+    if (esc && uncertified != nullptr) uncertified[0] = 0;
+  }
+}
+
+// 3xTF32 operand split (see kernels.h).  float4 in, three float4 out per vector.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, long long rows, int dim,
+                                                         int gallery_layout, float* __restrict__ out,
+                                                         const int32_t* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  const int v4 = dim / 4;
+  const long long n4 = rows * v4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / v4;
+    const int c = (int)(i - r * v4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    float4* o = reinterpret_cast<float4*>(out) + r * (3LL * v4) + c;
+    o[0] = h;
+    o[v4] = gallery_layout ? l : h;
+    o[2 * v4] = gallery_layout ? h : l;
   }
 }
 
@@ -484,6 +535,7 @@ FinParams make_fin_params(const FinalizeArgs& a, const K1Plan* plan) {
   p.qsq = a.qsq; p.gsq_max = a.gsq_max; p.kappa = a.kappa;
   p.out_dist = a.out_dist; p.out_index = reinterpret_cast<long long*>(a.out_index);
   p.uncertified = a.uncertified; p.flags = a.flags;
+  p.gate = a.gate;
   return p;
 }
 
@@ -502,6 +554,7 @@ RankParams make_rank_params(const RankArgs& a) {
   p.dropped = a.dropped;
   p.out_rank = reinterpret_cast<long long*>(a.out_rank);
   p.missing_rank = a.missing_rank;
+  p.gate = a.gate;
   return p;
 }
 
@@ -557,7 +610,32 @@ int launch_rank_finalize(const RankArgs& a, cudaStream_t st) {
   SBIR_CHECK_LAUNCH();
   rank_finalize_kernel<<<(unsigned)((a.num_q + 255) / 256), 256, 0, st>>>(p);
   SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_rank_fallback(const RankArgs& a, cudaStream_t st) {
+  if (a.num_q <= 0) return SBIR_OK;
+  const RankParams p = make_rank_params(a);
+  const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
   SBIR_DISPATCH_T(a.dtype, vec, rank_fallback_kernel, (unsigned)a.num_q, kFbThreads, 0, st, p);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_escalate_decide(const int32_t* flags, const int32_t* dropped, int64_t num_q, int64_t max_bad,
+                           int32_t* gate, int32_t* uncertified, cudaStream_t st) {
+  escalate_decide_kernel<<<1, 1024, 0, st>>>(flags, dropped, (long long)num_q, (long long)max_bad, gate, uncertified);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_split_tf32(const float* x, int64_t rows, int64_t dim, int gallery_layout, float* out,
+                      const int32_t* gate, cudaStream_t st) {
+  if (rows <= 0) return SBIR_OK;
+  const long long n4 = (long long)rows * (dim / 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, (long long)rows, (int)dim, gallery_layout, out, gate);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }

@@ -26,7 +26,7 @@ int launch_triplet(const float* a, const float* p, const float* n, int64_t batch
 // ---- dist_topk.cu (K1) ----------------------------------------------------------
 constexpr int kTileQ = 128;        // query rows per tile (UMMA M, TMEM lanes)
 constexpr int kTileG = 256;        // gallery rows per tile (UMMA N, TMEM columns)
-constexpr int kUncertainPerQuery = 64;  // uncertain-pool capacity = this × num_q (min 65536)
+constexpr int kUncertainPerQuery = 256;  // uncertain-pool capacity = this × num_q (min 65536)
 constexpr int kMaxK = 116;         // largest supported k (list capacity 128 minus slack)
 
 enum K1Mode { kModeTopk = 0, kModeTopkRank = 1, kModeDump = 2, kModeHard = 3 };
@@ -54,6 +54,7 @@ struct K1Args {
   int dtype, metric, mode;
   const float* gvec;  // [num_g_tiles * kTileG] epilogue vector (‖g‖² | −1/max(‖g‖,eps)), padded
   const float* gmin;  // [num_g_tiles * kTileG / 32] minimum of gvec over each run of 32 rows (select modes)
+  const int32_t* gate;  // optional device flag: every kernel of the launch is a no-op unless *gate != 0
   // top-k candidate lists, layout [partition][q_tile_stride][lists_per_row][cap][kTileQ]
   float* cand_val;
   int32_t* cand_idx;
@@ -99,6 +100,7 @@ struct FinalizeArgs {
   int64_t* out_index;      // [num_q][k]
   int32_t* uncertified;    // [1] counter (may be NULL)
   int32_t* flags;          // [num_q] bit0: top-k selection not certified
+  const int32_t* gate;     // optional device flag (escalation pass)
 };
 int launch_finalize_topk(const FinalizeArgs& a, const K1Plan& plan, cudaStream_t st);
 // Brute-force exact top-k for the queries flagged by finalize (flags[q] & 1).
@@ -127,9 +129,19 @@ struct RankArgs {
   int32_t* dropped;
   int64_t* out_rank;         // [num_q]
   int64_t missing_rank;      // value for queries without a positive (num_g in the reference)
+  const int32_t* gate;       // optional device flag (escalation pass)
 };
 int launch_rank_band(const RankArgs& a, cudaStream_t st);
-int launch_rank_finalize(const RankArgs& a, cudaStream_t st);
+int launch_rank_finalize(const RankArgs& a, cudaStream_t st);   // pool resolution + rank (or -1 = needs brute force)
+int launch_rank_fallback(const RankArgs& a, cudaStream_t st);   // exact brute force for the -1 entries
+// Escalation (fp32 inputs): after the TF32 pass, gate[0] = 1 iff more than `max_bad` queries failed
+// the top-k certificate or overflowed the rank pool; then the 3xTF32 pass re-does everything.
+int launch_escalate_decide(const int32_t* flags, const int32_t* dropped, int64_t num_q, int64_t max_bad,
+                           int32_t* gate, int32_t* uncertified, cudaStream_t st);
+// x [rows, dim] fp32 -> out [rows, 3*dim]: query layout [hi | hi | lo], gallery layout [hi | lo | hi],
+// hi = x with the 13 low mantissa bits cleared (what kind::tf32 reads), lo = x - hi (exact).
+int launch_split_tf32(const float* x, int64_t rows, int64_t dim, int gallery_layout, float* out,
+                      const int32_t* gate, cudaStream_t st);
 int launch_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
                              int dtype, int metric, const int64_t* pos_index, double* out,
                              cudaStream_t st);
@@ -147,6 +159,19 @@ int launch_batch_hard(const float* a, const float* p, const float* n, int64_t ba
                       void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 // relative error bound of the tensor-core dot product
-inline float k1_kappa(int dtype) { return dtype == 0 /*F32→tf32*/ ? 1.0f / 512.0f * 1.01f : 1.0f / 262144.0f; }
+// Bound on |e_tc − e_exact| relative to (‖q‖² + ‖g‖²):
+//   * kind::tf32 on fp32 data truncates both operands to 10 mantissa bits: 2^-9 (×1.01);
+//   * every MMA k-step (32 bytes of K) adds into the fp32 accumulator with one rounding of at most
+//     2^-23 of the running sum (≤ ‖q‖·‖g‖ ≤ (‖q‖²+‖g‖²)/2); with same-signed data (post-ReLU
+//     features) these do not cancel, so the term grows linearly with the number of k-steps;
+//   * the 3xTF32 split drops ql·gl and truncates the lo parts: 2^-20.
+inline float k1_accum_kappa(int64_t dim, size_t elem_bytes) {
+  const double ksteps = (double)(dim * (int64_t)elem_bytes + 31) / 32.0;
+  return (float)((ksteps + 16.0) * 1.1920929e-07);  // (k-steps + 16) · 2^-23
+}
+inline float k1_kappa(int dtype, int64_t dim) {
+  return dtype == 0 /*F32→tf32*/ ? 1.0f / 512.0f * 1.01f + k1_accum_kappa(dim, 4) : k1_accum_kappa(dim, 2);
+}
+inline float k1_kappa_precise(int64_t dim) { return k1_accum_kappa(3 * dim, 4) + 1.0f / 1048576.0f; }
 
 }  // namespace sbir

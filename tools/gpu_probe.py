@@ -419,6 +419,41 @@ def case_host():
             "rank_equal": bool((r.cpu() == orank).all()), "unc": unc.value}
 
 
+def case_escal_debug():
+    """Why do ranks differ on cancellation-heavy data?  Compare against an on-device fp64 evaluation."""
+    import torch
+    from art_sbir_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    nq, ng, d = 300, 6000, 256
+    G = (8.0 + 0.5 * torch.randn(ng, d, generator=g)).cuda()
+    Q = (8.0 + 0.5 * torch.randn(nq, d, generator=g)).cuda()
+    pos = torch.randint(0, ng, (nq,), generator=g).cuda()
+    vals, idx, rank, unc = ops.pairwise_topk(Q, G, 10, "euclidean", pos_index=pos, return_uncertified=True)
+    # exact per-element fp32 arithmetic, fp64 accumulation (what the library's exact kernels do)
+    diff = (Q[:, None, :] - G[None, :, :]) + torch.tensor(1e-6, device="cuda", dtype=torch.float32)
+    d64 = (diff.double() ** 2).sum(-1).sqrt()
+    dpos = d64.gather(1, pos[:, None])
+    r64 = (d64 < dpos).sum(1)
+    d32 = d64.float()
+    dpos32 = d32.gather(1, pos[:, None])
+    r32 = ((d32 < dpos32) | ((d32 == dpos32) & (torch.arange(ng, device="cuda")[None, :] < pos[:, None]))).sum(1)
+    # real-number formula on fp64-cast inputs (the oracle's fp64 mode)
+    dr = ((Q.double()[:, None, :] - G.double()[None, :, :] + 1e-6) ** 2).sum(-1).sqrt()
+    rr = (dr < dr.gather(1, pos[:, None])).sum(1)
+    out = {"unc": int(unc.item()), "match_r64": (rank == r64).float().mean().item(), "match_r32canon": (rank == r32).float().mean().item(),
+           "match_oracle_fp64": (rank == rr).float().mean().item(), "r64_vs_oracle": (r64 == rr).float().mean().item(),
+           "maxdiff_r64": (rank - r64).abs().max().item()}
+    bad = (rank != r64).nonzero().flatten()[:5]
+    det = []
+    for i in bad.tolist():
+        gap = (d64[i] - dpos[i]).abs()
+        gap[pos[i]] = 1e9
+        near = torch.topk(gap, 4, largest=False).values.tolist()
+        det.append({"q": i, "ours": int(rank[i]), "r64": int(r64[i]), "nearest_gaps_in_d": near, "dpos": dpos[i].item()})
+    out["detail"] = det
+    return out
+
+
 CASES = ["rowops", "dump_small", "dump_shapes", "topk_small", "topk_mid", "triplet", "batch_hard", "host", "peaks", "time"]
 
 if __name__ == "__main__":
@@ -440,3 +475,4 @@ if __name__ == "__main__":
             log.write(msg)
             log.flush()
             print(msg)
+

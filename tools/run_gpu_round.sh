@@ -1,3 +1,3 @@
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 600 python tools/gpu_probe.py ab > gpurun_out/ab.log 2>&1
-timeout 300 python bench.py --steps 3 --no-cpu --no-e2e > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err
+timeout 300 python tools/gpu_probe.py time > gpurun_out/time.log 2>&1
+timeout 300 python tools/e2e_cfg5.py --gallery 20000 --queries 2000 > gpurun_out/cfg5_n1.json 2> gpurun_out/cfg5_n1.err
