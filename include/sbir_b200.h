@@ -94,7 +94,10 @@ int sbir_pairwise_distance_bwd(const float* x1, int64_t rows1, const float* x2, 
  * per-query selection, the K(+slack) survivors are re-scored with the exact
  * reference formula, and `out_uncertified[0]` counts queries whose selection could
  * not be proven exact (they are then recomputed by the brute-force exact kernel, so
- * results are exact either way; the counter is diagnostic).
+ * results are exact either way; the counter is diagnostic).  For fp32 inputs a
+ * device-gated second pass in 3xTF32 precision takes over when many queries cannot
+ * be certified; its operand copies are part of the workspace (3x the inputs, when
+ * that is below 12 GiB).
  * k <= 116; dim*sizeof(elem) must be a multiple of 16 bytes; pointers 16-byte aligned.
  * out_rank, pos_index, out_uncertified may be NULL. */
 size_t sbir_pairwise_topk_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int k,
