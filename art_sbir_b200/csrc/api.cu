@@ -428,6 +428,16 @@ int sbir_batch_hard_triplet_loss(const float* a, const float* p, const float* n,
                            static_cast<cudaStream_t>(stream));
 }
 
+int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms, int32_t* out) {
+  if (num_q <= 0 || num_g <= 0 || dim <= 0 || k <= 0 || k > kMaxK || !dtype_ok(dtype) || num_sms <= 0 || out == nullptr)
+    return SBIR_ERR_INVALID_ARG;
+  const K1Plan p = make_k1_plan(num_q, num_g, dim, k, dtype, num_sms);
+  const int32_t v[12] = {p.cap, p.lists_per_row, p.num_q_tiles, p.num_g_tiles, p.num_splits, p.tiles_per_split,
+                         p.num_chunks, p.tiles_per_chunk, p.num_units, p.part_fastest, p.pair, p.q_tile_stride};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  return SBIR_OK;
+}
+
 size_t sbir_debug_dist_matrix_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int dtype) {
   if (num_q <= 0 || num_g <= 0 || dim <= 0 || !dtype_ok(dtype)) return 0;
   const K1Plan plan = make_k1_plan(num_q, num_g, dim, 1, dtype, num_sms_cached());

@@ -191,6 +191,10 @@ int sbir_profile_collect(double* k1_ms_sum, int64_t* k1_launches, int64_t* kerne
  * Writes the raw epilogue matrix E[num_q, num_g] (euclidean: ||g||²-2qg, cosine:
  * -q·g/max(||g||,eps)) computed by the tcgen05 tiles; used by tests to validate the
  * tensor-core path in isolation.  out_e is fp32 [num_q, num_g]. */
+/* Host-only: the work decomposition K1 would use (no device access).  out[12] = {cap,
+ * lists_per_row, num_q_tiles, num_g_tiles, num_partitions, tiles_per_partition, num_chunks,
+ * tiles_per_chunk, num_units, part_fastest, pair, q_tile_stride}. */
+int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms, int32_t* out);
 size_t sbir_debug_dist_matrix_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int dtype);
 int sbir_debug_dist_matrix(const void* q, int64_t num_q, const void* g, int64_t num_g,
                            int64_t dim, int dtype, int metric, float* out_e, void* workspace,

@@ -80,3 +80,43 @@ def test_shard_bounds_partition_the_gallery():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _plan(lib, nq, ng, d, k, dtype, sms=148):
+    import ctypes
+    out = (ctypes.c_int32 * 12)()
+    assert lib.sbir_debug_plan(nq, ng, d, k, dtype, sms, out) == 0
+    keys = ("cap", "lists", "q_tiles", "g_tiles", "parts", "tiles_per_part", "chunks", "tiles_per_chunk", "units",
+            "part_fastest", "pair", "q_tile_stride")
+    return dict(zip(keys, list(out)))
+
+
+@pytest.mark.parametrize("nq,ng,d,k,dtype", [
+    (100_000, 10_000_000, 512, 10, 1), (12_500, 75_000, 2048, 100, 0), (12_500, 75_000, 2048, 10, 0),
+    (1_000, 10_000, 2048, 10, 0), (1, 513, 1024, 10, 0), (300, 9001, 512, 10, 1), (5, 7, 64, 3, 0),
+    (257, 3001, 512, 50, 1), (100_000, 1_250_000, 512, 10, 1)])
+def test_k1_plan_covers_every_tile_exactly_once(sbir_lib, nq, ng, d, k, dtype):
+    """The unit grid (query tile x partition x chunk) must tile the Q x G problem exactly: every
+    (query tile, gallery tile) pair belongs to one unit, chunks of a partition are contiguous and
+    ordered, capacities hold k plus slack, and the gallery chunk of a unit stays L2-sized."""
+    p = _plan(sbir_lib, nq, ng, d, k, dtype)
+    assert p["q_tiles"] == -(-nq // 128) and p["g_tiles"] == -(-ng // 256)
+    assert p["cap"] in (16, 32, 64, 128) and p["cap"] >= k + 6 and p["cap"] * p["lists"] * p["parts"] <= 4096
+    assert p["q_tile_stride"] >= p["q_tiles"] and p["q_tile_stride"] % 2 == 0
+    assert p["units"] == p["chunks"] * p["parts"] * p["q_tiles"]
+    covered = []
+    for part in range(p["parts"]):
+        b = part * p["tiles_per_part"]
+        e = min(b + p["tiles_per_part"], p["g_tiles"])
+        for c in range(p["chunks"]):
+            t0 = min(b + c * p["tiles_per_chunk"], e)
+            t1 = min(t0 + p["tiles_per_chunk"], e)
+            covered.extend(range(t0, t1))
+    assert covered == list(range(p["g_tiles"]))                       # each gallery tile once, in order
+    es = 2 if dtype == 1 else 4
+    assert p["tiles_per_chunk"] == 1 or p["tiles_per_chunk"] * 256 * d * es <= (13 << 20)   # ~12 MB chunks
+    # few query tiles -> partitions supply the parallelism; many -> a single partition
+    if p["q_tiles"] >= 2 * 148:
+        assert p["parts"] == 1
+    ws = sbir_lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, dtype, 0, 1)
+    assert ws > 0 and ws >= p["parts"] * p["q_tile_stride"] * p["lists"] * p["cap"] * 128 * 8
