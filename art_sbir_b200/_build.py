@@ -6,6 +6,7 @@ art_sbir_b200/lib/ (git-ignored, shipped to the GPU box by gpurun).
 from __future__ import annotations
 
 import concurrent.futures
+import fcntl
 import hashlib
 import os
 import shutil
@@ -48,8 +49,26 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     BUILD_DIR.mkdir(exist_ok=True)
     stamp = LIB_DIR / "build.sha256"
     digest = _digest()
-    if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text().strip() == digest:
+
+    def fresh() -> bool:
+        return LIB_PATH.exists() and stamp.exists() and stamp.read_text().strip() == digest
+
+    if not force and fresh():
         return LIB_PATH
+    # Several ranks of one torchrun job may get here at once: one builds, the others wait on the
+    # lock and then find the library fresh.  The .so is linked under a temporary name and renamed
+    # into place, so a reader never sees a half-written file.
+    with open(LIB_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return LIB_PATH
+            return _build_locked(digest, stamp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(digest: str, stamp: Path, verbose: bool) -> Path:
     nvcc = _nvcc()
 
     def compile_one(src: str) -> tuple[str, str]:
@@ -63,11 +82,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         results = list(ex.map(compile_one, SOURCES))
     (LIB_DIR / "ptxas.log").write_text("\n".join(log for _, log in results))
-    link = [nvcc, "-shared", "-o", str(LIB_PATH), *[o for o, _ in results],
+    tmp = LIB_DIR / f".libsbir_b200.{os.getpid()}.so"
+    link = [nvcc, "-shared", "-o", str(tmp), *[o for o, _ in results],
             "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     stamp.write_text(digest)
     if verbose:
         print(f"built {LIB_PATH}")
