@@ -66,6 +66,7 @@ struct TopkLayout {
   bool precise;        // fp32 inputs small enough for the 3xTF32 escalation workspace
   K1Plan plan3;        // plan of the escalation pass (dim' = 3·dim), same partitions / lists as `plan`
   size_t off_gate, off_q3, off_g3;  // off_sched: unit counter + chunk_done (zeroed together)
+  size_t off_mu, off_colpart;       // column mean of the gallery + its partial sums (centred escalation pass)
   size_t off_pos_dist, off_lo, off_hi, off_cnt, off_dropped, off_pool_count, off_pool_q, off_pool_idx;
   uint32_t pool_cap;
   size_t total;
@@ -105,6 +106,8 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
     L.off_gate = take(256);
     L.off_q3 = take((size_t)num_q * dim * 3 * sizeof(float));
     L.off_g3 = take((size_t)num_g * dim * 3 * sizeof(float));
+    L.off_mu = take((size_t)dim * sizeof(float));
+    L.off_colpart = take(col_mean_workspace_bytes(dim));
   }
   if (want_rank) {
     L.off_pos_dist = take(nq * sizeof(double));
@@ -247,9 +250,23 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
     int64_t max_bad = num_q / 50;
     if (max_bad < 4) max_bad = 4;
     SBIR_TRY(launch_escalate_decide(flags, want_rank ? ra.dropped : nullptr, num_q, max_bad, gate, uncert, st));
-    SBIR_TRY(launch_split_tf32(static_cast<const float*>(q), num_q, dim, 0, q3, gate, st));
-    SBIR_TRY(launch_split_tf32(static_cast<const float*>(g), num_g, dim, 1, g3, gate, st));
-    SBIR_TRY(run_pass(q3, g3, 3 * dim, L.plan3, k1_kappa_precise(dim), gate));
+    if (metric == SBIR_EUCLIDEAN && dim % 4 == 0) {
+      // Euclidean distances are translation-invariant: centre both operands on the gallery's column
+      // mean before the split, so the error band scales with the spread of the embeddings, not with
+      // their norms (collapsed / post-ReLU features).  ‖q−µ‖², ‖g−µ‖² and their maximum replace the
+      // raw norms for this pass (nothing after it reads them: the fallbacks are exact).
+      float* mu = reinterpret_cast<float*>(ws + L.off_mu);
+      float* colpart = reinterpret_cast<float*>(ws + L.off_colpart);
+      SBIR_TRY(launch_col_mean(static_cast<const float*>(g), num_g, dim, colpart, mu, gmax, gate, st));
+      SBIR_TRY(launch_center_split_tf32(static_cast<const float*>(q), num_q, num_q, dim, mu, 0, q3, qsq, 0.f, nullptr, gate, st));
+      SBIR_TRY(launch_center_split_tf32(static_cast<const float*>(g), num_g, padded, dim, mu, 1, g3, gvec, INFINITY, gmax, gate, st));
+      SBIR_TRY(launch_chunk_min(gvec, padded / 32, gmin, st));  // ungated: recomputes the same values when the pass is off
+      SBIR_TRY(run_pass(q3, g3, 3 * dim, L.plan3, k1_kappa_centred(dim), gate));
+    } else {
+      SBIR_TRY(launch_split_tf32(static_cast<const float*>(q), num_q, dim, 0, q3, gate, st));
+      SBIR_TRY(launch_split_tf32(static_cast<const float*>(g), num_g, dim, 1, g3, gate, st));
+      SBIR_TRY(run_pass(q3, g3, 3 * dim, L.plan3, k1_kappa_precise(dim), gate));
+    }
   }
   // Whatever is still unresolved is recomputed exactly by brute force.
   fa.gate = nullptr;

@@ -46,7 +46,7 @@ __device__ __forceinline__ double e_margin(int metric, float qsq, float gsq_max,
   if (metric == SBIR_EUCLIDEAN) {
     const double s = (double)qsq + (double)gsq_max;
     // tensor-core rounding of 2·q·g  +  the reference's +1e-6 per component  +  fp32 epilogue rounding
-    return (double)kappa * s + 4e-6 * sqrt((double)dim * s) + 4e-7 * s + 1e-30;
+    return (double)kappa * s + 4e-6 * sqrt((double)dim * s) + 1e-12 * (double)dim + 4e-7 * s + 1e-30;
   }
   const double nq = sqrt((double)qsq);
   return (double)kappa * nq + 1e-6 * nq + 1e-30;
@@ -438,6 +438,90 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
+// ---- mean-centred 3xTF32 operands (euclidean escalation pass) ----
+// Distances are translation-invariant, tensor-core rounding is not: its error scales with
+// ‖q‖·‖g‖, so embeddings that share a large common component (post-ReLU features, collapsed or
+// untrained encoders) lose the small differences that decide the ranking.  The escalation pass
+// therefore subtracts the gallery's column mean µ from both operands before the hi/lo split:
+// ‖q−g‖ = ‖(q−µ)−(g−µ)‖ exactly, fl32(x−µ) carries 2^-24 relative rounding per element, and
+// the error band then scales with the SPREAD of the embeddings instead of their norms.
+constexpr int kColBlocks = 592;  // 4 per SM: partial column sums [kColBlocks][dim]
+
+__global__ void __launch_bounds__(256) col_partial_kernel(const float* __restrict__ x, long long rows, int dim,
+                                                          float* __restrict__ partial, const int32_t* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  const int v4 = dim / 4;
+  for (int c = threadIdx.x; c < v4; c += 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * dim) + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * dim)[c] = acc;
+  }
+}
+
+// µ[c] = Σ_b partial[b][c] / rows (fixed order: deterministic); also clears the running maximum
+// the centred gallery pass accumulates into.
+__global__ void __launch_bounds__(256) col_mean_kernel(const float* __restrict__ partial, int num_blocks, long long rows,
+                                                       int dim, float* __restrict__ mu, float* __restrict__ max_reset,
+                                                       const int32_t* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c == 0 && max_reset != nullptr) *max_reset = 0.f;
+  if (c >= dim) return;
+  double acc = 0.0;
+  for (int b = 0; b < num_blocks; ++b) acc += (double)partial[(size_t)b * dim + c];
+  mu[c] = (float)(acc / (double)rows);
+}
+
+// x [rows, dim] fp32 -> out [rows, 3*dim]: c = fl32(x − µ) split like split_tf32_kernel; also
+// vec[r] = ‖c_r‖² (what K1's epilogue and the certificate use as ‖q‖² / ‖g‖² in this pass),
+// vec[rows..rows_padded) = pad_value, *max_out = max ‖c_r‖².  One warp per row.
+__global__ void __launch_bounds__(256) center_split_tf32_kernel(const float* __restrict__ x, long long rows,
+                                                                long long rows_padded, int dim,
+                                                                const float* __restrict__ mu, int gallery_layout,
+                                                                float* __restrict__ out, float* __restrict__ vec,
+                                                                float pad_value, float* __restrict__ max_out,
+                                                                const int32_t* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int v4 = dim / 4;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  float local_max = 0.f;
+  for (long long r = warp0; r < rows_padded; r += nwarps) {
+    if (r >= rows) {
+      if (lane == 0) vec[r] = pad_value;
+      continue;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + r * dim);
+    float4* o = reinterpret_cast<float4*>(out + r * 3LL * dim);
+    double acc = 0.0;
+    for (int i = lane; i < v4; i += 32) {
+      const float4 v = __ldg(xr + i);
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + i);
+      const float c[4] = {__fsub_rn(v.x, m.x), __fsub_rn(v.y, m.y), __fsub_rn(v.z, m.z), __fsub_rn(v.w, m.w)};
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = __uint_as_float(__float_as_uint(c[e]) & 0xFFFFE000u);
+        l[e] = c[e] - h[e];
+        acc += (double)c[e] * (double)c[e];
+      }
+      const float4 h4 = make_float4(h[0], h[1], h[2], h[3]), l4 = make_float4(l[0], l[1], l[2], l[3]);
+      o[i] = h4;
+      o[v4 + i] = gallery_layout ? l4 : h4;
+      o[2 * v4 + i] = gallery_layout ? h4 : l4;
+    }
+    const float sq = (float)warp_sum(acc);
+    local_max = fmaxf(local_max, sq);
+    if (lane == 0) vec[r] = sq;
+  }
+  if (max_out != nullptr && lane == 0 && local_max > 0.f)
+    atomicMax(reinterpret_cast<int*>(max_out), __float_as_int(local_max));
+}
+
 __global__ void fill_i32_kernel(int32_t* out, long long n, int32_t value) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = value;
@@ -636,6 +720,32 @@ int launch_split_tf32(const float* x, int64_t rows, int64_t dim, int gallery_lay
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
   split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, (long long)rows, (int)dim, gallery_layout, out, gate);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+size_t col_mean_workspace_bytes(int64_t dim) { return (size_t)kColBlocks * (size_t)dim * sizeof(float); }
+
+int launch_col_mean(const float* x, int64_t rows, int64_t dim, float* partial, float* mu, float* max_reset,
+                    const int32_t* gate, cudaStream_t st) {
+  if (rows <= 0) return SBIR_OK;
+  const int blocks = (int)(rows < kColBlocks ? rows : kColBlocks);
+  col_partial_kernel<<<blocks, 256, 0, st>>>(x, (long long)rows, (int)dim, partial, gate);
+  SBIR_CHECK_LAUNCH();
+  col_mean_kernel<<<(unsigned)((dim + 255) / 256), 256, 0, st>>>(partial, blocks, (long long)rows, (int)dim, mu,
+                                                                max_reset, gate);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_center_split_tf32(const float* x, int64_t rows, int64_t rows_padded, int64_t dim, const float* mu,
+                             int gallery_layout, float* out, float* vec, float pad_value, float* max_out,
+                             const int32_t* gate, cudaStream_t st) {
+  if (rows_padded <= 0) return SBIR_OK;
+  long long blocks = (rows_padded + 7) / 8;
+  if (blocks > 148LL * 8 * 16) blocks = 148LL * 8 * 16;
+  center_split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, (long long)rows, (long long)rows_padded, (int)dim, mu,
+                                                             gallery_layout, out, vec, pad_value, max_out, gate);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }

@@ -142,6 +142,15 @@ int launch_escalate_decide(const int32_t* flags, const int32_t* dropped, int64_t
 // hi = x with the 13 low mantissa bits cleared (what kind::tf32 reads), lo = x - hi (exact).
 int launch_split_tf32(const float* x, int64_t rows, int64_t dim, int gallery_layout, float* out,
                       const int32_t* gate, cudaStream_t st);
+// Mean-centred variant for the euclidean escalation pass: µ = column mean of the gallery
+// (launch_col_mean; `partial` holds col_mean_workspace_bytes(dim)), then c = fl32(x − µ) is split
+// as above and vec[r] = ‖c_r‖² (padded rows: pad_value; *max_out = max, cleared by launch_col_mean).
+size_t col_mean_workspace_bytes(int64_t dim);
+int launch_col_mean(const float* x, int64_t rows, int64_t dim, float* partial, float* mu, float* max_reset,
+                    const int32_t* gate, cudaStream_t st);
+int launch_center_split_tf32(const float* x, int64_t rows, int64_t rows_padded, int64_t dim, const float* mu,
+                             int gallery_layout, float* out, float* vec, float pad_value, float* max_out,
+                             const int32_t* gate, cudaStream_t st);
 int launch_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
                              int dtype, int metric, const int64_t* pos_index, double* out,
                              cudaStream_t st);
@@ -173,5 +182,7 @@ inline float k1_kappa(int dtype, int64_t dim) {
   return dtype == 0 /*F32→tf32*/ ? 1.0f / 512.0f * 1.01f + k1_accum_kappa(dim, 4) : k1_accum_kappa(dim, 2);
 }
 inline float k1_kappa_precise(int64_t dim) { return k1_accum_kappa(3 * dim, 4) + 1.0f / 1048576.0f; }
+// ... plus the rounding of the centring itself, fl32(x − µ): 2^-24 per element of either operand
+inline float k1_kappa_centred(int64_t dim) { return k1_kappa_precise(dim) + 1.0f / 2097152.0f; }
 
 }  // namespace sbir

@@ -224,6 +224,33 @@ def test_cancellation_heavy_fp32_escalates_to_3xtf32(ops):
         assert int(unc.item()) <= nq // 50 + 4                   # the escalated pass certified (almost) everything
 
 
+def test_collapsed_embeddings_use_the_centred_pass(ops):
+    """Embeddings that share a large common component and differ only slightly (an untrained encoder,
+    BASELINE cfg5; post-ReLU features): TF32 — and even 3xTF32 on the raw operands — cannot tell the
+    rows apart, so the escalation pass centres both operands on the gallery mean (distances are
+    translation-invariant).  Results must be exact and (almost) every query certified."""
+    nq, ng, d = 200, 8000, 256
+    Q0, G0, pos = O.synthetic_embeddings(nq, ng, d, seed=9, beta=0.12)
+    base = 3.0 * torch.rand(1, d, generator=torch.Generator().manual_seed(1))
+    Q, G = (base + 0.02 * Q0).contiguous(), (base + 0.02 * G0).contiguous()
+    vals, idx, rank, unc = ops.pairwise_topk(Q.cuda(), G.cuda(), 10, "euclidean", pos_index=pos.cuda(), return_uncertified=True)
+    # ground truth = the reference formula element by element in fp32, long sum in fp64
+    rows = []
+    for a in range(0, nq, 25):
+        diff = (Q[a:a + 25, None, :] - G[None, :, :]) + torch.tensor(1e-6)
+        rows.append((diff.double() ** 2).sum(-1).sqrt().float())
+    dd = torch.cat(rows)
+    dp = dd.gather(1, pos[:, None])
+    ref_r = ((dd < dp) | ((dd == dp) & (torch.arange(ng)[None, :] < pos[:, None]))).sum(1)
+    ref_v, ref_i = torch.topk(dd, 10, dim=1, largest=False)
+    assert torch.allclose(vals.cpu(), ref_v, rtol=DIST_RTOL, atol=1e-7)
+    idx_c = idx.cpu()
+    for i, j in (idx_c != ref_i).nonzero().tolist():      # swaps only between fp32-level ties
+        assert abs(dd[i, idx_c[i, j]].item() - ref_v[i, j].item()) <= TIE_RTOL * abs(ref_v[i, j].item())
+    assert torch.equal(rank.cpu(), ref_r)
+    assert int(unc.item()) <= nq // 50 + 4
+
+
 def test_fp64_gallery_like_csv_features(ops):
     """F8: CSV-loaded galleries are float64 in the reference; ranks must still agree."""
     from art_sbir_b200 import inference as inf

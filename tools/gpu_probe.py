@@ -454,6 +454,55 @@ def case_escal_debug():
     return out
 
 
+def case_centred():
+    """Collapsed / non-centred fp32 embeddings (a large common component, small differences — what an
+    untrained encoder or post-ReLU features give): exactness and time of the centred escalation pass."""
+    import torch
+    from art_sbir_b200 import ops
+    out = []
+    for (nq, ng, d, scale, structured) in ((2000, 25000, 1024, 0.02, True), (2000, 25000, 1024, 0.02, False),
+                                           (12500, 75000, 2048, 0.05, True), (12500, 75000, 2048, 0.05, False)):
+        q, g, pos = _clustered(nq, ng, d, torch.float32)
+        if not structured:
+            pos = torch.randint(0, ng, (nq,), device="cuda")
+        base = 3.0 * torch.rand(1, d, device="cuda")
+        q = (base + scale * q).contiguous()
+        g = (base + scale * g).contiguous()
+        for metric in ("euclidean", "cosine"):
+            res = ops.pairwise_topk(q, g, 10, metric, pos_index=pos, return_uncertified=True)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            ops.pairwise_topk(q, g, 10, metric, pos_index=pos)
+            ev[1].record()
+            ops.pairwise_topk(q, g, 10, metric, pos_index=pos)
+            ev[2].record()
+            torch.cuda.synchronize()
+            row = {"shape": [nq, ng, d, scale, structured, metric], "ms": min(ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])),
+                   "uncertified": int(res[-1].item())}
+            if nq * ng <= 60_000_000:   # exact check on device (fp32 elementwise, fp64 sum), chunked over queries
+                bad_r = bad_i = 0
+                for a in range(0, nq, 20):
+                    qq = q[a:a + 20]
+                    if metric == "euclidean":
+                        diff = (qq[:, None, :] - g[None, :, :]) + torch.tensor(1e-6, device="cuda")
+                        dd = (diff.double() ** 2).sum(-1).sqrt().float()
+                    else:
+                        qn = qq / qq.norm(dim=1, keepdim=True).clamp_min(1e-8)
+                        gn = g / g.norm(dim=1, keepdim=True).clamp_min(1e-8)
+                        dd = (1.0 - (qn[:, None, :] * gn[None, :, :]).double().sum(-1)).float()
+                    pp = pos[a:a + 20]
+                    dp = dd.gather(1, pp[:, None])
+                    r = ((dd < dp) | ((dd == dp) & (torch.arange(ng, device="cuda")[None, :] < pp[:, None]))).sum(1)
+                    bad_r += int((r != res[2][a:a + 20]).sum())
+                    ti = torch.topk(dd, 10, dim=1, largest=False).indices
+                    bad_i += int((ti.sort(1).values != res[1][a:a + 20].sort(1).values).any(1).sum())
+                row["rank_mismatch"] = bad_r
+                row["topk_set_mismatch"] = bad_i
+            out.append(row)
+    return out
+
+
 CASES = ["rowops", "dump_small", "dump_shapes", "topk_small", "topk_mid", "triplet", "batch_hard", "host", "peaks", "time"]
 
 if __name__ == "__main__":
