@@ -80,7 +80,7 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   const size_t nq = (size_t)(num_q > 0 ? num_q : 1);
   L.off_gvec = take((size_t)L.plan.num_g_tiles * kTileG * sizeof(float));
   L.off_gmax = take(sizeof(float));
-  L.off_gmin = take((size_t)L.plan.num_g_tiles * (kTileG / 32) * sizeof(float));
+  L.off_gmin = take((size_t)L.plan.num_g_tiles * (kTileG / 8) * sizeof(float));
   L.off_qsq = take(nq * sizeof(float));
   const size_t cand = (size_t)L.plan.num_splits * L.plan.q_tile_stride * L.plan.lists_per_row * L.plan.cap * kTileQ;
   L.off_cand_val = take(cand * sizeof(float));
@@ -169,7 +169,7 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
                            metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""), gvec, gmax, st));
   SBIR_TRY(launch_row_norm(q, num_q, num_q, dim, dtype, 0, 0.f, qsq, nullptr, st));
   float* gmin = reinterpret_cast<float*>(ws + L.off_gmin);
-  SBIR_TRY(launch_chunk_min(gvec, padded / 32, gmin, st));
+  SBIR_TRY(launch_chunk_min(gvec, padded / 8, gmin, st));
 
   RankArgs ra{};
   if (want_rank) {
@@ -260,7 +260,7 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
       SBIR_TRY(launch_col_mean(static_cast<const float*>(g), num_g, dim, colpart, mu, gmax, gate, st));
       SBIR_TRY(launch_center_split_tf32(static_cast<const float*>(q), num_q, num_q, dim, mu, 0, q3, qsq, 0.f, nullptr, gate, st));
       SBIR_TRY(launch_center_split_tf32(static_cast<const float*>(g), num_g, padded, dim, mu, 1, g3, gvec, INFINITY, gmax, gate, st));
-      SBIR_TRY(launch_chunk_min(gvec, padded / 32, gmin, st));  // ungated: recomputes the same values when the pass is off
+      SBIR_TRY(launch_chunk_min(gvec, padded / 8, gmin, st));  // ungated: recomputes the same values when the pass is off
       SBIR_TRY(run_pass(q3, g3, 3 * dim, L.plan3, k1_kappa_centred(dim), gate));
     } else {
       SBIR_TRY(launch_split_tf32(static_cast<const float*>(q), num_q, dim, 0, q3, gate, st));

@@ -122,7 +122,7 @@ struct K1Config {
 
 struct K1Params {
   const float* gvec;
-  const float* gmin;   // per 32 gallery rows: min of gvec (euclidean) / min of gvec = -1/min-norm (cosine)
+  const float* gmin;   // per 8 gallery rows: min of gvec (‖g‖² | −1/max(‖g‖,eps)), NaN padding ignored
   int num_q, num_g;
   int num_q_tiles, num_g_tiles, num_k_blocks;
   int num_row_tiles;   // query tiles (kPair = 1) or query-tile pairs (kPair = 2): rows of the unit grid
@@ -452,164 +452,169 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
+          const int gcol0 = t * kTileG + col_begin + c * 32;  // gallery row of column 0 of this chunk
           if constexpr (kSelect) {
             // Cheap conservative screen before any per-element work: every e of this chunk is
             // >= bound (rounding is monotone, so this holds for the computed values too);
-            // when no row of the warp can beat its threshold the chunk costs 31 FMNMX + 1 FFMA.
-            const float smax = reduce32<true>([&](int j) { return __uint_as_float(r[j]); });
-            const float gmin = __ldg(prm.gmin + ((size_t)t * kTileG + col_begin) / 32 + c);
-            const float bound = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, smax, gmin) : fminf(0.f, __fmul_rn(smax, gmin));
-            const float lim0 = kRank ? fmaxf(thr, hi) : thr;
-            if (!(prm.flags & 16) && !__any_sync(kFullMask, bound < lim0)) continue;
-          }
-          float e[32];
-          const float4* gv4 = reinterpret_cast<const float4*>(gv + c * 32);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 g4 = __ldg(gv4 + j4);
-            const float gj[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float s = __uint_as_float(r[j4 * 4 + u]);
-              e[j4 * 4 + u] = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, s, gj[u]) : __fmul_rn(s, gj[u]);
+            // when no row of the warp can beat its threshold the chunk costs ~20 FMNMX + 1 FFMA.
+            {
+              const float smax = reduce32<true>([&](int j) { return __uint_as_float(r[j]); });
+              const float4 gm4 = __ldg(reinterpret_cast<const float4*>(prm.gmin + (size_t)gcol0 / 8));
+              const float gmin = fminf(fmin3(gm4.x, gm4.y, gm4.z), gm4.w);
+              const float bound = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, smax, gmin) : fminf(0.f, __fmul_rn(smax, gmin));
+              const float lim0 = kRank ? fmaxf(thr, hi) : thr;
+              if (!(prm.flags & 16) && !__any_sync(kFullMask, bound < lim0)) continue;
             }
-          }
-          const int gcol0 = t * kTileG + col_begin + c * 32;  // gallery row of e[0]
-
-          if constexpr (kMode == kModeDump) {
-            if (q_valid) {
+            float e[32];
+            const float4* gv4 = reinterpret_cast<const float4*>(gv + c * 32);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (gcol0 + j < prm.num_g) prm.dump[(size_t)q * prm.num_g + gcol0 + j] = e[j];
-            }
-          } else if constexpr (kMode == kModeHard) {
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 g4 = __ldg(gv4 + j4);
+              const float gj[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int gj = gcol0 + j;
-              if (gj < prm.num_g) {
-                const bool is_pos = (prm.row_label == nullptr) ? (gj == q) : (prm.col_label[gj] == my_label);
-                if (is_pos) {
-                  if (e[j] > hp) { hp = e[j]; hpi = gj; }
-                } else {
-                  if (e[j] < hn) { hn = e[j]; hni = gj; }
-                }
+              for (int u = 0; u < 4; ++u) {
+                const float s = __uint_as_float(r[j4 * 4 + u]);
+                e[j4 * 4 + u] = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, s, gj[u]) : __fmul_rn(s, gj[u]);
               }
             }
-          } else {
-            const float m = reduce32<false>([&](int j) { return e[j]; });
+            // exact minima per sub-chunk of 8 columns (FMNMX3: 4 instructions each) and of the chunk
+            float mg[4];
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8)
+              mg[g8] = fminf(fmin3(fmin3(e[8 * g8], e[8 * g8 + 1], e[8 * g8 + 2]), fmin3(e[8 * g8 + 3], e[8 * g8 + 4], e[8 * g8 + 5]), e[8 * g8 + 6]),
+                             e[8 * g8 + 7]);
+            const float m = fminf(fmin3(mg[0], mg[1], mg[2]), mg[3]);
             // rank: rows closer than the band (e < lo <= hi <= lim) are counted inside the gated
             // path below — a chunk whose minimum is not below lim has none of them
             const float lim = kRank ? fmaxf(thr, hi) : thr;
-            if (__any_sync(kFullMask, m < lim)) {
-              // One candidate of this row: maybe enters the list, maybe sits in the rank band.
-              auto consume = [&](float ej, int gidx_e) {
-                if (ej < thr) {
-                  lv[maxpos * kTileQ + row] = ej;
-                  li[maxpos * kTileQ + row] = gidx_e;
-                  float mx = -INFINITY;
-                  int mp = 0;
-                  if constexpr (Cfg::kTwoLevel) {
-                    // lists of 64/128 keep a maximum per group of 8: refresh the touched group,
-                    // pick the group holding the overall maximum, locate it inside that group
-                    // (24-32 shared loads instead of kCap)
-                    const int g = maxpos >> 3;
-                    float gm = -INFINITY;
-                    int gp = 0;
+            if (!__any_sync(kFullMask, m < lim)) continue;
+            // One candidate of this row: maybe enters the list, maybe sits in the rank band.
+            auto consume = [&](float ej, int gidx_e) {
+              if (ej < thr) {
+                lv[maxpos * kTileQ + row] = ej;
+                li[maxpos * kTileQ + row] = gidx_e;
+                float mx = -INFINITY;
+                int mp = 0;
+                if constexpr (Cfg::kTwoLevel) {
+                  // lists of 64/128 keep a maximum per group of 8: refresh the touched group,
+                  // pick the group holding the overall maximum, locate it inside that group
+                  // (24-32 shared loads instead of kCap).  Maxima come from FMNMX3 trees and the
+                  // positions from independent equality tests, so no step is a long
+                  // compare-and-select chain (one epilogue warp per scheduler: latency is exposed).
+                  const int g = maxpos >> 3;
+                  float w[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                      const float v = lv[(g * 8 + u) * kTileQ + row];
-                      if (v > gm) { gm = v; gp = g * 8 + u; }
-                    }
-                    lg[g * kTileQ + row] = gm;
-                    int bg = 0;
+                  for (int u = 0; u < 8; ++u) w[u] = lv[(g * 8 + u) * kTileQ + row];
+                  const float gm = fmaxf(fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), w[6]), w[7]);
+                  lg[g * kTileQ + row] = gm;
+                  constexpr int kGroups = kCap / 8;
+                  float gmx[kGroups];
 #pragma unroll
-                    for (int u = 0; u < kCap / 8; ++u) {
-                      const float v = lg[u * kTileQ + row];
-                      if (v > mx) { mx = v; bg = u; }
-                    }
-                    if (bg == g) {
-                      mp = gp;
-                    } else {
-                      float bm = -INFINITY;
+                  for (int u = 0; u < kGroups; ++u) gmx[u] = lg[u * kTileQ + row];
+                  float t8[kGroups / 2];
 #pragma unroll
-                      for (int u = 0; u < 8; ++u) {
-                        const float v = lv[(bg * 8 + u) * kTileQ + row];
-                        if (v > bm) { bm = v; mp = bg * 8 + u; }
-                      }
-                    }
-                  } else {
+                  for (int u = 0; u < kGroups / 2; ++u) t8[u] = fmaxf(gmx[2 * u], gmx[2 * u + 1]);
+                  if constexpr (kGroups == 16)
+                    mx = fmax3(fmax3(t8[0], t8[1], t8[2]), fmax3(t8[3], t8[4], t8[5]), fmaxf(t8[6], t8[7]));
+                  else
+                    mx = fmaxf(fmax3(t8[0], t8[1], t8[2]), t8[3]);
+                  int bg = 0;
+#pragma unroll
+                  for (int u = 1; u < kGroups; ++u) bg = (gmx[u] == mx) ? u : bg;
+                  if (bg != g) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) w[u] = lv[(bg * 8 + u) * kTileQ + row];
+                  }
+                  mp = bg * 8;
+#pragma unroll
+                  for (int u = 1; u < 8; ++u) mp = (w[u] == mx) ? bg * 8 + u : mp;
+                } else {
 #pragma unroll 8
-                    for (int p = 0; p < kCap; ++p) {
-                      const float v = lv[p * kTileQ + row];
-                      if (v > mx) { mx = v; mp = p; }
-                    }
-                  }
-                  own_max = mx;
-                  thr = fminf(thr, mx);
-                  maxpos = mp;
-                }
-                if constexpr (kRank) {
-                  if (ej >= lo && ej < hi) {
-                    // approximate comparison against d_pos is not trustworthy: queue the
-                    // pair for exact evaluation (finalize.cu: rank_resolve_kernel)
-                    const uint32_t slot = atomicAdd(prm.pool_count, 1u);
-                    if (slot < prm.pool_cap) {
-                      prm.pool_q[slot] = q;
-                      prm.pool_idx[slot] = gidx_e;
-                    } else {
-                      atomicAdd(prm.dropped + q, 1);
-                    }
+                  for (int p = 0; p < kCap; ++p) {
+                    const float v = lv[p * kTileQ + row];
+                    if (v > mx) { mx = v; mp = p; }
                   }
                 }
-              };
-              // Each lane queues its own hits of this chunk (up to 4, in registers) so that the
-              // lanes' insertions run side by side instead of one gallery column at a time.
-              float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
-              int c0 = 0, c1 = 0, c2 = 0, c3 = 0, nh = 0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if constexpr (kRank) cnt += (e[j] < lo) ? 1 : 0;
-                if (e[j] < lim) {
-                  h3 = h2; c3 = c2;
-                  h2 = h1; c2 = c1;
-                  h1 = h0; c1 = c0;
-                  h0 = e[j]; c0 = j;
-                  ++nh;
+                own_max = mx;
+                thr = fminf(thr, mx);
+                maxpos = mp;
+              }
+              if constexpr (kRank) {
+                if (ej >= lo && ej < hi) {
+                  // approximate comparison against d_pos is not trustworthy: queue the
+                  // pair for exact evaluation (finalize.cu: rank_resolve_kernel)
+                  const uint32_t slot = atomicAdd(prm.pool_count, 1u);
+                  if (slot < prm.pool_cap) {
+                    prm.pool_q[slot] = q;
+                    prm.pool_idx[slot] = gidx_e;
+                  } else {
+                    atomicAdd(prm.dropped + q, 1);
+                  }
                 }
               }
-              const int maxh = __reduce_max_sync(kFullMask, nh);
-              if (maxh <= 4) {
-                if (nh > 0) consume(h0, gcol0 + c0);
-                __syncwarp();
-                if (maxh > 1) {
-                  if (nh > 1) consume(h1, gcol0 + c1);
-                  __syncwarp();
-                }
-                if (maxh > 2) {
-                  if (nh > 2) consume(h2, gcol0 + c2);
-                  __syncwarp();
-                }
-                if (maxh > 3) {
-                  if (nh > 3) consume(h3, gcol0 + c3);
-                  __syncwarp();
-                }
-              } else {
-                // Dense chunk (list warm-up): walk the hit columns of the whole warp.  Column j is
-                // re-read for every row (warp-uniform TMEM address) and e recomputed with the
-                // identical instruction, so it is bit-equal to e[j].
-                uint32_t mask = 0;
+            };
+            // Hit mask of this row, built only for the sub-chunks of 8 columns in which some row of
+            // the warp has a hit (once the lists have warmed up: a few lanes, one hit each).
+            uint32_t mask = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mask |= (e[j] < lim ? 1u : 0u) << j;
-                uint32_t pending = __reduce_or_sync(kFullMask, mask);
-                while (pending) {
-                  const int j = __ffs(pending) - 1;
-                  pending &= pending - 1;
-                  const float s = __uint_as_float(tmem_ld_32x32b_x1(taddr + j));
-                  tmem_ld_wait();
-                  const float gj = __ldg(gv + c * 32 + j);
-                  const float ej = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, s, gj) : __fmul_rn(s, gj);
-                  consume(ej, gcol0 + j);
-                  __syncwarp();
+            for (int g8 = 0; g8 < 4; ++g8) {
+              if (!__any_sync(kFullMask, mg[g8] < lim)) continue;
+#pragma unroll
+              for (int j = 8 * g8; j < 8 * g8 + 8; ++j) {
+                if constexpr (kRank) cnt += (e[j] < lo) ? 1 : 0;
+                mask |= (e[j] < lim ? 1u : 0u) << j;
+              }
+            }
+            // Every lane drains ITS OWN hits, one per round, all lanes side by side: the number of
+            // rounds is the largest hit count of any row, not the number of columns that have a hit
+            // somewhere (list warm-up: 2-5x fewer rounds).  The value of the lane's next hit column
+            // is picked out of the registers with a 5-level select tree.
+            while (__any_sync(kFullMask, mask != 0)) {
+              if (mask != 0) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                float s16[16], s8[8], s4[4];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) s16[u] = (j & 1) ? e[2 * u + 1] : e[2 * u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s8[u] = (j & 2) ? s16[2 * u + 1] : s16[2 * u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s4[u] = (j & 4) ? s8[2 * u + 1] : s8[2 * u];
+                const float s2a = (j & 8) ? s4[1] : s4[0], s2b = (j & 8) ? s4[3] : s4[2];
+                consume((j & 16) ? s2b : s2a, gcol0 + j);
+              }
+              __syncwarp();
+            }
+          } else {
+            float e[32];
+            const float4* gv4 = reinterpret_cast<const float4*>(gv + c * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 g4 = __ldg(gv4 + j4);
+              const float gj[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float s = __uint_as_float(r[j4 * 4 + u]);
+                e[j4 * 4 + u] = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, s, gj[u]) : __fmul_rn(s, gj[u]);
+              }
+            }
+            if constexpr (kMode == kModeDump) {
+              if (q_valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (gcol0 + j < prm.num_g) prm.dump[(size_t)q * prm.num_g + gcol0 + j] = e[j];
+              }
+            } else if constexpr (kMode == kModeHard) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int gj = gcol0 + j;
+                if (gj < prm.num_g) {
+                  const bool is_pos = (prm.row_label == nullptr) ? (gj == q) : (prm.col_label[gj] == my_label);
+                  if (is_pos) {
+                    if (e[j] > hp) { hp = e[j]; hpi = gj; }
+                  } else {
+                    if (e[j] < hn) { hn = e[j]; hni = gj; }
+                  }
                 }
               }
             }
@@ -818,7 +823,12 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   // Chunks: ~12 MB of gallery rows per (partition, chunk) so that the rows every CTA of a chunk
   // step streams stay in L2 together with the live query tiles.
   const int64_t tile_bytes = (int64_t)kTileG * dim * (int64_t)es;
-  int64_t tpc = (12LL << 20) / (tile_bytes > 0 ? tile_bytes : 1);
+  int64_t chunk_mb = 12;
+  if (const char* e = std::getenv("SBIR_K1_CHUNK_MB")) {  // experiments only
+    const int v = std::atoi(e);
+    if (v > 0) chunk_mb = v;
+  }
+  int64_t tpc = (chunk_mb << 20) / (tile_bytes > 0 ? tile_bytes : 1);
   if (tpc < 1) tpc = 1;
   if (tpc > p.tiles_per_split) tpc = p.tiles_per_split;
   p.num_chunks = (int)((p.tiles_per_split + tpc - 1) / tpc);

@@ -348,11 +348,105 @@ __global__ void __launch_bounds__(kRankWarps * 32) positive_distance_kernel(
 }
 
 // ------------------------------------------------------------------ K4 merge ----
-// Rank-by-counting merge of `num_lists` ascending lists of length k per query: element x
-// of list l lands at position Σ_l' #{y ∈ l' : y ranks before x}; positions < k are written.
-// One warp per query; fully parallel and deterministic (ties by index).
+// k best of `num_lists` ascending lists of length k per query; order = (distance, index), padding
+// entries (index < 0, +inf) last.  Deterministic.
+//
+// Bandwidth form (the one that runs): a block takes `qb` consecutive queries; for every list
+// their entries are ONE contiguous run of qb·k values in the gathered [list][query][k] buffer,
+// read with coalesced loads into shared memory.  The lists are then merged pairwise in
+// ⌈log2 num_lists⌉ rounds; in a round one thread produces one output element by a merge-path
+// binary search (≤ log2 k steps), so the work per query is ~num_lists·k·log2 k instead of the
+// num_lists²·k·log2 k of rank-by-counting.  The merged rows leave as one contiguous run.
+// HBM traffic = the algorithmic num_lists·Q·k·12 bytes in + Q·k·12 out, once.
+constexpr int kMergeThreads = 128;
+// (da, ia) precedes (db, ib).  Padding entries carry +inf, so the distance alone decides unless
+// the two are equal (then valid-before-padding, smaller index first).
+__device__ __forceinline__ bool merge_before(float da, float db, const long long* pia, const long long* pib) {
+  if (da != db) return da < db;
+  const long long ia = *pia, ib = *pib;
+  return ia >= 0 && (ib < 0 || ia < ib);
+}
+// x / d for block-local counters (x < 2^16, d <= a few thousand): exact via one float multiply.
+__device__ __forceinline__ int small_div(int x, float inv_d) { return __float2int_rz(((float)x + 0.5f) * inv_d); }
+
+__global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(
+    const float* __restrict__ dist, const long long* __restrict__ index, int num_lists, int num_q,
+    int k, int qb, float* __restrict__ out_dist, long long* __restrict__ out_index) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  const int half_lists = (num_lists + 1) / 2;
+  // ping [qb][num_lists][k], pong [qb][half_lists][k]; indices first (8-byte aligned), then distances
+  long long* i_ping = reinterpret_cast<long long*>(merge_smem);
+  long long* i_pong = i_ping + (size_t)qb * num_lists * k;
+  float* d_ping = reinterpret_cast<float*>(i_pong + (size_t)qb * half_lists * k);
+  float* d_pong = d_ping + (size_t)qb * num_lists * k;
+  const int q0 = blockIdx.x * qb;
+  const int nq = min(qb, num_q - q0);
+  const int run = nq * k;  // contiguous entries per list for this block
+  const float inv_k = 1.0f / (float)k;
+  for (int x = threadIdx.x; x < run; x += kMergeThreads) {
+    const int qi = small_div(x, inv_k), i = x - qi * k;
+    const int dst = qi * num_lists * k + i;
+    const size_t src = (size_t)q0 * k + x;
+#pragma unroll 4
+    for (int l = 0; l < num_lists; ++l) {
+      d_ping[dst + l * k] = __ldg(dist + (size_t)l * num_q * k + src);
+      i_ping[dst + l * k] = __ldg(index + (size_t)l * num_q * k + src);
+    }
+  }
+  __syncthreads();
+  const float* sd = d_ping;
+  const long long* si = i_ping;
+  float* td = d_pong;
+  long long* ti = i_pong;
+  int n = num_lists, s_stride = num_lists, t_stride = half_lists;
+  while (n > 1) {
+    const int pairs = n >> 1, n_next = (n + 1) >> 1;
+    const int per_q = n_next * k;
+    const int outs = nq * per_q;
+    const float inv_per_q = 1.0f / (float)per_q;
+    for (int x = threadIdx.x; x < outs; x += kMergeThreads) {
+      const int qi = small_div(x, inv_per_q), r = x - qi * per_q;
+      const int pr = small_div(r, inv_k), o = r - pr * k;
+      const int dst = (qi * t_stride + pr) * k + o;
+      if (pr >= pairs) {  // odd list out: carried to the next round unchanged
+        td[dst] = sd[(qi * s_stride + n - 1) * k + o];
+        ti[dst] = si[(qi * s_stride + n - 1) * k + o];
+        continue;
+      }
+      const int a = (qi * s_stride + 2 * pr) * k, b = a + k;
+      int lo = 0, hi = o;  // number of A elements among the first o merged elements
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        // A[mid] belongs to the first o elements unless B[o-1-mid] strictly precedes it
+        if (!merge_before(sd[b + o - 1 - mid], sd[a + mid], si + b + o - 1 - mid, si + a + mid)) lo = mid + 1;
+        else hi = mid;
+      }
+      const int ia = a + lo, ib = b + o - lo;
+      const int pick = merge_before(sd[ib], sd[ia], si + ib, si + ia) ? ib : ia;
+      td[dst] = sd[pick];
+      ti[dst] = si[pick];
+    }
+    __syncthreads();
+    // the output of this round becomes the input of the next
+    const float* nd = td; const long long* ni = ti;
+    td = const_cast<float*>(sd); ti = const_cast<long long*>(si);
+    sd = nd; si = ni;
+    const int tmp = s_stride; s_stride = t_stride; t_stride = tmp;
+    n = n_next;
+  }
+  const size_t obase = (size_t)q0 * k;
+  for (int x = threadIdx.x; x < run; x += kMergeThreads) {
+    const int qi = small_div(x, inv_k), i = x - qi * k;
+    const long long ix = si[(qi * s_stride) * k + i];
+    out_dist[obase + x] = ix >= 0 ? sd[(qi * s_stride) * k + i] : INFINITY;
+    out_index[obase + x] = ix >= 0 ? ix : -1;
+  }
+}
+
+// Generic form for list sets that do not fit in shared memory (hundreds of lists × large k):
+// one warp per query, binary searches straight in global memory.
 constexpr int kMergeWarps = 4;
-__global__ void __launch_bounds__(kMergeWarps * 32) topk_merge_kernel(
+__global__ void __launch_bounds__(kMergeWarps * 32) topk_merge_generic_kernel(
     const float* __restrict__ dist, const long long* __restrict__ index, int num_lists, int num_q,
     int k, float* __restrict__ out_dist, long long* __restrict__ out_index) {
   const int lane = threadIdx.x & 31;
@@ -364,12 +458,12 @@ __global__ void __launch_bounds__(kMergeWarps * 32) topk_merge_kernel(
     const size_t base = ((size_t)l * num_q + q) * k;
     const float dx = dist[base + i];
     const long long ix = index[base + i];
-    if (ix < 0) continue;  // padding entry of a short list
-    int pos = i;           // elements before x in its own list
+    if (ix < 0) continue;
+    int pos = i;
     for (int l2 = 0; l2 < num_lists; ++l2) {
       if (l2 == l) continue;
       const size_t b2 = ((size_t)l2 * num_q + q) * k;
-      int lo = 0, hi = k;  // first element of l2 that does NOT rank before x
+      int lo = 0, hi = k;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         const float dm = dist[b2 + mid];
@@ -773,12 +867,29 @@ int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, in
                       float* out_dist, int64_t* out_index, cudaStream_t st) {
   if (num_q <= 0 || k <= 0) return SBIR_OK;
   const size_t n = (size_t)num_q * k;
+  const size_t per_q = ((size_t)num_lists + (num_lists + 1) / 2) * k * 12;  // gathered lists + one round of merged lists
+  if (num_lists > 0 && per_q <= 96 * 1024) {
+    // ~16 KB of shared memory per block (a dozen blocks per SM keep loads in flight while others merge)
+    int qb = (int)((16 * 1024) / per_q);
+    if (qb < 1) qb = 1;
+    if (qb > 32) qb = 32;
+    const size_t smem = (size_t)qb * per_q;
+    if (smem > 48 * 1024)
+      SBIR_CUDA_TRY(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((num_q + qb - 1) / qb);
+    topk_merge_kernel<<<grid, kMergeThreads, smem, st>>>(dist, reinterpret_cast<const long long*>(index), num_lists,
+                                                         (int)num_q, k, qb, out_dist,
+                                                         reinterpret_cast<long long*>(out_index));
+    SBIR_CHECK_LAUNCH();
+    return SBIR_OK;
+  }
   fill_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_dist, reinterpret_cast<long long*>(out_index), n);
   SBIR_CHECK_LAUNCH();
+  if (num_lists <= 0) return SBIR_OK;
   const unsigned grid = (unsigned)((num_q + kMergeWarps - 1) / kMergeWarps);
-  topk_merge_kernel<<<grid, kMergeWarps * 32, 0, st>>>(dist, reinterpret_cast<const long long*>(index), num_lists,
-                                                       (int)num_q, k, out_dist,
-                                                       reinterpret_cast<long long*>(out_index));
+  topk_merge_generic_kernel<<<grid, kMergeWarps * 32, 0, st>>>(dist, reinterpret_cast<const long long*>(index), num_lists,
+                                                               (int)num_q, k, out_dist,
+                                                               reinterpret_cast<long long*>(out_index));
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }

@@ -10,7 +10,7 @@ namespace sbir {
 // mode 0: ‖x‖² ; mode 1: −1/max(‖x‖,1e-8).  Rows [rows, rows_padded) get pad_value.
 int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int dtype,
                     int mode, float pad_value, float* out, float* max_sqnorm_out, cudaStream_t st);
-// out[i] = min(gvec[32 i .. 32 i + 31]) (NaN entries ignored)
+// out[i] = min(gvec[8 i .. 8 i + 7]) (NaN entries ignored)
 int launch_chunk_min(const float* gvec, int64_t num_chunks, float* out, cudaStream_t st);
 int launch_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype, float eps,
                         cudaStream_t st);
@@ -53,7 +53,7 @@ struct K1Args {
   int64_t num_q, num_g, dim;
   int dtype, metric, mode;
   const float* gvec;  // [num_g_tiles * kTileG] epilogue vector (‖g‖² | −1/max(‖g‖,eps)), padded
-  const float* gmin;  // [num_g_tiles * kTileG / 32] minimum of gvec over each run of 32 rows (select modes)
+  const float* gmin;  // [num_g_tiles * kTileG / 8] minimum of gvec over each run of 8 rows (select modes)
   const int32_t* gate;  // optional device flag: every kernel of the launch is a no-op unless *gate != 0
   // top-k candidate lists, layout [partition][q_tile_stride][lists_per_row][cap][kTileQ]
   float* cand_val;

@@ -334,13 +334,11 @@ __global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) chunk_min_kernel(const float* __restrict__ gvec, long long num_chunks,
                                                         float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= num_chunks) return;
-  float v = gvec[w * 32 + lane];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFullMask, v, o));
-  if (lane == 0) out[w] = v;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(gvec) + 2 * w);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(gvec) + 2 * w + 1);
+  out[w] = fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
 }
 
 template <typename T>
@@ -371,7 +369,7 @@ int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t di
 
 int launch_chunk_min(const float* gvec, int64_t num_chunks, float* out, cudaStream_t st) {
   if (num_chunks <= 0) return SBIR_OK;
-  chunk_min_kernel<<<(unsigned)((num_chunks * 32 + 255) / 256), 256, 0, st>>>(gvec, (long long)num_chunks, out);
+  chunk_min_kernel<<<(unsigned)((num_chunks + 255) / 256), 256, 0, st>>>(gvec, (long long)num_chunks, out);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }

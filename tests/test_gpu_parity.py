@@ -375,6 +375,31 @@ def test_sharded_merge_equals_single_pass(ops):
         assert torch.equal(im, i1) and torch.equal(vm, v1) and torch.equal(cnt, r1)
 
 
+@pytest.mark.parametrize("lists,nq,k", [(8, 1000, 10), (2, 77, 100), (3, 5, 1), (8, 333, 116), (40, 9, 116)])
+def test_topk_merge_against_a_sort(ops, lists, nq, k):
+    """K4: k best of the gathered per-shard lists, ties by index, padding entries (index -1, +inf)
+    of short lists ignored; (40, 9, 116) exceeds the shared-memory form and takes the generic kernel."""
+    g = torch.Generator().manual_seed(lists * 1000 + k)
+    d = torch.randint(0, 50, (lists, nq, k), generator=g).float() * 0.25     # many exact ties
+    i = torch.randperm(lists * nq * k, generator=g).reshape(lists, nq, k) % 100000
+    short = torch.randint(0, k + 1, (lists, nq), generator=g)                # valid entries per list
+    short[0] = k if lists > 1 else short[0]
+    pad = torch.arange(k)[None, None, :] >= short[:, :, None]
+    d[pad] = float("inf")
+    i[pad] = -1
+    # each list ascending by (distance, index), padding last
+    key = torch.where(pad, torch.full_like(d, 1e30), d).double() * 1e6 + i.clamp_min(0).double()
+    order = key.argsort(dim=2)
+    d, i = d.gather(2, order), i.gather(2, order)
+    vm, im = ops.topk_merge(d.cuda(), i.cuda())
+    dd = d.permute(1, 0, 2).reshape(nq, -1)
+    ii = i.permute(1, 0, 2).reshape(nq, -1)
+    key = torch.where(ii < 0, torch.full_like(dd, 1e30), dd).double() * 1e6 + ii.clamp_min(0).double()
+    o = key.argsort(dim=1)[:, :k]
+    ref_d, ref_i = dd.gather(1, o), ii.gather(1, o)
+    assert torch.equal(vm.cpu(), ref_d) and torch.equal(im.cpu(), ref_i)
+
+
 @pytest.mark.parametrize("chunk_rows", [0, 4096])
 def test_retrieve_host_equals_device_path(ops, sbir_lib, chunk_rows, monkeypatch):
     """Host-buffer entry point == device path, also when the gallery is uploaded and scored in

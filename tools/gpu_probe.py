@@ -503,6 +503,108 @@ def case_centred():
     return out
 
 
+def _k1_ms(q, g, k, pos=None, iters=4):
+    import ctypes
+    import torch
+    from art_sbir_b200 import _binding as B, ops
+    lib = B.load()
+    ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
+    torch.cuda.synchronize()
+    lib.sbir_profile_enable(1)
+    ms, n, l = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+    lib.sbir_profile_collect(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(l))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(iters):
+        ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
+    ev[1].record()
+    torch.cuda.synchronize()
+    lib.sbir_profile_collect(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(l))
+    lib.sbir_profile_enable(0)
+    return round(ms.value / iters, 3), round(ev[0].elapsed_time(ev[1]) / iters, 3)
+
+
+def case_k100():
+    """Where does top-100 lose time against top-10?  K1 / whole-call ms for k=10 vs k=100 as the gallery
+    grows (list warm-up is a fixed cost per (query tile, partition) chain; steady-state insertions grow
+    with log N) and with one chunk per partition (no list park / restore between chunks)."""
+    import torch
+    out = {}
+    for nq, ng, d, dt in [(12500, 75000, 2048, "float32"), (12500, 300000, 2048, "float32"), (12500, 75000, 2048, "bfloat16"),
+                          (20000, 1000000, 512, "bfloat16")]:
+        q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
+        for chunk in ("12", "100000"):
+            os.environ["SBIR_K1_CHUNK_MB"] = chunk
+            for k in (10, 100):
+                out[f"{nq}x{ng}x{d} {dt} k={k} chunkMB={chunk}"] = _k1_ms(q, g, k)
+    os.environ.pop("SBIR_K1_CHUNK_MB", None)
+    return out
+
+
+def _graph_us(fn, replays=50):
+    """Device time of fn() in microseconds: captured once into a CUDA graph and replayed back to back,
+    so host-side launch overhead (Python, ctypes, allocator) is not in the measurement."""
+    import torch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / replays * 1e3
+
+
+def case_small():
+    """Device time (CUDA-graph replay) of the small kernels: K4 merge, cfg2 triplet / batch-hard steps,
+    retrieval metrics, cfg1-sized retrieval."""
+    import torch
+    from art_sbir_b200 import _binding as B, ops
+    lib = B.load()
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    res = {}
+    for lists, nq, k in ((8, 100_000, 10), (8, 100_000, 100), (2, 100_000, 10)):
+        d = torch.sort(torch.rand(lists, nq, k, device="cuda"), dim=2).values.contiguous()
+        i = torch.randint(0, 10_000_000, (lists, nq, k), device="cuda")
+        od, oi = torch.empty(nq, k, device="cuda"), torch.empty(nq, k, dtype=torch.int64, device="cuda")
+        us = _graph_us(lambda: B.check(lib.sbir_topk_merge(d.data_ptr(), i.data_ptr(), lists, nq, k, od.data_ptr(), oi.data_ptr(), st()), "merge"))
+        res[f"topk_merge {lists}x{nq}x{k}"] = {"us": us, "GB/s": (d.numel() * 12 + nq * k * 12) / us / 1e3}
+    a, p, n = (torch.randn(256, 2048, device="cuda") for _ in range(3))
+    loss, per_row = torch.empty((), device="cuda"), torch.empty(256, device="cuda")
+    ga, gp, gn = (torch.empty_like(a) for _ in range(3))
+    for metric, name in ((B.SBIR_EUCLIDEAN, "euclidean"), (B.SBIR_COSINE, "cosine")):
+        us = _graph_us(lambda: B.check(lib.sbir_triplet_margin_loss(a.data_ptr(), p.data_ptr(), n.data_ptr(), 256, 2048, 0.2, metric,
+                                                                   loss.data_ptr(), per_row.data_ptr(), ga.data_ptr(), gp.data_ptr(),
+                                                                   gn.data_ptr(), st()), "triplet"))
+        res[f"cfg2 triplet fwd+bwd 256x2048 {name}"] = {"us": us, "GB/s": 6 * a.numel() * 4 / us / 1e3}
+        ws = torch.empty(lib.sbir_batch_hard_workspace_bytes(256, 2048), dtype=torch.uint8, device="cuda")
+        hard = torch.empty(256, 2, dtype=torch.int64, device="cuda")
+        us = _graph_us(lambda: B.check(lib.sbir_batch_hard_triplet_loss(a.data_ptr(), p.data_ptr(), n.data_ptr(), 256, 2048, 0.2, metric, None, None,
+                                                                       loss.data_ptr(), hard.data_ptr(), ga.data_ptr(), gp.data_ptr(), gn.data_ptr(),
+                                                                       ws.data_ptr(), ws.numel(), st()), "batch_hard"))
+        res[f"cfg2 batch-hard fwd+bwd 256x512x2048 {name}"] = {"us": us}
+    ta, tp, tn = (t.clone().requires_grad_(True) for t in (a, p, n))
+
+    def torch_step():
+        ta.grad = tp.grad = tn.grad = None
+        torch.nn.functional.triplet_margin_loss(ta, tp, tn, margin=0.2).backward()
+    res["cfg2 triplet fwd+bwd 256x2048 torch library (same GPU)"] = {"us": _graph_us(torch_step)}
+    q, g, pos = _clustered(1000, 10000, 2048, torch.float32)
+    res["cfg1 retrieval 1000x10000x2048 fp32 top-10+rank"] = {"us": _graph_us(lambda: ops.pairwise_topk(q, g, 10, "euclidean", pos_index=pos))}
+    return res
+
+
 CASES = ["rowops", "dump_small", "dump_shapes", "topk_small", "topk_mid", "triplet", "batch_hard", "host", "peaks", "time"]
 
 if __name__ == "__main__":
