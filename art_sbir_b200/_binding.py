@@ -43,6 +43,7 @@ PROTOTYPES = {
     "sbir_profile_enable": (c_int, [c_int]),
     "sbir_profile_collect": (c_int, [_P, _P, _P]),
     "sbir_debug_plan": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, c_int, _P]),
+    "sbir_debug_k1_diag": (c_int, [_P, c_int]),
     "sbir_debug_dist_matrix_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "sbir_debug_dist_matrix": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P, c_size_t, _P]),
 }

@@ -455,6 +455,11 @@ int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   return SBIR_OK;
 }
 
+int sbir_debug_k1_diag(uint64_t* out, int n) {
+  if (out == nullptr || n <= 0) return SBIR_ERR_INVALID_ARG;
+  return k1_diag_read(reinterpret_cast<unsigned long long*>(out), n);
+}
+
 size_t sbir_debug_dist_matrix_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int dtype) {
   if (num_q <= 0 || num_g <= 0 || dim <= 0 || !dtype_ok(dtype)) return 0;
   const K1Plan plan = make_k1_plan(num_q, num_g, dim, 1, dtype, num_sms_cached());

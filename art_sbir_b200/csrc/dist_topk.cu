@@ -48,6 +48,11 @@ constexpr int kSmemLimit = 227 * 1024;
 constexpr int kTmemCols = 512;  // two 256-column fp32 accumulators
 constexpr int kSchedDepth = 4;  // unit ring between the scheduler and the other warps
 
+// Diagnostics (SBIR_K1_FLAGS & 64): cycles per CTA spent by the MMA issuer waiting for a free
+// accumulator [0] and for operands [1], its whole loop [2], and by epilogue warp 0 waiting for a
+// finished accumulator [3] and inside list insertions [4]; read with sbir_debug_k1_diag.
+__device__ unsigned long long g_k1_diag[148 * 8];
+
 // Monotone float <-> int32 map so a float minimum can be taken with an integer atomicMin.
 __device__ __forceinline__ int32_t float_to_ordered_int(float f) {
   const int32_t b = __float_as_int(f);
@@ -101,7 +106,15 @@ struct K1Config {
   static constexpr int kStageBytesG = kStageBytesGFull / kPair;
   static constexpr int kStageBytes = kStageBytesQ + kStageBytesG;
   static constexpr int kMaxStages = kPair == 2 ? 6 : 4;
-  static constexpr int kListsPerRow = kEpiWarps / 4;
+  // Two epilogue warps share every TMEM lane quarter when kEpiWarps == 8 and split the columns.
+  // Small lists: each of them keeps its own list (two lists per row).  Lists of 64/128 entries do
+  // not fit twice beside the operand ring: the first warp OWNS the row's single list and the
+  // second one FEEDS it — it screens its columns against the owner's published threshold and
+  // forwards the rare hits through a small per-row queue in shared memory.
+  static constexpr int kColSplit = kEpiWarps / 4;
+  static constexpr int kListsPerRow = (kEpiWarps == 8 && kCap <= 32) ? 2 : 1;
+  static constexpr bool kFeed = kColSplit == 2 && kListsPerRow == 1;
+  static constexpr int kFeedDepth = 4;  // queue entries per row
   // distance keys of the running lists always live in shared memory (they are re-scanned on
   // every insertion); the gallery indices are write-only inside the kernel and go straight to
   // the global candidate buffer when they do not fit beside the operand ring.
@@ -109,13 +122,15 @@ struct K1Config {
   static constexpr int kValBytes = kCap * kListsPerRow * kTileQ * 4;
   static constexpr bool kTwoLevel = kCap >= 64;  // per-group-of-8 maxima beside the keys
   static constexpr int kGroupBytes = kTwoLevel ? (kCap / 8) * kListsPerRow * kTileQ * 4 : 0;
-  static constexpr int kListBytes = kValBytes + (kIdxInSmem ? kValBytes : 0) + kGroupBytes;
+  // feed region: queue values + indices [depth][128], tail / head / published threshold [128], 8 flags
+  static constexpr int kFeedBytes = kFeed ? (2 * kFeedDepth + 3) * kTileQ * 4 + 32 : 0;
+  static constexpr int kListBytes = kValBytes + (kIdxInSmem ? kValBytes : 0) + kGroupBytes + kFeedBytes;
   static constexpr int kBarrierBytes = 384;
   static constexpr int kStagesFit = (kSmemLimit - 1024 - kListBytes - kBarrierBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : kStagesFit;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kListBytes + kBarrierBytes;
   static constexpr int kThreads = 64 + kEpiWarps * 32;
-  static constexpr int kColsPerWarp = kTileG / kListsPerRow;
+  static constexpr int kColsPerWarp = kTileG / kColSplit;
   static_assert(kStages >= 2, "operand ring needs at least two stages");
   static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps must cover the 4 TMEM lane quarters");
 };
@@ -204,7 +219,15 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint8_t* smem_g = smem + kStages * kStageBytesQ;
   float* list_val_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);
   int32_t* list_idx_s = reinterpret_cast<int32_t*>(list_val_s + kCap * Cfg::kListsPerRow * kTileQ);
-  float* list_grp_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + Cfg::kListBytes - Cfg::kGroupBytes);
+  float* list_grp_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + Cfg::kListBytes - Cfg::kFeedBytes - Cfg::kGroupBytes);
+  // feeder queue (Cfg::kFeed): SPSC ring per row; counters run on for the whole kernel
+  float* fq_val = reinterpret_cast<float*>(smem + kStages * kStageBytes + Cfg::kListBytes - Cfg::kFeedBytes);  // [depth][128]
+  int32_t* fq_idx = reinterpret_cast<int32_t*>(fq_val + Cfg::kFeedDepth * kTileQ);                                // [depth][128]
+  volatile uint32_t* fq_tail = reinterpret_cast<volatile uint32_t*>(fq_idx + Cfg::kFeedDepth * kTileQ);           // [128] pushed
+  volatile uint32_t* fq_head = fq_tail + kTileQ;                                                                  // [128] consumed
+  volatile float* thr_pub = reinterpret_cast<volatile float*>(fq_head + kTileQ);                                  // [128] owner's threshold
+  volatile int32_t* unit_ready = reinterpret_cast<volatile int32_t*>(thr_pub + kTileQ);                           // [4] per quarter
+  volatile int32_t* feeder_done = unit_ready + 4;                                                                 // [4] per quarter
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + Cfg::kListBytes);
   uint64_t* full_bar = bars;                         // [kStages]
   uint64_t* empty_bar = bars + kStages;              // [kStages]
@@ -238,6 +261,14 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (warp == 1) {
     if constexpr (kPair == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
     else tmem_alloc(tmem_slot, kTmemCols);
+  }
+  if constexpr (Cfg::kFeed) {
+    if (threadIdx.x < kTileQ) {
+      fq_tail[threadIdx.x] = 0;
+      fq_head[threadIdx.x] = 0;
+      thr_pub[threadIdx.x] = INFINITY;
+      if (threadIdx.x < 8) unit_ready[threadIdx.x] = -1;  // unit_ready[0..3], feeder_done[0..3]
+    }
   }
   tc_fence_before();
   if constexpr (kPair == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive
@@ -313,17 +344,24 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const bool diag = (prm.flags & 64) != 0;
+      long long w_acc = 0, w_full = 0;
+      const long long t_loop0 = clock64();
       for (int it = 0;; ++it) {
         const int unit = next_unit_consumer(it);
         release_unit_slot(it);
         if (unit < 0) break;
         const UnitCoord uc = decode_unit(unit, prm);
         for (int t = uc.t_begin; t < uc.t_end; ++t) {
+          long long tw = diag ? clock64() : 0;
           mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+          if (diag) w_acc += clock64() - tw;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kTileG;
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
+            tw = diag ? clock64() : 0;
             mbar_wait(&full_bar[stage], phase);
+            if (diag) w_full += clock64() - tw;
             tc_fence_after();
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_q + stage * kStageBytesQ));
             const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_g + stage * kStageBytesG));
@@ -342,6 +380,11 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (acc == 0) acc_phase ^= 1;
         }
       }
+      if (diag && blockIdx.x < 148) {
+        g_k1_diag[blockIdx.x * 8 + 0] = (unsigned long long)w_acc;
+        g_k1_diag[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
+        g_k1_diag[blockIdx.x * 8 + 2] = (unsigned long long)(clock64() - t_loop0);
+      }
     }
     __syncwarp();
   } else {
@@ -351,6 +394,10 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int half = ew >> 2;      // column half when two warps share a lane quarter
     const int row = quarter * 32 + lane;
     const int col_begin = half * Cfg::kColsPerWarp;
+    const int lhalf = Cfg::kListsPerRow == 2 ? half : 0;  // which of the row's lists this warp works on
+    const bool feeder = Cfg::kFeed && half == 1;          // forwards its hits to the quarter's list owner
+    uint32_t fq_pos = 0;  // owner: entries consumed from this row's queue; feeder: entries pushed
+    [[maybe_unused]] float thr_pubbed = INFINITY;  // owner: last threshold published to the feeder
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -367,13 +414,13 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
       // This thread's list: entry p lives at [p * kTileQ + row] (conflict-free / coalesced).
       // Global slot of the list: keyed by (partition, query tile), shared by all its chunks.
-      const size_t list_slot = ((size_t)uc.part * prm.q_tile_stride + q_tile) * Cfg::kListsPerRow + half;
-      float* lv = list_val_s + half * kCap * kTileQ;
-      [[maybe_unused]] float* lg = list_grp_s + half * (kCap / 8) * kTileQ;
+      const size_t list_slot = ((size_t)uc.part * prm.q_tile_stride + q_tile) * Cfg::kListsPerRow + lhalf;
+      float* lv = list_val_s + lhalf * kCap * kTileQ;
+      [[maybe_unused]] float* lg = list_grp_s + lhalf * (kCap / 8) * kTileQ;
       float* gval = prm.cand_val + list_slot * kCap * kTileQ;
       int32_t* gidx = prm.cand_idx + list_slot * kCap * kTileQ;
       int32_t* li;
-      if constexpr (Cfg::kIdxInSmem) li = list_idx_s + half * kCap * kTileQ;
+      if constexpr (Cfg::kIdxInSmem) li = list_idx_s + lhalf * kCap * kTileQ;
       else li = gidx;
       int32_t* done_flag = prm.chunk_done + (size_t)uc.part * prm.q_tile_stride + q_tile;
       float thr = INFINITY;      // insertion threshold = min(own list maximum, shared threshold)
@@ -382,8 +429,24 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int maxpos = 0;
       float lo = -INFINITY, hi = -INFINITY;
       int cnt = 0;
+      constexpr int kPend = 4;  // accepted candidates waiting per lane (flush_pending)
+      float pe0 = 0.f, pe1 = 0.f, pe2 = 0.f, pe3 = 0.f;
+      int pi0 = 0, pi1 = 0, pi2 = 0, pi3 = 0, pn = 0;
       if constexpr (kSelect) {
-        if (uc.chunk == 0) {
+        if (feeder) {
+          // the owner publishes this unit's starting threshold before the feeder may filter with it
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (unit_ready[quarter] != it) {
+              if (clock64() - t0 > 4000000000LL) {
+                printf("sbir: feeder start timed out (unit %d)\n", unit);
+                __trap();
+              }
+            }
+          }
+          __syncwarp();
+          __threadfence_block();
+        } else if (uc.chunk == 0) {
 #pragma unroll 4
           for (int p = 0; p < kCap; ++p) lv[p * kTileQ + row] = INFINITY;
           if constexpr (Cfg::kTwoLevel) {
@@ -402,10 +465,29 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           __syncwarp();
           (void)ld_acquire(done_flag);
+          // latency-bound (one L2 round trip per batch of loads in flight): 16-32 loads per batch
+          if (prm.flags & 32) {  // A/B: four loads in flight
 #pragma unroll 4
-          for (int p = 0; p < kCap; ++p) {
-            lv[p * kTileQ + row] = __ldcg(gval + p * kTileQ + row);
-            if constexpr (Cfg::kIdxInSmem) li[p * kTileQ + row] = __ldcg(gidx + p * kTileQ + row);
+            for (int p = 0; p < kCap; ++p) {
+              lv[p * kTileQ + row] = __ldcg(gval + p * kTileQ + row);
+              if constexpr (Cfg::kIdxInSmem) li[p * kTileQ + row] = __ldcg(gidx + p * kTileQ + row);
+            }
+          } else
+#pragma unroll
+          for (int p0 = 0; p0 < kCap; p0 += 32) {
+            constexpr int kBatch = kCap < 32 ? kCap : 32;
+            float tv[kBatch];
+            [[maybe_unused]] int32_t ti[kBatch];
+#pragma unroll
+            for (int p = 0; p < kBatch; ++p) {
+              tv[p] = __ldcg(gval + (p0 + p) * kTileQ + row);
+              if constexpr (Cfg::kIdxInSmem) ti[p] = __ldcg(gidx + (p0 + p) * kTileQ + row);
+            }
+#pragma unroll
+            for (int p = 0; p < kBatch; ++p) {
+              lv[(p0 + p) * kTileQ + row] = tv[p];
+              if constexpr (Cfg::kIdxInSmem) li[(p0 + p) * kTileQ + row] = ti[p];
+            }
           }
           if constexpr (Cfg::kTwoLevel) {
             for (int u = 0; u < kCap / 8; ++u) {
@@ -418,6 +500,15 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           own_max = __ldcg(prm.row_max + list_slot * kTileQ + row);
           maxpos = __ldcg(prm.row_maxpos + list_slot * kTileQ + row);
           thr = own_max;
+        }
+        if constexpr (Cfg::kFeed) {
+          if (!feeder) {
+            thr_pub[row] = thr;
+            thr_pubbed = thr;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) unit_ready[quarter] = it;
+          }
         }
       }
       if constexpr (kRank) {
@@ -435,15 +526,167 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (prm.row_label != nullptr && q_valid) my_label = prm.row_label[q];
       }
 
+      // One candidate of this row enters the list when it beats the threshold (owner side) ...
+      auto insert_list = [&](float ej, int gidx_e) {
+        if (ej < thr) {
+          lv[maxpos * kTileQ + row] = ej;
+          li[maxpos * kTileQ + row] = gidx_e;
+          float mx = -INFINITY;
+          int mp = 0;
+          if constexpr (Cfg::kTwoLevel) {
+            // lists of 64/128 keep a maximum per group of 8: refresh the touched group,
+            // pick the group holding the overall maximum, locate it inside that group
+            // (24-32 shared loads instead of kCap).  Maxima come from FMNMX3 trees and the
+            // positions from independent equality tests, so no step is a long
+            // compare-and-select chain (one epilogue warp per scheduler: latency is exposed).
+            const int g = maxpos >> 3;
+            float w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = lv[(g * 8 + u) * kTileQ + row];
+            const float gm = fmaxf(fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), w[6]), w[7]);
+            lg[g * kTileQ + row] = gm;
+            constexpr int kGroups = kCap / 8;
+            float gmx[kGroups];
+#pragma unroll
+            for (int u = 0; u < kGroups; ++u) gmx[u] = lg[u * kTileQ + row];
+            float t8[kGroups / 2];
+#pragma unroll
+            for (int u = 0; u < kGroups / 2; ++u) t8[u] = fmaxf(gmx[2 * u], gmx[2 * u + 1]);
+            if constexpr (kGroups == 16)
+              mx = fmax3(fmax3(t8[0], t8[1], t8[2]), fmax3(t8[3], t8[4], t8[5]), fmaxf(t8[6], t8[7]));
+            else
+              mx = fmaxf(fmax3(t8[0], t8[1], t8[2]), t8[3]);
+            int bg = 0;
+#pragma unroll
+            for (int u = 1; u < kGroups; ++u) bg = (gmx[u] == mx) ? u : bg;
+            if (bg != g) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) w[u] = lv[(bg * 8 + u) * kTileQ + row];
+            }
+            mp = bg * 8;
+#pragma unroll
+            for (int u = 1; u < 8; ++u) mp = (w[u] == mx) ? bg * 8 + u : mp;
+          } else {
+#pragma unroll 8
+            for (int p = 0; p < kCap; ++p) {
+              const float v = lv[p * kTileQ + row];
+              if (v > mx) { mx = v; mp = p; }
+            }
+          }
+          own_max = mx;
+          thr = fminf(thr, mx);
+          maxpos = mp;
+        }
+      };
+      // ... and is queued for exact evaluation when it sits in the rank band.
+      auto band_check = [&](float ej, int gidx_e) {
+        if constexpr (kRank) {
+          if (ej >= lo && ej < hi) {
+            // approximate comparison against d_pos is not trustworthy: queue the
+            // pair for exact evaluation (finalize.cu: rank_resolve_kernel)
+            const uint32_t slot = atomicAdd(prm.pool_count, 1u);
+            if (slot < prm.pool_cap) {
+              prm.pool_q[slot] = q;
+              prm.pool_idx[slot] = gidx_e;
+            } else {
+              atomicAdd(prm.dropped + q, 1);
+            }
+          }
+        }
+      };
+      // Once the lists have warmed up hits are sparse — one lane of the warp at a time — and an
+      // insertion executed for a single lane costs the warp as much as one for all 32.  Accepted
+      // candidates therefore wait in a per-lane queue of kPend registers and the lists are only
+      // updated when some lane's queue is full (or the unit ends): then every lane inserts its
+      // pending candidates side by side, ~15 per round instead of 1.  The thresholds lag by at
+      // most kPend insertions per row, which only lets a few more candidates through.
+      auto flush_pending = [&]() {
+        const int maxn = __reduce_max_sync(kFullMask, pn);
+        if (maxn > 0) { if (pn > 0) insert_list(pe0, pi0); __syncwarp(); }
+        if (maxn > 1) { if (pn > 1) insert_list(pe1, pi1); __syncwarp(); }
+        if (maxn > 2) { if (pn > 2) insert_list(pe2, pi2); __syncwarp(); }
+        if (maxn > 3) { if (pn > 3) insert_list(pe3, pi3); __syncwarp(); }
+        pn = 0;
+      };
+      auto pend_push = [&](float ej, int gidx_e) {  // caller made sure pn < kPend
+        pe3 = pe2; pi3 = pi2;
+        pe2 = pe1; pi2 = pi1;
+        pe1 = pe0; pi1 = pi0;
+        pe0 = ej; pi0 = gidx_e;
+        ++pn;
+      };
+      // Feeder side of a candidate: forward it to the owner of the row's list.
+      auto push_feed = [&](float ej, int gidx_e) {
+        if constexpr (Cfg::kFeed) {
+          const long long t0 = clock64();
+          while (fq_pos - fq_head[row] >= (uint32_t)Cfg::kFeedDepth) {  // queue full: the owner drains it
+            if (clock64() - t0 > 4000000000LL) {
+              printf("sbir: feeder queue stuck (unit %d)\n", unit);
+              __trap();
+            }
+          }
+          const int slot = (int)(fq_pos % (uint32_t)Cfg::kFeedDepth);
+          fq_val[slot * kTileQ + row] = ej;
+          fq_idx[slot * kTileQ + row] = gidx_e;
+          __threadfence_block();
+          fq_tail[row] = ++fq_pos;
+        }
+      };
+      auto consume = [&](float ej, int gidx_e) {
+        if (feeder) {
+          if (ej < thr) push_feed(ej, gidx_e);
+        } else if (ej < thr) {
+          pend_push(ej, gidx_e);
+        }
+        band_check(ej, gidx_e);
+      };
+      // Owner side of the queue: insert what the feeder forwarded (one entry per row and round).
+      auto drain_feed = [&]() {
+        if constexpr (Cfg::kFeed) {
+          uint32_t tail = fq_tail[row];
+          while (__any_sync(kFullMask, tail != fq_pos)) {
+            if (__any_sync(kFullMask, pn == kPend)) flush_pending();
+            if (tail != fq_pos) {
+              __threadfence_block();
+              const int slot = (int)(fq_pos % (uint32_t)Cfg::kFeedDepth);
+              const float ej = fq_val[slot * kTileQ + row];
+              const int gidx_e = fq_idx[slot * kTileQ + row];
+              if (ej < thr) pend_push(ej, gidx_e);
+              __threadfence_block();
+              fq_head[row] = ++fq_pos;
+            }
+            __syncwarp();
+            tail = fq_tail[row];
+          }
+        }
+      };
+
       for (int t = uc.t_begin; t < uc.t_end; ++t) {
+        if constexpr (kSelect && Cfg::kFeed) {
+          if (!feeder) {
+            // The feeder may lag a tile behind and fill its queue while this accumulator's next
+            // turn still waits for the feeder's own arrival: keep draining while waiting.
+            const long long t0 = clock64();
+            while (__shfl_sync(kFullMask, (int)mbar_try_wait(&acc_full_bar[acc], acc_phase), 0) == 0) {
+              drain_feed();
+              if (clock64() - t0 > 4000000000LL) {
+                printf("sbir: accumulator wait timed out (unit %d)\n", unit);
+                __trap();
+              }
+            }
+          }
+        }
+        const long long tw_e = (prm.flags & 64) ? clock64() : 0;
         mbar_wait(&acc_full_bar[acc], acc_phase);
+        if ((prm.flags & 64) && ew == 0 && lane == 0 && blockIdx.x < 148)
+          g_k1_diag[blockIdx.x * 8 + 3] += (unsigned long long)(clock64() - tw_e);
         tc_fence_after();
         if constexpr (kSelect) {
           // Another partition (or the other column half) scanning the same query may already
           // hold `cap` candidates below some value: nothing at or above it can reach the final
           // best-`cap`, so adopt it as an upper bound on this list's threshold.  The value was
           // requested before waiting for the accumulator (L2 round trip off the critical path).
-          thr = fminf(thr, ordered_int_to_float(shared_next));
+          if (!feeder) thr = fminf(thr, ordered_int_to_float(shared_next));
         }
         const float* gv = prm.gvec + (size_t)t * kTileG + col_begin;
 #pragma unroll 1
@@ -453,6 +696,17 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
           const int gcol0 = t * kTileG + col_begin + c * 32;  // gallery row of column 0 of this chunk
+          if constexpr (kSelect && Cfg::kFeed) {
+            if (feeder) {
+              thr = thr_pub[row];  // may lag behind the owner: then a few extra hits are forwarded
+            } else {
+              drain_feed();
+              if (thr < thr_pubbed) {
+                thr_pub[row] = thr;
+                thr_pubbed = thr;
+              }
+            }
+          }
           if constexpr (kSelect) {
             // Cheap conservative screen before any per-element work: every e of this chunk is
             // >= bound (rounding is monotone, so this holds for the computed values too);
@@ -488,71 +742,6 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             // path below — a chunk whose minimum is not below lim has none of them
             const float lim = kRank ? fmaxf(thr, hi) : thr;
             if (!__any_sync(kFullMask, m < lim)) continue;
-            // One candidate of this row: maybe enters the list, maybe sits in the rank band.
-            auto consume = [&](float ej, int gidx_e) {
-              if (ej < thr) {
-                lv[maxpos * kTileQ + row] = ej;
-                li[maxpos * kTileQ + row] = gidx_e;
-                float mx = -INFINITY;
-                int mp = 0;
-                if constexpr (Cfg::kTwoLevel) {
-                  // lists of 64/128 keep a maximum per group of 8: refresh the touched group,
-                  // pick the group holding the overall maximum, locate it inside that group
-                  // (24-32 shared loads instead of kCap).  Maxima come from FMNMX3 trees and the
-                  // positions from independent equality tests, so no step is a long
-                  // compare-and-select chain (one epilogue warp per scheduler: latency is exposed).
-                  const int g = maxpos >> 3;
-                  float w[8];
-#pragma unroll
-                  for (int u = 0; u < 8; ++u) w[u] = lv[(g * 8 + u) * kTileQ + row];
-                  const float gm = fmaxf(fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), w[6]), w[7]);
-                  lg[g * kTileQ + row] = gm;
-                  constexpr int kGroups = kCap / 8;
-                  float gmx[kGroups];
-#pragma unroll
-                  for (int u = 0; u < kGroups; ++u) gmx[u] = lg[u * kTileQ + row];
-                  float t8[kGroups / 2];
-#pragma unroll
-                  for (int u = 0; u < kGroups / 2; ++u) t8[u] = fmaxf(gmx[2 * u], gmx[2 * u + 1]);
-                  if constexpr (kGroups == 16)
-                    mx = fmax3(fmax3(t8[0], t8[1], t8[2]), fmax3(t8[3], t8[4], t8[5]), fmaxf(t8[6], t8[7]));
-                  else
-                    mx = fmaxf(fmax3(t8[0], t8[1], t8[2]), t8[3]);
-                  int bg = 0;
-#pragma unroll
-                  for (int u = 1; u < kGroups; ++u) bg = (gmx[u] == mx) ? u : bg;
-                  if (bg != g) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) w[u] = lv[(bg * 8 + u) * kTileQ + row];
-                  }
-                  mp = bg * 8;
-#pragma unroll
-                  for (int u = 1; u < 8; ++u) mp = (w[u] == mx) ? bg * 8 + u : mp;
-                } else {
-#pragma unroll 8
-                  for (int p = 0; p < kCap; ++p) {
-                    const float v = lv[p * kTileQ + row];
-                    if (v > mx) { mx = v; mp = p; }
-                  }
-                }
-                own_max = mx;
-                thr = fminf(thr, mx);
-                maxpos = mp;
-              }
-              if constexpr (kRank) {
-                if (ej >= lo && ej < hi) {
-                  // approximate comparison against d_pos is not trustworthy: queue the
-                  // pair for exact evaluation (finalize.cu: rank_resolve_kernel)
-                  const uint32_t slot = atomicAdd(prm.pool_count, 1u);
-                  if (slot < prm.pool_cap) {
-                    prm.pool_q[slot] = q;
-                    prm.pool_idx[slot] = gidx_e;
-                  } else {
-                    atomicAdd(prm.dropped + q, 1);
-                  }
-                }
-              }
-            };
             // Hit mask of this row, built only for the sub-chunks of 8 columns in which some row of
             // the warp has a hit (once the lists have warmed up: a few lanes, one hit each).
             uint32_t mask = 0;
@@ -570,6 +759,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             // somewhere (list warm-up: 2-5x fewer rounds).  The value of the lane's next hit column
             // is picked out of the registers with a 5-level select tree.
             while (__any_sync(kFullMask, mask != 0)) {
+              if (!feeder && __any_sync(kFullMask, pn == kPend)) flush_pending();
               if (mask != 0) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -621,7 +811,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
         }
         if constexpr (kSelect) {
-          if (own_max < published) {  // list is full and its maximum dropped: share it
+          if (!feeder && own_max < published) {  // list is full and its maximum dropped: share it
             atomicMin(prm.shared_thr + q_tile * kTileQ + row, float_to_ordered_int(own_max));
             published = own_max;
           }
@@ -639,21 +829,44 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
 
       if constexpr (kSelect) {
-        // Park the list in global memory: the next chunk of this (partition, query tile) — on
-        // whichever SM it lands — or finalize.cu picks it up from there.
-#pragma unroll 4
-        for (int p = 0; p < kCap; ++p) {
-          gval[p * kTileQ + row] = lv[p * kTileQ + row];
-          if constexpr (Cfg::kIdxInSmem) gidx[p * kTileQ + row] = li[p * kTileQ + row];
-        }
-        prm.row_max[list_slot * kTileQ + row] = own_max;
-        prm.row_maxpos[list_slot * kTileQ + row] = maxpos;
         if constexpr (kRank) {
           if (q_valid && cnt) atomicAdd(prm.cnt_less + q, cnt);
         }
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");  // all epilogue warps parked their lists
-        if (ew == 0 && lane == 0) st_release(done_flag, uc.chunk + 1);
+        if (feeder) {
+          // everything this warp forwarded is in the queue: tell the owner, then run ahead
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) feeder_done[quarter] = it;
+        } else {
+          if constexpr (Cfg::kFeed) {
+            // keep draining until the feeder has finished the unit and its queue is empty
+            const long long t0 = clock64();
+            for (;;) {
+              const bool done = __shfl_sync(kFullMask, (int)(feeder_done[quarter] >= it), 0) != 0;
+              __threadfence_block();
+              drain_feed();
+              if (done) break;
+              if (clock64() - t0 > 4000000000LL) {
+                printf("sbir: feeder hand-over timed out (unit %d)\n", unit);
+                __trap();
+              }
+            }
+          }
+          flush_pending();
+          // Park the list in global memory: the next chunk of this (partition, query tile) — on
+          // whichever SM it lands — or finalize.cu picks it up from there.
+#pragma unroll 4
+          for (int p = 0; p < kCap; ++p) {
+            gval[p * kTileQ + row] = lv[p * kTileQ + row];
+            if constexpr (Cfg::kIdxInSmem) gidx[p * kTileQ + row] = li[p * kTileQ + row];
+          }
+          prm.row_max[list_slot * kTileQ + row] = own_max;
+          prm.row_maxpos[list_slot * kTileQ + row] = maxpos;
+          __threadfence();
+          // all list-owning epilogue warps parked their lists
+          asm volatile("bar.sync 1, %0;" ::"r"((Cfg::kFeed ? 4 : kEpiWarps) * 32) : "memory");
+          if (ew == 0 && lane == 0) st_release(done_flag, uc.chunk + 1);
+        }
       }
       if constexpr (kMode == kModeHard) {
         // one unit == one gallery tile; slot [part][q_tile*128+row][half]
@@ -747,26 +960,29 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& pr
 template <bool kTF32, int kMetric, int kEpiWarps>
 int dispatch_mode_cap(int mode, int cap, int pair, const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm,
                       int num_sms, cudaStream_t st) {
-  // 8 epilogue warps (two lists per row) exist only for the small capacities
-#define SBIR_K1_CASE(M, C)                                                                              \
-  if constexpr (kEpiWarps == 4 || C <= 32) {                                                            \
-    if (mode == M && cap == C) {                                                                        \
-      if (pair == 2) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 2>(tq, tg, prm, num_sms, st);  \
-      return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 1>(tq, tg, prm, num_sms, st);                 \
-    }                                                                                                   \
+#define SBIR_K1_CASE(M, C)                                                                            \
+  if (mode == M && cap == C) {                                                                        \
+    if (pair == 2) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 2>(tq, tg, prm, num_sms, st);  \
+    return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 1>(tq, tg, prm, num_sms, st);                 \
   }
 #define SBIR_K1_CASE1(M, C) \
   if (mode == M && cap == C) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 1>(tq, tg, prm, num_sms, st);
-  SBIR_K1_CASE(kModeTopk, 16)
-  SBIR_K1_CASE(kModeTopk, 32)
+  // instantiated combinations: fp32 small lists run 4 warps, bf16 small lists 8 (two lists per
+  // row), large lists 8 (owner + feeder) or 4 (SBIR_K1_FEED=0)
+  if constexpr ((kEpiWarps == 8) != kTF32) {
+    SBIR_K1_CASE(kModeTopk, 16)
+    SBIR_K1_CASE(kModeTopk, 32)
+    SBIR_K1_CASE(kModeTopkRank, 16)
+    SBIR_K1_CASE(kModeTopkRank, 32)
+    SBIR_K1_CASE(kModeDump, 16)
+  }
   SBIR_K1_CASE(kModeTopk, 64)
   SBIR_K1_CASE(kModeTopk, 128)
-  SBIR_K1_CASE(kModeTopkRank, 16)
-  SBIR_K1_CASE(kModeTopkRank, 32)
   SBIR_K1_CASE(kModeTopkRank, 64)
   SBIR_K1_CASE(kModeTopkRank, 128)
-  SBIR_K1_CASE(kModeDump, 16)
-  SBIR_K1_CASE1(kModeHard, 16)
+  if constexpr (kEpiWarps == 4 && kTF32) {
+    SBIR_K1_CASE1(kModeHard, 16)
+  }
 #undef SBIR_K1_CASE
 #undef SBIR_K1_CASE1
   return SBIR_ERR_UNSUPPORTED;
@@ -774,9 +990,20 @@ int dispatch_mode_cap(int mode, int cap, int pair, const CUtensorMap& tq, const 
 
 }  // namespace
 
-// fp32 embeddings → kind::tf32, 4 epilogue warps; bf16 → kind::f16, 8 epilogue warps when the
-// lists are small (the bf16 tiles complete 2-4× sooner, so two warps share each TMEM lane quarter).
-static int epi_warps_for(int dtype, int cap) { return (dtype == SBIR_BF16 && cap <= 32) ? 8 : 4; }
+// Epilogue warps.  Small lists (cap <= 32): fp32 embeddings (kind::tf32) take 4; bf16 tiles complete
+// 2-4× sooner, so two warps share each TMEM lane quarter, each with its own list.  Lists of 64/128
+// entries make the epilogue the critical path at any width (one warp per scheduler issues one
+// dependent instruction every ~4 cycles): 8 warps, the second of each quarter feeding the first
+// (K1Config::kFeed).  SBIR_K1_FEED=0 falls back to 4 warps (A/B runs).
+static int epi_warps_for(int dtype, int cap) {
+  if (cap <= 32) return dtype == SBIR_BF16 ? 8 : 4;
+  static int feed = -1;
+  if (feed < 0) {
+    const char* e = std::getenv("SBIR_K1_FEED");
+    feed = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return feed ? 8 : 4;
+}
 
 // Single-CTA tiles are the default: on B200 the CTA-pair kernel (cta_group::2, M = 256) measured
 // 4-5 % slower on the power-capped cfg4 pass (profiles/r01_pair_vs_single_cfg4.txt) — its coarser
@@ -791,13 +1018,23 @@ static int k1_pair_default() {
   return v;
 }
 
+int k1_diag_read(unsigned long long* out, int n) {
+  unsigned long long host[148 * 8];
+  if (cudaMemcpyFromSymbol(host, g_k1_diag, sizeof(host)) != cudaSuccess) return SBIR_ERR_CUDA;
+  for (int i = 0; i < n && i < 148 * 8; ++i) out[i] = host[i];
+  static const unsigned long long zeros[148 * 8] = {};
+  if (cudaMemcpyToSymbol(g_k1_diag, zeros, sizeof(zeros)) != cudaSuccess) return SBIR_ERR_CUDA;
+  return SBIR_OK;
+}
+
 K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms) {
   K1Plan p{};
   // capacity = k + slack; fp32/tf32 carries a wider error band, so it gets more slack
   const int want = dtype == SBIR_BF16 ? k + 6 : k + 16;
   p.cap = want <= 16 ? 16 : want <= 32 ? 32 : want <= 64 ? 64 : 128;
   if (k + 12 > 128) p.cap = 128;
-  p.lists_per_row = epi_warps_for(dtype, p.cap) / 4;
+  p.epi_warps = epi_warps_for(dtype, p.cap);
+  p.lists_per_row = (p.epi_warps == 8 && p.cap <= 32) ? 2 : 1;
   p.num_q_tiles = (int)((num_q + kTileQ - 1) / kTileQ);
   p.num_g_tiles = (int)((num_g + kTileG - 1) / kTileG);
   if (p.num_q_tiles < 1) p.num_q_tiles = 1;
@@ -904,16 +1141,20 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   SBIR_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   const int cap = (a.mode == kModeDump || a.mode == kModeHard) ? 16 : plan.cap;
 
+  // dump / batch-hard launches carry no plan of their own: 4 warps for fp32, 8 for bf16
+  const int epi = select ? plan.epi_warps : (a.dtype == SBIR_BF16 ? 8 : 4);
+#define SBIR_K1_DISPATCH(TF32, EPI)                                                                                        \
+  do {                                                                                                                     \
+    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<TF32, SBIR_EUCLIDEAN, EPI>(a.mode, cap, pair, tq, tg, prm, num_sms, st); \
+    return dispatch_mode_cap<TF32, SBIR_COSINE, EPI>(a.mode, cap, pair, tq, tg, prm, num_sms, st);                      \
+  } while (0)
   if (a.dtype == SBIR_F32) {
-    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<true, SBIR_EUCLIDEAN, 4>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
-    return dispatch_mode_cap<true, SBIR_COSINE, 4>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
+    if (epi == 8) SBIR_K1_DISPATCH(true, 8);
+    SBIR_K1_DISPATCH(true, 4);
   }
-  if (plan.lists_per_row == 2) {
-    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 8>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
-    return dispatch_mode_cap<false, SBIR_COSINE, 8>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
-  }
-  if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<false, SBIR_EUCLIDEAN, 4>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
-  return dispatch_mode_cap<false, SBIR_COSINE, 4>(a.mode, cap, pair, tq, tg, prm, num_sms, st);
+  if (epi == 8) SBIR_K1_DISPATCH(false, 8);
+  SBIR_K1_DISPATCH(false, 4);
+#undef SBIR_K1_DISPATCH
 }
 
 }  // namespace sbir

@@ -112,13 +112,27 @@ __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinPar
   const int nfinite = s_nfinite;
   const int R = nfinite < p.cap ? nfinite : p.cap;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Only candidates that can still belong to the exact top-k are re-scored: with a_k the k-th
+  // smallest APPROXIMATE value, k candidates have exact e <= a_k + m, so one whose approximate
+  // value exceeds a_k + 2m (exact e > a_k + m) is out.  The gather of candidate rows is what this
+  // kernel's time goes to (k=100, 2048-d fp32: 1 MB per query), so the cut is worth a third of it.
+  int RS = R;
+  if (p.k <= R) {
+    const double lim = (double)sv[p.k - 1] + 2.0 * e_margin(p.metric, p.qsq[q], p.gsq_max[0], p.kappa, p.dim);
+    int lo = p.k, hi = R;  // sv[0..R) ascending: first position whose value exceeds lim
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((double)sv[mid] <= lim) lo = mid + 1; else hi = mid;
+    }
+    RS = lo;
+  }
   const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
   for (int c = threadIdx.x; c < 128; c += kFinThreads) {
     ex[c] = INFINITY;
     exi[c] = INT_MAX;
   }
   __syncthreads();
-  for (int c = warp; c < R; c += kFinThreads / 32) {
+  for (int c = warp; c < RS; c += kFinThreads / 32) {
     const int32_t gi = si[c];
     const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)gi * p.dim,
                                                   p.dim, p.metric, lane);
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinPar
   bitonic_sort_smem<double>(ex, exi, 128);
 
   for (int i = threadIdx.x; i < p.k; i += kFinThreads) {
-    const bool have = i < R;
+    const bool have = i < RS;
     p.out_dist[(size_t)q * p.k + i] = have ? (float)ex[i] : INFINITY;
     p.out_index[(size_t)q * p.k + i] = have ? (long long)exi[i] + p.index_offset : -1LL;
   }

@@ -36,7 +36,8 @@ enum K1Mode { kModeTopk = 0, kModeTopkRank = 1, kModeDump = 2, kModeHard = 3 };
 // (query tile, partition, chunk) — see make_k1_plan / decode_unit in dist_topk.cu.
 struct K1Plan {
   int cap;            // per-list capacity (16, 32, 64 or 128)
-  int lists_per_row;  // 1 (4 epilogue warps) or 2 (8 epilogue warps: one list per column half)
+  int lists_per_row;  // 1, or 2 (8 epilogue warps and cap <= 32: one list per column half)
+  int epi_warps;      // 4 or 8 epilogue warps (8 with one list per row: owner + feeder warps, dist_topk.cu)
   int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks;
   int band_q;         // unit-grid rows per L2 band (unit numbering, see decode_unit in dist_topk.cu)
   int num_chunks, tiles_per_chunk;  // every partition is scanned in `num_chunks` serial chunks
@@ -83,6 +84,8 @@ struct K1Args {
   int32_t* hard_idx;          // same shape
 };
 int launch_k1(const K1Args& args, const K1Plan& plan, cudaStream_t st);
+// Reads and clears the per-CTA cycle counters the kernel fills when SBIR_K1_FLAGS & 64 (8 per CTA).
+int k1_diag_read(unsigned long long* out, int n);
 
 // ---- finalize.cu ----------------------------------------------------------------
 struct FinalizeArgs {

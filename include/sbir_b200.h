@@ -195,6 +195,11 @@ int sbir_profile_collect(double* k1_ms_sum, int64_t* k1_launches, int64_t* kerne
  * lists_per_row, num_q_tiles, num_g_tiles, num_partitions, tiles_per_partition, num_chunks,
  * tiles_per_chunk, num_units, part_fastest, pair, q_tile_stride}. */
 int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms, int32_t* out);
+/* Profiling aid: when the environment variable SBIR_K1_FLAGS has bit 64 set, the distance kernel
+ * records per CTA (8 uint64 each, 148 CTAs) the cycles its MMA issuer waited for a free
+ * accumulator [0] and for operands [1], its whole loop [2], and the cycles epilogue warp 0 waited
+ * for finished accumulators [3].  Copies up to n values to the host buffer `out` and clears them. */
+int sbir_debug_k1_diag(uint64_t* out, int n);
 size_t sbir_debug_dist_matrix_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int dtype);
 int sbir_debug_dist_matrix(const void* q, int64_t num_q, const void* g, int64_t num_g,
                            int64_t dim, int dtype, int metric, float* out_e, void* workspace,

@@ -605,6 +605,68 @@ def case_small():
     return res
 
 
+def case_k100_mainloop():
+    """k=100 (cap 128: 3 operand stages) with the epilogue switched off: is it the mainloop?"""
+    import torch
+    out = {}
+    for nq, ng, d, dt in [(20000, 1000000, 512, "bfloat16"), (12500, 75000, 2048, "float32")]:
+        q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
+        for k in (10, 100):
+            for flags in ("0", "8"):
+                os.environ["SBIR_K1_FLAGS"] = flags
+                out[f"{nq}x{ng}x{d} {dt} k={k} flags={flags}"] = _k1_ms(q, g, k)
+    os.environ.pop("SBIR_K1_FLAGS", None)
+    return out
+
+
+def case_ab2():
+    """Interleaved A/B of K1 variants in one process (SBIR_K1_FLAGS bits): median of several rounds."""
+    import statistics
+    import torch
+    out = {}
+    for nq, ng, d, dt, k in [(12500, 75000, 2048, "float32", 100), (20000, 1000000, 512, "bfloat16", 100),
+                             (12500, 75000, 2048, "float32", 10), (20000, 1000000, 512, "bfloat16", 10)]:
+        q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
+        res = {}
+        for rnd in range(5):
+            for flags in ("0", "32", "8"):
+                os.environ["SBIR_K1_FLAGS"] = flags
+                res.setdefault(flags, []).append(_k1_ms(q, g, k, iters=3)[0])
+        out[f"{nq}x{ng}x{d} {dt} k={k}"] = {f: [round(statistics.median(v), 3), round(min(v), 3)] for f, v in res.items()}
+    os.environ.pop("SBIR_K1_FLAGS", None)
+    return out
+
+
+def case_diag():
+    """Where does the MMA issuer wait?  Per-CTA cycle counters (SBIR_K1_FLAGS=64) for the headline-like
+    shapes: share of the MMA loop spent waiting for a free accumulator (epilogue-bound) or for operands
+    (TMA / L2-bound)."""
+    import ctypes
+    import numpy as np
+    import torch
+    from art_sbir_b200 import _binding as B, ops
+    lib = B.load()
+    out = {}
+    buf = (ctypes.c_uint64 * (148 * 8))()
+    for nq, ng, d, dt, k in [(20000, 1000000, 512, "bfloat16", 10), (20000, 1000000, 512, "bfloat16", 100),
+                             (12500, 75000, 2048, "float32", 10), (12500, 75000, 2048, "float32", 100)]:
+        q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
+        os.environ["SBIR_K1_FLAGS"] = "64"
+        ops.pairwise_topk(q, g, k, "euclidean")
+        torch.cuda.synchronize()
+        lib.sbir_debug_k1_diag(buf, 148 * 8)
+        ops.pairwise_topk(q, g, k, "euclidean")
+        torch.cuda.synchronize()
+        lib.sbir_debug_k1_diag(buf, 148 * 8)
+        a = np.array(list(buf), dtype=np.float64).reshape(148, 8)
+        loop = a[:, 2].mean()
+        out[f"{nq}x{ng}x{d} {dt} k={k}"] = {"mma_loop_Mclk": round(loop / 1e6, 2), "wait_acc_frac": round(a[:, 0].mean() / loop, 3),
+                                            "wait_operands_frac": round(a[:, 1].mean() / loop, 3),
+                                            "epi_wait_acc_full_frac": round(a[:, 3].mean() / loop, 3)}
+    os.environ.pop("SBIR_K1_FLAGS", None)
+    return out
+
+
 CASES = ["rowops", "dump_small", "dump_shapes", "topk_small", "topk_mid", "triplet", "batch_hard", "host", "peaks", "time"]
 
 if __name__ == "__main__":
