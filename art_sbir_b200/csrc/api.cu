@@ -58,20 +58,6 @@ int num_sms_cached() {
 bool dtype_ok(int d) { return d == SBIR_F32 || d == SBIR_BF16; }
 bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 
-// Workspace of sbir_pairwise_topk / _shard (all offsets 256-byte aligned).
-struct TopkLayout {
-  K1Plan plan;
-  size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert, off_shared_thr;
-  size_t off_row_max, off_row_maxpos, off_sched, sched_bytes, off_gmin;
-  bool precise;        // fp32 inputs small enough for the 3xTF32 escalation workspace
-  K1Plan plan3;        // plan of the escalation pass (dim' = 3·dim), same partitions / lists as `plan`
-  size_t off_gate, off_q3, off_g3;  // off_sched: unit counter + chunk_done (zeroed together)
-  size_t off_mu, off_colpart;       // column mean of the gallery + its partial sums (centred escalation pass)
-  size_t off_pos_dist, off_lo, off_hi, off_cnt, off_dropped, off_pool_count, off_pool_q, off_pool_idx;
-  uint32_t pool_cap;
-  size_t total;
-};
-
 TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int want_rank) {
   TopkLayout L{};
   L.plan = make_k1_plan(num_q, num_g, dim, k, dtype, num_sms_cached());
@@ -125,17 +111,27 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   return L;
 }
 
-// Shared implementation of sbir_pairwise_topk (pos_index given, full rank) and
-// sbir_pairwise_topk_shard (pos_dist given, local count).
-int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
-              int metric, int k, int64_t index_offset, const int64_t* pos_index,
-              const double* pos_dist_in, const int64_t* pos_tie, int64_t tie_offset, float* out_dist, int64_t* out_index, int64_t* out_rank,
-              int64_t missing_rank, int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
-              cudaStream_t st) {
+}  // namespace
+
+// ---- one retrieval pass in three phases (kernels.h: TopkPass) ----
+// begin: argument checks, workspace carve-up, counters zeroed, query norms.
+// feed:  gallery rows [fed, row_end) are resident — their norms, then K1 over their chunk steps
+//        (the candidate lists carry over from feed to feed like they do from chunk to chunk).
+// finish: exact re-scoring + certificate, rank resolution, the device-gated escalation pass
+//        (fp32) and the brute-force fallbacks.
+// sbir_pairwise_topk / _shard run begin, ONE feed of the whole gallery, finish;
+// sbir_retrieve_host (host_path.cu) feeds the gallery as its chunks arrive over PCIe.
+int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+                    int metric, int k, int64_t index_offset, const int64_t* pos_index, const double* pos_dist_in,
+                    const int64_t* pos_tie, int64_t tie_offset, float* out_dist, int64_t* out_index,
+                    int64_t* out_rank, int64_t missing_rank, int32_t* out_uncertified, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+  P = TopkPass{};
   if (!dtype_ok(dtype) || !metric_ok(metric)) return SBIR_ERR_INVALID_ARG;
   if (num_q < 0 || num_g < 0 || dim <= 0 || k <= 0) return SBIR_ERR_INVALID_ARG;
   if (k > kMaxK) return SBIR_ERR_UNSUPPORTED;
   if (num_q > INT32_MAX / 2 || num_g > INT32_MAX / 2 || dim > (1 << 20)) return SBIR_ERR_UNSUPPORTED;
+  P.done = true;
   if (num_q == 0) return SBIR_OK;
   if (q == nullptr || out_dist == nullptr || out_index == nullptr) return SBIR_ERR_INVALID_ARG;
   if (num_g > 0 && g == nullptr) return SBIR_ERR_INVALID_ARG;
@@ -144,18 +140,23 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   if ((dim * (int64_t)elem_size(dtype)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
 
-  const TopkLayout L = topk_layout(num_q, num_g, dim, k, dtype, want_rank ? 1 : 0);
+  P.L = topk_layout(num_q, num_g, dim, k, dtype, want_rank ? 1 : 0);
+  const TopkLayout& L = P.L;
   if (workspace == nullptr || reinterpret_cast<uintptr_t>(workspace) % 256 != 0 || workspace_bytes < L.total)
     return SBIR_ERR_WORKSPACE;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  float* gvec = reinterpret_cast<float*>(ws + L.off_gvec);
-  float* gmax = reinterpret_cast<float*>(ws + L.off_gmax);
-  float* qsq = reinterpret_cast<float*>(ws + L.off_qsq);
+  P.ws = ws; P.st = st; P.want_rank = want_rank;
+  P.q = q; P.g = g; P.num_q = num_q; P.num_g = num_g; P.dim = dim; P.dtype = dtype; P.metric = metric;
+  P.gvec = reinterpret_cast<float*>(ws + L.off_gvec);
+  P.gmax = reinterpret_cast<float*>(ws + L.off_gmax);
+  P.gmin = reinterpret_cast<float*>(ws + L.off_gmin);
+  P.qsq = reinterpret_cast<float*>(ws + L.off_qsq);
+  P.flags = reinterpret_cast<int32_t*>(ws + L.off_flags);
+  P.uncert = out_uncertified ? out_uncertified : reinterpret_cast<int32_t*>(ws + L.off_uncert);
+  P.padded = (int64_t)L.plan.num_g_tiles * kTileG;
   float* cand_val = reinterpret_cast<float*>(ws + L.off_cand_val);
   int32_t* cand_idx = reinterpret_cast<int32_t*>(ws + L.off_cand_idx);
-  int32_t* flags = reinterpret_cast<int32_t*>(ws + L.off_flags);
-  int32_t* uncert = out_uncertified ? out_uncertified : reinterpret_cast<int32_t*>(ws + L.off_uncert);
-  SBIR_CUDA_TRY(cudaMemsetAsync(uncert, 0, sizeof(int32_t), st));
+  SBIR_CUDA_TRY(cudaMemsetAsync(P.uncert, 0, sizeof(int32_t), st));
 
   if (num_g == 0) {
     // Empty gallery: no neighbours; every query's positive is missing.
@@ -163,21 +164,15 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
     if (want_rank) SBIR_TRY(launch_fill_i64(out_rank, num_q, missing_rank, st));
     return SBIR_OK;
   }
+  P.done = false;
 
-  const int64_t padded = (int64_t)L.plan.num_g_tiles * kTileG;
-  SBIR_TRY(launch_row_norm(g, num_g, padded, dim, dtype, metric == SBIR_EUCLIDEAN ? 0 : 1,
-                           metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""), gvec, gmax, st));
-  SBIR_TRY(launch_row_norm(q, num_q, num_q, dim, dtype, 0, 0.f, qsq, nullptr, st));
-  float* gmin = reinterpret_cast<float*>(ws + L.off_gmin);
-  SBIR_TRY(launch_chunk_min(gvec, padded / 8, gmin, st));
-
-  RankArgs ra{};
+  RankArgs& ra = P.ra;
   if (want_rank) {
     ra.q = q; ra.g = g; ra.num_q = num_q; ra.num_g = num_g; ra.dim = dim;
     ra.dtype = dtype; ra.metric = metric;
     ra.pos_index = pos_index; ra.pos_dist_in = pos_dist_in;
     ra.pos_tie = pos_tie; ra.tie_offset = tie_offset;
-    ra.qsq = qsq; ra.gsq_max = gmax;
+    ra.qsq = P.qsq; ra.gsq_max = P.gmax;
     ra.pos_dist = reinterpret_cast<double*>(ws + L.off_pos_dist);
     ra.rank_lo = reinterpret_cast<float*>(ws + L.off_lo);
     ra.rank_hi = reinterpret_cast<float*>(ws + L.off_hi);
@@ -190,12 +185,12 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
     ra.out_rank = out_rank;
     ra.missing_rank = missing_rank;
   }
-  K1Args ka{};
+  K1Args& ka = P.ka;
   ka.num_q = num_q; ka.num_g = num_g;
   ka.dtype = dtype; ka.metric = metric;
   ka.mode = want_rank ? kModeTopkRank : kModeTopk;
-  ka.gvec = gvec;
-  ka.gmin = gmin;
+  ka.gvec = P.gvec;
+  ka.gmin = P.gmin;
   ka.cand_val = cand_val; ka.cand_idx = cand_idx;
   ka.row_max = reinterpret_cast<float*>(ws + L.off_row_max);
   ka.row_maxpos = reinterpret_cast<int32_t*>(ws + L.off_row_maxpos);
@@ -206,21 +201,86 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   ka.pool_count = ra.pool_count; ka.pool_cap = ra.pool_cap; ka.pool_q = ra.pool_q; ka.pool_idx = ra.pool_idx;
   ka.dropped = ra.dropped;
   ka.shared_thr = reinterpret_cast<int32_t*>(ws + L.off_shared_thr);
-  FinalizeArgs fa{};
+  FinalizeArgs& fa = P.fa;
   fa.q = q; fa.g = g; fa.num_q = num_q; fa.num_g = num_g; fa.dim = dim;
   fa.dtype = dtype; fa.metric = metric; fa.k = k; fa.index_offset = index_offset;
   fa.cand_val = cand_val; fa.cand_idx = cand_idx;
-  fa.qsq = qsq; fa.gsq_max = gmax;
+  fa.qsq = P.qsq; fa.gsq_max = P.gmax;
   fa.out_dist = out_dist; fa.out_index = out_index;
-  fa.uncertified = uncert; fa.flags = flags;
+  fa.uncertified = P.uncert; fa.flags = P.flags;
 
-  // One scoring pass: (rank band) -> K1 -> finalize (+ rank pool resolution).  `gate` makes every
-  // kernel of the pass a no-op unless the device flag is set.
+  // Pass 1 runs the tensor-core tiles on the embeddings as they are (fp32 -> kind::tf32, bf16 -> kind::f16).
+  const float kappa = k1_kappa(dtype, dim);
+  ra.kappa = kappa; ra.gate = nullptr;
+  fa.kappa = kappa; fa.gate = nullptr;
+  ka.q = q; ka.g = g; ka.dim = dim; ka.gate = nullptr;
+  SBIR_TRY(launch_row_norm(q, num_q, num_q, dim, dtype, 0, 0.f, P.qsq, nullptr, st));
+  SBIR_CUDA_TRY(cudaMemsetAsync(P.gmax, 0, sizeof(float), st));
+  if (want_rank) {
+    SBIR_CUDA_TRY(cudaMemsetAsync(ra.cnt_less, 0, (size_t)num_q * sizeof(int32_t), st));
+    SBIR_CUDA_TRY(cudaMemsetAsync(ra.dropped, 0, (size_t)num_q * sizeof(int32_t), st));
+    SBIR_CUDA_TRY(cudaMemsetAsync(ra.pool_count, 0, sizeof(uint32_t), st));
+  }
+  SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_sched, 0, L.sched_bytes, st));
+  SBIR_TRY(launch_fill_i32(ka.shared_thr, (int64_t)L.plan.q_tile_stride * kTileQ, 0x7f800000, st));
+  return SBIR_OK;
+}
+
+int64_t topk_pass_feed_granule(const TopkPass& P) {
+  // intermediate feeds must end on a chunk-step boundary of the single gallery partition
+  if (P.done || P.L.plan.num_splits != 1) return 0;
+  return (int64_t)P.L.plan.tiles_per_chunk * kTileG;
+}
+
+int topk_pass_feed(TopkPass& P, int64_t row_end) {
+  if (P.done) return SBIR_OK;
+  const TopkLayout& L = P.L;
+  cudaStream_t st = P.st;
+  const int64_t row0 = P.fed_rows;
+  if (row_end <= row0 || row_end > P.num_g) return SBIR_ERR_INVALID_ARG;
+  const bool last = row_end == P.num_g;
+  const int64_t granule = (int64_t)L.plan.tiles_per_chunk * kTileG;
+  if (!(row0 == 0 && last)) {
+    if (L.plan.num_splits != 1 || row0 % granule != 0 || (!last && row_end % granule != 0)) return SBIR_ERR_INVALID_ARG;
+  }
+  const size_t row_bytes = (size_t)P.dim * elem_size(P.dtype);
+  const int64_t pad_end = last ? P.padded : row_end;  // the padding rows of the last tile belong to the last feed
+  SBIR_TRY(launch_row_norm(static_cast<const uint8_t*>(P.g) + (size_t)row0 * row_bytes, row_end - row0, pad_end - row0, P.dim,
+                           P.dtype, P.metric == SBIR_EUCLIDEAN ? 0 : 1,
+                           P.metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""), P.gvec + row0, P.gmax, st, /*accumulate_max=*/true));
+  SBIR_TRY(launch_chunk_min(P.gvec + row0, (pad_end - row0) / 8, P.gmin + row0 / 8, st));
+  // the rank band uses the largest gallery norm seen so far (it only widens from feed to feed)
+  if (P.want_rank) SBIR_TRY(launch_rank_band(P.ra, st));
+  SBIR_CUDA_TRY(cudaMemsetAsync(P.ws + L.off_sched, 0, 256, st));  // unit counter of this launch
+  P.ka.chunk_begin = (row0 == 0) ? 0 : (int)(row0 / granule);
+  P.ka.chunk_end = last ? 0 : (int)(row_end / granule);
+  SBIR_TRY(launch_k1(P.ka, L.plan, st));
+  P.fed_rows = row_end;
+  return SBIR_OK;
+}
+
+int topk_pass_finish(TopkPass& P) {
+  if (P.done) return SBIR_OK;
+  if (P.fed_rows != P.num_g) return SBIR_ERR_INVALID_ARG;
+  const TopkLayout& L = P.L;
+  cudaStream_t st = P.st;
+  uint8_t* ws = P.ws;
+  RankArgs& ra = P.ra;
+  K1Args& ka = P.ka;
+  FinalizeArgs& fa = P.fa;
+  const bool want_rank = P.want_rank;
+  const int64_t num_q = P.num_q, num_g = P.num_g, dim = P.dim;
+  SBIR_TRY(launch_finalize_topk(fa, L.plan, st));
+  if (want_rank) SBIR_TRY(launch_rank_finalize(ra, st));
+
+  // One whole-gallery scoring pass: (rank band) -> K1 -> finalize (+ rank pool resolution).  `gate`
+  // makes every kernel of the pass a no-op unless the device flag is set.
   auto run_pass = [&](const void* kq, const void* kg, int64_t kdim, const K1Plan& plan, float kappa,
                       const int32_t* gate) -> int {
     ra.kappa = kappa; ra.gate = gate;
     fa.kappa = kappa; fa.gate = gate;
     ka.q = kq; ka.g = kg; ka.dim = kdim; ka.gate = gate;
+    ka.chunk_begin = 0; ka.chunk_end = 0;
     if (want_rank) {
       SBIR_CUDA_TRY(cudaMemsetAsync(ra.cnt_less, 0, (size_t)num_q * sizeof(int32_t), st));
       SBIR_CUDA_TRY(cudaMemsetAsync(ra.dropped, 0, (size_t)num_q * sizeof(int32_t), st));
@@ -235,21 +295,23 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
     return SBIR_OK;
   };
 
-  // Pass 1: tensor-core tiles on the embeddings as they are (fp32 -> kind::tf32, bf16 -> kind::f16).
-  SBIR_TRY(run_pass(q, g, dim, L.plan, k1_kappa(dtype, dim), nullptr));
-
   // Pass 2 (fp32 only, device-gated): when more than 2 % of the queries could not be certified or
   // overflowed the rank pool — embeddings whose norms dwarf their distances, positives deep in an
   // unstructured distribution — the TF32 error band is the problem, so redo the pass with the
   // operands split into TF32 hi/lo parts concatenated along K ([qh|qh|ql]·[gh|gl|gh] = 3xTF32,
   // error ~2^-20): same kernel, 3x the MMA work, far cheaper than brute-forcing every query.
   if (L.precise) {
+    const void* q = P.q;
+    const void* g = P.g;
+    const int metric = P.metric;
+    float* gvec = P.gvec; float* gmax = P.gmax; float* gmin = P.gmin; float* qsq = P.qsq;
+    const int64_t padded = P.padded;
     int32_t* gate = reinterpret_cast<int32_t*>(ws + L.off_gate);
     float* q3 = reinterpret_cast<float*>(ws + L.off_q3);
     float* g3 = reinterpret_cast<float*>(ws + L.off_g3);
     int64_t max_bad = num_q / 50;
     if (max_bad < 4) max_bad = 4;
-    SBIR_TRY(launch_escalate_decide(flags, want_rank ? ra.dropped : nullptr, num_q, max_bad, gate, uncert, st));
+    SBIR_TRY(launch_escalate_decide(P.flags, want_rank ? ra.dropped : nullptr, num_q, max_bad, gate, P.uncert, st));
     if (metric == SBIR_EUCLIDEAN && dim % 4 == 0) {
       // Euclidean distances are translation-invariant: centre both operands on the gallery's column
       // mean before the split, so the error band scales with the spread of the embeddings, not with
@@ -273,7 +335,26 @@ int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_
   ra.gate = nullptr;
   SBIR_TRY(launch_topk_fallback(fa, st));
   if (want_rank) SBIR_TRY(launch_rank_fallback(ra, st));
+  P.done = true;
   return SBIR_OK;
+}
+
+namespace {
+
+// Shared implementation of sbir_pairwise_topk (pos_index given, full rank) and
+// sbir_pairwise_topk_shard (pos_dist given, local count).
+int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+              int metric, int k, int64_t index_offset, const int64_t* pos_index,
+              const double* pos_dist_in, const int64_t* pos_tie, int64_t tie_offset, float* out_dist, int64_t* out_index, int64_t* out_rank,
+              int64_t missing_rank, int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
+              cudaStream_t st) {
+  TopkPass P;
+  SBIR_TRY(topk_pass_begin(P, q, num_q, g, num_g, dim, dtype, metric, k, index_offset, pos_index, pos_dist_in, pos_tie,
+                           tie_offset, out_dist, out_index, out_rank, missing_rank, out_uncertified, workspace,
+                           workspace_bytes, st));
+  if (P.done) return SBIR_OK;
+  SBIR_TRY(topk_pass_feed(P, num_g));
+  return topk_pass_finish(P);
 }
 
 }  // namespace

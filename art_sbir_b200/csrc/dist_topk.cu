@@ -142,6 +142,7 @@ struct K1Params {
   int num_q_tiles, num_g_tiles, num_k_blocks;
   int num_row_tiles;   // query tiles (kPair = 1) or query-tile pairs (kPair = 2): rows of the unit grid
   int num_parts, tiles_per_part, num_chunks, tiles_per_chunk, num_units, part_fastest;
+  int chunk_begin;     // first chunk step of this launch (streamed galleries: later launches continue the lists)
   int q_tile_stride;   // query-tile stride of candidate slots (num_q_tiles rounded up to even)
   int elems_per_kblock;
   const int32_t* gate;     // optional: the kernel is a no-op unless *gate != 0 (escalation pass)
@@ -171,14 +172,16 @@ struct K1Params {
 // Unit → (row of the unit grid, partition, chunk) and the gallery tiles it covers.  Chunk-major;
 // inside a chunk step either the query row or the partition varies fastest (plan.part_fastest:
 // wide fp32 rows keep fewer query tiles live in L2 when partitions of one query tile run together).
+__device__ __forceinline__ int prm_chunk_begin(const K1Params& p) { return p.chunk_begin; }
 struct UnitCoord {
   int row_tile, part, chunk, t_begin, t_end;
 };
 __device__ __forceinline__ UnitCoord decode_unit(int unit, const K1Params& p) {
   const int per_step = p.num_parts * p.num_row_tiles;
   UnitCoord c;
-  c.chunk = unit / per_step;
-  const int r = unit - c.chunk * per_step;
+  const int step = unit / per_step;
+  c.chunk = prm_chunk_begin(p) + step;
+  const int r = unit - step * per_step;
   if (p.part_fastest) {
     c.row_tile = r / p.num_parts;
     c.part = r - c.row_tile * p.num_parts;
@@ -1103,7 +1106,14 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.tiles_per_part = plan.tiles_per_split;
   prm.num_chunks = plan.num_chunks > 0 ? plan.num_chunks : 1;
   prm.tiles_per_chunk = plan.tiles_per_chunk > 0 ? plan.tiles_per_chunk : plan.tiles_per_split;
-  prm.num_units = plan.num_units;
+  prm.chunk_begin = a.chunk_begin;
+  {
+    // a launch may cover only the chunk steps [chunk_begin, chunk_end) of the plan (streamed gallery)
+    const int c_end = a.chunk_end > 0 ? a.chunk_end : prm.num_chunks;
+    const int per_step = plan.num_units / (plan.num_chunks > 0 ? plan.num_chunks : 1);
+    prm.num_units = (c_end - a.chunk_begin) * per_step;
+    if (prm.num_units <= 0) return SBIR_OK;
+  }
   prm.part_fastest = plan.part_fastest;
   prm.q_tile_stride = plan.q_tile_stride;
   prm.elems_per_kblock = (int)(kSwizzleBytes / elem_size(a.dtype));

@@ -1,13 +1,18 @@
 // host_path.cu — sbir_retrieve_host: the same retrieval pass as sbir_pairwise_topk, called
 // with HOST buffers (what a caller holding numpy / torch-CPU embeddings would bind).  The
 // gallery is uploaded in row chunks on a copy stream while earlier chunks are scored on the
-// compute stream (each chunk is a gallery shard: local top-k + local count-less-than, then
-// the K4 merge), so PCIe transfer overlaps the tensor-core work.  Device staging buffers
-// are cached per process and released by sbir_release_host_staging.
+// compute stream, so PCIe transfer overlaps the tensor-core work.  Normally the chunks are FED
+// to one retrieval pass (api.cu: topk_pass_begin / feed / finish): the distance kernel is launched
+// per uploaded chunk and continues the same candidate lists, so re-scoring, rank resolution and
+// list warm-up happen once, not once per chunk; the first chunk is small (128 MB, doubling up to
+// 1 GiB) so that scoring starts early.  When the plan cuts the gallery into several partitions
+// (few queries) a multi-chunk gallery is scored chunk by chunk as shards and merged (K4).
+// Device / pinned staging buffers are cached per process and released by sbir_release_host_staging.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -19,6 +24,8 @@ namespace {
 struct Staging {
   void* buf = nullptr;
   size_t bytes = 0;
+  void* pinned = nullptr;  // host staging for the gathered positive rows
+  size_t pinned_bytes = 0;
   int device = -1;
   cudaStream_t compute = nullptr, copy = nullptr;
   std::vector<cudaEvent_t> events;
@@ -37,8 +44,33 @@ int ensure_staging(size_t bytes) {
     g_staging.bytes = bytes;
     g_staging.device = dev;
   }
+  return SBIR_OK;
+}
+
+int ensure_streams() {
   if (!g_staging.compute) SBIR_CUDA_TRY(cudaStreamCreateWithFlags(&g_staging.compute, cudaStreamNonBlocking));
   if (!g_staging.copy) SBIR_CUDA_TRY(cudaStreamCreateWithFlags(&g_staging.copy, cudaStreamNonBlocking));
+  return SBIR_OK;
+}
+
+int ensure_pinned(size_t bytes) {
+  if (g_staging.pinned_bytes < bytes) {
+    if (g_staging.pinned) cudaFreeHost(g_staging.pinned);
+    g_staging.pinned = nullptr;
+    g_staging.pinned_bytes = 0;
+    SBIR_CUDA_TRY(cudaHostAlloc(&g_staging.pinned, bytes, cudaHostAllocDefault));
+    g_staging.pinned_bytes = bytes;
+  }
+  return SBIR_OK;
+}
+
+int event_at(size_t i, cudaEvent_t* out) {
+  while (g_staging.events.size() <= i) {
+    cudaEvent_t e;
+    SBIR_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_staging.events.push_back(e);
+  }
+  *out = g_staging.events[i];
   return SBIR_OK;
 }
 
@@ -61,6 +93,9 @@ extern "C" int sbir_release_host_staging(void) {
   if (g_staging.buf) cudaFree(g_staging.buf);
   g_staging.buf = nullptr;
   g_staging.bytes = 0;
+  if (g_staging.pinned) cudaFreeHost(g_staging.pinned);
+  g_staging.pinned = nullptr;
+  g_staging.pinned_bytes = 0;
   for (cudaEvent_t e : g_staging.events) cudaEventDestroy(e);
   g_staging.events.clear();
   if (g_staging.compute) cudaStreamDestroy(g_staging.compute);
@@ -84,25 +119,48 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   const size_t es = elem_size(dtype);
   const size_t row_bytes = (size_t)dim * es;
 
-  // Chunking: ~1 GiB of gallery rows per chunk (at least 4 chunks when the gallery is large
-  // enough to make overlap worthwhile), chunk rows a multiple of the gallery tile.
-  int64_t chunk_rows = (int64_t)((size_t(1) << 30) / row_bytes);
-  if (const char* env = std::getenv("SBIR_HOST_CHUNK_ROWS")) {  // test hook: force small chunks
-    const long long v = std::atoll(env);
-    if (v > 0) chunk_rows = v;
+  // Upload schedule: row counts of the gallery chunks.  Streamed feeds need chunk ends on the
+  // distance kernel's chunk-step boundaries (`granule` rows; 0 = the plan has several gallery
+  // partitions and cannot be fed in pieces).
+  const int64_t granule = [&]() -> int64_t {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+    const K1Plan plan = make_k1_plan(num_q, num_g, dim, k, dtype, sms);  // the plan topk_pass_begin will make
+    return plan.num_splits == 1 ? (int64_t)plan.tiles_per_chunk * kTileG : 0;
+  }();
+  std::vector<int64_t> chunk_end;
+  {
+    int64_t forced = 0;
+    if (const char* env = std::getenv("SBIR_HOST_CHUNK_ROWS")) forced = std::atoll(env);  // test hook: small chunks
+    const int64_t unit = granule > 0 ? granule : kTileG;
+    size_t target = granule > 0 ? (size_t(128) << 20) : (size_t(1) << 30);
+    int64_t next = 0;
+    while (next < num_g) {
+      int64_t rows = forced > 0 ? forced : (int64_t)(target / row_bytes);
+      rows = std::max<int64_t>(unit, rows / unit * unit);
+      int64_t end = next + rows;
+      if (end + unit / 2 >= num_g) end = num_g;  // do not leave a sliver for a last chunk
+      chunk_end.push_back(end);
+      next = end;
+      target = std::min<size_t>(target * 2, size_t(1) << 30);
+    }
   }
-  chunk_rows = std::max<int64_t>(kTileG, chunk_rows / kTileG * kTileG);
-  if (chunk_rows > num_g) chunk_rows = num_g;
-  const int num_chunks = (int)((num_g + chunk_rows - 1) / chunk_rows);
+  const int num_chunks = (int)chunk_end.size();
+  const bool streamed = granule > 0 || num_chunks == 1;  // one pass fed chunk by chunk (or all at once)
+  int64_t max_rows = 0;
+  for (int c = 0; c < num_chunks; ++c) max_rows = std::max(max_rows, chunk_end[c] - (c ? chunk_end[c - 1] : 0));
 
   // Device layout: Q | G (whole gallery, chunks land in place) | gathered positives |
-  // per-chunk top-k lists | merged outputs | rank accumulators | workspace.
+  // per-chunk top-k lists (shard mode) | merged outputs | rank accumulators | workspace.
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + (bytes ? bytes : 1), 256); return r; };
   const size_t off_q = take((size_t)num_q * row_bytes);
   const size_t off_g = take((size_t)num_g * row_bytes);
-  const size_t off_lists_d = take((size_t)num_chunks * num_q * k * sizeof(float));
-  const size_t off_lists_i = take((size_t)num_chunks * num_q * k * sizeof(int64_t));
+  const int num_lists = streamed ? 0 : num_chunks;
+  const size_t off_lists_d = take((size_t)num_lists * num_q * k * sizeof(float));
+  const size_t off_lists_i = take((size_t)num_lists * num_q * k * sizeof(int64_t));
   const size_t off_out_d = take((size_t)num_q * k * sizeof(float));
   const size_t off_out_i = take((size_t)num_q * k * sizeof(int64_t));
   const size_t off_uncert = take(sizeof(int32_t) * (size_t)(num_chunks + 1));
@@ -115,20 +173,16 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
     off_rank = take((size_t)num_q * sizeof(int64_t));
     off_cnt = take((size_t)num_q * sizeof(int64_t));
   }
-  const int64_t last_rows = num_g - (int64_t)(num_chunks - 1) * chunk_rows;
-  const size_t ws_bytes = std::max(
-      sbir_pairwise_topk_workspace_bytes(num_q, chunk_rows, dim, k, dtype, metric, want_rank ? 1 : 0),
-      sbir_pairwise_topk_workspace_bytes(num_q, last_rows, dim, k, dtype, metric, want_rank ? 1 : 0));
+  const size_t ws_bytes = streamed
+      ? sbir_pairwise_topk_workspace_bytes(num_q, num_g, dim, k, dtype, metric, want_rank ? 1 : 0)
+      : sbir_pairwise_topk_workspace_bytes(num_q, max_rows, dim, k, dtype, metric, want_rank ? 1 : 0);
   if (ws_bytes == 0) return SBIR_ERR_UNSUPPORTED;
   const size_t off_ws = take(ws_bytes);
   SBIR_TRY(ensure_staging(o));
+  SBIR_TRY(ensure_streams());
   uint8_t* base = static_cast<uint8_t*>(g_staging.buf);
   cudaStream_t cs = g_staging.compute, xs = g_staging.copy;
-  while ((int)g_staging.events.size() < num_chunks + 1) {
-    cudaEvent_t e;
-    SBIR_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    g_staging.events.push_back(e);
-  }
+  cudaEvent_t ev = nullptr;
 
   uint8_t* d_q = base + off_q;
   uint8_t* d_g = base + off_g;
@@ -138,62 +192,96 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   long long* d_rank = nullptr;
   const int64_t* d_pos_global = nullptr;
   if (want_rank) {
-    // The positive's row may sit in any chunk: gather those rows on the host once, upload
-    // them, and evaluate d(q, pos) up front so every chunk can count against it.
-    std::vector<uint8_t> gathered((size_t)num_q * row_bytes);
-    std::vector<int64_t> ident((size_t)num_q);
-    for (int64_t i = 0; i < num_q; ++i) {
-      const int64_t pi = pos_index_host[i];
-      if (pi >= 0 && pi < num_g) {
-        std::memcpy(gathered.data() + (size_t)i * row_bytes, static_cast<const uint8_t*>(g_host) + (size_t)pi * row_bytes, row_bytes);
-        ident[i] = i;
-      } else {
-        std::memset(gathered.data() + (size_t)i * row_bytes, 0, row_bytes);
-        ident[i] = -1;
+    // The positive's row may sit in any chunk: gather those rows on the host once (pinned buffer,
+    // a few threads), upload them, and evaluate d(q, pos) up front so every chunk can count
+    // against it.
+    const size_t gather_bytes = align_up((size_t)num_q * row_bytes, 256);
+    SBIR_TRY(ensure_pinned(gather_bytes + (size_t)num_q * sizeof(int64_t)));
+    uint8_t* gathered = static_cast<uint8_t*>(g_staging.pinned);
+    int64_t* ident = reinterpret_cast<int64_t*>(gathered + gather_bytes);
+    auto gather = [&](int64_t i0, int64_t i1) {
+      for (int64_t i = i0; i < i1; ++i) {
+        const int64_t pi = pos_index_host[i];
+        if (pi >= 0 && pi < num_g) {
+          std::memcpy(gathered + (size_t)i * row_bytes, static_cast<const uint8_t*>(g_host) + (size_t)pi * row_bytes, row_bytes);
+          ident[i] = i;
+        } else {
+          std::memset(gathered + (size_t)i * row_bytes, 0, row_bytes);
+          ident[i] = -1;
+        }
       }
+    };
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)((size_t)num_q * row_bytes >> 22)));
+    if (nthreads <= 1) {
+      gather(0, num_q);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back(gather, num_q * t / nthreads, num_q * (t + 1) / nthreads);
+      for (auto& th : pool) th.join();
     }
-    SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_pos, gathered.data(), gathered.size(), cudaMemcpyHostToDevice, xs));
-    SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_posidx, ident.data(), ident.size() * sizeof(int64_t), cudaMemcpyHostToDevice, xs));
+    SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_pos, gathered, (size_t)num_q * row_bytes, cudaMemcpyHostToDevice, xs));
+    SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_posidx, ident, (size_t)num_q * sizeof(int64_t), cudaMemcpyHostToDevice, xs));
     SBIR_CUDA_TRY(cudaMemcpyAsync(base + off_posglobal, pos_index_host, (size_t)num_q * sizeof(int64_t), cudaMemcpyHostToDevice, xs));
     d_pos_global = reinterpret_cast<const int64_t*>(base + off_posglobal);
-    SBIR_CUDA_TRY(cudaStreamSynchronize(xs));  // the two vectors above go out of scope
     d_pos_dist = reinterpret_cast<double*>(base + off_pos_dist);
     d_rank = reinterpret_cast<long long*>(base + off_rank);
     SBIR_TRY(launch_positive_distance(d_q, num_q, base + off_pos, num_q, dim, dtype, metric,
                                       reinterpret_cast<const int64_t*>(base + off_posidx), d_pos_dist, xs));
-    SBIR_CUDA_TRY(cudaMemsetAsync(d_rank, 0, (size_t)num_q * sizeof(int64_t), xs));
+    if (!streamed) SBIR_CUDA_TRY(cudaMemsetAsync(d_rank, 0, (size_t)num_q * sizeof(int64_t), xs));
   }
-  SBIR_CUDA_TRY(cudaEventRecord(g_staging.events[num_chunks], xs));
-  SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, g_staging.events[num_chunks], 0));
+  SBIR_TRY(event_at((size_t)num_chunks, &ev));
+  SBIR_CUDA_TRY(cudaEventRecord(ev, xs));
+  SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, ev, 0));
 
-  float* d_lists_d = reinterpret_cast<float*>(base + off_lists_d);
-  int64_t* d_lists_i = reinterpret_cast<int64_t*>(base + off_lists_i);
+  float* d_out_d = reinterpret_cast<float*>(base + off_out_d);
+  int64_t* d_out_i = reinterpret_cast<int64_t*>(base + off_out_i);
   int32_t* d_uncert = reinterpret_cast<int32_t*>(base + off_uncert);
-  for (int c = 0; c < num_chunks; ++c) {
-    const int64_t r0 = (int64_t)c * chunk_rows;
-    const int64_t rows = std::min<int64_t>(chunk_rows, num_g - r0);
+  auto upload_chunk = [&](int c) -> int {
+    const int64_t r0 = c ? chunk_end[c - 1] : 0;
     SBIR_CUDA_TRY(cudaMemcpyAsync(d_g + (size_t)r0 * row_bytes, static_cast<const uint8_t*>(g_host) + (size_t)r0 * row_bytes,
-                                  (size_t)rows * row_bytes, cudaMemcpyHostToDevice, xs));
-    SBIR_CUDA_TRY(cudaEventRecord(g_staging.events[c], xs));
-    SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, g_staging.events[c], 0));
-    int64_t* d_cnt = want_rank ? reinterpret_cast<int64_t*>(base + off_cnt) : nullptr;
-    SBIR_TRY(sbir_pairwise_topk_shard(d_q, num_q, d_g + (size_t)r0 * row_bytes, rows, dim, dtype, metric, k, r0,
-                                      d_pos_dist, d_pos_global, d_lists_d + (size_t)c * num_q * k,
-                                      d_lists_i + (size_t)c * num_q * k, d_cnt, d_uncert + 1 + c,
-                                      base + off_ws, ws_bytes, cs));
+                                  (size_t)(chunk_end[c] - r0) * row_bytes, cudaMemcpyHostToDevice, xs));
+    SBIR_TRY(event_at((size_t)c, &ev));
+    SBIR_CUDA_TRY(cudaEventRecord(ev, xs));
+    SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, ev, 0));
+    return SBIR_OK;
+  };
+  if (streamed) {
+    TopkPass pass;
+    SBIR_TRY(topk_pass_begin(pass, d_q, num_q, d_g, num_g, dim, dtype, metric, k, /*index_offset=*/0, nullptr, d_pos_dist,
+                             d_pos_global, /*tie_offset=*/0, d_out_d, d_out_i,
+                             want_rank ? reinterpret_cast<int64_t*>(d_rank) : nullptr, /*missing_rank=*/num_g,
+                             d_uncert + 1, base + off_ws, ws_bytes, cs));
+    for (int c = 0; c < num_chunks; ++c) {
+      SBIR_TRY(upload_chunk(c));
+      SBIR_TRY(topk_pass_feed(pass, chunk_end[c]));
+    }
+    SBIR_TRY(topk_pass_finish(pass));
+  } else {
+    float* d_lists_d = reinterpret_cast<float*>(base + off_lists_d);
+    int64_t* d_lists_i = reinterpret_cast<int64_t*>(base + off_lists_i);
+    for (int c = 0; c < num_chunks; ++c) {
+      const int64_t r0 = c ? chunk_end[c - 1] : 0;
+      const int64_t rows = chunk_end[c] - r0;
+      SBIR_TRY(upload_chunk(c));
+      int64_t* d_cnt = want_rank ? reinterpret_cast<int64_t*>(base + off_cnt) : nullptr;
+      SBIR_TRY(sbir_pairwise_topk_shard(d_q, num_q, d_g + (size_t)r0 * row_bytes, rows, dim, dtype, metric, k, r0,
+                                        d_pos_dist, d_pos_global, d_lists_d + (size_t)c * num_q * k,
+                                        d_lists_i + (size_t)c * num_q * k, d_cnt, d_uncert + 1 + c,
+                                        base + off_ws, ws_bytes, cs));
+      if (want_rank) {
+        add_i64_kernel<<<(unsigned)((num_q + 255) / 256), 256, 0, cs>>>(d_rank, reinterpret_cast<long long*>(d_cnt), num_q);
+        SBIR_CHECK_LAUNCH();
+      }
+    }
+    SBIR_TRY(launch_topk_merge(d_lists_d, d_lists_i, num_chunks, num_q, k, d_out_d, d_out_i, cs));
     if (want_rank) {
-      add_i64_kernel<<<(unsigned)((num_q + 255) / 256), 256, 0, cs>>>(d_rank, reinterpret_cast<long long*>(d_cnt), num_q);
+      missing_rank_kernel<<<(unsigned)((num_q + 255) / 256), 256, 0, cs>>>(d_rank, d_pos_dist, num_q, num_g);
       SBIR_CHECK_LAUNCH();
     }
   }
-  float* d_out_d = reinterpret_cast<float*>(base + off_out_d);
-  int64_t* d_out_i = reinterpret_cast<int64_t*>(base + off_out_i);
-  SBIR_TRY(launch_topk_merge(d_lists_d, d_lists_i, num_chunks, num_q, k, d_out_d, d_out_i, cs));
-  if (want_rank) {
-    missing_rank_kernel<<<(unsigned)((num_q + 255) / 256), 256, 0, cs>>>(d_rank, d_pos_dist, num_q, num_g);
-    SBIR_CHECK_LAUNCH();
+  if (want_rank)
     SBIR_CUDA_TRY(cudaMemcpyAsync(out_rank_host, d_rank, (size_t)num_q * sizeof(int64_t), cudaMemcpyDeviceToHost, cs));
-  }
   SBIR_CUDA_TRY(cudaMemcpyAsync(out_dist_host, d_out_d, (size_t)num_q * k * sizeof(float), cudaMemcpyDeviceToHost, cs));
   SBIR_CUDA_TRY(cudaMemcpyAsync(out_index_host, d_out_i, (size_t)num_q * k * sizeof(int64_t), cudaMemcpyDeviceToHost, cs));
   std::vector<int32_t> unc((size_t)num_chunks + 1, 0);
@@ -201,7 +289,7 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   SBIR_CUDA_TRY(cudaStreamSynchronize(cs));
   if (out_uncertified_host) {
     int32_t total = 0;
-    for (int c = 0; c < num_chunks; ++c) total += unc[1 + c];
+    for (int c = 0; c < (streamed ? 1 : num_chunks); ++c) total += unc[1 + c];
     *out_uncertified_host = total;
   }
   return SBIR_OK;

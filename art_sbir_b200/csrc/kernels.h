@@ -8,8 +8,10 @@ namespace sbir {
 
 // ---- rowops.cu ----------------------------------------------------------------
 // mode 0: ‖x‖² ; mode 1: −1/max(‖x‖,1e-8).  Rows [rows, rows_padded) get pad_value.
+// max_sqnorm_out is cleared first unless accumulate_max (then the running maximum is kept).
 int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int dtype,
-                    int mode, float pad_value, float* out, float* max_sqnorm_out, cudaStream_t st);
+                    int mode, float pad_value, float* out, float* max_sqnorm_out, cudaStream_t st,
+                    bool accumulate_max = false);
 // out[i] = min(gvec[8 i .. 8 i + 7]) (NaN entries ignored)
 int launch_chunk_min(const float* gvec, int64_t num_chunks, float* out, cudaStream_t st);
 int launch_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype, float eps,
@@ -53,6 +55,7 @@ struct K1Args {
   const void* g;
   int64_t num_q, num_g, dim;
   int dtype, metric, mode;
+  int chunk_begin, chunk_end;  // chunk steps [begin, end) of the plan this launch runs (0, 0 = all)
   const float* gvec;  // [num_g_tiles * kTileG] epilogue vector (‖g‖² | −1/max(‖g‖,eps)), padded
   const float* gmin;  // [num_g_tiles * kTileG / 8] minimum of gvec over each run of 8 rows (select modes)
   const int32_t* gate;  // optional device flag: every kernel of the launch is a no-op unless *gate != 0
@@ -162,6 +165,45 @@ int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, in
 int launch_fill_i32(int32_t* out, int64_t n, int32_t value, cudaStream_t st);
 int launch_fill_i64(int64_t* out, int64_t n, int64_t value, cudaStream_t st);
 int launch_retrieval_metrics(const int64_t* rank0, int64_t num_q, int k, double* out, cudaStream_t st);
+
+// ---- api.cu: one retrieval pass in phases (sbir_pairwise_topk*, sbir_retrieve_host) ----
+// Workspace of sbir_pairwise_topk / _shard (all offsets 256-byte aligned).
+struct TopkLayout {
+  K1Plan plan;
+  size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert, off_shared_thr;
+  size_t off_row_max, off_row_maxpos, off_sched, sched_bytes, off_gmin;
+  bool precise;        // fp32 inputs small enough for the 3xTF32 escalation workspace
+  K1Plan plan3;        // plan of the escalation pass (dim' = 3·dim), same partitions / lists as `plan`
+  size_t off_gate, off_q3, off_g3;  // off_sched: unit counter + chunk_done (zeroed together)
+  size_t off_mu, off_colpart;       // column mean of the gallery + its partial sums (centred escalation pass)
+  size_t off_pos_dist, off_lo, off_hi, off_cnt, off_dropped, off_pool_count, off_pool_q, off_pool_idx;
+  uint32_t pool_cap;
+  size_t total;
+};
+struct TopkPass {
+  TopkLayout L;
+  K1Args ka;
+  FinalizeArgs fa;
+  RankArgs ra;
+  bool want_rank, done;  // done: nothing (left) to do (empty inputs, or finish ran)
+  uint8_t* ws;
+  cudaStream_t st;
+  const void* q;
+  const void* g;
+  int64_t num_q, num_g, dim, padded, fed_rows;
+  int dtype, metric;
+  float *gvec, *gmax, *gmin, *qsq;
+  int32_t *flags, *uncert;
+};
+int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+                    int metric, int k, int64_t index_offset, const int64_t* pos_index, const double* pos_dist_in,
+                    const int64_t* pos_tie, int64_t tie_offset, float* out_dist, int64_t* out_index,
+                    int64_t* out_rank, int64_t missing_rank, int32_t* out_uncertified, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+// Rows per intermediate feed must be a multiple of this (0: the gallery cannot be fed in pieces).
+int64_t topk_pass_feed_granule(const TopkPass& P);
+int topk_pass_feed(TopkPass& P, int64_t row_end);  // gallery rows [fed_rows, row_end) are resident
+int topk_pass_finish(TopkPass& P);
 
 // ---- batch_hard.cu (K3) -----------------------------------------------------------
 size_t batch_hard_workspace_bytes(int64_t batch, int64_t dim);

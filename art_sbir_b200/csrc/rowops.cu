@@ -358,10 +358,10 @@ int launch_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, i
 }  // namespace
 
 int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int dtype,
-                    int mode, float pad_value, float* out, float* max_out, cudaStream_t st) {
+                    int mode, float pad_value, float* out, float* max_out, cudaStream_t st, bool accumulate_max) {
   if (rows_padded <= 0) return SBIR_OK;
   const bool vec = rows_vectorizable(x, dim, dtype);
-  if (max_out) SBIR_CUDA_TRY(cudaMemsetAsync(max_out, 0, sizeof(float), st));
+  if (max_out && !accumulate_max) SBIR_CUDA_TRY(cudaMemsetAsync(max_out, 0, sizeof(float), st));
   if (dtype == SBIR_F32)
     return launch_norm<float>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
   return launch_norm<__nv_bfloat16>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);

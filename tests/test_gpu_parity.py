@@ -422,6 +422,32 @@ def test_retrieve_host_equals_device_path(ops, sbir_lib, chunk_rows, monkeypatch
     sbir_lib.sbir_release_host_staging()
 
 
+def test_retrieve_host_streams_chunks_into_one_pass(ops, sbir_lib, monkeypatch):
+    """With enough query tiles for a single gallery partition the uploaded chunks are FED to one
+    retrieval pass (the distance kernel continues the same candidate lists from launch to launch).
+    Small chunk steps (SBIR_K1_CHUNK_MB) and 8192-row uploads force four feeds here; the result must
+    equal the device path bit for bit, ranks included, for top-10 and top-100."""
+    from art_sbir_b200 import _binding as B
+    monkeypatch.setenv("SBIR_K1_CHUNK_MB", "1")
+    monkeypatch.setenv("SBIR_HOST_CHUNK_ROWS", "8192")
+    nq, ng, d = 24000, 30000, 64
+    Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=12, beta=0.3)
+    pos[::97] = -1                                        # some queries without a positive
+    q, g = Q.bfloat16().pin_memory(), G.bfloat16().pin_memory()
+    for k in (10, 100):
+        od = torch.empty(nq, k).pin_memory()
+        oi = torch.empty(nq, k, dtype=torch.int64).pin_memory()
+        orank = torch.empty(nq, dtype=torch.int64).pin_memory()
+        unc = ctypes.c_int32(-1)
+        B.check(sbir_lib.sbir_retrieve_host(q.data_ptr(), nq, g.data_ptr(), ng, d, B.SBIR_BF16, B.SBIR_EUCLIDEAN, k,
+                                            pos.data_ptr(), od.data_ptr(), oi.data_ptr(), orank.data_ptr(), ctypes.byref(unc)),
+                "sbir_retrieve_host")
+        v, i, r = ops.pairwise_topk(q.cuda(), g.cuda(), k, "euclidean", pos_index=pos.cuda())
+        assert torch.equal(i.cpu(), oi) and torch.equal(v.cpu(), od) and torch.equal(r.cpu(), orank) and unc.value == 0
+        assert int((orank == ng).sum()) == int((pos < 0).sum())
+    sbir_lib.sbir_release_host_staging()
+
+
 # ------------------------------------------------------------ BASELINE-size property checks ----
 def _device_clustered(nq, ng, d, dtype, seed=1234):
     gen = torch.Generator(device="cuda").manual_seed(seed)
