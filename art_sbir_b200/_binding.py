@@ -39,6 +39,8 @@ PROTOTYPES = {
     "sbir_batch_hard_triplet_loss": (c_int, [_P, _P, _P, c_int64, c_int64, c_float, c_int, _P, _P, _P, _P, _P,
                                              _P, _P, _P, c_size_t, _P]),
     "sbir_retrieve_host": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "sbir_retrieve_host_shard": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P, _P,
+                                         _P, _P, _P]),
     "sbir_release_host_staging": (c_int, []),
     "sbir_profile_enable": (c_int, [c_int]),
     "sbir_profile_collect": (c_int, [_P, _P, _P]),

@@ -294,3 +294,89 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   }
   return SBIR_OK;
 }
+
+// One rank's part of a gallery-sharded retrieval with the shard in HOST memory: like
+// sbir_pairwise_topk_shard, but the shard's rows are uploaded in chunks on a copy stream and fed
+// to the pass as they arrive (same staging cache as sbir_retrieve_host).  Queries, the positives'
+// distances / global indices and the outputs are DEVICE buffers; work is ordered after `stream`
+// and the call returns when the outputs are complete.
+extern "C" int sbir_retrieve_host_shard(const void* q_dev, int64_t num_q, const void* g_host, int64_t num_g,
+                                        int64_t dim, int dtype, int metric, int k, int64_t index_offset,
+                                        const double* pos_dist_dev, const int64_t* pos_index_global_dev,
+                                        float* out_dist_dev, int64_t* out_index_dev, int64_t* out_count_less_dev,
+                                        int32_t* out_uncertified_host, void* stream) {
+  if (num_q <= 0 || num_g < 0 || dim <= 0 || k <= 0) return SBIR_ERR_INVALID_ARG;
+  if (q_dev == nullptr || out_dist_dev == nullptr || out_index_dev == nullptr) return SBIR_ERR_INVALID_ARG;
+  if (num_g > 0 && g_host == nullptr) return SBIR_ERR_INVALID_ARG;
+  if (out_count_less_dev != nullptr && pos_dist_dev == nullptr) return SBIR_ERR_INVALID_ARG;
+  if (dtype != SBIR_F32 && dtype != SBIR_BF16) return SBIR_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(g_staging_mu);
+  const bool want_rank = out_count_less_dev != nullptr;
+  const size_t row_bytes = (size_t)dim * elem_size(dtype);
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    sms = 148;
+  int64_t granule = 0;
+  if (num_g > 0) {
+    const K1Plan plan = make_k1_plan(num_q, num_g, dim, k, dtype, sms);
+    granule = plan.num_splits == 1 ? (int64_t)plan.tiles_per_chunk * kTileG : 0;
+  }
+  std::vector<int64_t> chunk_end;
+  if (granule > 0) {
+    size_t target = size_t(128) << 20;
+    if (const char* env = std::getenv("SBIR_HOST_CHUNK_ROWS")) {  // test hook: small chunks
+      const long long v = std::atoll(env);
+      if (v > 0) target = (size_t)v * row_bytes;
+    }
+    int64_t next = 0;
+    while (next < num_g) {
+      const int64_t rows = std::max<int64_t>(granule, (int64_t)(target / row_bytes) / granule * granule);
+      int64_t end = next + rows;
+      if (end + granule / 2 >= num_g) end = num_g;
+      chunk_end.push_back(end);
+      next = end;
+      target = std::min<size_t>(target * 2, size_t(1) << 30);
+    }
+  } else if (num_g > 0) {
+    chunk_end.push_back(num_g);  // several gallery partitions: upload everything, then one feed
+  }
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + (bytes ? bytes : 1), 256); return r; };
+  const size_t off_g = take((size_t)num_g * row_bytes);
+  const size_t off_uncert = take(sizeof(int32_t));
+  const size_t ws_bytes = sbir_pairwise_topk_workspace_bytes(num_q, num_g, dim, k, dtype, metric, want_rank ? 1 : 0);
+  if (ws_bytes == 0) return SBIR_ERR_UNSUPPORTED;
+  const size_t off_ws = take(ws_bytes);
+  SBIR_TRY(ensure_staging(o));
+  SBIR_TRY(ensure_streams());
+  uint8_t* base = static_cast<uint8_t*>(g_staging.buf);
+  cudaStream_t cs = g_staging.compute, xs = g_staging.copy;
+  cudaEvent_t ev = nullptr;
+  // everything here runs after the work already queued on the caller's stream
+  SBIR_TRY(event_at(chunk_end.size(), &ev));
+  SBIR_CUDA_TRY(cudaEventRecord(ev, static_cast<cudaStream_t>(stream)));
+  SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, ev, 0));
+  uint8_t* d_g = base + off_g;
+  int32_t* d_uncert = reinterpret_cast<int32_t*>(base + off_uncert);
+  TopkPass pass;
+  // A query without a positive anywhere (NaN pos_dist) contributes a local count of 0.
+  SBIR_TRY(topk_pass_begin(pass, q_dev, num_q, d_g, num_g, dim, dtype, metric, k, index_offset, nullptr, pos_dist_dev,
+                           pos_index_global_dev, index_offset, out_dist_dev, out_index_dev, out_count_less_dev,
+                           /*missing_rank=*/0, d_uncert, base + off_ws, ws_bytes, cs));
+  for (size_t c = 0; c < chunk_end.size(); ++c) {
+    const int64_t r0 = c ? chunk_end[c - 1] : 0;
+    SBIR_CUDA_TRY(cudaMemcpyAsync(d_g + (size_t)r0 * row_bytes, static_cast<const uint8_t*>(g_host) + (size_t)r0 * row_bytes,
+                                  (size_t)(chunk_end[c] - r0) * row_bytes, cudaMemcpyHostToDevice, xs));
+    SBIR_TRY(event_at(c, &ev));
+    SBIR_CUDA_TRY(cudaEventRecord(ev, xs));
+    SBIR_CUDA_TRY(cudaStreamWaitEvent(cs, ev, 0));
+    SBIR_TRY(topk_pass_feed(pass, chunk_end[c]));
+  }
+  SBIR_TRY(topk_pass_finish(pass));
+  int32_t unc = 0;
+  SBIR_CUDA_TRY(cudaMemcpyAsync(&unc, d_uncert, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+  SBIR_CUDA_TRY(cudaStreamSynchronize(cs));
+  if (out_uncertified_host) *out_uncertified_host = unc;
+  return SBIR_OK;
+}

@@ -73,7 +73,11 @@ def sharded_pairwise_topk(queries: torch.Tensor, gallery_shard: torch.Tensor, k:
         pos_dist = torch.where(pair[1] > 0, pair[0], torch.full_like(pair[0], float("nan")))
 
     vals, idx, cnt = local_fn(queries, gallery_shard, k, loss_type, shard_offset, pos_dist, pos_index)
+    return _exchange(vals, idx, cnt, pos_dist, num_gallery_total, world, group, merge_fn)
 
+
+def _exchange(vals, idx, cnt, pos_dist, num_gallery_total, world, group, merge_fn):
+    """The path's one exchange step: all-gather of the per-shard lists + K4 merge, all-reduce of the counts."""
     if world > 1:
         all_vals = [torch.empty_like(vals) for _ in range(world)]
         all_idx = [torch.empty_like(idx) for _ in range(world)]
@@ -83,6 +87,57 @@ def sharded_pairwise_topk(queries: torch.Tensor, gallery_shard: torch.Tensor, k:
         if cnt is not None:
             dist.all_reduce(cnt, group=group)
     rank_out = None
-    if pos_index is not None:
+    if pos_dist is not None:
         rank_out = torch.where(pos_dist != pos_dist, torch.full_like(cnt, num_gallery_total), cnt)
     return vals, idx, rank_out
+
+
+def sharded_retrieve_host(queries_host: torch.Tensor, gallery_shard_host: torch.Tensor, k: int,
+                          loss_type: str = "euclidean", pos_index: Optional[torch.Tensor] = None,
+                          shard_offset: int = 0, num_gallery_total: Optional[int] = None, group=None,
+                          device: Optional[torch.device] = None):
+    """`sharded_pairwise_topk` for embeddings that live in HOST memory (pinned for full PCIe speed):
+    the rank's gallery shard is uploaded in chunks while earlier chunks are scored
+    (sbir_retrieve_host_shard), the positives' rows are gathered on the host by their owner rank.
+    Returns device tensors (values, global indices, rank or None), the same on every rank."""
+    from . import _binding as B
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    n_local = gallery_shard_host.shape[0]
+    if num_gallery_total is None:
+        sizes = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(sizes, group=group)
+        num_gallery_total = int(sizes.item())
+    if queries_host.dtype != gallery_shard_host.dtype:
+        queries_host, gallery_shard_host = queries_host.float(), gallery_shard_host.float()
+    g_host = gallery_shard_host.contiguous()
+    q = queries_host.to(dev, non_blocking=True).contiguous()
+    nq, d = q.shape
+    pos_dist = pos_g = None
+    if pos_index is not None:
+        pos_cpu = pos_index.to("cpu", torch.int64)
+        mine = (pos_cpu >= shard_offset) & (pos_cpu < shard_offset + n_local)
+        sel = mine.nonzero().flatten()
+        rows = g_host[pos_cpu[sel] - shard_offset].to(dev) if sel.numel() else torch.empty(0, d, dtype=q.dtype, device=dev)
+        local = torch.full((nq,), -1, dtype=torch.int64)
+        local[sel] = torch.arange(sel.numel())
+        mine_d = mine.to(dev)
+        d_local = ops.positive_distance(q, rows, local.to(dev), loss_type) if sel.numel() else torch.zeros(nq, dtype=torch.float64, device=dev)
+        pair = torch.stack([torch.where(mine_d, d_local, torch.zeros_like(d_local)), mine_d.to(torch.float64)])
+        if world > 1:
+            dist.all_reduce(pair, group=group)
+        pos_dist = torch.where(pair[1] > 0, pair[0], torch.full_like(pair[0], float("nan"))).contiguous()
+        pos_g = pos_cpu.to(dev)
+    vals = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    cnt = torch.zeros(nq, dtype=torch.int64, device=dev) if pos_dist is not None else None
+    import ctypes
+    unc = ctypes.c_int32(0)
+    with torch.cuda.device(dev):
+        B.check(B.load().sbir_retrieve_host_shard(
+            q.data_ptr(), nq, g_host.data_ptr() if n_local else None, n_local, d, ops._dtype_id(q), ops.metric_id(loss_type), k,
+            int(shard_offset), None if pos_dist is None else pos_dist.data_ptr(), None if pos_g is None else pos_g.data_ptr(),
+            vals.data_ptr(), idx.data_ptr(), None if cnt is None else cnt.data_ptr(), ctypes.byref(unc),
+            torch.cuda.current_stream().cuda_stream), "sbir_retrieve_host_shard")
+    return _exchange(vals, idx, cnt, pos_dist, num_gallery_total, world, group, ops.topk_merge)

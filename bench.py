@@ -306,11 +306,9 @@ def main():
                                                ph.data_ptr(), od.data_ptr(), oi.data_ptr(), orank.data_ptr(),
                                                ctypes.byref(c_unc)), "sbir_retrieve_host")
             else:
-                qd = qh.to(dev, non_blocking=True)
-                gd = gh.to(dev, non_blocking=True)
-                pd = ph.to(dev, non_blocking=True)
-                v, i, r = sharded.sharded_pairwise_topk(qd, gd, k, "euclidean", pos_index=pd, shard_offset=r0,
-                                                        num_gallery_total=num_g)
+                # each rank streams its shard from pinned host memory (sbir_retrieve_host_shard)
+                v, i, r = sharded.sharded_retrieve_host(qh, gh, k, "euclidean", pos_index=ph, shard_offset=r0,
+                                                        num_gallery_total=num_g, device=dev)
                 od.copy_(v, non_blocking=True)
                 oi.copy_(i, non_blocking=True)
                 orank.copy_(r, non_blocking=True)

@@ -176,7 +176,18 @@ int sbir_retrieve_host(const void* q_host, int64_t num_q, const void* g_host, in
                        int64_t dim, int dtype, int metric, int k, const int64_t* pos_index_host,
                        float* out_dist_host, int64_t* out_index_host, int64_t* out_rank_host,
                        int32_t* out_uncertified_host);
-/* Frees the cached staging memory of sbir_retrieve_host. */
+/* One rank's part of a gallery-sharded retrieval with the shard's rows in HOST (preferably pinned)
+ * memory: sbir_pairwise_topk_shard semantics (global indices = local row + index_offset; local
+ * count of rows closer than pos_dist; NaN pos_dist = no positive), with the rows uploaded in
+ * chunks on a copy stream and scored as they arrive.  q, pos_dist, pos_index_global and the
+ * outputs are DEVICE buffers; the work is ordered after `stream`; synchronous like
+ * sbir_retrieve_host.  Used by art_sbir_b200/sharded.py: sharded_retrieve_host. */
+int sbir_retrieve_host_shard(const void* q_dev, int64_t num_q, const void* g_host, int64_t num_g,
+                             int64_t dim, int dtype, int metric, int k, int64_t index_offset,
+                             const double* pos_dist_dev, const int64_t* pos_index_global_dev,
+                             float* out_dist_dev, int64_t* out_index_dev, int64_t* out_count_less_dev,
+                             int32_t* out_uncertified_host, void* stream);
+/* Frees the cached staging memory of sbir_retrieve_host / sbir_retrieve_host_shard. */
 int sbir_release_host_staging(void);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------

@@ -448,6 +448,43 @@ def test_retrieve_host_streams_chunks_into_one_pass(ops, sbir_lib, monkeypatch):
     sbir_lib.sbir_release_host_staging()
 
 
+def test_sharded_host_path_equals_single_pass(ops, sbir_lib, monkeypatch):
+    """sbir_retrieve_host_shard: each rank's shard comes from HOST memory in chunks fed to one pass.
+    Two and three shards scored one after the other on this GPU + K4 merge must equal the
+    single-GPU device path; sharded_retrieve_host (world size 1) as well."""
+    from art_sbir_b200 import _binding as B, sharded
+    monkeypatch.setenv("SBIR_K1_CHUNK_MB", "1")
+    monkeypatch.setenv("SBIR_HOST_CHUNK_ROWS", "8192")
+    nq, ng, d, k = 24000, 41000, 64, 10
+    Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=14, beta=0.3)
+    pos[::101] = -1
+    qh, gh = Q.bfloat16().pin_memory(), G.bfloat16().pin_memory()
+    qc, gc, pc = qh.cuda(), gh.cuda(), pos.cuda()
+    v1, i1, r1 = ops.pairwise_topk(qc, gc, k, "euclidean", pos_index=pc)
+    v0, i0, r0 = sharded.sharded_retrieve_host(qh, gh, k, "euclidean", pos_index=pos, shard_offset=0, num_gallery_total=ng)
+    assert torch.equal(i0, i1) and torch.equal(v0, v1) and torch.equal(r0, r1)
+    own = ops.positive_distance(qc, gc, pc)                      # NaN where there is no positive
+    for world in (2, 3):
+        vs, is_, total = [], [], torch.zeros(nq, dtype=torch.int64, device="cuda")
+        for r in range(world):
+            a, b = sharded.shard_bounds(ng, world, r)
+            shard = gh[a:b].contiguous().pin_memory()
+            v = torch.empty(nq, k, device="cuda")
+            i = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+            c = torch.zeros(nq, dtype=torch.int64, device="cuda")
+            unc = ctypes.c_int32(-1)
+            B.check(sbir_lib.sbir_retrieve_host_shard(qc.data_ptr(), nq, shard.data_ptr(), b - a, d, B.SBIR_BF16, B.SBIR_EUCLIDEAN, k, a,
+                                                      own.data_ptr(), pc.data_ptr(), v.data_ptr(), i.data_ptr(), c.data_ptr(),
+                                                      ctypes.byref(unc), torch.cuda.current_stream().cuda_stream),
+                    "sbir_retrieve_host_shard")
+            assert unc.value == 0
+            vs.append(v); is_.append(i); total += c
+        vm, im = ops.topk_merge(torch.stack(vs), torch.stack(is_))
+        rk = torch.where(own != own, torch.full_like(total, ng), total)
+        assert torch.equal(im, i1) and torch.equal(vm, v1) and torch.equal(rk, r1)
+    sbir_lib.sbir_release_host_staging()
+
+
 # ------------------------------------------------------------ BASELINE-size property checks ----
 def _device_clustered(nq, ng, d, dtype, seed=1234):
     gen = torch.Generator(device="cuda").manual_seed(seed)
