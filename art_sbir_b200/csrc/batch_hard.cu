@@ -147,26 +147,43 @@ __global__ void __launch_bounds__(kBhThreads) bh_grad_anchor_kernel(
 }
 
 // One block per candidate row j: walk the anchors in index order and accumulate the
-// contributions of those that selected j (fixed order → bitwise reproducible).
+// contributions of those that selected j (fixed order → bitwise reproducible).  The selections
+// are scanned 128 anchors at a time (one per thread, flags through shared memory, so the walk
+// itself is a handful of broadcast loads) and the gradient row is accumulated in shared memory
+// (`acc`, dim floats; global memory when the row does not fit) and written once.
 __global__ void __launch_bounds__(kBhThreads) bh_grad_cand_kernel(
     const float* __restrict__ a, const float* __restrict__ x, int batch, int dim, int metric,
     const float* __restrict__ weight, const long long* __restrict__ sel, float* __restrict__ gp,
-    float* __restrict__ gn) {
+    float* __restrict__ gn, int acc_in_smem) {
+  extern __shared__ float bh_acc[];
   __shared__ double red[4];
+  __shared__ unsigned char s_flag[kBhThreads];
   const int j = blockIdx.x;
   float* out = j < batch ? (gp ? gp + (size_t)j * dim : nullptr) : (gn ? gn + (size_t)(j - batch) * dim : nullptr);
   if (out == nullptr) return;
-  for (int e = threadIdx.x; e < dim; e += kBhThreads) out[e] = 0.f;
+  float* acc = acc_in_smem ? bh_acc : out;
+  for (int e = threadIdx.x; e < dim; e += kBhThreads) acc[e] = 0.f;
   const float* xr = x + (size_t)j * dim;
-  for (int i = 0; i < batch; ++i) {
-    const float w = weight[i];
-    if (w == 0.f) continue;
-    const bool as_pos = sel[2 * i] == j, as_neg = sel[2 * i + 1] == j;
-    if (!as_pos && !as_neg) continue;
-    const float* ar = a + (size_t)i * dim;
-    const PairStats st = pair_stats(ar, xr, dim, metric, red);
-    if (as_pos) accumulate_pair_grad(ar, xr, dim, metric, st, w, true, out);
-    if (as_neg) accumulate_pair_grad(ar, xr, dim, metric, st, -w, true, out);
+  for (int base = 0; base < batch; base += kBhThreads) {
+    const int i_mine = base + threadIdx.x;
+    unsigned char f = 0;
+    if (i_mine < batch && weight[i_mine] != 0.f) f = (sel[2 * i_mine] == j ? 1 : 0) | (sel[2 * i_mine + 1] == j ? 2 : 0);
+    __syncthreads();  // previous chunk's flags fully consumed (and acc zeroed on the first pass)
+    s_flag[threadIdx.x] = f;
+    __syncthreads();
+    for (int u = 0; u < kBhThreads; ++u) {
+      const unsigned char fu = s_flag[u];  // same value for every thread: uniform branch
+      if (fu == 0) continue;
+      const int i = base + u;
+      const float w = weight[i];
+      const float* ar = a + (size_t)i * dim;
+      const PairStats st = pair_stats(ar, xr, dim, metric, red);
+      if (fu & 1) accumulate_pair_grad(ar, xr, dim, metric, st, w, true, acc);
+      if (fu & 2) accumulate_pair_grad(ar, xr, dim, metric, st, -w, true, acc);
+    }
+  }
+  if (acc_in_smem) {
+    for (int e = threadIdx.x; e < dim; e += kBhThreads) out[e] = acc[e];  // each thread wrote these itself
   }
 }
 
@@ -265,8 +282,9 @@ int launch_batch_hard(const float* a, const float* p, const float* n, int64_t ba
     SBIR_CHECK_LAUNCH();
   }
   if (gp || gn) {
-    bh_grad_cand_kernel<<<(unsigned)(2 * batch), kBhThreads, 0, st>>>(a, x, (int)batch, (int)dim, metric,
-                                                                     weight, sel, gp, gn);
+    const int acc_in_smem = (size_t)dim * sizeof(float) <= 40 * 1024 ? 1 : 0;
+    bh_grad_cand_kernel<<<(unsigned)(2 * batch), kBhThreads, acc_in_smem ? (size_t)dim * sizeof(float) : 0, st>>>(
+        a, x, (int)batch, (int)dim, metric, weight, sel, gp, gn, acc_in_smem);
     SBIR_CHECK_LAUNCH();
   }
   return SBIR_OK;

@@ -600,6 +600,19 @@ def case_small():
         ta.grad = tp.grad = tn.grad = None
         torch.nn.functional.triplet_margin_loss(ta, tp, tn, margin=0.2).backward()
     res["cfg2 triplet fwd+bwd 256x2048 torch library (same GPU)"] = {"us": _graph_us(torch_step)}
+
+    eye = torch.zeros(256, 512, dtype=torch.bool, device="cuda")
+    eye[torch.arange(256, device="cuda"), torch.arange(256, device="cuda")] = True
+
+    def torch_batch_hard():
+        # the same definition written with library ops: broadcast distance + masks + autograd
+        ta.grad = tp.grad = tn.grad = None
+        x = torch.cat([tp, tn])
+        dm = (ta[:, None, :] - x[None, :, :] + 1e-6).norm(dim=2)
+        hp = dm.masked_fill(~eye, float("-inf")).max(dim=1).values
+        hn = dm.masked_fill(eye, float("inf")).min(dim=1).values
+        torch.clamp_min(0.2 + hp - hn, 0).mean().backward()
+    res["cfg2 batch-hard fwd+bwd 256x512x2048 torch library ops (same GPU)"] = {"us": _graph_us(torch_batch_hard, replays=20)}
     q, g, pos = _clustered(1000, 10000, 2048, torch.float32)
     res["cfg1 retrieval 1000x10000x2048 fp32 top-10+rank"] = {"us": _graph_us(lambda: ops.pairwise_topk(q, g, 10, "euclidean", pos_index=pos))}
     return res
