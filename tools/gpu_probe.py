@@ -664,20 +664,40 @@ def case_diag():
     for nq, ng, d, dt, k in [(20000, 1000000, 512, "bfloat16", 10), (20000, 1000000, 512, "bfloat16", 100),
                              (12500, 75000, 2048, "float32", 10), (12500, 75000, 2048, "float32", 100)]:
         q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
-        os.environ["SBIR_K1_FLAGS"] = "64"
-        ops.pairwise_topk(q, g, k, "euclidean")
-        torch.cuda.synchronize()
-        lib.sbir_debug_k1_diag(buf, 148 * 8)
-        ops.pairwise_topk(q, g, k, "euclidean")
-        torch.cuda.synchronize()
-        lib.sbir_debug_k1_diag(buf, 148 * 8)
-        a = np.array(list(buf), dtype=np.float64).reshape(148, 8)
-        loop = a[:, 2].mean()
-        out[f"{nq}x{ng}x{d} {dt} k={k}"] = {"mma_loop_Mclk": round(loop / 1e6, 2), "wait_acc_frac": round(a[:, 0].mean() / loop, 3),
-                                            "wait_operands_frac": round(a[:, 1].mean() / loop, 3),
-                                            "epi_wait_acc_full_frac": round(a[:, 3].mean() / loop, 3)}
+        for flags in ("64", "72"):   # 72 = 64 + 8: epilogue switched off (mainloop alone)
+            os.environ["SBIR_K1_FLAGS"] = flags
+            ops.pairwise_topk(q, g, k, "euclidean")
+            torch.cuda.synchronize()
+            lib.sbir_debug_k1_diag(buf, 148 * 8)
+            ops.pairwise_topk(q, g, k, "euclidean")
+            torch.cuda.synchronize()
+            lib.sbir_debug_k1_diag(buf, 148 * 8)
+            a = np.array(list(buf), dtype=np.float64).reshape(148, 8)
+            a = a[a[:, 2] > 0]                      # CTA pairs: only the leaders record
+            loop = a[:, 2].mean()
+            out[f"{nq}x{ng}x{d} {dt} k={k} flags={flags}"] = {
+                "mma_loop_Mclk": round(loop / 1e6, 2), "wait_acc_frac": round(a[:, 0].mean() / loop, 3),
+                "wait_operands_frac": round(a[:, 1].mean() / loop, 3), "epi_wait_acc_full_frac": round(a[:, 3].mean() / loop, 3)}
     os.environ.pop("SBIR_K1_FLAGS", None)
     return out
+
+
+def case_l2n():
+    """l2_normalize of 10M x 512 bf16 (and 4M x 256 fp32): device time for the current SBIR_L2N_VARIANT."""
+    import torch
+    from art_sbir_b200 import ops
+    res = {"variant": os.environ.get("SBIR_L2N_VARIANT", "default")}
+    x = torch.randn(10_000_000, 512, device="cuda", dtype=torch.bfloat16)
+    y = ops.l2_normalize(x)
+    ref = torch.nn.functional.normalize(x[:1000].float(), dim=1)
+    res["max_err"] = (y[:1000].float() - ref).abs().max().item()
+    us = _graph_us(lambda: ops.l2_normalize(x), 10)
+    res["10Mx512 bf16"] = {"us": us, "GB/s": 2 * x.numel() * 2 / us / 1e3}
+    del x, y
+    z = torch.randn(4_000_000, 256, device="cuda")
+    us = _graph_us(lambda: ops.l2_normalize(z), 10)
+    res["4Mx256 fp32"] = {"us": us, "GB/s": 2 * z.numel() * 4 / us / 1e3}
+    return res
 
 
 CASES = ["rowops", "dump_small", "dump_shapes", "topk_small", "topk_mid", "triplet", "batch_hard", "host", "peaks", "time"]
