@@ -198,6 +198,45 @@ def test_edge_cases(ops):
         ops.pairwise_topk(torch.randn(3, 66, device=dev), torch.randn(5, 66, device=dev), 3)   # rows not 16-byte multiples
 
 
+@pytest.mark.parametrize("dtype,lt,k", [("bfloat16", "euclidean", 100), ("float32", "euclidean", 60), ("bfloat16", "cosine", 116),
+                                        ("float32", "cosine", 100)])
+def test_large_lists_on_hit_dense_data_with_duplicates(ops, dtype, lt, k):
+    """Lists of 64/128 entries run the owner + feeder epilogue (8 warps, one list per row, hits of the
+    second column half forwarded through a shared-memory queue, insertions batched per lane).  Stress it:
+    unstructured data sorted so that later gallery rows are CLOSER (every tile keeps producing hits and
+    the queues overflow), every row present three times (exact ties), several query tiles and gallery
+    tiles that do not divide evenly.  Exact top-k sets, tie order by index, exact ranks."""
+    g = torch.Generator().manual_seed(77)
+    nq, base, d = 2600, 7000, 64
+    tdt = getattr(torch, dtype)
+    Q = torch.randn(nq, d, generator=g).to(tdt)
+    G0 = torch.randn(base, d, generator=g)
+    # gallery rows ordered by decreasing distance to the mean query: thresholds keep dropping during the scan
+    order = (G0 - Q.float().mean(0)).norm(dim=1).argsort(descending=True)
+    G = G0[order].repeat(3, 1).to(tdt)                      # rows j, j + base, j + 2·base are identical
+    ng = G.shape[0]
+    pos = torch.randint(0, ng, (nq,), generator=g)
+    vals, idx, rank, unc = ops.pairwise_topk(Q.cuda(), G.cuda(), k, lt, pos_index=pos.cuda(), return_uncertified=True)
+    Qf, Gf = Q.float(), G.float()
+    ref_v, ref_i = O.pairwise_topk_batched(Qf, Gf, k, lt)
+    dist_rows = [O.distances(Qf[i:i + 1], Gf, lt) for i in range(nq)]
+    vals_c, idx_c = vals.cpu(), idx.cpu()
+    assert torch.allclose(vals_c, ref_v.float(), rtol=DIST_RTOL, atol=1e-6)
+    for i in range(nq):                                     # same multiset of distances; ties ordered by index
+        got = dist_rows[i][idx_c[i]]
+        assert torch.allclose(got, ref_v[i].float(), rtol=TIE_RTOL, atol=1e-6), i
+        same = vals_c[i, 1:] == vals_c[i, :-1]
+        assert (idx_c[i, 1:][same] > idx_c[i, :-1][same]).all(), i
+    # rank = rows strictly closer + equally distant rows with a smaller index (canonical order); fp32-level
+    # near-ties around d_pos may move it by a duplicate group
+    dpos = torch.stack([dist_rows[i][pos[i]] for i in range(nq)])
+    lower = torch.stack([(dist_rows[i] < dpos[i] * (1 - TIE_RTOL)).sum() for i in range(nq)])
+    upper = torch.stack([(dist_rows[i] <= dpos[i] * (1 + TIE_RTOL)).sum() for i in range(nq)])
+    r = rank.cpu()
+    assert ((r >= lower) & (r < upper)).all()
+    assert int(unc.item()) <= nq // 50 + 4
+
+
 def test_cancellation_heavy_fp32_escalates_to_3xtf32(ops):
     """Embeddings whose norms dwarf their distances (post-ReLU-like: a large common component) and
     positives unrelated to the queries: the TF32 error band covers much of the distance
