@@ -176,10 +176,13 @@ __global__ void __launch_bounds__(kFbThreads) topk_fallback_kernel(const FinPara
   __shared__ int32_t wi[kFbWarps][128];
   __shared__ double md[1024];
   __shared__ int32_t mi[1024];
-  const int q = blockIdx.x;
-  if ((p.flags[q] & 1) == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = p.k;
+  // a few blocks per SM walk the queries: when nothing is flagged (the normal case) the launch costs
+  // a couple of microseconds instead of one empty block per query
+  for (int q = blockIdx.x; q < p.num_q; q += gridDim.x) {
+  if ((p.flags[q] & 1) == 0) continue;
+  __syncthreads();  // shared lists of the previous flagged query fully consumed
   for (int i = lane; i < k; i += 32) {
     wd[warp][i] = INFINITY;
     wi[warp][i] = INT_MAX;
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(kFbThreads) topk_fallback_kernel(const FinPara
     const bool have = mi[i] != INT_MAX;
     p.out_dist[(size_t)q * k + i] = have ? (float)md[i] : INFINITY;
     p.out_index[(size_t)q * k + i] = have ? (long long)mi[i] + p.index_offset : -1LL;
+  }
   }
 }
 
@@ -327,9 +331,10 @@ __global__ void __launch_bounds__(256) rank_finalize_kernel(const RankParams p) 
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kFbThreads) rank_fallback_kernel(const RankParams p) {
   __shared__ int red[kFbWarps];
-  const int q = blockIdx.x;
-  if (p.out_rank[q] != -1) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = blockIdx.x; q < p.num_q; q += gridDim.x) {
+  if (p.out_rank[q] != -1) continue;  // uniform across the block (read before anyone writes it)
+  __syncthreads();
   const double dpos = p.pos_dist[q];
   const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
   int cnt = 0;
@@ -344,6 +349,7 @@ __global__ void __launch_bounds__(kFbThreads) rank_fallback_kernel(const RankPar
     long long r = 0;
     for (int w = 0; w < kFbWarps; ++w) r += red[w];
     p.out_rank[q] = r;
+  }
   }
 }
 
@@ -779,7 +785,8 @@ int launch_topk_fallback(const FinalizeArgs& a, cudaStream_t st) {
   if (a.num_q <= 0) return SBIR_OK;
   const FinParams p = make_fin_params(a, nullptr);
   const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
-  SBIR_DISPATCH_T(a.dtype, vec, topk_fallback_kernel, (unsigned)a.num_q, kFbThreads, 0, st, p);
+  const unsigned grid = (unsigned)(a.num_q < 148 * 8 ? a.num_q : 148 * 8);
+  SBIR_DISPATCH_T(a.dtype, vec, topk_fallback_kernel, grid, kFbThreads, 0, st, p);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }
@@ -809,7 +816,8 @@ int launch_rank_fallback(const RankArgs& a, cudaStream_t st) {
   if (a.num_q <= 0) return SBIR_OK;
   const RankParams p = make_rank_params(a);
   const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
-  SBIR_DISPATCH_T(a.dtype, vec, rank_fallback_kernel, (unsigned)a.num_q, kFbThreads, 0, st, p);
+  const unsigned grid = (unsigned)(a.num_q < 148 * 8 ? a.num_q : 148 * 8);
+  SBIR_DISPATCH_T(a.dtype, vec, rank_fallback_kernel, grid, kFbThreads, 0, st, p);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }
