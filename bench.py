@@ -35,6 +35,8 @@ WORKLOADS = {
     # name: (num_q, num_g, dim, dtype, k, description)
     "cfg4": (100_000, 10_000_000, 512, "bfloat16", 10,
              "BASELINE cfg4: 100k queries x 10M gallery, 512-d bf16, top-10 + rank, gallery-sharded"),
+    "cfg4k100": (100_000, 10_000_000, 512, "bfloat16", 100,
+                 "BASELINE cfg4 with K=100: 100k queries x 10M gallery, 512-d bf16, top-100 + rank, gallery-sharded"),
     "cfg3": (12_500, 75_000, 2048, "float32", 100, "BASELINE cfg3: 12.5k x 75k, 2048-d fp32, top-100 + rank"),
     "cfg3k10": (12_500, 75_000, 2048, "float32", 10, "cfg3 shape with top-10 + rank (2048-d fp32 target line)"),
     "cfg1": (1_000, 10_000, 2048, "float32", 10, "BASELINE cfg1: 1k x 10k, 2048-d fp32, top-10 + rank"),
