@@ -101,11 +101,23 @@ __device__ __forceinline__ float reduce32(F get) {
 // kPair = 1: one CTA computes a 128×256 tile (cta_group::1).  kPair = 2: a 2-CTA cluster computes
 // a 256×256 tile with one M=256 tcgen05.mma (cta_group::2): each CTA loads its own 128 query rows
 // and only HALF of the gallery tile.
-template <int kCap, int kEpiWarps, int kPair>
+// kQRes (bf16 rows of at most 1 KB, single-CTA tiles): the 128-row QUERY tile of a unit stays resident
+// in tensor memory (256 of the 512 columns) and is the MMA's A operand from there (tcgen05.mma with
+// A in TMEM); only gallery k-slices travel through the shared-memory ring.  The MMA rate of the
+// all-smem form follows the operand bytes it reads from shared memory (12 KB per K step for a 128×256
+// tile); with A in TMEM that is 8 KB per 256 gallery rows, the L2→SM traffic drops by a third and the
+// ring gets deeper.  The accumulators shrink to two buffers of 128 columns: a 256-row gallery tile is
+// computed as two half-tiles.
+template <int kCap, int kEpiWarps, int kPair, bool kQRes = false>
 struct K1Config {
-  static constexpr int kStageBytesG = kStageBytesGFull / kPair;
-  static constexpr int kStageBytes = kStageBytesQ + kStageBytesG;
-  static constexpr int kMaxStages = kPair == 2 ? 6 : 4;
+  static constexpr int kAccCols = kQRes ? kTileG / 2 : kTileG;  // columns per accumulator buffer = MMA N
+  static constexpr int kSubTiles = kTileG / kAccCols;           // accumulator-sized pieces per gallery tile
+  static constexpr int kAccBase = kQRes ? 256 : 0;              // first accumulator column (Q tile below it)
+  static constexpr int kStageBytesG = kQRes ? kAccCols * kSwizzleBytes : kStageBytesGFull / kPair;
+  static constexpr int kStageBytesA = kQRes ? 0 : kStageBytesQ;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesG;
+  static constexpr int kMaxStages = kQRes ? 10 : (kPair == 2 ? 6 : 4);
+  static_assert(!kQRes || kPair == 1, "the resident-query form uses single-CTA tiles");
   // Two epilogue warps share every TMEM lane quarter when kEpiWarps == 8 and split the columns.
   // Small lists: each of them keeps its own list (two lists per row).  Lists of 64/128 entries do
   // not fit twice beside the operand ring: the first warp OWNS the row's single list and the
@@ -125,12 +137,12 @@ struct K1Config {
   // feed region: queue values + indices [depth][128], tail / head / published threshold [128], 8 flags
   static constexpr int kFeedBytes = kFeed ? (2 * kFeedDepth + 3) * kTileQ * 4 + 32 : 0;
   static constexpr int kListBytes = kValBytes + (kIdxInSmem ? kValBytes : 0) + kGroupBytes + kFeedBytes;
-  static constexpr int kBarrierBytes = 384;
+  static constexpr int kBarrierBytes = 512;
   static constexpr int kStagesFit = (kSmemLimit - 1024 - kListBytes - kBarrierBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : kStagesFit;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kListBytes + kBarrierBytes;
   static constexpr int kThreads = 64 + kEpiWarps * 32;
-  static constexpr int kColsPerWarp = kTileG / kColSplit;
+  static constexpr int kColsPerWarp = kAccCols / kColSplit;
   static_assert(kStages >= 2, "operand ring needs at least two stages");
   static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps must cover the 4 TMEM lane quarters");
 };
@@ -145,6 +157,8 @@ struct K1Params {
   int chunk_begin;     // first chunk step of this launch (streamed galleries: later launches continue the lists)
   int q_tile_stride;   // query-tile stride of candidate slots (num_q_tiles rounded up to even)
   int elems_per_kblock;
+  const void* q_raw;   // query matrix in global memory (resident-query form: loaded into TMEM by the epilogue warps)
+  int dim_elems;
   const int32_t* gate;     // optional: the kernel is a no-op unless *gate != 0 (escalation pass)
   int flags;               // diagnostics (SBIR_K1_FLAGS): 8 = epilogue skips the accumulator (mainloop alone), 16 = no chunk screen
   uint32_t* unit_counter;  // [1] zeroed by the caller: next unit to hand out (kPair = 1)
@@ -197,11 +211,14 @@ __device__ __forceinline__ UnitCoord decode_unit(int unit, const K1Params& p) {
   return c;
 }
 
-template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps, int kPair>
-__global__ void __launch_bounds__(K1Config<kCap, kEpiWarps, kPair>::kThreads, 1)
+template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps, int kPair, bool kQRes = false>
+__global__ void __launch_bounds__(K1Config<kCap, kEpiWarps, kPair, kQRes>::kThreads, 1)
 dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                  const __grid_constant__ CUtensorMap tmap_g, const K1Params prm) {
-  using Cfg = K1Config<kCap, kEpiWarps, kPair>;
+  using Cfg = K1Config<kCap, kEpiWarps, kPair, kQRes>;
+  static_assert(!kQRes || !kTF32, "the resident-query form is kind::f16 only");
+  constexpr int kAccCols = Cfg::kAccCols;
+  constexpr int kSubTiles = Cfg::kSubTiles;
   if (prm.gate != nullptr && *prm.gate == 0) return;  // uniform across the grid: nothing was set up yet
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytesG = Cfg::kStageBytesG;
@@ -219,7 +236,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
-  uint8_t* smem_g = smem + kStages * kStageBytesQ;
+  uint8_t* smem_g = smem + kStages * Cfg::kStageBytesA;
   float* list_val_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);
   int32_t* list_idx_s = reinterpret_cast<int32_t*>(list_val_s + kCap * Cfg::kListsPerRow * kTileQ);
   float* list_grp_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + Cfg::kListBytes - Cfg::kFeedBytes - Cfg::kGroupBytes);
@@ -240,6 +257,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   uint64_t* sched_empty_bar = bars + 2 * kStages + 4 + kSchedDepth;  // [kSchedDepth]
   int32_t* sched_unit = reinterpret_cast<int32_t*>(bars + 2 * kStages + 4 + 2 * kSchedDepth);  // [kSchedDepth]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_unit + kSchedDepth);
+  uint64_t* q_ready_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // resident-query form: Q tile of the unit is in TMEM
 
   const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -259,6 +277,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(&sched_full_bar[s], 1);
       mbar_init(&sched_empty_bar[s], 1 + kEpiWarps);  // MMA issuer + every epilogue warp
     }
+    mbar_init(q_ready_bar, 4);  // one arrival per TMEM lane quarter
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -316,10 +335,15 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (unit < 0) break;
         const UnitCoord uc = decode_unit(unit, prm);
         const int q_tile = uc.row_tile * kPair + cta_rank;
-        for (int t = uc.t_begin; t < uc.t_end; ++t) {
+        for (int t = uc.t_begin * kSubTiles; t < uc.t_end * kSubTiles; ++t) {
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if constexpr (kPair == 2) {
+            if constexpr (kQRes) {
+              // only the gallery half-tile's k-slice: the query tile is already in tensor memory
+              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+              tma_load_2d(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
+                          kb * prm.elems_per_kblock, t * kAccCols);
+            } else if constexpr (kPair == 2) {
               // the leader's barrier collects the bytes of both CTAs' loads
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
               tma_load_2d_pair(smem_q + stage * kStageBytesQ, &tmap_q, &full_bar[stage],
@@ -341,26 +365,39 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     __syncwarp();  // reconverge before the (warp-aligned) teardown barriers
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer ----
-    if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = make_instr_desc(kTF32 ? 2u : 1u, kTileQ * kPair, kTileG);
+    // The WHOLE warp runs this loop and only lane 0 executes the tcgen05.mma / commit instructions.
+    // Their operands (smem descriptors, TMEM addresses, barrier addresses) must be provably
+    // warp-uniform — values read from shared memory go through a shuffle — so that the compiler
+    // keeps them in uniform registers.  With a single divergent thread it wraps every UTCHMMA in an
+    // ELECT / R2UR.BROADCAST waterfall (~60 cycles per instruction), the issue loop then takes ~600
+    // cycles per k-block of 512 MMA cycles and the tensor pipe starves (tools/gpu_probe.py diag).
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = make_instr_desc(kTF32 ? 2u : 1u, kTileQ * kPair, kAccCols);
+      const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);
+      const bool issuer = lane == 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       const bool diag = (prm.flags & 64) != 0;
-      long long w_acc = 0, w_full = 0;
+      long long w_acc = 0, w_full = 0, w_issue = 0, w_commit = 0, n_kb = 0;
       const long long t_loop0 = clock64();
       for (int it = 0;; ++it) {
-        const int unit = next_unit_consumer(it);
-        release_unit_slot(it);
+        const int unit = __shfl_sync(kFullMask, next_unit_consumer(it), 0);
+        __syncwarp();  // every lane has read the ring slot
+        if (issuer) release_unit_slot(it);
         if (unit < 0) break;
         const UnitCoord uc = decode_unit(unit, prm);
-        for (int t = uc.t_begin; t < uc.t_end; ++t) {
+        if constexpr (kQRes) {
+          mbar_wait(q_ready_bar, (uint32_t)it & 1u);  // the epilogue warps stored this unit's query tile
+          tc_fence_after();
+        }
+        for (int t = uc.t_begin * kSubTiles; t < uc.t_end * kSubTiles; ++t) {
           long long tw = diag ? clock64() : 0;
           mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
           if (diag) w_acc += clock64() - tw;
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * kTileG;
+          const uint32_t d_tmem = tmem_u + Cfg::kAccBase + acc * kAccCols;
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
             tw = diag ? clock64() : 0;
             mbar_wait(&full_bar[stage], phase);
@@ -368,25 +405,39 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             tc_fence_after();
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_q + stage * kStageBytesQ));
             const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_g + stage * kStageBytesG));
+            tw = diag ? clock64() : 0;
+            if (issuer) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 × 32-byte K steps inside the 128-byte swizzle atom
-              if constexpr (kPair == 2) umma_ss_pair<kTF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-              else umma_ss<kTF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) {  // 4 × 32-byte K steps inside the 128-byte swizzle atom
+                if constexpr (kQRes) umma_ts_f16(d_tmem, tmem_u + kb * 32 + k * 8, b_desc + 2 * k, idesc, (kb | k) != 0);
+                else if constexpr (kPair == 2) umma_ss_pair<kTF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                else umma_ss<kTF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              }
             }
-            if constexpr (kPair == 2) umma_commit_pair(&empty_bar[stage]);
-            else umma_commit(&empty_bar[stage]);
+            if (diag) { const long long t1 = clock64(); w_issue += t1 - tw; tw = t1; }
+            if (issuer) {
+              if constexpr (kPair == 2) umma_commit_pair(&empty_bar[stage]);
+              else umma_commit(&empty_bar[stage]);
+            }
+            if (diag) { w_commit += clock64() - tw; ++n_kb; }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if constexpr (kPair == 2) umma_commit_pair(&acc_full_bar[acc]);
-          else umma_commit(&acc_full_bar[acc]);
+          if (issuer) {
+            if constexpr (kPair == 2) umma_commit_pair(&acc_full_bar[acc]);
+            else umma_commit(&acc_full_bar[acc]);
+          }
+          __syncwarp();
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
       }
-      if (diag && blockIdx.x < 148) {
+      if (diag && issuer && blockIdx.x < 148) {
         g_k1_diag[blockIdx.x * 8 + 0] = (unsigned long long)w_acc;
         g_k1_diag[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
         g_k1_diag[blockIdx.x * 8 + 2] = (unsigned long long)(clock64() - t_loop0);
+        g_k1_diag[blockIdx.x * 8 + 5] = (unsigned long long)w_issue;   // cycles inside the 4-MMA issue blocks
+        g_k1_diag[blockIdx.x * 8 + 6] = (unsigned long long)w_commit;  // cycles inside tcgen05.commit
+        g_k1_diag[blockIdx.x * 8 + 7] = (unsigned long long)n_kb;      // k-blocks issued
       }
     }
     __syncwarp();
@@ -414,6 +465,31 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int q_tile = uc.row_tile * kPair + cta_rank;
       const int q = q_tile * kTileQ + row;
       const bool q_valid = q < prm.num_q;
+
+      if constexpr (kQRes) {
+        // Every MMA of the previous unit has completed (its last accumulator was seen full), so the
+        // query tile in TMEM can be replaced: this thread stores ITS row (TMEM lane = query row,
+        // column j = 32-bit word j of the row, i.e. two bf16 per column, K-major) — one warp per
+        // lane quarter — and the MMA issuer is released once all four quarters are in.
+        if (half == 0) {
+          const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(prm.q_raw) + (size_t)q * prm.dim_elems * 2);
+          const int row_words = prm.dim_elems / 2;
+          for (int j = 0; j < prm.num_k_blocks; ++j) {
+            uint32_t w[32];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
+              if (q_valid && j * 32 + v * 4 < row_words) t4 = __ldg(src + j * 8 + v);
+              w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
+            }
+            tmem_st_32x32b_x32(tmem_base + lane_addr + j * 32, w);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(q_ready_bar);
+        }
+      }
 
       // This thread's list: entry p lives at [p * kTileQ + row] (conflict-free / coalesced).
       // Global slot of the list: keyed by (partition, query tile), shared by all its chunks.
@@ -664,7 +740,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       };
 
-      for (int t = uc.t_begin; t < uc.t_end; ++t) {
+      for (int t = uc.t_begin * kSubTiles; t < uc.t_end * kSubTiles; ++t) {  // t counts accumulator-sized pieces
         if constexpr (kSelect && Cfg::kFeed) {
           if (!feeder) {
             // The feeder may lag a tile behind and fill its queue while this accumulator's next
@@ -691,14 +767,14 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           // requested before waiting for the accumulator (L2 round trip off the critical path).
           if (!feeder) thr = fminf(thr, ordered_int_to_float(shared_next));
         }
-        const float* gv = prm.gvec + (size_t)t * kTileG + col_begin;
+        const float* gv = prm.gvec + (size_t)t * kAccCols + col_begin;
 #pragma unroll 1
         for (int c = 0; c < ((prm.flags & 8) ? 0 : Cfg::kColsPerWarp / 32); ++c) {
-          const uint32_t taddr = tmem_base + lane_addr + acc * kTileG + col_begin + c * 32;
+          const uint32_t taddr = tmem_base + Cfg::kAccBase + lane_addr + acc * kAccCols + col_begin + c * 32;
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
-          const int gcol0 = t * kTileG + col_begin + c * 32;  // gallery row of column 0 of this chunk
+          const int gcol0 = t * kAccCols + col_begin + c * 32;  // gallery row of column 0 of this chunk
           if constexpr (kSelect && Cfg::kFeed) {
             if (feeder) {
               thr = thr_pub[row];  // may lag behind the owner: then a few extra hits are forwarded
@@ -930,10 +1006,10 @@ int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int
   return SBIR_OK;
 }
 
-template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps, int kPair>
+template <bool kTF32, int kMetric, int kMode, int kCap, int kEpiWarps, int kPair, bool kQRes = false>
 int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm, int num_sms, cudaStream_t st) {
-  using Cfg = K1Config<kCap, kEpiWarps, kPair>;
-  auto kern = dist_topk_kernel<kTF32, kMetric, kMode, kCap, kEpiWarps, kPair>;
+  using Cfg = K1Config<kCap, kEpiWarps, kPair, kQRes>;
+  auto kern = dist_topk_kernel<kTF32, kMetric, kMode, kCap, kEpiWarps, kPair, kQRes>;
   SBIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   int workers = num_sms / kPair;
   if (workers > prm.num_units) workers = prm.num_units;
@@ -961,8 +1037,20 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& pr
 }
 
 template <bool kTF32, int kMetric, int kEpiWarps>
-int dispatch_mode_cap(int mode, int cap, int pair, const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm,
+int dispatch_mode_cap(int mode, int cap, int pair, bool qres, const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& prm,
                       int num_sms, cudaStream_t st) {
+  if constexpr (!kTF32 && kEpiWarps == 8) {
+    if (qres) {  // resident-query form (bf16 rows <= 1 KB, small lists)
+#define SBIR_K1_QRES_CASE(M, C) \
+  if (mode == M && cap == C) return launch_inst<false, kMetric, M, C, 8, 1, true>(tq, tg, prm, num_sms, st);
+      SBIR_K1_QRES_CASE(kModeTopk, 16)
+      SBIR_K1_QRES_CASE(kModeTopk, 32)
+      SBIR_K1_QRES_CASE(kModeTopkRank, 16)
+      SBIR_K1_QRES_CASE(kModeTopkRank, 32)
+#undef SBIR_K1_QRES_CASE
+      return SBIR_ERR_UNSUPPORTED;
+    }
+  }
 #define SBIR_K1_CASE(M, C)                                                                            \
   if (mode == M && cap == C) {                                                                        \
     if (pair == 2) return launch_inst<kTF32, kMetric, M, C, kEpiWarps, 2>(tq, tg, prm, num_sms, st);  \
@@ -1088,10 +1176,18 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.g)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
   if (a.num_q <= 0 || a.num_g <= 0) return SBIR_OK;
   const int pair = plan.pair == 2 ? 2 : 1;
+  const bool select_mode = a.mode == kModeTopk || a.mode == kModeTopkRank;
+  // Resident-query form (SBIR_K1_QRES=1; off by default): bf16 rows of at most 1 KB (the query tile fits
+  // 256 TMEM columns), small lists.  Validated, but measured slower on B200: its N=128 MMAs with A in
+  // TMEM take ~150 cycles each instead of 64 (20k × 1M × 512: 23.8 ms vs 18.1 ms; cfg4 1180 ms vs 861 ms),
+  // see DESIGN.md.
+  const char* qres_e = std::getenv("SBIR_K1_QRES");
+  const bool qres = qres_e != nullptr && qres_e[0] == '1' && select_mode && pair == 1 && a.dtype == SBIR_BF16 && plan.epi_warps == 8 &&
+                    plan.cap <= 32 && a.dim * 2 <= 1024 && a.dim % 8 == 0;
   CUtensorMap tq, tg;
   SBIR_TRY(make_tmap(&tq, a.q, a.num_q, a.dim, a.dtype, kTileQ));
-  // pair mode: each CTA of the pair loads half of the 256-row gallery tile
-  SBIR_TRY(make_tmap(&tg, a.g, a.num_g, a.dim, a.dtype, pair == 2 ? kTileG / 2 : kTileG));
+  // pair mode / resident-query form: gallery boxes of half a tile (128 rows)
+  SBIR_TRY(make_tmap(&tg, a.g, a.num_g, a.dim, a.dtype, (pair == 2 || qres) ? kTileG / 2 : kTileG));
   K1Params prm{};
   prm.gvec = a.gvec;
   prm.gmin = a.gmin;
@@ -1117,6 +1213,8 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.part_fastest = plan.part_fastest;
   prm.q_tile_stride = plan.q_tile_stride;
   prm.elems_per_kblock = (int)(kSwizzleBytes / elem_size(a.dtype));
+  prm.q_raw = a.q;
+  prm.dim_elems = (int)a.dim;
   {
     const char* fe = std::getenv("SBIR_K1_FLAGS");
     prm.flags = fe ? std::atoi(fe) : 0;
@@ -1155,8 +1253,8 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   const int epi = select ? plan.epi_warps : (a.dtype == SBIR_BF16 ? 8 : 4);
 #define SBIR_K1_DISPATCH(TF32, EPI)                                                                                        \
   do {                                                                                                                     \
-    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<TF32, SBIR_EUCLIDEAN, EPI>(a.mode, cap, pair, tq, tg, prm, num_sms, st); \
-    return dispatch_mode_cap<TF32, SBIR_COSINE, EPI>(a.mode, cap, pair, tq, tg, prm, num_sms, st);                      \
+    if (a.metric == SBIR_EUCLIDEAN) return dispatch_mode_cap<TF32, SBIR_EUCLIDEAN, EPI>(a.mode, cap, pair, qres, tq, tg, prm, num_sms, st); \
+    return dispatch_mode_cap<TF32, SBIR_COSINE, EPI>(a.mode, cap, pair, qres, tq, tg, prm, num_sms, st);                \
   } while (0)
   if (a.dtype == SBIR_F32) {
     if (epi == 8) SBIR_K1_DISPATCH(true, 8);

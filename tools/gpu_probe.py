@@ -677,7 +677,9 @@ def case_diag():
             loop = a[:, 2].mean()
             out[f"{nq}x{ng}x{d} {dt} k={k} flags={flags}"] = {
                 "mma_loop_Mclk": round(loop / 1e6, 2), "wait_acc_frac": round(a[:, 0].mean() / loop, 3),
-                "wait_operands_frac": round(a[:, 1].mean() / loop, 3), "epi_wait_acc_full_frac": round(a[:, 3].mean() / loop, 3)}
+                "wait_operands_frac": round(a[:, 1].mean() / loop, 3), "epi_wait_acc_full_frac": round(a[:, 3].mean() / loop, 3),
+                "per_kblock_clk": {"loop": round(loop / a[:, 7].mean(), 1), "wait_operands": round(a[:, 1].mean() / a[:, 7].mean(), 1),
+                                   "issue_4_mma": round(a[:, 5].mean() / a[:, 7].mean(), 1), "commit": round(a[:, 6].mean() / a[:, 7].mean(), 1)}}
     os.environ.pop("SBIR_K1_FLAGS", None)
     return out
 
