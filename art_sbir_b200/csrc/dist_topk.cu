@@ -316,7 +316,11 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   if (warp == 0) {
     // ------------------------------------------------- scheduler + TMA producer ----
-    if (lane == 0) {
+    // Like the MMA issuer: the whole warp runs the loop with warp-uniform state, lane 0 executes the
+    // TMA / barrier instructions (their operands then live in uniform registers; with one divergent
+    // thread every UTMALDG is wrapped in an R2UR.BROADCAST waterfall).
+    {
+      const bool issuer = lane == 0;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0;; ++it) {
@@ -324,10 +328,14 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if constexpr (kDynamic) {
           const int slot = it % kSchedDepth;
           mbar_wait(&sched_empty_bar[slot], ((uint32_t)(it / kSchedDepth) & 1u) ^ 1u);
-          const uint32_t u = atomicAdd(prm.unit_counter, 1u);
+          uint32_t u = 0;
+          if (issuer) u = atomicAdd(prm.unit_counter, 1u);
+          u = __shfl_sync(kFullMask, u, 0);
           unit = u < (uint32_t)prm.num_units ? (int)u : -1;
-          *reinterpret_cast<volatile int32_t*>(&sched_unit[slot]) = unit;
-          mbar_arrive(&sched_full_bar[slot]);  // release semantics: the store above is visible to waiters
+          if (issuer) {
+            *reinterpret_cast<volatile int32_t*>(&sched_unit[slot]) = unit;
+            mbar_arrive(&sched_full_bar[slot]);  // release semantics: the store above is visible to waiters
+          }
         } else {
           unit = worker + it * num_workers;
           if (unit >= prm.num_units) unit = -1;
@@ -338,7 +346,9 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int t = uc.t_begin * kSubTiles; t < uc.t_end * kSubTiles; ++t) {
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if constexpr (kQRes) {
+            if (!issuer) {
+              // nothing to issue on this lane
+            } else if constexpr (kQRes) {
               // only the gallery half-tile's k-slice: the query tile is already in tensor memory
               mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
               tma_load_2d(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
