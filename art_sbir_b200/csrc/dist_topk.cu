@@ -1106,17 +1106,16 @@ static int epi_warps_for(int dtype, int cap) {
   return feed ? 8 : 4;
 }
 
-// Single-CTA tiles are the default: on B200 the CTA-pair kernel (cta_group::2, M = 256) measured
-// 4-5 % slower on the power-capped cfg4 pass (profiles/r01_pair_vs_single_cfg4.txt) — its coarser
-// work granularity and pair-wide accumulator hand-off cost more than the halved gallery traffic
-// saves.  SBIR_K1_PAIR=2 selects it (A/B runs, tests).
-static int k1_pair_default() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("SBIR_K1_PAIR");
-    v = (e != nullptr && e[0] == '2') ? 2 : 1;
-  }
-  return v;
+// Single-CTA tiles or CTA pairs (cta_group::2, M = 256: each CTA loads its own query tile and HALF of the
+// gallery tile).  Pairs have the faster mainloop (20k × 1M × 512 bf16, epilogue off: 13.6 vs 14.6 ms) but
+// one MMA then waits for the slowest of 16 epilogue warps, so with small lists single-CTA tiles win
+// (cfg4: 816 vs 930 ms).  With the 128-entry lists of top-100 on fp32 rows only 3 single-CTA operand
+// stages fit and the mainloop starves (operand wait 300 of 680 cycles per k-block); the pair's 32 KB
+// stages fit 4: cfg3 K1 7.0 -> 6.2 ms.  SBIR_K1_PAIR=1 / 2 forces either form (A/B runs, tests).
+static int k1_pair_for(int dtype, int cap) {
+  const char* e = std::getenv("SBIR_K1_PAIR");
+  if (e != nullptr && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  return (dtype == SBIR_F32 && cap >= 64) ? 2 : 1;
 }
 
 int k1_diag_read(unsigned long long* out, int n) {
@@ -1141,7 +1140,7 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   if (p.num_q_tiles < 1) p.num_q_tiles = 1;
   if (p.num_g_tiles < 1) p.num_g_tiles = 1;
   p.q_tile_stride = (p.num_q_tiles + 1) & ~1;
-  p.pair = (p.num_q_tiles >= 2 && num_sms >= 2) ? k1_pair_default() : 1;
+  p.pair = (p.num_q_tiles >= 2 && num_sms >= 2) ? k1_pair_for(dtype, p.cap) : 1;
   const int row_tiles = (p.num_q_tiles + p.pair - 1) / p.pair;  // rows of the unit grid
   const int workers = num_sms / p.pair;                           // CTAs or CTA pairs
   const size_t es = dtype == SBIR_BF16 ? 2 : 4;
