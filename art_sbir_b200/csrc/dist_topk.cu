@@ -346,7 +346,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int t = uc.t_begin * kSubTiles; t < uc.t_end * kSubTiles; ++t) {
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (!issuer) {
+            if (!elect_one()) {
               // nothing to issue on this lane
             } else if constexpr (kQRes) {
               // only the gallery half-tile's k-slice: the query tile is already in tensor memory
@@ -375,12 +375,14 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     __syncwarp();  // reconverge before the (warp-aligned) teardown barriers
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer ----
-    // The WHOLE warp runs this loop and only lane 0 executes the tcgen05.mma / commit instructions.
-    // Their operands (smem descriptors, TMEM addresses, barrier addresses) must be provably
-    // warp-uniform — values read from shared memory go through a shuffle — so that the compiler
-    // keeps them in uniform registers.  With a single divergent thread it wraps every UTCHMMA in an
-    // ELECT / R2UR.BROADCAST waterfall (~60 cycles per instruction), the issue loop then takes ~600
-    // cycles per k-block of 512 MMA cycles and the tensor pipe starves (tools/gpu_probe.py diag).
+    // The WHOLE warp runs this loop and one lane chosen by elect.sync executes the tcgen05.mma /
+    // commit instructions.  Their operands (smem descriptors, TMEM addresses, barrier addresses) must
+    // be provably warp-uniform — values read from shared memory go through a shuffle — so that the
+    // compiler keeps them in uniform registers, and the predicate must come from elect.sync so that it
+    // emits the instructions back to back.  With a single divergent thread (or an `if (lane == 0)`)
+    // it wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall (~60 cycles per instruction), the
+    // issue loop then takes ~600 cycles per k-block of 512 MMA cycles and the tensor pipe starves
+    // (tools/gpu_probe.py diag).
     if (cta_rank == 0) {
       constexpr uint32_t idesc = make_instr_desc(kTF32 ? 2u : 1u, kTileQ * kPair, kAccCols);
       const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);
@@ -416,7 +418,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_q + stage * kStageBytesQ));
             const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_g + stage * kStageBytesG));
             tw = diag ? clock64() : 0;
-            if (issuer) {
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {  // 4 × 32-byte K steps inside the 128-byte swizzle atom
                 if constexpr (kQRes) umma_ts_f16(d_tmem, tmem_u + kb * 32 + k * 8, b_desc + 2 * k, idesc, (kb | k) != 0);
@@ -425,14 +427,14 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               }
             }
             if (diag) { const long long t1 = clock64(); w_issue += t1 - tw; tw = t1; }
-            if (issuer) {
+            if (elect_one()) {
               if constexpr (kPair == 2) umma_commit_pair(&empty_bar[stage]);
               else umma_commit(&empty_bar[stage]);
             }
             if (diag) { w_commit += clock64() - tw; ++n_kb; }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if (issuer) {
+          if (elect_one()) {
             if constexpr (kPair == 2) umma_commit_pair(&acc_full_bar[acc]);
             else umma_commit(&acc_full_bar[acc]);
           }
@@ -1186,13 +1188,12 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   if (a.num_q <= 0 || a.num_g <= 0) return SBIR_OK;
   const int pair = plan.pair == 2 ? 2 : 1;
   const bool select_mode = a.mode == kModeTopk || a.mode == kModeTopkRank;
-  // Resident-query form (SBIR_K1_QRES=1; off by default): bf16 rows of at most 1 KB (the query tile fits
-  // 256 TMEM columns), small lists.  Validated, but measured slower on B200: its N=128 MMAs with A in
-  // TMEM take ~150 cycles each instead of 64 (20k × 1M × 512: 23.8 ms vs 18.1 ms; cfg4 1180 ms vs 861 ms),
-  // see DESIGN.md.
+  // Resident-query form: bf16 rows of at most 1 KB (the query tile fits 256 TMEM columns), small lists.
+  // cfg4: 795 -> 765 ms (K1 1346 TFLOP/s, 98.8 % of the measured sustained bf16 peak).  SBIR_K1_QRES=0
+  // switches it off (A/B runs).
   const char* qres_e = std::getenv("SBIR_K1_QRES");
-  const bool qres = qres_e != nullptr && qres_e[0] == '1' && select_mode && pair == 1 && a.dtype == SBIR_BF16 && plan.epi_warps == 8 &&
-                    plan.cap <= 32 && a.dim * 2 <= 1024 && a.dim % 8 == 0;
+  const bool qres = !(qres_e != nullptr && qres_e[0] == '0') && select_mode && pair == 1 && a.dtype == SBIR_BF16 &&
+                    plan.epi_warps == 8 && plan.cap <= 32 && a.dim * 2 <= 1024 && a.dim % 8 == 0;
   CUtensorMap tq, tg;
   SBIR_TRY(make_tmap(&tq, a.q, a.num_q, a.dim, a.dtype, kTileQ));
   // pair mode / resident-query form: gallery boxes of half a tile (128 rows)

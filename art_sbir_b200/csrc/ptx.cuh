@@ -98,6 +98,19 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// One lane of the (converged) warp, chosen by the hardware: the predicate the compiler recognises for
+// single-thread issue of tcgen05 / TMA instructions from warp-uniform code.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem] · B[smem]ᵀ ; both operands K-major, described by 64-bit smem descriptors.
 template <bool kTF32>
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,

@@ -238,15 +238,16 @@ def test_large_lists_on_hit_dense_data_with_duplicates(ops, dtype, lt, k):
 
 
 def test_resident_query_form_matches_default_kernel(ops, monkeypatch):
-    """SBIR_K1_QRES=1: the query tile lives in tensor memory and is the MMA's A operand from there
-    (tcgen05.mma with A in TMEM), gallery half-tiles stream through shared memory.  Off by default
-    (slower on B200) but kept validated: identical results, ragged shapes included."""
+    """Resident-query form (default for bf16 rows of at most 1 KB and small lists): the query tile lives
+    in tensor memory and is the MMA's A operand from there (tcgen05.mma with A in TMEM), gallery
+    half-tiles stream through shared memory.  SBIR_K1_QRES=0 selects the all-shared-memory form:
+    identical results, ragged shapes included."""
     for nq, ng, d, lt, k in ((257, 3001, 512, "euclidean", 10), (1000, 20000, 192, "cosine", 20), (130, 700, 64, "euclidean", 1)):
         Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=nq, beta=0.3 if d < 512 else None)
         q, g, p = Q.bfloat16().cuda(), G.bfloat16().cuda(), pos.cuda()
-        monkeypatch.delenv("SBIR_K1_QRES", raising=False)
+        monkeypatch.setenv("SBIR_K1_QRES", "0")
         v0, i0, r0 = ops.pairwise_topk(q, g, k, lt, pos_index=p)
-        monkeypatch.setenv("SBIR_K1_QRES", "1")
+        monkeypatch.delenv("SBIR_K1_QRES", raising=False)
         v1, i1, r1 = ops.pairwise_topk(q, g, k, lt, pos_index=p)
         assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(r0, r1)
 
