@@ -1059,6 +1059,10 @@ int dispatch_mode_cap(int mode, int cap, int pair, bool qres, const CUtensorMap&
       SBIR_K1_QRES_CASE(kModeTopk, 32)
       SBIR_K1_QRES_CASE(kModeTopkRank, 16)
       SBIR_K1_QRES_CASE(kModeTopkRank, 32)
+      SBIR_K1_QRES_CASE(kModeTopk, 64)
+      SBIR_K1_QRES_CASE(kModeTopk, 128)
+      SBIR_K1_QRES_CASE(kModeTopkRank, 64)
+      SBIR_K1_QRES_CASE(kModeTopkRank, 128)
 #undef SBIR_K1_QRES_CASE
       return SBIR_ERR_UNSUPPORTED;
     }
@@ -1188,12 +1192,12 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   if (a.num_q <= 0 || a.num_g <= 0) return SBIR_OK;
   const int pair = plan.pair == 2 ? 2 : 1;
   const bool select_mode = a.mode == kModeTopk || a.mode == kModeTopkRank;
-  // Resident-query form: bf16 rows of at most 1 KB (the query tile fits 256 TMEM columns), small lists.
+  // Resident-query form: bf16 rows of at most 1 KB (the query tile fits 256 TMEM columns).
   // cfg4: 795 -> 765 ms (K1 1346 TFLOP/s, 98.8 % of the measured sustained bf16 peak).  SBIR_K1_QRES=0
   // switches it off (A/B runs).
   const char* qres_e = std::getenv("SBIR_K1_QRES");
   const bool qres = !(qres_e != nullptr && qres_e[0] == '0') && select_mode && pair == 1 && a.dtype == SBIR_BF16 &&
-                    plan.epi_warps == 8 && plan.cap <= 32 && a.dim * 2 <= 1024 && a.dim % 8 == 0;
+                    plan.epi_warps == 8 && a.dim * 2 <= 1024 && a.dim % 8 == 0;
   CUtensorMap tq, tg;
   SBIR_TRY(make_tmap(&tq, a.q, a.num_q, a.dim, a.dtype, kTileQ));
   // pair mode / resident-query form: gallery boxes of half a tile (128 rows)
