@@ -103,7 +103,10 @@ def test_k1_plan_covers_every_tile_exactly_once(sbir_lib, nq, ng, d, k, dtype):
     assert p["q_tiles"] == -(-nq // 128) and p["g_tiles"] == -(-ng // 256)
     assert p["cap"] in (16, 32, 64, 128) and p["cap"] >= k + 6 and p["cap"] * p["lists"] * p["parts"] <= 4096
     assert p["q_tile_stride"] >= p["q_tiles"] and p["q_tile_stride"] % 2 == 0
-    assert p["units"] == p["chunks"] * p["parts"] * p["q_tiles"]
+    # rows of the unit grid: query tiles, or PAIRS of them when the plan uses CTA pairs
+    # (chosen for fp32 embeddings with the 64/128-entry lists of large k)
+    assert p["pair"] == (2 if (dtype == 0 and p["cap"] >= 64 and p["q_tiles"] >= 2) else 1)
+    assert p["units"] == p["chunks"] * p["parts"] * -(-p["q_tiles"] // p["pair"])
     covered = []
     for part in range(p["parts"]):
         b = part * p["tiles_per_part"]
