@@ -198,6 +198,27 @@ def test_edge_cases(ops):
         ops.pairwise_topk(torch.randn(3, 66, device=dev), torch.randn(5, 66, device=dev), 3)   # rows not 16-byte multiples
 
 
+@pytest.mark.parametrize("nq,ng,d,k", [(3, 5, 64, 10), (1, 1, 8, 1), (130, 257, 72, 4), (129, 129, 512, 16), (40, 3000, 200, 26)])
+def test_bf16_small_and_ragged_shapes(ops, nq, ng, d, k):
+    """bf16 rows of at most 1 KB take the resident-query form (query tile in tensor memory): fewer
+    gallery rows than k, single rows, row lengths that do not fill the last 128-byte k-block, tile
+    boundaries off by one.  Indices / ranks against the oracle on the bf16-rounded inputs."""
+    g = torch.Generator().manual_seed(nq * 1000 + ng)
+    Q = torch.randn(nq, d, generator=g).bfloat16()
+    G = torch.randn(ng, d, generator=g).bfloat16()
+    pos = torch.randint(0, ng, (nq,), generator=g)
+    for lt in ("euclidean", "cosine"):
+        vals, idx, rank = ops.pairwise_topk(Q.cuda(), G.cuda(), k, lt, pos_index=pos.cuda())
+        kk = min(k, ng)
+        ref_v, ref_i = O.pairwise_topk_batched(Q.float(), G.float(), kk, lt)
+        ref_r = O.rank_of_positive_batched(Q.float(), G.float(), pos, lt)
+        dist_rows = [O.distances(Q[i:i + 1].float(), G.float(), lt) for i in range(nq)]
+        assert_topk_matches(vals[:, :kk], idx[:, :kk], ref_v, ref_i, dist_rows)
+        assert (idx[:, kk:] == -1).all() and torch.isinf(vals[:, kk:]).all()
+        assert (rank.cpu() - ref_r).abs().max() <= 1          # bf16 data: occasional fp32-level ties around d_pos
+        assert (rank.cpu() == ref_r).float().mean() >= 0.95
+
+
 @pytest.mark.parametrize("dtype,lt,k", [("bfloat16", "euclidean", 100), ("float32", "euclidean", 60), ("bfloat16", "cosine", 116),
                                         ("float32", "cosine", 100)])
 def test_large_lists_on_hit_dense_data_with_duplicates(ops, dtype, lt, k):
