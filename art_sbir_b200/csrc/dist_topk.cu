@@ -1166,7 +1166,18 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   // Chunks: ~12 MB of gallery rows per (partition, chunk) so that the rows every CTA of a chunk
   // step streams stay in L2 together with the live query tiles.
   const int64_t tile_bytes = (int64_t)kTileG * dim * (int64_t)es;
-  int64_t chunk_mb = 12;
+  // Resident-query form (dist_topk_kernel<..., kQRes>): bf16 rows of at most 1 KB — the query tile fits
+  // 256 TMEM columns — on single-CTA tiles.  cfg4: 795 -> 765 ms (chunk 12 MB) -> 740 ms (48 MB).
+  // SBIR_K1_QRES=0 switches it off (A/B runs, tests).
+  {
+    const char* e = std::getenv("SBIR_K1_QRES");
+    p.qres = (!(e != nullptr && e[0] == '0') && dtype == SBIR_BF16 && p.pair == 1 && p.epi_warps == 8 && dim * 2 <= 1024 &&
+              dim % 8 == 0) ? 1 : 0;
+  }
+  // Chunk size: with the queries streamed through L2 as well, 12 MB keeps a chunk's gallery rows AND the
+  // live query tiles resident; the resident-query form reads only gallery rows through L2, and longer
+  // units mean fewer list hand-overs and query-tile loads (cfg4: 12 / 24 / 48 / 96 MB -> 787 / 765 / 740 / 736 ms).
+  int64_t chunk_mb = p.qres ? 48 : 12;
   if (const char* e = std::getenv("SBIR_K1_CHUNK_MB")) {  // experiments only
     const int v = std::atoi(e);
     if (v > 0) chunk_mb = v;
@@ -1192,12 +1203,7 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   if (a.num_q <= 0 || a.num_g <= 0) return SBIR_OK;
   const int pair = plan.pair == 2 ? 2 : 1;
   const bool select_mode = a.mode == kModeTopk || a.mode == kModeTopkRank;
-  // Resident-query form: bf16 rows of at most 1 KB (the query tile fits 256 TMEM columns).
-  // cfg4: 795 -> 765 ms (K1 1346 TFLOP/s, 98.8 % of the measured sustained bf16 peak).  SBIR_K1_QRES=0
-  // switches it off (A/B runs).
-  const char* qres_e = std::getenv("SBIR_K1_QRES");
-  const bool qres = !(qres_e != nullptr && qres_e[0] == '0') && select_mode && pair == 1 && a.dtype == SBIR_BF16 &&
-                    plan.epi_warps == 8 && a.dim * 2 <= 1024 && a.dim % 8 == 0;
+  const bool qres = plan.qres == 1 && select_mode && pair == 1 && a.dtype == SBIR_BF16 && plan.epi_warps == 8;
   CUtensorMap tq, tg;
   SBIR_TRY(make_tmap(&tq, a.q, a.num_q, a.dim, a.dtype, kTileQ));
   // pair mode / resident-query form: gallery boxes of half a tile (128 rows)

@@ -40,6 +40,7 @@ struct K1Plan {
   int cap;            // per-list capacity (16, 32, 64 or 128)
   int lists_per_row;  // 1, or 2 (8 epilogue warps and cap <= 32: one list per column half)
   int epi_warps;      // 4 or 8 epilogue warps (8 with one list per row: owner + feeder warps, dist_topk.cu)
+  int qres;           // 1: resident-query form (query tile in tensor memory; bf16 rows of at most 1 KB)
   int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks;
   int band_q;         // unit-grid rows per L2 band (unit numbering, see decode_unit in dist_topk.cu)
   int num_chunks, tiles_per_chunk;  // every partition is scanned in `num_chunks` serial chunks

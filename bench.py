@@ -350,8 +350,10 @@ def main():
     # ncu capture of the single-GPU launch of this workload (profiles/); per-rank launches at N > 1
     # cover a shard and were not captured separately
     traffic = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch") if (traffic_file.is_file() and world == 1) else None
+    burst = peaks["bf16"] if dtype == torch.bfloat16 else peak
     roofline = {"bound": "tensor", "kernel": "dist_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_note": peak_note,
+                "frac_of_burst_peak": (achieved / burst) if achieved else None,
                 "k1_ms_per_launch": k1_ms_per_launch, "k1_share_of_step": k1_ms_per_launch / ms_per_step}
 
     cpu = None
