@@ -19,7 +19,8 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 BUILD_DIR = PKG / "lib" / "obj"
 LIB_PATH = LIB_DIR / "libsbir_b200.so"
-SOURCES = ["api.cu", "rowops.cu", "dist_topk.cu", "finalize.cu", "batch_hard.cu", "host_path.cu"]
+SOURCES = ["dist_topk_bf16_euclidean.cu", "dist_topk_bf16_cosine.cu", "dist_topk_f32_euclidean.cu", "dist_topk_f32_cosine.cu",
+           "api.cu", "rowops.cu", "dist_topk.cu", "finalize.cu", "batch_hard.cu", "host_path.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -79,7 +80,7 @@ def _build_locked(digest: str, stamp: Path, verbose: bool) -> Path:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         return str(obj), r.stderr
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), max(4, os.cpu_count() or 4))) as ex:
         results = list(ex.map(compile_one, SOURCES))
     (LIB_DIR / "ptxas.log").write_text("\n".join(log for _, log in results))
     tmp = LIB_DIR / f".libsbir_b200.{os.getpid()}.so"

@@ -1,7 +1,7 @@
 // batch_hard.cu — K3: batch-hard triplet mining + margin loss + gradients (H8, a north_star
 // extension; the reference forms triplets in its datasets, data_preparation.py:67-69,214-222,
 // and only evaluates nn.TripletMarginLoss / TripletMarginWithDistanceLoss on them,
-// train.py:164-175).  Mining runs on the same tcgen05 tiles as retrieval (dist_topk.cu in
+// train.py:164-175).  Mining runs on the same tcgen05 tiles as retrieval (dist_topk_kernel.cuh in
 // kModeHard); this file selects across tiles, re-scores the selected pairs exactly and
 // scatters gradients deterministically (no floating-point atomics).
 #include "common.cuh"

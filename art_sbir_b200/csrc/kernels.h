@@ -25,7 +25,7 @@ int launch_triplet(const float* a, const float* p, const float* n, int64_t batch
                    float margin, int metric, float* out_loss, float* per_row, float* ga, float* gp,
                    float* gn, cudaStream_t st);
 
-// ---- dist_topk.cu (K1) ----------------------------------------------------------
+// ---- dist_topk.cu / dist_topk_kernel.cuh (K1) ----------------------------------------------------------
 constexpr int kTileQ = 128;        // query rows per tile (UMMA M, TMEM lanes)
 constexpr int kTileG = 256;        // gallery rows per tile (UMMA N, TMEM columns)
 constexpr int kUncertainPerQuery = 256;  // uncertain-pool capacity = this × num_q (min 65536)
@@ -35,14 +35,14 @@ enum K1Mode { kModeTopk = 0, kModeTopkRank = 1, kModeDump = 2, kModeHard = 3 };
 
 // Work decomposition of one K1 launch: `num_splits` gallery partitions of `tiles_per_split` tiles
 // (independent candidate lists), each scanned in `num_chunks` serial chunks; a unit is
-// (query tile, partition, chunk) — see make_k1_plan / decode_unit in dist_topk.cu.
+// (query tile, partition, chunk) — see make_k1_plan (dist_topk.cu) / decode_unit (dist_topk_kernel.cuh).
 struct K1Plan {
   int cap;            // per-list capacity (16, 32, 64 or 128)
   int lists_per_row;  // 1, or 2 (8 epilogue warps and cap <= 32: one list per column half)
-  int epi_warps;      // 4 or 8 epilogue warps (8 with one list per row: owner + feeder warps, dist_topk.cu)
+  int epi_warps;      // 4 or 8 epilogue warps (8 with one list per row: owner + feeder warps, dist_topk_kernel.cuh)
   int qres;           // 1: resident-query form (query tile in tensor memory; bf16 rows of at most 1 KB)
   int num_q_tiles, num_g_tiles, num_splits, tiles_per_split, num_units, num_k_blocks;
-  int band_q;         // unit-grid rows per L2 band (unit numbering, see decode_unit in dist_topk.cu)
+  int band_q;         // unit-grid rows per L2 band (unit numbering, see decode_unit in dist_topk_kernel.cuh)
   int num_chunks, tiles_per_chunk;  // every partition is scanned in `num_chunks` serial chunks
   int part_fastest;   // unit numbering inside a chunk step: partitions (1) or query tiles (0) vary fastest
   int pair;           // 1: single-CTA tiles (cta_group::1); 2: CTA-pair tiles (cta_group::2, M = 256)
