@@ -6,16 +6,22 @@
 //
 // Structure (one persistent CTA per SM, warp-specialised):
 //   warp 0      scheduler + TMA producer: claims work units from a global counter, publishes
-//               them to the other warps through a small shared-memory ring, and streams
-//               Q k-slices [128 × 128 B] + G k-slices [256 × 128 B] (SWIZZLE_128B, mbarrier
-//               complete_tx) through a 4-stage ring                        (UTMALDG in SASS)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (kind::tf32 for fp32 embeddings,
-//               kind::f16 for bf16) M=128 × N=256 into one of two 256-column TMEM accumulators;
-//               tcgen05.commit releases smem stages and publishes the accumulator   (UTC*MMA)
+//               them to the other warps through a small shared-memory ring, and streams the
+//               operand k-slices (SWIZZLE_128B boxes of 128 bytes × 128/256 rows, mbarrier
+//               complete_tx) through a 3-10-stage ring                     (UTMALDG in SASS)
+//   warp 1      MMA issue: tcgen05.mma (kind::tf32 for fp32 embeddings, kind::f16 for bf16) into
+//               one of two TMEM accumulators; tcgen05.commit releases smem stages and publishes
+//               the accumulator                                        (UTCHMMA / UTCBAR)
+//               Both loops run warp-uniform with one lane elected by elect.sync: the operands
+//               stay in uniform registers and the instructions issue back to back.
 //   warps 2..   epilogue: tcgen05.ld 32 lanes × 32 columns → e = ‖g‖² − 2·q·g (euclidean) or
 //               e = −q·g/max(‖g‖,eps) (cosine); a thread owns one query row and keeps that
 //               query's running best-`cap` list; only chunks whose minimum beats the row's
 //               current threshold take the insertion path                             (LDTM)
+// Operand forms (K1Config): all-smem — Q [128 × 128 B] + G [256 × 128 B] per stage, M128 × N256
+// MMAs, two 256-column accumulators; resident-query (kQRes, bf16 rows <= 1 KB) — the unit's query
+// tile lives in 256 TMEM columns and is the A operand from there, G half-tiles [128 × 128 B] per
+// stage, M128 × N128 MMAs, two 128-column accumulators; CTA pairs (kPair = 2, cta_group::2, M = 256).
 // e orders gallery rows exactly like the distance does for a fixed query (‖q‖² and the
 // query norm are per-row constants); exact distances are recomputed for the survivors by
 // finalize.cu, so tensor-core rounding never reaches the caller.
