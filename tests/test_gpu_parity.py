@@ -523,6 +523,38 @@ def test_retrieve_host_streams_chunks_into_one_pass(ops, sbir_lib, monkeypatch):
     sbir_lib.sbir_release_host_staging()
 
 
+def test_retrieve_host_streamed_fp32_with_escalation(ops, sbir_lib, monkeypatch):
+    """Streamed feeds followed by the device-gated escalation pass: collapsed fp32 embeddings (a large
+    common component) uploaded in several chunks — the first pass (fed chunk by chunk) cannot certify
+    them, the centred 3xTF32 pass over the now-resident gallery must, and the host entry point must
+    return what the device path returns."""
+    from art_sbir_b200 import _binding as B
+    monkeypatch.setenv("SBIR_K1_CHUNK_MB", "1")
+    monkeypatch.setenv("SBIR_HOST_CHUNK_ROWS", "4096")
+    nq, ng, d, k = 24000, 14000, 64, 10
+    Q0, G0, pos = O.synthetic_embeddings(nq, ng, d, seed=15, beta=0.3)
+    base = 3.0 * torch.rand(1, d, generator=torch.Generator().manual_seed(2))
+    q, g = (base + 0.02 * Q0).contiguous().pin_memory(), (base + 0.02 * G0).contiguous().pin_memory()
+    od = torch.empty(nq, k).pin_memory()
+    oi = torch.empty(nq, k, dtype=torch.int64).pin_memory()
+    orank = torch.empty(nq, dtype=torch.int64).pin_memory()
+    unc = ctypes.c_int32(-1)
+    B.check(sbir_lib.sbir_retrieve_host(q.data_ptr(), nq, g.data_ptr(), ng, d, B.SBIR_F32, B.SBIR_EUCLIDEAN, k,
+                                        pos.data_ptr(), od.data_ptr(), oi.data_ptr(), orank.data_ptr(), ctypes.byref(unc)),
+            "sbir_retrieve_host")
+    v, i, r, u = ops.pairwise_topk(q.cuda(), g.cuda(), k, "euclidean", pos_index=pos.cuda(), return_uncertified=True)
+    assert torch.equal(i.cpu(), oi) and torch.equal(v.cpu(), od) and torch.equal(r.cpu(), orank)
+    assert unc.value == int(u.item()) and unc.value <= nq // 50 + 4
+    # and both agree with the reference formula evaluated directly (spot check on 200 queries)
+    sel = torch.arange(0, nq, 120)
+    dd = ((q[sel, None, :] - g[None, :, :]) + torch.tensor(1e-6)).double().pow(2).sum(-1).sqrt().float()
+    ref_v, ref_i = torch.topk(dd, k, dim=1, largest=False)
+    assert torch.allclose(od[sel], ref_v, rtol=DIST_RTOL, atol=1e-7)
+    for a, b in (oi[sel] != ref_i).nonzero().tolist():
+        assert abs(dd[a, oi[sel][a, b]].item() - ref_v[a, b].item()) <= TIE_RTOL * abs(ref_v[a, b].item())
+    sbir_lib.sbir_release_host_staging()
+
+
 def test_sharded_host_path_equals_single_pass(ops, sbir_lib, monkeypatch):
     """sbir_retrieve_host_shard: each rank's shard comes from HOST memory in chunks fed to one pass.
     Two and three shards scored one after the other on this GPU + K4 merge must equal the
