@@ -661,8 +661,11 @@ def case_diag():
     lib = B.load()
     out = {}
     buf = (ctypes.c_uint64 * (148 * 8))()
-    for nq, ng, d, dt, k in [(20000, 1000000, 512, "bfloat16", 10), (20000, 1000000, 512, "bfloat16", 100),
-                             (12500, 75000, 2048, "float32", 10), (12500, 75000, 2048, "float32", 100)]:
+    shapes = [(20000, 1000000, 512, "bfloat16", 10), (20000, 1000000, 512, "bfloat16", 100),
+              (12500, 75000, 2048, "float32", 10), (12500, 75000, 2048, "float32", 100)]
+    if os.environ.get("SBIR_DIAG_SMALL"):
+        shapes = [(1000, 10000, 2048, "float32", 10), (1000, 10000, 512, "bfloat16", 10)]
+    for nq, ng, d, dt, k in shapes:
         q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
         for flags in ("64", "72"):   # 72 = 64 + 8: epilogue switched off (mainloop alone)
             os.environ["SBIR_K1_FLAGS"] = flags
