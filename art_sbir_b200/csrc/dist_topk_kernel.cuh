@@ -162,7 +162,6 @@ struct K1Config {
 // Unit → (row of the unit grid, partition, chunk) and the gallery tiles it covers.  Chunk-major;
 // inside a chunk step either the query row or the partition varies fastest (plan.part_fastest:
 // wide fp32 rows keep fewer query tiles live in L2 when partitions of one query tile run together).
-__device__ __forceinline__ int prm_chunk_begin(const K1Params& p) { return p.chunk_begin; }
 struct UnitCoord {
   int row_tile, part, chunk, t_begin, t_end;
 };
@@ -170,7 +169,7 @@ __device__ __forceinline__ UnitCoord decode_unit(int unit, const K1Params& p) {
   const int per_step = p.num_parts * p.num_row_tiles;
   UnitCoord c;
   const int step = unit / per_step;
-  c.chunk = prm_chunk_begin(p) + step;
+  c.chunk = p.chunk_begin + step;
   const int r = unit - step * per_step;
   if (p.part_fastest) {
     c.row_tile = r / p.num_parts;
