@@ -65,6 +65,12 @@ def test_status_strings_and_argument_checks(sbir_lib):
     assert lib.sbir_triplet_margin_loss(None, None, None, 4, 8, 0.2, 0, None, None, None, None, None, None) == 1
     assert lib.sbir_pairwise_topk_workspace_bytes(1000, 10000, 2048, 10, 0, 0, 1) > 0
     assert lib.sbir_pairwise_topk_workspace_bytes(1000, 10000, 2048, 1000, 0, 0, 1) == 0
+    # host-buffer entry points: argument checks come before any device work
+    assert lib.sbir_retrieve_host(None, 4, None, 4, 8, 0, 0, 10, None, None, None, None, None) == 1            # NULL buffers
+    assert lib.sbir_retrieve_host(None, 0, None, 4, 8, 0, 0, 10, None, None, None, None, None) == 1            # no queries
+    assert lib.sbir_retrieve_host_shard(None, 4, None, 4, 8, 0, 0, 10, 0, None, None, None, None, None, None, None) == 1
+    assert lib.sbir_retrieve_host_shard(None, 4, None, 4, 8, 9, 0, 10, 0, None, None, None, None, None, None, None) == 1  # bad dtype
+    assert lib.sbir_debug_k1_diag(None, 8) == 1
     # empty problems are a no-op success
     assert lib.sbir_l2_normalize(None, None, 0, 8, 0, 1e-8, None) == 0
     assert lib.sbir_pairwise_topk(None, 0, None, 4, 8, 0, 0, 10, 0, None, None, None, None, None, None, 0, None) == 0
