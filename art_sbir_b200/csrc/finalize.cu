@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinPar
       exi[c] = gi;
     }
   }
-  bitonic_sort_smem<double>(ex, exi, 128);
+  // only the re-scored entries need sorting (the rest of ex[] holds +inf): k = 10 sorts 16 entries, not 128
+  int n_sort = 2;
+  while (n_sort < RS) n_sort <<= 1;
+  bitonic_sort_smem<double>(ex, exi, n_sort);
 
   for (int i = threadIdx.x; i < p.k; i += kFinThreads) {
     const bool have = i < RS;
