@@ -79,11 +79,16 @@ def sharded_pairwise_topk(queries: torch.Tensor, gallery_shard: torch.Tensor, k:
 def _exchange(vals, idx, cnt, pos_dist, num_gallery_total, world, group, merge_fn):
     """The path's one exchange step: all-gather of the per-shard lists + K4 merge, all-reduce of the counts."""
     if world > 1:
-        all_vals = [torch.empty_like(vals) for _ in range(world)]
-        all_idx = [torch.empty_like(idx) for _ in range(world)]
-        dist.all_gather(all_vals, vals.contiguous(), group=group)
-        dist.all_gather(all_idx, idx.contiguous(), group=group)
-        vals, idx = merge_fn(torch.stack(all_vals), torch.stack(all_idx))
+        # gathered straight into the [world, Q, k] layout K4 reads (no per-rank list, no stack copy)
+        all_vals = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
+        all_idx = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(all_vals, vals.contiguous(), group=group)
+            dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=group)
+        else:  # gloo (CPU tests of the plumbing): list form
+            dist.all_gather(list(all_vals.unbind(0)), vals.contiguous(), group=group)
+            dist.all_gather(list(all_idx.unbind(0)), idx.contiguous(), group=group)
+        vals, idx = merge_fn(all_vals, all_idx)
         if cnt is not None:
             dist.all_reduce(cnt, group=group)
     rank_out = None
