@@ -51,12 +51,13 @@ def sketch_key(sketch_path, image_paths: Sequence[Path]) -> str:
 
 
 def positive_indices(sketch_paths: Sequence, image_paths: Sequence[Path], verbose: bool = True) -> torch.Tensor:
-    """int64 [Q]: gallery index of each sketch's photo, -1 when there is none (N3: one dict
-    build instead of a linear scan per query)."""
+    """int64 [Q]: gallery index of each sketch's photo, -1 when there is none (N3: ONE explicit
+    stem→index dict per call instead of a linear scan per query, utils.py:22-25)."""
     out = []
+    stem_index = utils.build_stem_index(image_paths) if len(sketch_paths) > 1 else None
     for sp in sketch_paths:
         name = sketch_key(sp, image_paths)
-        idx = utils.find_image_index(image_paths, name)
+        idx = utils.find_image_index(image_paths, name, stem_index)
         if idx < 0 and verbose:
             print(f"No image found: {sp} | {name}")  # inference.py:40
         out.append(idx)
@@ -80,7 +81,13 @@ def get_ranking_position(sketch_path, image_paths: List[Path], sketch_feature: t
 # just one sketch per call
 def get_topk_images(k: int, image_paths: List[Path], sketch_feature: torch.Tensor, image_features: torch.Tensor,
                     loss_type) -> List[Tuple[str, float]]:
-    """inference.py:60-69."""
+    """inference.py:60-69.  Like `distances.topk(k)` there, k > len(image_features) raises
+    (the batched `ops.pairwise_topk` pads with (+inf, -1) instead; a path must never be looked up
+    with -1)."""
+    if loss_type not in ("euclidean", "cosine"):
+        raise Exception(f"loss type not correct {loss_type}")
+    if k > image_features.shape[0]:
+        raise RuntimeError("selected index k out of range")  # torch's message for topk(k > N)
     q, g = _common_dtype(_to_device(sketch_feature.reshape(1, -1)), _to_device(image_features))
     values, indices = ops.pairwise_topk(q, g, k, loss_type)
     values, indices = values[0].tolist(), indices[0].tolist()
@@ -133,6 +140,9 @@ def process_inference(model, dataset, inference_dataset, dataloader, image_featu
     pos = positive_indices(sketch_paths, inference_dataset.image_paths)
 
     sample_ids = sorted({i for i in random_indices if i < n})
+    if sample_ids and k > image_features.shape[0]:
+        # get_topk_images(k=10, ...) of a sampled query (inference.py:120-121): topk(k > N) raises
+        raise RuntimeError("selected index k out of range")
     ev = evaluate_embeddings(sketch_features, image_features, pos, loss_type, k, sample_ids)
     retrieval_samples = []
     image_paths = inference_dataset.image_paths
@@ -213,6 +223,13 @@ def run_inference(model, dataset, folder_name: str = None, loss_type="euclidean"
     from torch.utils.data import DataLoader
     start_time = timer()
     with_classification = "with_classification" in type(model).__name__
+    name = dataset.state_dict["dataset"] if hasattr(dataset, "state_dict") else ""
+    two_sets = "Kaggle" in name or "Mixed" in name
+    if two_sets and second_dataset is None:
+        # the reference always returns the three-key dict for these datasets (inference.py:157-160);
+        # returning the flat dict instead would silently change what visualization.visualize reads
+        raise ValueError(f"run_inference on {name} evaluates a second sketch set (KaggleInferenceV1, "
+                         "inference.py:157-160): pass it as second_dataset=")
     if folder_name:
         feature_folder = folder_name
         image_paths, image_features = utils.load_image_features(folder_name)
@@ -223,8 +240,7 @@ def run_inference(model, dataset, folder_name: str = None, loss_type="euclidean"
     dataloader = DataLoader(dataset=dataset, batch_size=64, num_workers=0, shuffle=False)  # N4: batched queries
     inference_dict = process_inference(model, dataset, inference_dataset, dataloader, image_features, start_time,
                                        with_classification, loss_type)
-    name = dataset.state_dict["dataset"] if hasattr(dataset, "state_dict") else ""
-    if ("Kaggle" in name or "Mixed" in name) and second_dataset is not None:
+    if two_sets:
         dataloader2 = DataLoader(dataset=second_dataset, batch_size=64, num_workers=0, shuffle=False)
         inference_dict2 = process_inference(model, second_dataset, inference_dataset, dataloader2, image_features,
                                             inference_dict["inference_time"], with_classification, loss_type)

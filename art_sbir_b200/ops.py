@@ -7,7 +7,7 @@ a missing library raise.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -123,6 +123,31 @@ def pairwise_distance(x1: torch.Tensor, x2: torch.Tensor, loss_type: str = "eucl
 
 
 # ------------------------------------------------------------- H1+H3+H4 batched ----
+def _check_retrieval_args(queries: torch.Tensor, gallery: torch.Tensor, k: Optional[int] = None,
+                          per_query: Sequence[Tuple[str, Optional[torch.Tensor]]] = ()):
+    """Validation shared by every entry point that hands raw pointers of a (queries, gallery) pair to the
+    C ABI: CUDA + contiguous, 2-D, equal dim, equal dtype (mixed dtypes — e.g. fp32 queries against a
+    float64 CSV-loaded or bf16 gallery, F8 — are scored in fp32), same device, k in range, and per-query
+    vectors of length Q on the same device.  Returns the (possibly converted) operands."""
+    q, g = _dev(queries, "queries"), _dev(gallery, "gallery")
+    if q.dim() != 2 or g.dim() != 2 or q.shape[1] != g.shape[1]:
+        raise ValueError(f"expected [Q,D] and [N,D], got {tuple(q.shape)} and {tuple(g.shape)}")
+    if q.device != g.device:
+        raise ValueError(f"queries ({q.device}) and gallery ({g.device}) must live on the same device")
+    if q.dtype != g.dtype or q.dtype not in (torch.float32, torch.bfloat16):
+        q, g = q.float(), g.float()
+    if k is not None and not 1 <= k <= B.MAX_K:
+        raise ValueError(f"k must be in [1, {B.MAX_K}]")
+    for name, t in per_query:
+        if t is None:
+            continue
+        if t.dim() != 1 or t.shape[0] != q.shape[0]:
+            raise ValueError(f"{name} must have one entry per query ({q.shape[0]}), got {tuple(t.shape)}")
+        if t.device != q.device:
+            raise ValueError(f"{name} ({t.device}) must live on the queries' device ({q.device})")
+    return q, g
+
+
 def pairwise_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, loss_type: str = "euclidean",
                   pos_index: Optional[torch.Tensor] = None, index_offset: int = 0,
                   return_uncertified: bool = False):
@@ -131,21 +156,15 @@ def pairwise_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, loss_typ
     gallery row: the batched form of inference.py:30-69.
 
     Returns (values fp32 [Q,k], indices int64 [Q,k]) or (values, indices, rank int64 [Q])."""
-    q, g = _dev(queries, "queries"), _dev(gallery, "gallery")
-    if q.dim() != 2 or g.dim() != 2 or q.shape[1] != g.shape[1]:
-        raise ValueError(f"expected [Q,D] and [N,D], got {tuple(q.shape)} and {tuple(g.shape)}")
-    if q.dtype != g.dtype:
-        q, g = q.float(), g.float()
-    if not 1 <= k <= B.MAX_K:
-        raise ValueError(f"k must be in [1, {B.MAX_K}]")
+    want_rank = pos_index is not None
+    pos = _dev(pos_index.to(torch.int64), "pos_index") if want_rank else None
+    q, g = _check_retrieval_args(queries, gallery, k, (("pos_index", pos),))
     metric = metric_id(loss_type)
     nq, ng, d = q.shape[0], g.shape[0], q.shape[1]
     dev = q.device
     vals = torch.empty((nq, k), dtype=torch.float32, device=dev)
     idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    want_rank = pos_index is not None
     rank = torch.empty(nq, dtype=torch.int64, device=dev) if want_rank else None
-    pos = _dev(pos_index.to(torch.int64), "pos_index") if want_rank else None
     unc = torch.zeros(1, dtype=torch.int32, device=dev)
     lib = B.load()
     with torch.cuda.device(dev):
@@ -166,9 +185,10 @@ def rank_of_positive(queries: torch.Tensor, gallery: torch.Tensor, pos_index: to
 
 
 def positive_distance(queries, gallery_shard, pos_index_local, loss_type="euclidean") -> torch.Tensor:
-    q, g = _dev(queries, "queries"), _dev(gallery_shard, "gallery")
-    out = torch.empty(q.shape[0], dtype=torch.float64, device=q.device)
+    """Exact d(q_i, shard[pos_index_local[i]]) as fp64 [Q]; NaN where the index is outside the shard."""
     pos = _dev(pos_index_local.to(torch.int64), "pos_index")
+    q, g = _check_retrieval_args(queries, gallery_shard, None, (("pos_index_local", pos),))
+    out = torch.empty(q.shape[0], dtype=torch.float64, device=q.device)
     with torch.cuda.device(q.device):
         B.check(B.load().sbir_positive_distance(q.data_ptr(), q.shape[0], g.data_ptr(), g.shape[0], q.shape[1],
                                                 _dtype_id(q), metric_id(loss_type), pos.data_ptr(), out.data_ptr(),
@@ -179,16 +199,16 @@ def positive_distance(queries, gallery_shard, pos_index_local, loss_type="euclid
 def pairwise_topk_shard(queries, gallery_shard, k, loss_type, index_offset, pos_dist=None, pos_index_global=None):
     """One gallery shard's contribution: local top-k with global indices and, if pos_dist
     (fp64 [Q], NaN = no positive) is given, the local count of rows closer than it."""
-    q, g = _dev(queries, "queries"), _dev(gallery_shard, "gallery")
+    want = pos_dist is not None
+    pd = _dev(pos_dist.to(torch.float64), "pos_dist") if want else None
+    pg = _dev(pos_index_global.to(torch.int64), "pos_index_global") if (want and pos_index_global is not None) else None
+    q, g = _check_retrieval_args(queries, gallery_shard, k, (("pos_dist", pd), ("pos_index_global", pg)))
     metric = metric_id(loss_type)
     nq, ng, d = q.shape[0], g.shape[0], q.shape[1]
     dev = q.device
     vals = torch.empty((nq, k), dtype=torch.float32, device=dev)
     idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    want = pos_dist is not None
     cnt = torch.zeros(nq, dtype=torch.int64, device=dev) if want else None
-    pd = _dev(pos_dist.to(torch.float64), "pos_dist") if want else None
-    pg = _dev(pos_index_global.to(torch.int64), "pos_index_global") if (want and pos_index_global is not None) else None
     unc = torch.zeros(1, dtype=torch.int32, device=dev)
     lib = B.load()
     with torch.cuda.device(dev):

@@ -29,6 +29,27 @@ def shard_bounds(num_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def _resolve_offsets(n_local: int, shard_offset: Optional[int], num_gallery_total: Optional[int], world: int,
+                     rank: int, dev, group) -> Tuple[int, int]:
+    """First global row of this rank's shard and the gallery length.  Whatever the caller left out is
+    derived from an all-reduce of the shard sizes (prefix sum in rank order), so a missing
+    `shard_offset` can never silently mean 0 on every rank; what it passed is range-checked."""
+    if shard_offset is None or num_gallery_total is None:
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        sizes[rank] = n_local
+        if world > 1:
+            dist.all_reduce(sizes, group=group)
+        sizes = sizes.cpu()
+        if shard_offset is None:
+            shard_offset = int(sizes[:rank].sum())
+        if num_gallery_total is None:
+            num_gallery_total = int(sizes.sum())
+    if shard_offset < 0 or shard_offset + n_local > num_gallery_total:
+        raise ValueError(f"shard rows [{shard_offset}, {shard_offset + n_local}) fall outside the gallery of "
+                         f"{num_gallery_total} rows")
+    return int(shard_offset), int(num_gallery_total)
+
+
 def _cuda_local(queries, shard, k, loss_type, offset, pos_dist, pos_index_global=None):
     vals, idx, cnt, unc = ops.pairwise_topk_shard(queries, shard, k, loss_type, offset, pos_dist, pos_index_global)
     return vals, idx, cnt
@@ -53,13 +74,7 @@ def sharded_pairwise_topk(queries: torch.Tensor, gallery_shard: torch.Tensor, k:
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n_local = gallery_shard.shape[0]
     dev = queries.device
-    if shard_offset is None or num_gallery_total is None:
-        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-        sizes[rank] = n_local
-        if world > 1:
-            dist.all_reduce(sizes, group=group)
-        shard_offset = int(sizes[:rank].sum().item())
-        num_gallery_total = int(sizes.sum().item())
+    shard_offset, num_gallery_total = _resolve_offsets(n_local, shard_offset, num_gallery_total, world, rank, dev, group)
 
     pos_dist = None
     if pos_index is not None:
@@ -99,7 +114,7 @@ def _exchange(vals, idx, cnt, pos_dist, num_gallery_total, world, group, merge_f
 
 def sharded_retrieve_host(queries_host: torch.Tensor, gallery_shard_host: torch.Tensor, k: int,
                           loss_type: str = "euclidean", pos_index: Optional[torch.Tensor] = None,
-                          shard_offset: int = 0, num_gallery_total: Optional[int] = None, group=None,
+                          shard_offset: Optional[int] = None, num_gallery_total: Optional[int] = None, group=None,
                           device: Optional[torch.device] = None):
     """`sharded_pairwise_topk` for embeddings that live in HOST memory (pinned for full PCIe speed):
     the rank's gallery shard is uploaded in chunks while earlier chunks are scored
@@ -108,13 +123,16 @@ def sharded_retrieve_host(queries_host: torch.Tensor, gallery_shard_host: torch.
     from . import _binding as B
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if queries_host.dim() != 2 or gallery_shard_host.dim() != 2 or queries_host.shape[1] != gallery_shard_host.shape[1]:
+        raise ValueError(f"expected [Q,D] and [N,D], got {tuple(queries_host.shape)} and {tuple(gallery_shard_host.shape)}")
+    if not 1 <= k <= B.MAX_K:
+        raise ValueError(f"k must be in [1, {B.MAX_K}]")
+    if pos_index is not None and (pos_index.dim() != 1 or pos_index.shape[0] != queries_host.shape[0]):
+        raise ValueError("pos_index must have one entry per query")
     n_local = gallery_shard_host.shape[0]
-    if num_gallery_total is None:
-        sizes = torch.tensor([n_local], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(sizes, group=group)
-        num_gallery_total = int(sizes.item())
-    if queries_host.dtype != gallery_shard_host.dtype:
+    shard_offset, num_gallery_total = _resolve_offsets(n_local, shard_offset, num_gallery_total, world, rank, dev, group)
+    if queries_host.dtype != gallery_shard_host.dtype or queries_host.dtype not in (torch.float32, torch.bfloat16):
         queries_host, gallery_shard_host = queries_host.float(), gallery_shard_host.float()
     g_host = gallery_shard_host.contiguous()
     q = queries_host.to(dev, non_blocking=True).contiguous()

@@ -21,30 +21,30 @@ MARGIN = 0.2  # utils.py:77 ("Sketching without Worrying"); train.py:133 overwri
 
 
 # ---------------------------------------------------------------------------- N3 ----
-class _StemIndex:
-    """stem → first gallery index, built once per gallery list (the reference scans the list
-    linearly for every query, utils.py:22-25)."""
-
-    def __init__(self) -> None:
-        self._key = None
-        self._map: Dict[str, int] = {}
-
-    def lookup(self, image_paths: Sequence[Path], name: str) -> int:
-        key = (id(image_paths), len(image_paths))
-        if key != self._key:
-            m: Dict[str, int] = {}
-            for idx, path in enumerate(image_paths):
-                m.setdefault(Path(path).stem, idx)
-            self._map, self._key = m, key
-        return self._map.get(name, -1)
+def build_stem_index(image_paths: Sequence[Path]) -> Dict[str, int]:
+    """stem → FIRST gallery index (the reference's linear scan returns the first match,
+    utils.py:22-25).  Built explicitly by the caller once per gallery and passed along — no
+    hidden cache keyed on object identity, so two galleries of equal length can never alias."""
+    m: Dict[str, int] = {}
+    for idx, path in enumerate(image_paths):
+        m.setdefault(Path(path).stem, idx)
+    return m
 
 
-_stem_index = _StemIndex()
-
-
-def find_image_index(image_paths: List[Path], sketch_name: str) -> int:
-    """utils.py:22-25: index of the first path whose stem equals `sketch_name`, else -1."""
-    return _stem_index.lookup(image_paths, sketch_name)
+def find_image_index(image_paths: List[Path], sketch_name, stem_index: Dict[str, int] = None) -> int:
+    """utils.py:22-25: index of the first path whose stem equals `sketch_name`, else -1.
+    Stateless like the reference; pass `stem_index=build_stem_index(image_paths)` to replace the
+    O(N) scan by a dict lookup when many sketches are resolved against one gallery.  A name that
+    is not a string (inference.py:33-37 leaves a LIST for stems with more than three '-' parts)
+    matches nothing, as in the reference where `path.stem == [..]` is always False."""
+    if not isinstance(sketch_name, str):
+        return -1
+    if stem_index is not None:
+        return stem_index.get(sketch_name, -1)
+    for idx, path in enumerate(image_paths):
+        if Path(path).stem == sketch_name:
+            return idx
+    return -1
 
 
 # ------------------------------------------------------------------------ H1 / H2 ----

@@ -125,3 +125,61 @@ def test_k1_plan_covers_every_tile_exactly_once(sbir_lib, nq, ng, d, k, dtype):
         assert p["parts"] == 1
     ws = sbir_lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, dtype, 0, 1)
     assert ws > 0 and ws >= p["parts"] * p["q_tile_stride"] * p["lists"] * p["cap"] * 128 * 8
+
+
+def test_positive_lookup_is_stateless_across_galleries():
+    """Two galleries of equal length evaluated in one process (and a list mutated in place) must
+    each resolve against their own contents, like the reference's stateless scan (utils.py:22-25)."""
+    a, b, c = Path("p/a.jpg"), Path("p/b.jpg"), Path("p/c.jpg")
+    assert U.find_image_index([a, b, c], "b") == 1
+    assert U.find_image_index([b, a, c], "b") == 0
+    paths = [a, b, c]
+    assert inf.positive_indices(["s/b-1.png", "s/c-2.png"], paths, verbose=False).tolist() == [1, 2]
+    paths[0], paths[1] = paths[1], paths[0]                      # same object, same length, new order
+    assert inf.positive_indices(["s/b-1.png", "s/c-2.png"], paths, verbose=False).tolist() == [0, 2]
+    assert U.find_image_index(paths, "b", U.build_stem_index(paths)) == 0
+    # stems with more than three '-' parts stay a LIST in the reference (inference.py:33-37): never found
+    key = inf.sketch_key("s/1-2-3-4.png", paths)
+    assert isinstance(key, list) and O.find_image_index(paths, key) == -1
+    assert U.find_image_index(paths, key) == -1 and U.find_image_index(paths, key, U.build_stem_index(paths)) == -1
+    assert inf.positive_indices(["s/1-2-3-4.png", "s/a-1.png"], paths, verbose=False).tolist() == [-1, 1]
+
+
+def test_topk_larger_than_gallery_raises_like_torch():
+    paths = [Path("p/a.jpg"), Path("p/b.jpg")]
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        inf.get_topk_images(10, paths, torch.zeros(1, 8), torch.zeros(2, 8), "euclidean")
+    with pytest.raises(RuntimeError, match="selected index k out of range"):        # what the reference's call raises
+        O.get_topk_images(10, paths, torch.zeros(1, 8), torch.zeros(2, 8), "euclidean")
+
+
+def test_run_inference_needs_the_second_sketch_set_for_kaggle_and_mixed():
+    class DS:
+        state_dict = {"dataset": "KaggleDatasetV2"}
+    with pytest.raises(ValueError, match="second_dataset"):
+        inf.run_inference(torch.nn.Identity(), DS(), folder_name="unused")
+
+
+def test_shard_offsets_are_derived_or_checked():
+    assert sharded._resolve_offsets(10, None, None, 1, 0, "cpu", None) == (0, 10)
+    assert sharded._resolve_offsets(10, 5, 20, 1, 0, "cpu", None) == (5, 20)
+    with pytest.raises(ValueError, match="outside the gallery"):
+        sharded._resolve_offsets(10, 15, 20, 1, 0, "cpu", None)
+
+
+def test_ops_validate_operand_pairs_before_taking_pointers():
+    from art_sbir_b200 import ops
+    q = torch.zeros(3, 8)
+    # shape / k / per-query checks run on whatever device the tensors live on; _dev is the CUDA gate
+    import unittest.mock as mock
+    with mock.patch.object(ops, "_dev", lambda t, name: t.contiguous()):
+        with pytest.raises(ValueError, match=r"expected \[Q,D\]"):
+            ops._check_retrieval_args(q, torch.zeros(5, 9))
+        with pytest.raises(ValueError, match="k must be in"):
+            ops._check_retrieval_args(q, torch.zeros(5, 8), 500)
+        with pytest.raises(ValueError, match="one entry per query"):
+            ops._check_retrieval_args(q, torch.zeros(5, 8), 3, (("pos_index", torch.zeros(4, dtype=torch.int64)),))
+        a, b = ops._check_retrieval_args(q, torch.zeros(5, 8, dtype=torch.bfloat16), 3)
+        assert a.dtype == b.dtype == torch.float32                                  # mixed dtypes are scored in fp32
+        a, b = ops._check_retrieval_args(q.double(), torch.zeros(5, 8, dtype=torch.float64), 3)
+        assert a.dtype == b.dtype == torch.float32                                  # F8: CSV-loaded float64 galleries
