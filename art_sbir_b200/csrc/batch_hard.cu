@@ -1,234 +1,484 @@
-// batch_hard.cu — K3: batch-hard triplet mining + margin loss + gradients (H8, a north_star
-// extension; the reference forms triplets in its datasets, data_preparation.py:67-69,214-222,
-// and only evaluates nn.TripletMarginLoss / TripletMarginWithDistanceLoss on them,
-// train.py:164-175).  Mining runs on the same tcgen05 tiles as retrieval (dist_topk_kernel.cuh in
-// kModeHard); this file selects across tiles, re-scores the selected pairs exactly and
-// scatters gradients deterministically (no floating-point atomics).
+// batch_hard.cu — K3: batch-hard triplet mining + margin loss + gradients as ONE cooperative kernel
+// (H8, a north_star extension; the reference forms triplets in its datasets,
+// data_preparation.py:67-69,214-222, and only evaluates nn.TripletMarginLoss /
+// TripletMarginWithDistanceLoss on them, train.py:164-175).
+//
+// Candidates X = cat(p, n) are never concatenated: p and n are read in place through two tensor
+// maps.  The kernel runs three phases separated by grid-wide barriers (cooperative launch):
+//   1. MINING TILES  tcgen05 (kind::tf32) tiles of A·Xᵀ — 128 anchors × 32 candidates per unit, the
+//      K dimension split over several units so that a 256-anchor batch still spreads over ~128 SMs —
+//      TMA-fed (8-stage ring), accumulators in TMEM, raw dot products stored to a small L2-resident
+//      matrix [k_split][anchors][candidates].  While the first tiles are in flight the epilogue warps
+//      compute ‖a‖², ‖x‖² of all rows.
+//   2. SELECT + LOSS + ANCHOR GRADIENT  one warp per anchor: e = ‖x‖² − 2·a·x (or the cosine form)
+//      from the tiles, the approximate hardest positive / negative, then EVERY candidate whose
+//      approximate value lies within twice the tensor-core error bound of it (e_margin, the same
+//      certificate as the top-k path) is re-scored with the reference formula in fp32/fp64
+//      (common.cuh) — so the selected pair is provably the exact arg-max / arg-min of the exact
+//      distances, ties by the smaller index.  Hinge, weight, and the anchor's gradient row.
+//   3. CANDIDATE GRADIENTS + MEAN  one warp per candidate row walks the anchors in index order and
+//      accumulates the contributions of those that selected it (fixed order → bitwise
+//      reproducible, no floating-point atomics); one warp sums the hinge terms in fixed order.
+#include <cooperative_groups.h>
+
+#include <cuda.h>
+
 #include "common.cuh"
+#include "dist_topk_params.h"
 #include "kernels.h"
+#include "ptx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sbir {
 
 namespace {
 
-constexpr int kBhThreads = 128;
+constexpr int kBhTileA = 128;    // anchors per tile (UMMA M, TMEM lanes)
+constexpr int kBhTileC = 32;     // candidates per tile (UMMA N, TMEM columns per accumulator)
+constexpr int kBhStages = 8;
+constexpr int kBhStageA = kBhTileA * kSwizzleBytes;  // 16 KB
+constexpr int kBhStageC = kBhTileC * kSwizzleBytes;  // 4 KB
+constexpr int kBhThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kBhWarps = kBhThreads / 32;
+constexpr int kBhSmemBytes = 1024 + kBhStages * (kBhStageA + kBhStageC) + 256;
+constexpr int kBhTmemCols = 64;  // two accumulators of 32 columns
+constexpr int kBhMaxSplits = 8;
 
-__device__ __forceinline__ double bh_block_sum(double v, double* red4) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red4[threadIdx.x >> 5] = v;
-  __syncthreads();
-  return red4[0] + red4[1] + red4[2] + red4[3];
-}
-
-struct PairStats {
-  double d;         // exact distance
-  float ca, cx, s;  // cosine: clamped norms and similarity
-  float ma, mx;     // cosine: 1 when the norm is above eps (gradient flows through the norm)
+struct BhParams {
+  const float* a;
+  const float* p;
+  const float* n;
+  int batch, dim, metric;
+  float margin, kappa;
+  const long long* anchor_label;  // [batch] or NULL: positive of anchor i is candidate i
+  const long long* cand_label;    // [2*batch]
+  int num_q_tiles, tiles_per_half, k_splits, kb_per_split, num_k_blocks, num_units;
+  int dot_rows, dot_cols;         // padded extents of one split's dot matrix
+  float* dots;                    // [k_splits][dot_rows][dot_cols]
+  float* anorm;                   // [batch]   ‖a_i‖²
+  float* cnorm;                   // [2*batch] ‖x_j‖²
+  float* per_row;                 // [batch] hinge terms
+  float* weight;                  // [batch] ∂loss/∂hinge_i (1/batch where the hinge is active)
+  int* sel;                       // [batch][2] selected (positive, negative) candidate
+  double* pair_d;                 // [batch][2] exact distances of the selected pairs
+  float* pair_stat;               // [batch][8] cosine: ca, ma, cxp, sp, mxp, cxn, sn, mxn
+  float* out_loss;
+  long long* out_hard_index;
+  float* ga;
+  float* gp;
+  float* gn;
 };
 
-// Exact distance of (a_row, x_row) by the whole block, plus what the gradient needs.
-__device__ PairStats pair_stats(const float* __restrict__ ar, const float* __restrict__ xr, int dim,
-                                int metric, double* red4) {
-  PairStats st{};
-  const int t = threadIdx.x;
+__device__ __forceinline__ const float* cand_row(const BhParams& P, int j) {
+  return j < P.batch ? P.p + (size_t)j * P.dim : P.n + (size_t)(j - P.batch) * P.dim;
+}
+// column of candidate j in the dot matrix (each half is padded to whole tiles)
+__device__ __forceinline__ int cand_col(const BhParams& P, int j) {
+  return j < P.batch ? j : P.tiles_per_half * kBhTileC + (j - P.batch);
+}
+
+struct PairExact {
+  double d;        // exact distance (reference formula, fp32 elements, fp64 sum)
+  float cx, s, mx; // cosine: clamped candidate norm, similarity, 1 when ‖x‖ > eps
+};
+
+// Exact distance of (a_i, x_j) by one warp plus what the gradient needs.  ca = clamped anchor norm.
+template <bool kVec>
+__device__ __forceinline__ PairExact pair_exact(const float* __restrict__ ar, const float* __restrict__ xr, int dim,
+                                                int metric, float ca, int lane) {
+  PairExact st{};
   if (metric == SBIR_EUCLIDEAN) {
-    double s = 0.0;
-    for (int i = t; i < dim; i += kBhThreads) {
-      const float u = __fadd_rn(__fsub_rn(ar[i], xr[i]), kPairwiseEps);
-      s += (double)u * (double)u;
-    }
-    st.d = sqrt(bh_block_sum(s, red4));
+    st.d = sqrt(warp_sq_l2_eps<float, kVec>(ar, xr, dim, lane));
   } else {
-    double qa = 0.0, qx = 0.0;
-    for (int i = t; i < dim; i += kBhThreads) {
-      qa += (double)ar[i] * (double)ar[i];
-      qx += (double)xr[i] * (double)xr[i];
-    }
-    qa = bh_block_sum(qa, red4);
-    qx = bh_block_sum(qx, red4);
-    st.ca = clamped_norm(qa);
+    const double qx = warp_sq_norm<float, kVec>(xr, dim, lane);
     st.cx = clamped_norm(qx);
-    st.ma = (float)sqrt(qa) > kCosineEps ? 1.f : 0.f;
     st.mx = (float)sqrt(qx) > kCosineEps ? 1.f : 0.f;
-    double s = 0.0;
-    for (int i = t; i < dim; i += kBhThreads)
-      s += (double)__fmul_rn(__fdiv_rn(ar[i], st.ca), __fdiv_rn(xr[i], st.cx));
-    s = bh_block_sum(s, red4);
+    const double s = warp_cos_dot<float, kVec>(ar, xr, ca, st.cx, dim, lane);
     st.s = (float)s;
     st.d = 1.0 - s;
   }
   return st;
 }
 
-// One block per anchor: reduce the per-tile hardest candidates, re-score exactly, hinge.
-__global__ void __launch_bounds__(kBhThreads) bh_select_kernel(
-    const float* __restrict__ a, const float* __restrict__ x, int batch, int dim, int metric,
-    float margin, const float* __restrict__ hard_val, const int32_t* __restrict__ hard_idx,
-    int num_slots, int slot_stride_rows, int halves, float inv_batch, float* __restrict__ per_row,
-    float* __restrict__ weight, long long* __restrict__ sel, long long* __restrict__ out_hard_index) {
-  __shared__ double red[4];
-  __shared__ int s_hp, s_hn;
-  const int i = blockIdx.x;
-  if (threadIdx.x == 0) {
-    float hp = -INFINITY, hn = INFINITY;
-    int hpi = -1, hni = -1;
-    for (int s = 0; s < num_slots; ++s) {
-      for (int h = 0; h < halves; ++h) {
-        const size_t o = ((size_t)s * slot_stride_rows + i) * halves + h;
-        const float vp = hard_val[o * 2], vn = hard_val[o * 2 + 1];
-        const int ip = hard_idx[o * 2], in = hard_idx[o * 2 + 1];
-        if (ip >= 0 && (vp > hp || (vp == hp && ip < hpi) || hpi < 0)) { hp = vp; hpi = ip; }
-        if (in >= 0 && (vn < hn || (vn == hn && in < hni) || hni < 0)) { hn = vn; hni = in; }
+template <bool kVec>
+__global__ void __launch_bounds__(kBhThreads, 1)
+batch_hard_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_p,
+                        const __grid_constant__ CUtensorMap tmap_n, const BhParams P) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_c = smem + kBhStages * kBhStageA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBhStages * (kBhStageA + kBhStageC));
+  uint64_t* full_bar = bars;                        // [kBhStages]
+  uint64_t* empty_bar = bars + kBhStages;           // [kBhStages]
+  uint64_t* acc_full_bar = bars + 2 * kBhStages;    // [2]
+  uint64_t* acc_empty_bar = bars + 2 * kBhStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBhStages + 4);
+
+  const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const bool has_units = (int)blockIdx.x < P.num_units;
+
+  // ------------------------------------------------------------ phase 1: mining tiles ----
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_p);
+    tma_prefetch_desc(&tmap_n);
+    for (int s = 0; s < kBhStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&acc_full_bar[x], 1);
+      mbar_init(&acc_empty_bar[x], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kBhTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int u, int& q_tile, int& c_tile, int& kb0, int& kb1) {
+    const int split = u % P.k_splits;
+    const int t = u / P.k_splits;
+    c_tile = t % (2 * P.tiles_per_half);
+    q_tile = t / (2 * P.tiles_per_half);
+    kb0 = split * P.kb_per_split;
+    kb1 = min(kb0 + P.kb_per_split, P.num_k_blocks);
+    return split;
+  };
+
+  if (warp == 0) {
+    if (has_units) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < P.num_units; u += gridDim.x) {
+        int q_tile, c_tile, kb0, kb1;
+        decode(u, q_tile, c_tile, kb0, kb1);
+        const bool from_p = c_tile < P.tiles_per_half;
+        const int c_row = (from_p ? c_tile : c_tile - P.tiles_per_half) * kBhTileC;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], kBhStageA + kBhStageC);
+            tma_load_2d(smem_a + stage * kBhStageA, &tmap_a, &full_bar[stage], kb * 32, q_tile * kBhTileA);
+            if (from_p) tma_load_2d(smem_c + stage * kBhStageC, &tmap_p, &full_bar[stage], kb * 32, c_row);
+            else tma_load_2d(smem_c + stage * kBhStageC, &tmap_n, &full_bar[stage], kb * 32, c_row);
+          }
+          if (++stage == kBhStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
-    s_hp = hpi;
-    s_hn = hni;
-  }
-  __syncthreads();
-  const int hpi = s_hp, hni = s_hn;
-  float hinge = 0.f, w = 0.f;
-  if (hpi >= 0 && hni >= 0) {
-    const PairStats sp = pair_stats(a + (size_t)i * dim, x + (size_t)hpi * dim, dim, metric, red);
-    const PairStats sn = pair_stats(a + (size_t)i * dim, x + (size_t)hni * dim, dim, metric, red);
-    const float arg = __fsub_rn(__fadd_rn(margin, (float)sp.d), (float)sn.d);
-    hinge = fmaxf(arg, 0.f);
-    w = arg >= 0.f ? inv_batch : 0.f;
-  }
-  if (threadIdx.x == 0) {
-    per_row[i] = hinge;
-    weight[i] = w;
-    sel[2 * i] = hpi;
-    sel[2 * i + 1] = hni;
-    if (out_hard_index) {
-      out_hard_index[2 * i] = hpi;
-      out_hard_index[2 * i + 1] = hni;
+    __syncwarp();
+  } else if (warp == 1) {
+    if (has_units) {
+      constexpr uint32_t idesc = make_instr_desc(2u, kBhTileA, kBhTileC);
+      const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int u = blockIdx.x; u < P.num_units; u += gridDim.x) {
+        int q_tile, c_tile, kb0, kb1;
+        decode(u, q_tile, c_tile, kb0, kb1);
+        mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + acc * kBhTileC;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * kBhStageA));
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_c + stage * kBhStageC));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss<true>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (uint32_t)((kb - kb0) | k) != 0);
+          }
+          if (elect_one()) umma_commit(&empty_bar[stage]);
+          if (++stage == kBhStages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&acc_full_bar[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
-  }
-}
-
-// ∂d(a,x)/∂a (sign +1) or ∂d(a,x)/∂x (side 1), scaled by `scale`, accumulated into out[].
-__device__ __forceinline__ void accumulate_pair_grad(const float* __restrict__ ar, const float* __restrict__ xr,
-                                                     int dim, int metric, const PairStats& st, float scale,
-                                                     bool wrt_x, float* __restrict__ out) {
-  const int t = threadIdx.x;
-  if (metric == SBIR_EUCLIDEAN) {
-    const float c = st.d > 0.0 ? (float)((double)scale / st.d) : 0.f;
-    for (int i = t; i < dim; i += kBhThreads) {
-      const float u = __fadd_rn(__fsub_rn(ar[i], xr[i]), kPairwiseEps) * c;
-      out[i] += wrt_x ? -u : u;
-    }
+    __syncwarp();
   } else {
-    for (int i = t; i < dim; i += kBhThreads) {
-      const float ah = ar[i] / st.ca, xh = xr[i] / st.cx;
-      // d = 1 - s  →  ∂d/∂a = -(x̂ - s·â·[‖a‖>eps]) / ca
-      const float gval = wrt_x ? -(ah - st.s * xh * st.mx) / st.cx : -(xh - st.s * ah * st.ma) / st.ca;
-      out[i] += scale * gval;
+    // epilogue warps: row norms first (they would otherwise idle until the first accumulator is
+    // complete), then the tiles
+    {
+      const int gw = blockIdx.x * 4 + (warp - 2), nw = gridDim.x * 4;
+      for (int r = gw; r < 3 * P.batch; r += nw) {
+        const float* row = r < P.batch ? P.a + (size_t)r * P.dim : cand_row(P, r - P.batch);
+        const float sq = (float)warp_sq_norm<float, kVec>(row, P.dim, lane);
+        if (lane == 0) {
+          if (r < P.batch) P.anorm[r] = sq;
+          else P.cnorm[r - P.batch] = sq;
+        }
+      }
+    }
+    if (has_units) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < P.num_units; u += gridDim.x) {
+        int q_tile, c_tile, kb0, kb1;
+        const int split = decode(u, q_tile, c_tile, kb0, kb1);
+        mbar_wait(&acc_full_bar[acc], acc_phase);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * kBhTileC, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
+        float4* dst = reinterpret_cast<float4*>(P.dots + ((size_t)split * P.dot_rows + (size_t)q_tile * kBhTileA + row) * P.dot_cols +
+                                                (size_t)c_tile * kBhTileC);
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                               __uint_as_float(r[4 * v + 3]));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
   }
-}
-
-__global__ void __launch_bounds__(kBhThreads) bh_grad_anchor_kernel(
-    const float* __restrict__ a, const float* __restrict__ x, int dim, int metric,
-    const float* __restrict__ weight, const long long* __restrict__ sel, float* __restrict__ ga) {
-  __shared__ double red[4];
-  const int i = blockIdx.x;
-  float* out = ga + (size_t)i * dim;
-  for (int e = threadIdx.x; e < dim; e += kBhThreads) out[e] = 0.f;
-  const float w = weight[i];
-  if (w == 0.f) return;
-  const float* ar = a + (size_t)i * dim;
-  const float* xp = x + (size_t)sel[2 * i] * dim;
-  const float* xn = x + (size_t)sel[2 * i + 1] * dim;
-  const PairStats sp = pair_stats(ar, xp, dim, metric, red);
-  accumulate_pair_grad(ar, xp, dim, metric, sp, w, false, out);
-  const PairStats sn = pair_stats(ar, xn, dim, metric, red);
-  accumulate_pair_grad(ar, xn, dim, metric, sn, -w, false, out);
-}
-
-// One block per candidate row j: walk the anchors in index order and accumulate the
-// contributions of those that selected j (fixed order → bitwise reproducible).  The selections
-// are scanned 128 anchors at a time (one per thread, flags through shared memory, so the walk
-// itself is a handful of broadcast loads) and the gradient row is accumulated in shared memory
-// (`acc`, dim floats; global memory when the row does not fit) and written once.
-__global__ void __launch_bounds__(kBhThreads) bh_grad_cand_kernel(
-    const float* __restrict__ a, const float* __restrict__ x, int batch, int dim, int metric,
-    const float* __restrict__ weight, const long long* __restrict__ sel, float* __restrict__ gp,
-    float* __restrict__ gn, int acc_in_smem) {
-  extern __shared__ float bh_acc[];
-  __shared__ double red[4];
-  __shared__ unsigned char s_flag[kBhThreads];
-  const int j = blockIdx.x;
-  float* out = j < batch ? (gp ? gp + (size_t)j * dim : nullptr) : (gn ? gn + (size_t)(j - batch) * dim : nullptr);
-  if (out == nullptr) return;
-  float* acc = acc_in_smem ? bh_acc : out;
-  for (int e = threadIdx.x; e < dim; e += kBhThreads) acc[e] = 0.f;
-  const float* xr = x + (size_t)j * dim;
-  for (int base = 0; base < batch; base += kBhThreads) {
-    const int i_mine = base + threadIdx.x;
-    unsigned char f = 0;
-    if (i_mine < batch && weight[i_mine] != 0.f) f = (sel[2 * i_mine] == j ? 1 : 0) | (sel[2 * i_mine + 1] == j ? 2 : 0);
-    __syncthreads();  // previous chunk's flags fully consumed (and acc zeroed on the first pass)
-    s_flag[threadIdx.x] = f;
-    __syncthreads();
-    for (int u = 0; u < kBhThreads; ++u) {
-      const unsigned char fu = s_flag[u];  // same value for every thread: uniform branch
-      if (fu == 0) continue;
-      const int i = base + u;
-      const float w = weight[i];
-      const float* ar = a + (size_t)i * dim;
-      const PairStats st = pair_stats(ar, xr, dim, metric, red);
-      if (fu & 1) accumulate_pair_grad(ar, xr, dim, metric, st, w, true, acc);
-      if (fu & 2) accumulate_pair_grad(ar, xr, dim, metric, st, -w, true, acc);
-    }
-  }
-  if (acc_in_smem) {
-    for (int e = threadIdx.x; e < dim; e += kBhThreads) out[e] = acc[e];  // each thread wrote these itself
-  }
-}
-
-__global__ void __launch_bounds__(256) bh_mean_kernel(const float* __restrict__ per_row, int rows,
-                                                      float* __restrict__ out) {
-  __shared__ double red[256];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < rows; i += 256) acc += (double)per_row[i];
-  red[threadIdx.x] = acc;
+  tc_fence_before();
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-    __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kBhTmemCols);
+  __threadfence();
+  grid.sync();
+
+  // ------------------------------------ phase 2: exact selection, hinge, anchor gradient ----
+  const int gwarp = blockIdx.x * kBhWarps + warp, nwarps = gridDim.x * kBhWarps;
+  const int ncand = 2 * P.batch;
+  const size_t split_stride = (size_t)P.dot_rows * P.dot_cols;
+  for (int i = gwarp; i < P.batch; i += nwarps) {
+    const float* ar = P.a + (size_t)i * P.dim;
+    const float qsq = __ldcg(P.anorm + i);
+    const float ca = clamped_norm((double)qsq);  // fp32 norm as torch returns it, clamped (cosine)
+    const long long my_label = P.anchor_label ? P.anchor_label[i] : 0;
+    const float* drow = P.dots + (size_t)i * P.dot_cols;
+    auto e_of = [&](int j, float& cn_out) -> float {
+      const int col = cand_col(P, j);
+      float dot = 0.f;
+      for (int s = 0; s < P.k_splits; ++s) dot += __ldcg(drow + s * split_stride + col);
+      const float cn = __ldcg(P.cnorm + j);
+      cn_out = cn;
+      return P.metric == SBIR_EUCLIDEAN ? fmaf(-2.f, dot, cn) : -dot / fmaxf(sqrtf(cn), kCosineEps);
+    };
+    auto is_positive = [&](int j) -> bool { return P.anchor_label ? (P.cand_label[j] == my_label) : (j == i); };
+    // approximate extrema over the tiles
+    float ap = -INFINITY, an = INFINITY, gmax = 0.f;
+    for (int j = lane; j < ncand; j += 32) {
+      float cn;
+      const float e = e_of(j, cn);
+      gmax = fmaxf(gmax, cn);
+      if (is_positive(j)) ap = fmaxf(ap, e);
+      else an = fminf(an, e);
+    }
+    ap = warp_max(ap);
+    an = -warp_max(-an);
+    gmax = warp_max(gmax);
+    const float m2 = (float)(2.0 * e_margin(P.metric, qsq, gmax, P.kappa, P.dim));
+    // every candidate inside the error band of the approximate extremum is re-scored exactly
+    double bp = -1.0, bn = INFINITY;  // exact extrema in the canonical order (fp32 distance, index)
+    int ip = -1, in = -1;
+    PairExact sp{}, sn{};
+    for (int j0 = 0; j0 < ncand; j0 += 32) {
+      const int j = j0 + lane;
+      bool pos_hit = false, neg_hit = false;
+      if (j < ncand) {
+        float cn;
+        const float e = e_of(j, cn);
+        if (is_positive(j)) pos_hit = e >= ap - m2;
+        else neg_hit = e <= an + m2;
+      }
+      unsigned mask = __ballot_sync(kFullMask, pos_hit || neg_hit);
+      const unsigned pmask = __ballot_sync(kFullMask, pos_hit);
+      while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int jj = j0 + b;
+        const PairExact st = pair_exact<kVec>(ar, cand_row(P, jj), P.dim, P.metric, ca, lane);
+        const double d32 = (double)(float)st.d;
+        if ((pmask >> b) & 1u) {
+          if (d32 > bp) { bp = d32; ip = jj; sp = st; }   // ascending j: the first maximum wins ties
+        } else {
+          if (d32 < bn) { bn = d32; in = jj; sn = st; }
+        }
+      }
+    }
+    float hinge = 0.f, w = 0.f;
+    if (ip >= 0 && in >= 0) {
+      const float arg = __fsub_rn(__fadd_rn(P.margin, (float)sp.d), (float)sn.d);
+      hinge = fmaxf(arg, 0.f);
+      w = arg >= 0.f ? 1.0f / (float)P.batch : 0.f;  // torch's clamp_min backward passes grad at equality
+    }
+    const float ma = sqrtf(qsq) > kCosineEps ? 1.f : 0.f;
+    if (lane == 0) {
+      P.per_row[i] = hinge;
+      P.weight[i] = w;
+      P.sel[2 * i] = ip;
+      P.sel[2 * i + 1] = in;
+      P.pair_d[2 * i] = sp.d;
+      P.pair_d[2 * i + 1] = sn.d;
+      float* st = P.pair_stat + (size_t)i * 8;
+      st[0] = ca; st[1] = ma; st[2] = sp.cx; st[3] = sp.s; st[4] = sp.mx; st[5] = sn.cx; st[6] = sn.s; st[7] = sn.mx;
+      if (P.out_hard_index) {
+        P.out_hard_index[2 * i] = ip;
+        P.out_hard_index[2 * i + 1] = in;
+      }
+    }
+    if (P.ga != nullptr) {
+      float* out = P.ga + (size_t)i * P.dim;
+      if (w == 0.f) {
+        for (int e = lane; e < P.dim; e += 32) out[e] = 0.f;
+      } else {
+        const float* xp = cand_row(P, ip);
+        const float* xn = cand_row(P, in);
+        if (P.metric == SBIR_EUCLIDEAN) {
+          const float cp = sp.d > 0.0 ? (float)((double)w / sp.d) : 0.f;
+          const float cn = sn.d > 0.0 ? (float)((double)w / sn.d) : 0.f;
+          for (int e = lane; e < P.dim; e += 32) {
+            const float av = ar[e];
+            const float u = __fadd_rn(__fsub_rn(av, xp[e]), kPairwiseEps) * cp;
+            const float v = __fadd_rn(__fsub_rn(av, xn[e]), kPairwiseEps) * cn;
+            out[e] = u - v;
+          }
+        } else {
+          for (int e = lane; e < P.dim; e += 32) {
+            const float ah = ar[e] / ca;
+            // d = 1 − s  →  ∂d/∂a = −(x̂ − s·â·[‖a‖>eps]) / ca
+            const float gp_ = -(xp[e] / sp.cx - sp.s * ah * ma) / ca;
+            const float gn_ = -(xn[e] / sn.cx - sn.s * ah * ma) / ca;
+            out[e] = w * gp_ + (-w) * gn_;
+          }
+        }
+      }
+    }
   }
-  if (threadIdx.x == 0) out[0] = (float)(red[0] / (double)rows);
+  __threadfence();
+  grid.sync();
+
+  // -------------------------------------- phase 3: candidate gradients + mean of the hinges ----
+  if (gwarp == nwarps - 1) {  // last warp of the grid: deterministic mean (fixed order, fp64)
+    double acc = 0.0;
+    for (int i0 = 0; i0 < P.batch; i0 += 32) {
+      double v = (i0 + lane < P.batch) ? (double)__ldcg(P.per_row + i0 + lane) : 0.0;
+      // fixed-shape butterfly, then added chunk by chunk: the same order on every run
+      v = warp_sum(v);
+      acc += v;
+    }
+    if (lane == 0) P.out_loss[0] = (float)(acc / (double)P.batch);
+  }
+  if (P.gp == nullptr && P.gn == nullptr) return;
+  for (int j = gwarp; j < ncand; j += nwarps) {
+    float* out = j < P.batch ? (P.gp ? P.gp + (size_t)j * P.dim : nullptr)
+                             : (P.gn ? P.gn + (size_t)(j - P.batch) * P.dim : nullptr);
+    if (out == nullptr) continue;
+    const float* xr = cand_row(P, j);
+    // which anchors selected row j (bit 0: as their positive, bit 1: as their negative)
+    bool any = false;
+    for (int i0 = 0; i0 < P.batch && !any; i0 += 32) {
+      const int i = i0 + lane;
+      const bool f = i < P.batch && __ldcg(P.weight + i) != 0.f && (__ldcg(P.sel + 2 * i) == j || __ldcg(P.sel + 2 * i + 1) == j);
+      any = __any_sync(kFullMask, f);
+    }
+    if (!any) {
+      for (int e = lane; e < P.dim; e += 32) out[e] = 0.f;
+      continue;
+    }
+    // segments of 32 lanes × 8 elements, anchors walked in index order inside every segment
+    for (int e0 = 0; e0 < P.dim; e0 += 256) {
+      float acc[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) acc[v] = 0.f;
+      for (int i0 = 0; i0 < P.batch; i0 += 32) {
+        const int i = i0 + lane;
+        int f = 0;
+        if (i < P.batch && __ldcg(P.weight + i) != 0.f)
+          f = (__ldcg(P.sel + 2 * i) == j ? 1 : 0) | (__ldcg(P.sel + 2 * i + 1) == j ? 2 : 0);
+        unsigned mask = __ballot_sync(kFullMask, f != 0);
+        while (mask) {
+          const int b = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int ii = i0 + b;
+          const int fb = __shfl_sync(kFullMask, f, b);
+          const float w = __ldcg(P.weight + ii);
+          const float* ar = P.a + (size_t)ii * P.dim;
+          const float* st = P.pair_stat + (size_t)ii * 8;
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            if (!(fb & (1 << side))) continue;
+            const float scale = side == 0 ? w : -w;
+            if (P.metric == SBIR_EUCLIDEAN) {
+              const double d = __ldcg(P.pair_d + 2 * ii + side);
+              const float c = d > 0.0 ? (float)((double)scale / d) : 0.f;
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {
+                const int e = e0 + v * 32 + lane;
+                if (e < P.dim) acc[v] += -(__fadd_rn(__fsub_rn(ar[e], xr[e]), kPairwiseEps) * c);
+              }
+            } else {
+              const float ca = __ldcg(st + 0);
+              const float cx = __ldcg(st + 2 + 3 * side), s = __ldcg(st + 3 + 3 * side), mx = __ldcg(st + 4 + 3 * side);
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {
+                const int e = e0 + v * 32 + lane;
+                if (e < P.dim) {
+                  const float ah = ar[e] / ca, xh = xr[e] / cx;
+                  acc[v] += scale * (-(ah - s * xh * mx) / cx);
+                }
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const int e = e0 + v * 32 + lane;
+        if (e < P.dim) out[e] = acc[v];
+      }
+    }
+  }
 }
 
 struct BhLayout {
-  K1Plan plan;
-  size_t off_x, off_gvec, off_hard_val, off_hard_idx, off_per_row, off_weight, off_sel, off_counter, total;
+  int num_q_tiles, tiles_per_half, k_splits, kb_per_split, num_k_blocks, num_units, dot_rows, dot_cols;
+  size_t off_dots, off_anorm, off_cnorm, off_per_row, off_weight, off_sel, off_pair_d, off_pair_stat, total;
 };
 
 BhLayout bh_layout(int64_t batch, int64_t dim) {
   BhLayout L{};
-  L.plan = make_k1_plan(batch, 2 * batch, dim, 1, SBIR_F32, 148);
-  // single-CTA tiles, one unit per gallery tile: the epilogue state is per (tile, row)
-  L.plan.pair = 1;
-  L.plan.tiles_per_split = 1;
-  L.plan.num_splits = L.plan.num_g_tiles;
-  L.plan.band_q = L.plan.num_q_tiles;
-  L.plan.num_chunks = 1;
-  L.plan.tiles_per_chunk = 1;
-  L.plan.part_fastest = 0;
-  L.plan.num_units = L.plan.num_q_tiles * L.plan.num_splits;
+  L.num_q_tiles = (int)((batch + kBhTileA - 1) / kBhTileA);
+  L.tiles_per_half = (int)((batch + kBhTileC - 1) / kBhTileC);
+  L.num_k_blocks = (int)((dim * 4 + kSwizzleBytes - 1) / kSwizzleBytes);
+  // K split: enough units for ~128 SMs when the batch is small, at least 4 k-blocks per unit
+  const int tiles = L.num_q_tiles * 2 * L.tiles_per_half;
+  int want = (128 + tiles - 1) / tiles;
+  if (want > kBhMaxSplits) want = kBhMaxSplits;
+  if (want > L.num_k_blocks / 4) want = L.num_k_blocks / 4;
+  if (want < 1) want = 1;
+  L.kb_per_split = (L.num_k_blocks + want - 1) / want;
+  L.k_splits = (L.num_k_blocks + L.kb_per_split - 1) / L.kb_per_split;
+  L.num_units = tiles * L.k_splits;
+  L.dot_rows = L.num_q_tiles * kBhTileA;
+  L.dot_cols = 2 * L.tiles_per_half * kBhTileC;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + bytes, 256); return r; };
-  L.off_x = take((size_t)2 * batch * dim * sizeof(float));
-  L.off_gvec = take((size_t)L.plan.num_g_tiles * kTileG * sizeof(float));
-  const size_t hard_elems = (size_t)L.plan.num_splits * L.plan.q_tile_stride * kTileQ * L.plan.lists_per_row * 2;
-  L.off_hard_val = take(hard_elems * sizeof(float));
-  L.off_hard_idx = take(hard_elems * sizeof(int32_t));
+  L.off_dots = take((size_t)L.k_splits * L.dot_rows * L.dot_cols * sizeof(float));
+  L.off_anorm = take((size_t)batch * sizeof(float));
+  L.off_cnorm = take((size_t)2 * batch * sizeof(float));
   L.off_per_row = take((size_t)batch * sizeof(float));
   L.off_weight = take((size_t)batch * sizeof(float));
-  L.off_sel = take((size_t)batch * 2 * sizeof(long long));
-  L.off_counter = take(256);
+  L.off_sel = take((size_t)batch * 2 * sizeof(int));
+  L.off_pair_d = take((size_t)batch * 2 * sizeof(double));
+  L.off_pair_stat = take((size_t)batch * 8 * sizeof(float));
   L.total = o;
   return L;
 }
@@ -241,52 +491,64 @@ int launch_batch_hard(const float* a, const float* p, const float* n, int64_t ba
                       float margin, int metric, const int64_t* anchor_label, const int64_t* cand_label,
                       float* out_loss, int64_t* out_hard_index, float* ga, float* gp, float* gn,
                       void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (batch > (1 << 20) || dim > (1 << 20)) return SBIR_ERR_UNSUPPORTED;
   const BhLayout L = bh_layout(batch, dim);
   if (workspace == nullptr || workspace_bytes < L.total || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
     return SBIR_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(n)) % 16 != 0)
+    return SBIR_ERR_UNSUPPORTED;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  float* x = reinterpret_cast<float*>(ws + L.off_x);
-  float* gvec = reinterpret_cast<float*>(ws + L.off_gvec);
-  float* hard_val = reinterpret_cast<float*>(ws + L.off_hard_val);
-  int32_t* hard_idx = reinterpret_cast<int32_t*>(ws + L.off_hard_idx);
-  float* per_row = reinterpret_cast<float*>(ws + L.off_per_row);
-  float* weight = reinterpret_cast<float*>(ws + L.off_weight);
-  long long* sel = reinterpret_cast<long long*>(ws + L.off_sel);
+  BhParams P{};
+  P.a = a; P.p = p; P.n = n;
+  P.batch = (int)batch; P.dim = (int)dim; P.metric = metric;
+  P.margin = margin;
+  P.kappa = k1_kappa(SBIR_F32, dim) + (float)kBhMaxSplits * 1.1920929e-07f;  // + the fp32 sums over the K splits
+  P.anchor_label = reinterpret_cast<const long long*>(anchor_label);
+  P.cand_label = reinterpret_cast<const long long*>(cand_label);
+  P.num_q_tiles = L.num_q_tiles; P.tiles_per_half = L.tiles_per_half;
+  P.k_splits = L.k_splits; P.kb_per_split = L.kb_per_split; P.num_k_blocks = L.num_k_blocks; P.num_units = L.num_units;
+  P.dot_rows = L.dot_rows; P.dot_cols = L.dot_cols;
+  P.dots = reinterpret_cast<float*>(ws + L.off_dots);
+  P.anorm = reinterpret_cast<float*>(ws + L.off_anorm);
+  P.cnorm = reinterpret_cast<float*>(ws + L.off_cnorm);
+  P.per_row = reinterpret_cast<float*>(ws + L.off_per_row);
+  P.weight = reinterpret_cast<float*>(ws + L.off_weight);
+  P.sel = reinterpret_cast<int*>(ws + L.off_sel);
+  P.pair_d = reinterpret_cast<double*>(ws + L.off_pair_d);
+  P.pair_stat = reinterpret_cast<float*>(ws + L.off_pair_stat);
+  P.out_loss = out_loss;
+  P.out_hard_index = reinterpret_cast<long long*>(out_hard_index);
+  P.ga = ga; P.gp = gp; P.gn = gn;
 
-  const size_t half_bytes = (size_t)batch * dim * sizeof(float);
-  SBIR_CUDA_TRY(cudaMemcpyAsync(x, p, half_bytes, cudaMemcpyDeviceToDevice, st));
-  SBIR_CUDA_TRY(cudaMemcpyAsync(x + (size_t)batch * dim, n, half_bytes, cudaMemcpyDeviceToDevice, st));
-  const int64_t padded = (int64_t)L.plan.num_g_tiles * kTileG;
-  SBIR_TRY(launch_row_norm(x, 2 * batch, padded, dim, SBIR_F32, metric == SBIR_EUCLIDEAN ? 0 : 1,
-                           metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""), gvec, nullptr, st));
-  K1Args ka{};
-  ka.q = a; ka.g = x;
-  ka.num_q = batch; ka.num_g = 2 * batch; ka.dim = dim;
-  ka.dtype = SBIR_F32; ka.metric = metric; ka.mode = kModeHard;
-  ka.gvec = gvec;
-  ka.row_label = anchor_label; ka.col_label = cand_label;
-  ka.hard_val = hard_val; ka.hard_idx = hard_idx;
-  ka.unit_counter = reinterpret_cast<uint32_t*>(ws + L.off_counter);
-  SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_counter, 0, 256, st));
-  SBIR_TRY(launch_k1(ka, L.plan, st));
+  CUtensorMap ta, tp, tn;
+  SBIR_TRY(make_tmap(&ta, a, batch, dim, SBIR_F32, kBhTileA));
+  SBIR_TRY(make_tmap(&tp, p, batch, dim, SBIR_F32, kBhTileC));
+  SBIR_TRY(make_tmap(&tn, n, batch, dim, SBIR_F32, kBhTileC));
 
-  bh_select_kernel<<<(unsigned)batch, kBhThreads, 0, st>>>(
-      a, x, (int)batch, (int)dim, metric, margin, hard_val, hard_idx, L.plan.num_splits,
-      L.plan.q_tile_stride * kTileQ, L.plan.lists_per_row, 1.0f / (float)batch, per_row, weight, sel,
-      reinterpret_cast<long long*>(out_hard_index));
-  SBIR_CHECK_LAUNCH();
-  bh_mean_kernel<<<1, 256, 0, st>>>(per_row, (int)batch, out_loss);
-  SBIR_CHECK_LAUNCH();
-  if (ga) {
-    bh_grad_anchor_kernel<<<(unsigned)batch, kBhThreads, 0, st>>>(a, x, (int)dim, metric, weight, sel, ga);
-    SBIR_CHECK_LAUNCH();
+  // Cooperative launch: every CTA must be resident (the phases are separated by grid barriers).  One
+  // CTA per SM (164 KB of shared memory); fewer if the device cannot hold that many.
+  auto kern = batch_hard_fused_kernel<true>;
+  SBIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBhSmemBytes));
+  int dev = 0, num_sms = 0, per_sm = 0, coop = 0;
+  SBIR_CUDA_TRY(cudaGetDevice(&dev));
+  SBIR_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) return SBIR_ERR_UNSUPPORTED;
+  SBIR_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  SBIR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBhThreads, kBhSmemBytes));
+  if (per_sm < 1) return SBIR_ERR_UNSUPPORTED;
+  // enough warps for one per anchor / candidate row, never more CTAs than can be co-resident
+  int64_t want = (3 * batch + kBhWarps - 1) / kBhWarps;
+  if (want < L.num_units) want = L.num_units;
+  int grid = (int)(want < num_sms ? want : num_sms);
+  if (grid < 1) grid = 1;
+  void* args[] = {&ta, &tp, &tn, &P};
+  const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3((unsigned)grid), dim3(kBhThreads),
+                                                    args, kBhSmemBytes, st);
+  if (e != cudaSuccess) {
+    set_last_cuda_error((int)e);
+    return SBIR_ERR_CUDA;
   }
-  if (gp || gn) {
-    const int acc_in_smem = (size_t)dim * sizeof(float) <= 40 * 1024 ? 1 : 0;
-    bh_grad_cand_kernel<<<(unsigned)(2 * batch), kBhThreads, acc_in_smem ? (size_t)dim * sizeof(float) : 0, st>>>(
-        a, x, (int)batch, (int)dim, metric, weight, sel, gp, gn, acc_in_smem);
-    SBIR_CHECK_LAUNCH();
-  }
+  SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }
 

@@ -207,6 +207,22 @@ __device__ __forceinline__ double warp_exact_distance(const T* __restrict__ x,
   return 1.0 - warp_cos_dot<T, kVec>(x, y, cx, cy, dim, lane);
 }
 
+// e-space value of an exact distance (what K1's epilogue approximates) and the bound on
+// |approx − exact| for one query.
+__device__ __forceinline__ double e_of_distance(double d, int metric, float qsq) {
+  if (metric == SBIR_EUCLIDEAN) return d * d - (double)qsq;
+  return (d - 1.0) * (double)fmaxf(sqrtf(qsq), kCosineEps);
+}
+__device__ __forceinline__ double e_margin(int metric, float qsq, float gsq_max, float kappa, int dim) {
+  if (metric == SBIR_EUCLIDEAN) {
+    const double s = (double)qsq + (double)gsq_max;
+    // tensor-core rounding of 2·q·g  +  the reference's +1e-6 per component  +  fp32 epilogue rounding
+    return (double)kappa * s + 4e-6 * sqrt((double)dim * s) + 1e-12 * (double)dim + 4e-7 * s + 1e-30;
+  }
+  const double nq = sqrt((double)qsq);
+  return (double)kappa * nq + 1e-6 * nq + 1e-30;
+}
+
 // Total order used everywhere a ranked list is produced: ascending distance, ties by
 // ascending gallery index (the reference inherits torch.topk's unspecified tie order).
 __device__ __forceinline__ bool ranks_before(double da, int64_t ia, double db, int64_t ib) {

@@ -30,6 +30,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+}  // namespace
+
 // [rows, dim] row-major matrix → 2-D tensor map with a (128-byte × box_rows) SWIZZLE_128B box.
 int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int dtype, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
@@ -49,8 +51,6 @@ int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int
   }
   return SBIR_OK;
 }
-
-}  // namespace
 
 // Epilogue warps.  Small lists (cap <= 32): fp32 embeddings (kind::tf32) take 4; bf16 tiles complete
 // 2-4× sooner, so two warps share each TMEM lane quarter, each with its own list.  Lists of 64/128
@@ -212,10 +212,6 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.dropped = a.dropped;
   prm.shared_thr = a.shared_thr;
   prm.dump = a.dump;
-  prm.row_label = a.row_label;
-  prm.col_label = a.col_label;
-  prm.hard_val = a.hard_val;
-  prm.hard_idx = a.hard_idx;
   if (pair == 1 && prm.unit_counter == nullptr) return SBIR_ERR_INVALID_ARG;
   const bool select = a.mode == kModeTopk || a.mode == kModeTopkRank;
   if (select && (prm.chunk_done == nullptr || prm.row_max == nullptr || prm.row_maxpos == nullptr || prm.gmin == nullptr))
@@ -224,9 +220,9 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   int dev = 0, num_sms = 148;
   SBIR_CUDA_TRY(cudaGetDevice(&dev));
   SBIR_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  const int cap = (a.mode == kModeDump || a.mode == kModeHard) ? 16 : plan.cap;
+  const int cap = a.mode == kModeDump ? 16 : plan.cap;
 
-  // dump / batch-hard launches carry no plan of their own: 4 warps for fp32, 8 for bf16
+  // dump launches carry no plan of their own: 4 warps for fp32, 8 for bf16
   const int epi = select ? plan.epi_warps : (a.dtype == SBIR_BF16 ? 8 : 4);
   if (a.dtype == SBIR_F32) {
     if (a.metric == SBIR_EUCLIDEAN) return k1_launch_f32_euclidean(epi, a.mode, cap, pair, qres, tq, tg, prm, num_sms, st);

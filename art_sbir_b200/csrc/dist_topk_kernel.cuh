@@ -585,12 +585,6 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       int32_t shared_next = 0x7f800000;  // +inf in the ordered-int encoding
       if constexpr (kSelect) shared_next = ld_relaxed(prm.shared_thr + q_tile * kTileQ + row);
-      float hp = -INFINITY, hn = INFINITY;  // batch-hard: hardest positive / negative in e-space
-      int hpi = -1, hni = -1;
-      int64_t my_label = 0;
-      if constexpr (kMode == kModeHard) {
-        if (prm.row_label != nullptr && q_valid) my_label = prm.row_label[q];
-      }
 
       // One candidate of this row enters the list when it beats the threshold (owner side) ...
       auto insert_list = [&](float ej, int gidx_e) {
@@ -860,19 +854,6 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 for (int j = 0; j < 32; ++j)
                   if (gcol0 + j < prm.num_g) prm.dump[(size_t)q * prm.num_g + gcol0 + j] = e[j];
               }
-            } else if constexpr (kMode == kModeHard) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int gj = gcol0 + j;
-                if (gj < prm.num_g) {
-                  const bool is_pos = (prm.row_label == nullptr) ? (gj == q) : (prm.col_label[gj] == my_label);
-                  if (is_pos) {
-                    if (e[j] > hp) { hp = e[j]; hpi = gj; }
-                  } else {
-                    if (e[j] < hn) { hn = e[j]; hni = gj; }
-                  }
-                }
-              }
             }
           }
         }
@@ -933,14 +914,6 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           asm volatile("bar.sync 1, %0;" ::"r"((Cfg::kFeed ? 4 : kEpiWarps) * 32) : "memory");
           if (ew == 0 && lane == 0) st_release(done_flag, uc.chunk + 1);
         }
-      }
-      if constexpr (kMode == kModeHard) {
-        // one unit == one gallery tile; slot [part][q_tile*128+row][half]
-        const size_t o = (((size_t)uc.part * prm.q_tile_stride + q_tile) * kTileQ + row) * Cfg::kListsPerRow + half;
-        prm.hard_val[o * 2 + 0] = hp;
-        prm.hard_val[o * 2 + 1] = hn;
-        prm.hard_idx[o * 2 + 0] = hpi;
-        prm.hard_idx[o * 2 + 1] = hni;
       }
     }
   }
@@ -1024,9 +997,6 @@ int dispatch_mode_cap(int mode, int cap, int pair, bool qres, const CUtensorMap&
   SBIR_K1_CASE(kModeTopk, 128)
   SBIR_K1_CASE(kModeTopkRank, 64)
   SBIR_K1_CASE(kModeTopkRank, 128)
-  if constexpr (kEpiWarps == 4 && kTF32) {
-    SBIR_K1_CASE1(kModeHard, 16)
-  }
 #undef SBIR_K1_CASE
 #undef SBIR_K1_CASE1
   return SBIR_ERR_UNSUPPORTED;

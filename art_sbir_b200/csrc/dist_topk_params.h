@@ -39,11 +39,10 @@ struct K1Params {
   int32_t* dropped;
   int32_t* shared_thr;
   float* dump;
-  const int64_t* row_label;
-  const int64_t* col_label;
-  float* hard_val;
-  int32_t* hard_idx;
 };
+
+// [rows, dim] row-major matrix → 2-D tensor map with a (128-byte × box_rows) SWIZZLE_128B box (dist_topk.cu).
+int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int dtype, int box_rows);
 
 // One launcher per (input type, metric) translation unit: dist_topk_{f32,bf16}_{euclidean,cosine}.cu.
 // epi = epilogue warps (4 / 8), pair = 1 / 2 (CTA pairs), qres = resident-query form.

@@ -36,22 +36,6 @@ __device__ __forceinline__ void bitonic_sort_smem(Key* key, int32_t* idx, int n)
   __syncthreads();
 }
 
-// e-space value of an exact distance (what K1's epilogue approximates) and the bound on
-// |approx − exact| for one query.
-__device__ __forceinline__ double e_of_distance(double d, int metric, float qsq) {
-  if (metric == SBIR_EUCLIDEAN) return d * d - (double)qsq;
-  return (d - 1.0) * (double)fmaxf(sqrtf(qsq), kCosineEps);
-}
-__device__ __forceinline__ double e_margin(int metric, float qsq, float gsq_max, float kappa, int dim) {
-  if (metric == SBIR_EUCLIDEAN) {
-    const double s = (double)qsq + (double)gsq_max;
-    // tensor-core rounding of 2·q·g  +  the reference's +1e-6 per component  +  fp32 epilogue rounding
-    return (double)kappa * s + 4e-6 * sqrt((double)dim * s) + 1e-12 * (double)dim + 4e-7 * s + 1e-30;
-  }
-  const double nq = sqrt((double)qsq);
-  return (double)kappa * nq + 1e-6 * nq + 1e-30;
-}
-
 constexpr int kFinThreads = 128;
 
 struct FinParams {

@@ -31,7 +31,7 @@ constexpr int kTileG = 256;        // gallery rows per tile (UMMA N, TMEM column
 constexpr int kUncertainPerQuery = 256;  // uncertain-pool capacity = this × num_q (min 65536)
 constexpr int kMaxK = 116;         // largest supported k (list capacity 128 minus slack)
 
-enum K1Mode { kModeTopk = 0, kModeTopkRank = 1, kModeDump = 2, kModeHard = 3 };
+enum K1Mode { kModeTopk = 0, kModeTopkRank = 1, kModeDump = 2 };
 
 // Work decomposition of one K1 launch: `num_splits` gallery partitions of `tiles_per_split` tiles
 // (independent candidate lists), each scanned in `num_chunks` serial chunks; a unit is
@@ -81,11 +81,6 @@ struct K1Args {
   int32_t* shared_thr;
   // debug (mode kModeDump): full epilogue matrix [num_q][num_g]
   float* dump;
-  // batch-hard mining (mode kModeHard): per query row, the labels and outputs
-  const int64_t* row_label;   // [num_q]  (NULL: positive of row i is column i)
-  const int64_t* col_label;   // [num_g]
-  float* hard_val;            // [num_g_tiles][num_q_tiles*kTileQ][2]  (max pos, min neg) e-space
-  int32_t* hard_idx;          // same shape
 };
 int launch_k1(const K1Args& args, const K1Plan& plan, cudaStream_t st);
 // Reads and clears the per-CTA cycle counters the kernel fills when SBIR_K1_FLAGS & 64 (8 per CTA).
