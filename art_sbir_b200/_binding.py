@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libsbir_b200.so"
 SBIR_F32, SBIR_BF16 = 0, 1
 SBIR_EUCLIDEAN, SBIR_COSINE = 0, 1
 MAX_K = 116
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/sbir_b200.h one to one.
 _P = c_void_p
@@ -27,10 +28,11 @@ PROTOTYPES = {
     "sbir_pairwise_distance": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P]),
     "sbir_pairwise_distance_bwd": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, _P, _P, _P, _P]),
     "sbir_pairwise_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int]),
-    "sbir_pairwise_topk": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P,
+    "sbir_gallery_append": (c_int, [_P, c_int, c_int64, c_int64, _P, c_int, c_int64, c_int64, _P, c_int, _P]),
+    "sbir_pairwise_topk": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P,
                                    _P, _P, _P, c_size_t, _P]),
     "sbir_positive_distance": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P]),
-    "sbir_pairwise_topk_shard": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P,
+    "sbir_pairwise_topk_shard": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P,
                                          _P, _P, _P, _P, c_size_t, _P]),
     "sbir_topk_merge": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P]),
     "sbir_retrieval_metrics": (c_int, [_P, c_int64, c_int, _P, _P]),
@@ -67,7 +69,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sbir_abi_version() != 1:
+    if lib.sbir_abi_version() != ABI_VERSION:
         raise RuntimeError("libsbir_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -121,7 +121,7 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
 //        (fp32) and the brute-force fallbacks.
 // sbir_pairwise_topk / _shard run begin, ONE feed of the whole gallery, finish;
 // sbir_retrieve_host (host_path.cu) feeds the gallery as its chunks arrive over PCIe.
-int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, const float* g_sqnorm, int64_t num_g, int64_t dim, int dtype,
                     int metric, int k, int64_t index_offset, const int64_t* pos_index, const double* pos_dist_in,
                     const int64_t* pos_tie, int64_t tie_offset, float* out_dist, int64_t* out_index,
                     int64_t* out_rank, int64_t missing_rank, int32_t* out_uncertified, void* workspace,
@@ -146,7 +146,7 @@ int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, in
     return SBIR_ERR_WORKSPACE;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   P.ws = ws; P.st = st; P.want_rank = want_rank;
-  P.q = q; P.g = g; P.num_q = num_q; P.num_g = num_g; P.dim = dim; P.dtype = dtype; P.metric = metric;
+  P.q = q; P.g = g; P.g_sqnorm = g_sqnorm; P.num_q = num_q; P.num_g = num_g; P.dim = dim; P.dtype = dtype; P.metric = metric;
   P.gvec = reinterpret_cast<float*>(ws + L.off_gvec);
   P.gmax = reinterpret_cast<float*>(ws + L.off_gmax);
   P.gmin = reinterpret_cast<float*>(ws + L.off_gmin);
@@ -245,9 +245,14 @@ int topk_pass_feed(TopkPass& P, int64_t row_end) {
   }
   const size_t row_bytes = (size_t)P.dim * elem_size(P.dtype);
   const int64_t pad_end = last ? P.padded : row_end;  // the padding rows of the last tile belong to the last feed
-  SBIR_TRY(launch_row_norm(static_cast<const uint8_t*>(P.g) + (size_t)row0 * row_bytes, row_end - row0, pad_end - row0, P.dim,
-                           P.dtype, P.metric == SBIR_EUCLIDEAN ? 0 : 1,
-                           P.metric == SBIR_EUCLIDEAN ? INFINITY : nanf(""), P.gvec + row0, P.gmax, st, /*accumulate_max=*/true));
+  const int vec_mode = P.metric == SBIR_EUCLIDEAN ? 0 : 1;
+  const float vec_pad = P.metric == SBIR_EUCLIDEAN ? INFINITY : nanf("");
+  if (P.g_sqnorm != nullptr)  // gallery built by sbir_gallery_append / reloaded with its sidecar: N floats instead of N·dim elements
+    SBIR_TRY(launch_gvec_from_sqnorm(P.g_sqnorm + row0, row_end - row0, pad_end - row0, vec_mode, vec_pad, P.gvec + row0, P.gmax,
+                                     st, /*accumulate_max=*/true));
+  else
+    SBIR_TRY(launch_row_norm(static_cast<const uint8_t*>(P.g) + (size_t)row0 * row_bytes, row_end - row0, pad_end - row0, P.dim,
+                             P.dtype, vec_mode, vec_pad, P.gvec + row0, P.gmax, st, /*accumulate_max=*/true));
   SBIR_TRY(launch_chunk_min(P.gvec + row0, (pad_end - row0) / 8, P.gmin + row0 / 8, st));
   // the rank band uses the largest gallery norm seen so far (it only widens from feed to feed)
   if (P.want_rank) SBIR_TRY(launch_rank_band(P.ra, st));
@@ -343,13 +348,13 @@ namespace {
 
 // Shared implementation of sbir_pairwise_topk (pos_index given, full rank) and
 // sbir_pairwise_topk_shard (pos_dist given, local count).
-int topk_impl(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+int topk_impl(const void* q, int64_t num_q, const void* g, const float* g_sqnorm, int64_t num_g, int64_t dim, int dtype,
               int metric, int k, int64_t index_offset, const int64_t* pos_index,
               const double* pos_dist_in, const int64_t* pos_tie, int64_t tie_offset, float* out_dist, int64_t* out_index, int64_t* out_rank,
               int64_t missing_rank, int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
               cudaStream_t st) {
   TopkPass P;
-  SBIR_TRY(topk_pass_begin(P, q, num_q, g, num_g, dim, dtype, metric, k, index_offset, pos_index, pos_dist_in, pos_tie,
+  SBIR_TRY(topk_pass_begin(P, q, num_q, g, g_sqnorm, num_g, dim, dtype, metric, k, index_offset, pos_index, pos_dist_in, pos_tie,
                            tie_offset, out_dist, out_index, out_rank, missing_rank, out_uncertified, workspace,
                            workspace_bytes, st));
   if (P.done) return SBIR_OK;
@@ -419,6 +424,19 @@ int sbir_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dty
   return launch_l2_normalize(x, y, rows, dim, dtype, eps, static_cast<cudaStream_t>(stream));
 }
 
+int sbir_gallery_append(const void* block, int block_dtype, int64_t rows, int64_t dim, void* gallery, int gallery_dtype,
+                        int64_t gallery_rows, int64_t row0, float* gallery_sqnorm, int normalize, void* stream) {
+  if (!dtype_ok(block_dtype) || !dtype_ok(gallery_dtype) || rows < 0 || dim <= 0 || row0 < 0 || gallery_rows < 0)
+    return SBIR_ERR_INVALID_ARG;
+  if (row0 + rows > gallery_rows) return SBIR_ERR_INVALID_ARG;  // the block must fit the preallocated matrix
+  if (rows == 0) return SBIR_OK;
+  if (block == nullptr || gallery == nullptr) return SBIR_ERR_INVALID_ARG;
+  uint8_t* dst = static_cast<uint8_t*>(gallery) + (size_t)row0 * (size_t)dim * elem_size(gallery_dtype);
+  return launch_gallery_append(block, block_dtype, rows, dim, dst, gallery_dtype,
+                               gallery_sqnorm ? gallery_sqnorm + row0 : nullptr, normalize ? 1 : 0, kCosineEps,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int sbir_row_sqnorm(const void* x, int64_t rows, int64_t dim, int dtype, float* out, void* stream) {
   if (!dtype_ok(dtype) || rows < 0 || dim <= 0) return SBIR_ERR_INVALID_ARG;
   if (rows == 0) return SBIR_OK;
@@ -453,11 +471,11 @@ size_t sbir_pairwise_topk_workspace_bytes(int64_t num_q, int64_t num_g, int64_t 
   return topk_layout(num_q, num_g, dim, k, dtype, want_rank).total;
 }
 
-int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, const float* g_sqnorm, int64_t num_g, int64_t dim, int dtype,
                        int metric, int k, int64_t index_offset, const int64_t* pos_index, float* out_dist,
                        int64_t* out_index, int64_t* out_rank, int32_t* out_uncertified, void* workspace,
                        size_t workspace_bytes, void* stream) {
-  return topk_impl(q, num_q, g, num_g, dim, dtype, metric, k, index_offset, pos_index, nullptr, pos_index, 0, out_dist,
+  return topk_impl(q, num_q, g, g_sqnorm, num_g, dim, dtype, metric, k, index_offset, pos_index, nullptr, pos_index, 0, out_dist,
                    out_index, out_rank, /*missing_rank=*/num_g, out_uncertified, workspace, workspace_bytes,
                    static_cast<cudaStream_t>(stream));
 }
@@ -471,13 +489,13 @@ int sbir_positive_distance(const void* q, int64_t num_q, const void* g, int64_t 
                                   static_cast<cudaStream_t>(stream));
 }
 
-int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
+int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, const float* g_sqnorm, int64_t num_g, int64_t dim,
                              int dtype, int metric, int k, int64_t index_offset, const double* pos_dist,
                              const int64_t* pos_index_global, float* out_dist, int64_t* out_index, int64_t* out_count_less,
                              int32_t* out_uncertified, void* workspace, size_t workspace_bytes,
                              void* stream) {
   // A query without a positive anywhere (NaN pos_dist) contributes a local count of 0.
-  return topk_impl(q, num_q, g, num_g, dim, dtype, metric, k, index_offset, nullptr, pos_dist, pos_index_global,
+  return topk_impl(q, num_q, g, g_sqnorm, num_g, dim, dtype, metric, k, index_offset, nullptr, pos_dist, pos_index_global,
                    index_offset, out_dist,
                    out_index, out_count_less, /*missing_rank=*/0, out_uncertified, workspace, workspace_bytes,
                    static_cast<cudaStream_t>(stream));

@@ -128,6 +128,7 @@ __device__ __forceinline__ double warp_sq_l2_eps(const T* __restrict__ x, const 
   if constexpr (kVec) {
     constexpr int E = Vec16<T>::kElems;
     const int nvec = dim / E;
+#pragma unroll 4
     for (int i = lane; i < nvec; i += 32) {
       Vec16<T> a, b;
       a.load(x + (size_t)i * E);
@@ -153,6 +154,7 @@ __device__ __forceinline__ double warp_sq_norm(const T* __restrict__ x, int dim,
   if constexpr (kVec) {
     constexpr int E = Vec16<T>::kElems;
     const int nvec = dim / E;
+#pragma unroll 4
     for (int i = lane; i < nvec; i += 32) {
       Vec16<T> a;
       a.load(x + (size_t)i * E);
@@ -176,6 +178,7 @@ __device__ __forceinline__ double warp_cos_dot(const T* __restrict__ x, const T*
   if constexpr (kVec) {
     constexpr int E = Vec16<T>::kElems;
     const int nvec = dim / E;
+#pragma unroll 4
     for (int i = lane; i < nvec; i += 32) {
       Vec16<T> a, b;
       a.load(x + (size_t)i * E);

@@ -248,7 +248,7 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   };
   if (streamed) {
     TopkPass pass;
-    SBIR_TRY(topk_pass_begin(pass, d_q, num_q, d_g, num_g, dim, dtype, metric, k, /*index_offset=*/0, nullptr, d_pos_dist,
+    SBIR_TRY(topk_pass_begin(pass, d_q, num_q, d_g, nullptr, num_g, dim, dtype, metric, k, /*index_offset=*/0, nullptr, d_pos_dist,
                              d_pos_global, /*tie_offset=*/0, d_out_d, d_out_i,
                              want_rank ? reinterpret_cast<int64_t*>(d_rank) : nullptr, /*missing_rank=*/num_g,
                              d_uncert + 1, base + off_ws, ws_bytes, cs));
@@ -265,7 +265,7 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
       const int64_t rows = chunk_end[c] - r0;
       SBIR_TRY(upload_chunk(c));
       int64_t* d_cnt = want_rank ? reinterpret_cast<int64_t*>(base + off_cnt) : nullptr;
-      SBIR_TRY(sbir_pairwise_topk_shard(d_q, num_q, d_g + (size_t)r0 * row_bytes, rows, dim, dtype, metric, k, r0,
+      SBIR_TRY(sbir_pairwise_topk_shard(d_q, num_q, d_g + (size_t)r0 * row_bytes, nullptr, rows, dim, dtype, metric, k, r0,
                                         d_pos_dist, d_pos_global, d_lists_d + (size_t)c * num_q * k,
                                         d_lists_i + (size_t)c * num_q * k, d_cnt, d_uncert + 1 + c,
                                         base + off_ws, ws_bytes, cs));
@@ -361,7 +361,7 @@ extern "C" int sbir_retrieve_host_shard(const void* q_dev, int64_t num_q, const 
   int32_t* d_uncert = reinterpret_cast<int32_t*>(base + off_uncert);
   TopkPass pass;
   // A query without a positive anywhere (NaN pos_dist) contributes a local count of 0.
-  SBIR_TRY(topk_pass_begin(pass, q_dev, num_q, d_g, num_g, dim, dtype, metric, k, index_offset, nullptr, pos_dist_dev,
+  SBIR_TRY(topk_pass_begin(pass, q_dev, num_q, d_g, nullptr, num_g, dim, dtype, metric, k, index_offset, nullptr, pos_dist_dev,
                            pos_index_global_dev, index_offset, out_dist_dev, out_index_dev, out_count_less_dev,
                            /*missing_rank=*/0, d_uncert, base + off_ws, ws_bytes, cs));
   for (size_t c = 0; c < chunk_end.size(); ++c) {

@@ -12,6 +12,12 @@ namespace sbir {
 int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int dtype,
                     int mode, float pad_value, float* out, float* max_sqnorm_out, cudaStream_t st,
                     bool accumulate_max = false);
+// The same vector from stored ‖g‖² (gallery built by sbir_gallery_append / reloaded with its sidecar).
+int launch_gvec_from_sqnorm(const float* sqnorm, int64_t rows, int64_t rows_padded, int mode, float pad_value,
+                            float* out, float* max_out, cudaStream_t st, bool accumulate_max = false);
+// N1: rows of encoder output → the gallery's storage type (+ optional L2 normalisation) + ‖stored row‖².
+int launch_gallery_append(const void* block, int in_dtype, int64_t rows, int64_t dim, void* out_rows, int out_dtype,
+                          float* out_sqnorm, int normalize, float eps, cudaStream_t st);
 // out[i] = min(gvec[8 i .. 8 i + 7]) (NaN entries ignored)
 int launch_chunk_min(const float* gvec, int64_t num_chunks, float* out, cudaStream_t st);
 int launch_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dtype, float eps,
@@ -186,12 +192,13 @@ struct TopkPass {
   cudaStream_t st;
   const void* q;
   const void* g;
+  const float* g_sqnorm;  // optional stored ‖g‖² of the gallery rows (else computed from the rows)
   int64_t num_q, num_g, dim, padded, fed_rows;
   int dtype, metric;
   float *gvec, *gmax, *gmin, *qsq;
   int32_t *flags, *uncert;
 };
-int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim, int dtype,
+int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, const float* g_sqnorm, int64_t num_g, int64_t dim, int dtype,
                     int metric, int k, int64_t index_offset, const int64_t* pos_index, const double* pos_dist_in,
                     const int64_t* pos_tie, int64_t tie_offset, float* out_dist, int64_t* out_index,
                     int64_t* out_rank, int64_t missing_rank, int32_t* out_uncertified, void* workspace,

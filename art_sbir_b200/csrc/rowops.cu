@@ -197,6 +197,88 @@ __global__ void __launch_bounds__(kRowThreads) row_norm_kernel(const T* __restri
     atomicMax(reinterpret_cast<int*>(max_out), __float_as_int(local_max));
 }
 
+// ------------------------------------------- gallery append (N1) / gvec from norms ----
+// One block of encoder output (fp32 or bf16 [rows, dim]) written straight into rows
+// [row0, row0 + rows) of the preallocated gallery matrix in ITS storage type (fp32 or bf16),
+// optionally L2-normalised, together with ‖stored row‖² (fp32, fp64-accumulated, of the values as
+// stored — what K1's epilogue adds and the certificate bounds).  Replaces the reference's
+// torch.cat growth + .cpu() round trip (inference.py:85-88).  One warp per row, 16-byte loads.
+template <typename TIn, typename TOut, bool kVec>
+__global__ void __launch_bounds__(kRowThreads) gallery_append_kernel(const TIn* __restrict__ x, int64_t rows, int dim,
+                                                                    TOut* __restrict__ y, float* __restrict__ sqnorm,
+                                                                    int normalize, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const TIn* xr = x + r * dim;
+    TOut* yr = y + r * dim;
+    float c = 1.f, inv = 1.f;
+    if (normalize) {
+      c = fmaxf((float)sqrt(warp_sq_norm<TIn, kVec>(xr, dim, lane)), eps);
+      inv = 1.0f / c;
+    }
+    // fp32 storage: true division (bit-compatible with torch's x / norm); bf16 storage: the quotient is
+    // rounded to 8 mantissa bits anyway (same rule as l2_normalize_kernel)
+    auto scaled = [&](float v) { return !normalize ? v : (sizeof(TOut) == 2 ? v * inv : __fdiv_rn(v, c)); };
+    double acc = 0.0;
+    if constexpr (kVec) {
+      constexpr int E = Vec16<TIn>::kElems;  // elements per 16-byte input vector (4 fp32 / 8 bf16)
+      const int nvec = dim / E;
+#pragma unroll 4
+      for (int i = lane; i < nvec; i += 32) {
+        Vec16<TIn> a;
+        a.load(xr + (size_t)i * E);
+        TOut o[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          from_f32(o[e], scaled(a.v[e]));
+          const float st = to_f32(o[e]);
+          acc += (double)st * (double)st;
+        }
+        if constexpr (sizeof(TOut) * E == 16) {
+          *reinterpret_cast<uint4*>(yr + (size_t)i * E) = *reinterpret_cast<const uint4*>(o);
+        } else if constexpr (sizeof(TOut) * E == 8) {
+          *reinterpret_cast<uint2*>(yr + (size_t)i * E) = *reinterpret_cast<const uint2*>(o);
+        } else {  // bf16 in, fp32 out: 8 floats
+          reinterpret_cast<uint4*>(yr + (size_t)i * E)[0] = reinterpret_cast<const uint4*>(o)[0];
+          reinterpret_cast<uint4*>(yr + (size_t)i * E)[1] = reinterpret_cast<const uint4*>(o)[1];
+        }
+      }
+    } else {
+      for (int i = lane; i < dim; i += 32) {
+        TOut o;
+        from_f32(o, scaled(to_f32(xr[i])));
+        yr[i] = o;
+        const float st = to_f32(o);
+        acc += (double)st * (double)st;
+      }
+    }
+    const double sq = warp_sum(acc);
+    if (sqnorm != nullptr && lane == 0) sqnorm[r] = (float)sq;
+  }
+}
+
+// K1's gallery epilogue vector from stored ‖g‖² (a gallery built by sbir_gallery_append or reloaded
+// with its sidecar): N floats read instead of N·dim elements.  Same outputs as row_norm_kernel.
+__global__ void __launch_bounds__(256) gvec_from_sqnorm_kernel(const float* __restrict__ sq, int64_t rows,
+                                                               int64_t rows_padded, int mode, float pad_value,
+                                                               float* __restrict__ out, float* __restrict__ max_out) {
+  float local_max = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows_padded; r += (int64_t)gridDim.x * blockDim.x) {
+    if (r >= rows) {
+      out[r] = pad_value;
+      continue;
+    }
+    const float v = __ldg(sq + r);
+    local_max = fmaxf(local_max, v);
+    out[r] = (mode == 0) ? v : -1.0f / fmaxf((float)sqrt((double)v), kCosineEps);
+  }
+  local_max = warp_max(local_max);
+  if (max_out != nullptr && (threadIdx.x & 31) == 0 && local_max > 0.f)
+    atomicMax(reinterpret_cast<int*>(max_out), __float_as_int(local_max));
+}
+
 // ------------------------------------------------------- pairwise distance ----
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kRowThreads) pairwise_distance_kernel(
@@ -464,6 +546,34 @@ int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t di
   if (dtype == SBIR_F32)
     return launch_norm<float>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
   return launch_norm<__nv_bfloat16>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
+}
+
+int launch_gvec_from_sqnorm(const float* sqnorm, int64_t rows, int64_t rows_padded, int mode, float pad_value,
+                            float* out, float* max_out, cudaStream_t st, bool accumulate_max) {
+  if (rows_padded <= 0) return SBIR_OK;
+  if (max_out && !accumulate_max) SBIR_CUDA_TRY(cudaMemsetAsync(max_out, 0, sizeof(float), st));
+  int64_t blocks = (rows_padded + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gvec_from_sqnorm_kernel<<<(unsigned)blocks, 256, 0, st>>>(sqnorm, rows, rows_padded, mode, pad_value, out, max_out);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_gallery_append(const void* block, int in_dtype, int64_t rows, int64_t dim, void* out_rows, int out_dtype,
+                          float* out_sqnorm, int normalize, float eps, cudaStream_t st) {
+  if (rows <= 0) return SBIR_OK;
+  const bool vec = rows_vectorizable(block, dim, in_dtype) && rows_vectorizable(out_rows, dim, out_dtype) &&
+                   (dim % (in_dtype == SBIR_BF16 ? 8 : 4) == 0);
+  const int grid = row_grid(rows);
+  using B = __nv_bfloat16;
+#define SBIR_APPEND(TI, TO)                                                                                               do {                                                                                                                      if (vec) gallery_append_kernel<TI, TO, true><<<grid, kRowThreads, 0, st>>>((const TI*)block, rows, (int)dim, (TO*)out_rows, out_sqnorm, normalize, eps);     else gallery_append_kernel<TI, TO, false><<<grid, kRowThreads, 0, st>>>((const TI*)block, rows, (int)dim, (TO*)out_rows, out_sqnorm, normalize, eps);      } while (0)
+  if (in_dtype == SBIR_F32 && out_dtype == SBIR_F32) SBIR_APPEND(float, float);
+  else if (in_dtype == SBIR_F32) SBIR_APPEND(float, B);
+  else if (out_dtype == SBIR_F32) SBIR_APPEND(B, float);
+  else SBIR_APPEND(B, B);
+#undef SBIR_APPEND
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
 }
 
 int launch_chunk_min(const float* gvec, int64_t num_chunks, float* out, cudaStream_t st) {

@@ -94,13 +94,27 @@ def get_topk_images(k: int, image_paths: List[Path], sketch_feature: torch.Tenso
     return [(str(image_paths[i]), float(v)) for i, v in zip(indices, values)]
 
 
-def evaluate_embeddings(sketch_features: torch.Tensor, image_features: torch.Tensor, pos_index: torch.Tensor,
+def _split_gallery(image_features):
+    """(rows, stored ‖row‖² or None) of a gallery given as a tensor or as utils.GalleryFeatures."""
+    if isinstance(image_features, utils.GalleryFeatures):
+        return image_features.rows, image_features.sqnorm
+    return image_features, None
+
+
+def evaluate_embeddings(sketch_features: torch.Tensor, image_features, pos_index: torch.Tensor,
                         loss_type: str = "euclidean", k: int = 10, sample_indices: Sequence[int] = ()) -> Dict:
     """The arithmetic of process_inference (inference.py:109-133) for already-encoded sketches:
     ranks, MRR, cumulative top-k accuracy, describe() stats, and the top-k lists of the
-    sampled queries.  Returns the metrics dict plus 'ranks0' (device tensor) and 'samples'."""
-    q, g = _common_dtype(_to_device(sketch_features), _to_device(image_features))
-    values, indices, rank0 = ops.pairwise_topk(q, g, k, loss_type, pos_index=_to_device(pos_index))
+    sampled queries.  Returns the metrics dict plus 'ranks0' (device tensor) and 'samples'.
+    `image_features` may be a utils.GalleryFeatures: its stored norms then spare the pass a read of the gallery."""
+    rows, sqnorm = _split_gallery(image_features)
+    rows = _to_device(rows)
+    q, g = _common_dtype(_to_device(sketch_features), rows)
+    if sqnorm is not None and g.dtype == rows.dtype:
+        sqnorm = _to_device(sqnorm)
+    else:
+        sqnorm = None
+    values, indices, rank0 = ops.pairwise_topk(q, g, k, loss_type, pos_index=_to_device(pos_index), gallery_sqnorm=sqnorm)
     stats = ops.retrieval_metrics(rank0, k)
     samples = {}
     if len(sample_indices):
@@ -124,7 +138,8 @@ def process_inference(model, dataset, inference_dataset, dataloader, image_featu
     random.seed(11)
     random_indices = [random.randrange(0, len(dataset)) for _ in range(10)]
 
-    image_features = _to_device(image_features)
+    if not isinstance(image_features, utils.GalleryFeatures):
+        image_features = _to_device(image_features)
     model.to(device)
     model.eval()
     feats = []
@@ -164,34 +179,44 @@ def process_inference(model, dataset, inference_dataset, dataloader, image_featu
 
 
 def compute_image_features(model, dataset, with_classification: bool, batch_size: int = 50,
-                           inference_dataset=None, save: bool = True):
+                           inference_dataset=None, save: bool = True, gallery_dtype: Optional[torch.dtype] = None,
+                           row_range: Optional[Tuple[int, int]] = None, feature_root: Optional[Path] = None,
+                           write_csv: bool = True):
     """inference.py:72-92 (N1): gallery embeddings for the de-duplicated, sorted photo paths.
-    Writes into a preallocated [N, D] device buffer instead of growing a tensor with
-    torch.cat per batch, and keeps the result on the GPU for the scoring pass."""
-    from torch.utils.data import DataLoader
+    Every batch of encoder output goes through sbir_gallery_append straight into a preallocated [N, D]
+    device buffer (ops.GalleryBuffer: storage type `gallery_dtype`, default the encoder's; ‖row‖² written
+    by the same kernel) instead of the reference's torch.cat growth + .cpu(); the gallery stays on the GPU
+    for the scoring pass.  `row_range=(a, b)` encodes only those gallery rows — with one encoder replica
+    per GPU and sharded.shard_bounds this yields the row-sharded layout of the multi-GPU path directly.
+    Returns (inference_dataset, utils.GalleryFeatures, feature folder name or None)."""
+    from torch.utils.data import DataLoader, Subset
     if inference_dataset is None:
         inference_dataset = InferenceDataset(dataset.photo_paths, dataset.transform)
-    dataloader = DataLoader(dataset=inference_dataset, batch_size=batch_size, num_workers=0, shuffle=False)
+    a, b = (0, len(inference_dataset)) if row_range is None else row_range
+    source = inference_dataset if row_range is None else Subset(inference_dataset, range(a, b))
+    dataloader = DataLoader(dataset=source, batch_size=batch_size, num_workers=0, shuffle=False)
     model.to(device)
     model.eval()
-    image_features: Optional[torch.Tensor] = None
-    row = 0
+    buf: Optional[ops.GalleryBuffer] = None
     with torch.inference_mode():
         for images in dataloader:
             out = model(images.to(device))
             out = (out[0] if with_classification else out)
             out = out.reshape(-1, out.shape[-1])
-            if image_features is None:
-                image_features = torch.empty((len(inference_dataset), out.shape[1]), dtype=out.dtype, device=device)
-            image_features[row:row + out.shape[0]] = out
-            row += out.shape[0]
-    if image_features is None:
-        image_features = torch.empty((0, 0), device=device)
+            if buf is None:
+                store = gallery_dtype if gallery_dtype is not None else (torch.bfloat16 if out.dtype == torch.bfloat16 else torch.float32)
+                buf = ops.GalleryBuffer(b - a, out.shape[1], store, device=out.device)
+            buf.append(out)
+    if buf is None:
+        feats = utils.GalleryFeatures(torch.empty((0, 0), device=device), torch.empty(0, device=device))
+    else:
+        feats = utils.GalleryFeatures(buf.rows, buf.sqnorm)
     feature_path = None
     if save:
+        kw = {} if feature_root is None else {"root": feature_root}
         feature_path = utils.save_image_features(model.__class__.__name__, dataset.state_dict["dataset"],
-                                                 inference_dataset, image_features)
-    return inference_dataset, image_features, feature_path
+                                                 inference_dataset, feats, write_csv=write_csv, **kw)
+    return inference_dataset, feats, feature_path
 
 
 class InferenceDataset(torch.utils.data.Dataset):
@@ -216,10 +241,12 @@ class InferenceDataset(torch.utils.data.Dataset):
         return self.transform(img) if self.transform is not None else img
 
 
-def run_inference(model, dataset, folder_name: str = None, loss_type="euclidean", second_dataset=None) -> Dict:
+def run_inference(model, dataset, folder_name: str = None, loss_type="euclidean", second_dataset=None,
+                  inference_dataset=None, feature_root: Optional[Path] = None) -> Dict:
     """inference.py:140-165.  `second_dataset` stands for the KaggleInferenceV1 sketches the
     reference loads for Kaggle/Mixed datasets (inference.py:157-160); dataset construction is
-    outside this path, so the caller supplies it."""
+    outside this path, so the caller supplies it.  `inference_dataset` (optional) replaces the
+    InferenceDataset built from dataset.photo_paths; `feature_root` the reference's data/image_features."""
     from torch.utils.data import DataLoader
     start_time = timer()
     with_classification = "with_classification" in type(model).__name__
@@ -232,11 +259,13 @@ def run_inference(model, dataset, folder_name: str = None, loss_type="euclidean"
                          "inference.py:157-160): pass it as second_dataset=")
     if folder_name:
         feature_folder = folder_name
-        image_paths, image_features = utils.load_image_features(folder_name)
+        kw = {} if feature_root is None else {"root": feature_root}
+        image_paths, image_features = utils.load_image_features(folder_name, with_norms=True, **kw)
         inference_dataset = InferenceDataset(image_paths, getattr(model, "transform", None))
         print("Image features loaded from file")
     else:
-        inference_dataset, image_features, feature_folder = compute_image_features(model, dataset, with_classification)
+        inference_dataset, image_features, feature_folder = compute_image_features(
+            model, dataset, with_classification, inference_dataset=inference_dataset, feature_root=feature_root)
     dataloader = DataLoader(dataset=dataset, batch_size=64, num_workers=0, shuffle=False)  # N4: batched queries
     inference_dict = process_inference(model, dataset, inference_dataset, dataloader, image_features, start_time,
                                        with_classification, loss_type)

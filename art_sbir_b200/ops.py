@@ -74,6 +74,50 @@ def row_sqnorm(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# --------------------------------------------------------------------------- N1 ----
+class GalleryBuffer:
+    """Preallocated device gallery [capacity, dim] (fp32 or bf16) + ‖row‖² that encoder output is appended
+    to block by block (sbir_gallery_append) — what replaces the reference's torch.cat growth, .cpu() and
+    CSV dump in compute_image_features (inference.py:72-92).  `rows` / `sqnorm` are views of what has been
+    written; the buffer never leaves the GPU.  With one encoder replica per GPU every rank fills the buffer
+    of its own shard (sharded.shard_bounds) and the row-sharded layout of the multi-GPU path exists at once."""
+
+    def __init__(self, capacity: int, dim: int, dtype: torch.dtype = torch.float32, device=None, normalize: bool = False):
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("gallery storage is float32 or bfloat16")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("GalleryBuffer lives on a CUDA device: the sbir_b200 path has no CPU fallback")
+        self.storage = torch.empty((capacity, dim), dtype=dtype, device=device)
+        self.sqnorm_storage = torch.empty(capacity, dtype=torch.float32, device=device)
+        self.normalize = bool(normalize)
+        self.filled = 0
+
+    def append(self, block: torch.Tensor) -> None:
+        block = _dev(block.reshape(-1, block.shape[-1]), "block")
+        if block.dtype not in (torch.float32, torch.bfloat16):
+            block = block.float()
+        n, d = block.shape
+        if d != self.storage.shape[1] or block.device != self.storage.device:
+            raise ValueError(f"block [{n},{d}] on {block.device} does not match the gallery {tuple(self.storage.shape)} on {self.storage.device}")
+        if self.filled + n > self.storage.shape[0]:
+            raise ValueError(f"gallery buffer of {self.storage.shape[0]} rows cannot take {n} more after {self.filled}")
+        with torch.cuda.device(block.device):
+            B.check(B.load().sbir_gallery_append(block.data_ptr(), _dtype_id(block), n, d, self.storage.data_ptr(),
+                                                 _dtype_id(self.storage), self.storage.shape[0], self.filled,
+                                                 self.sqnorm_storage.data_ptr(), int(self.normalize), _stream()),
+                    "sbir_gallery_append")
+        self.filled += n
+
+    @property
+    def rows(self) -> torch.Tensor:
+        return self.storage[:self.filled]
+
+    @property
+    def sqnorm(self) -> torch.Tensor:
+        return self.sqnorm_storage[:self.filled]
+
+
 # ------------------------------------------------------------------------ H1 / H2 ----
 class _PairwiseDistanceFn(torch.autograd.Function):
     @staticmethod
@@ -148,17 +192,32 @@ def _check_retrieval_args(queries: torch.Tensor, gallery: torch.Tensor, k: Optio
     return q, g
 
 
+def _gallery_sqnorm(gallery_sqnorm: Optional[torch.Tensor], g: torch.Tensor, gallery: torch.Tensor):
+    """Stored ‖g‖² handed to the kernels — only valid for the rows exactly as they are scored."""
+    if gallery_sqnorm is None:
+        return None
+    if g.dtype != gallery.dtype:
+        return None  # the gallery was converted for scoring (e.g. float64 CSV features): norms of other values
+    sq = _dev(gallery_sqnorm, "gallery_sqnorm")
+    if sq.dtype != torch.float32 or sq.dim() != 1 or sq.shape[0] != g.shape[0] or sq.device != g.device:
+        raise ValueError("gallery_sqnorm must be float32 [num_gallery] on the gallery's device")
+    return sq
+
+
 def pairwise_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, loss_type: str = "euclidean",
                   pos_index: Optional[torch.Tensor] = None, index_offset: int = 0,
-                  return_uncertified: bool = False):
+                  return_uncertified: bool = False, gallery_sqnorm: Optional[torch.Tensor] = None):
     """k nearest gallery rows per query (ascending distance, ties by index) and, when
     `pos_index` (int64 [num_q], <0 = no positive) is given, the 0-based rank of that
     gallery row: the batched form of inference.py:30-69.
 
+    `gallery_sqnorm` (fp32 [N], optional): ‖g‖² of the rows as stored (GalleryBuffer / sidecar) — spares the
+    pass its own read of the gallery for the norms.
     Returns (values fp32 [Q,k], indices int64 [Q,k]) or (values, indices, rank int64 [Q])."""
     want_rank = pos_index is not None
     pos = _dev(pos_index.to(torch.int64), "pos_index") if want_rank else None
     q, g = _check_retrieval_args(queries, gallery, k, (("pos_index", pos),))
+    gsq = _gallery_sqnorm(gallery_sqnorm, g, gallery)
     metric = metric_id(loss_type)
     nq, ng, d = q.shape[0], g.shape[0], q.shape[1]
     dev = q.device
@@ -169,7 +228,7 @@ def pairwise_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, loss_typ
     lib = B.load()
     with torch.cuda.device(dev):
         ws = _workspace(lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, _dtype_id(q), metric, int(want_rank)), dev)
-        B.check(lib.sbir_pairwise_topk(q.data_ptr(), nq, g.data_ptr(), ng, d, _dtype_id(q), metric, k,
+        B.check(lib.sbir_pairwise_topk(q.data_ptr(), nq, g.data_ptr(), _ptr(gsq), ng, d, _dtype_id(q), metric, k,
                                        int(index_offset), _ptr(pos), vals.data_ptr(), idx.data_ptr(), _ptr(rank),
                                        unc.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "sbir_pairwise_topk")
     out = (vals, idx) + ((rank,) if want_rank else ())
@@ -196,13 +255,15 @@ def positive_distance(queries, gallery_shard, pos_index_local, loss_type="euclid
     return out
 
 
-def pairwise_topk_shard(queries, gallery_shard, k, loss_type, index_offset, pos_dist=None, pos_index_global=None):
+def pairwise_topk_shard(queries, gallery_shard, k, loss_type, index_offset, pos_dist=None, pos_index_global=None,
+                        gallery_sqnorm=None):
     """One gallery shard's contribution: local top-k with global indices and, if pos_dist
     (fp64 [Q], NaN = no positive) is given, the local count of rows closer than it."""
     want = pos_dist is not None
     pd = _dev(pos_dist.to(torch.float64), "pos_dist") if want else None
     pg = _dev(pos_index_global.to(torch.int64), "pos_index_global") if (want and pos_index_global is not None) else None
     q, g = _check_retrieval_args(queries, gallery_shard, k, (("pos_dist", pd), ("pos_index_global", pg)))
+    gsq = _gallery_sqnorm(gallery_sqnorm, g, gallery_shard)
     metric = metric_id(loss_type)
     nq, ng, d = q.shape[0], g.shape[0], q.shape[1]
     dev = q.device
@@ -213,7 +274,7 @@ def pairwise_topk_shard(queries, gallery_shard, k, loss_type, index_offset, pos_
     lib = B.load()
     with torch.cuda.device(dev):
         ws = _workspace(lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, _dtype_id(q), metric, int(want)), dev)
-        B.check(lib.sbir_pairwise_topk_shard(q.data_ptr(), nq, _ptr(g) if ng else None, ng, d, _dtype_id(q), metric,
+        B.check(lib.sbir_pairwise_topk_shard(q.data_ptr(), nq, _ptr(g) if ng else None, _ptr(gsq), ng, d, _dtype_id(q), metric,
                                              k, int(index_offset), _ptr(pd), _ptr(pg), vals.data_ptr(), idx.data_ptr(),
                                              _ptr(cnt), unc.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                 "sbir_pairwise_topk_shard")

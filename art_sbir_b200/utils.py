@@ -9,7 +9,7 @@ from __future__ import annotations
 import csv
 from datetime import datetime
 from pathlib import Path
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -183,24 +183,74 @@ def make_loss_fn(loss_type: str, with_classification: bool, dataset_name: str = 
 
 
 # ---------------------------------------------------------------------------- N2 ----
-def load_image_features(folder_name: str, root: Path = Path("data/image_features")) -> Tuple[list, torch.Tensor]:
-    """utils.py:258-263.  Reads the reference's CSV pair; if the binary sidecar written by
-    save_image_features is present it is used instead (fp32, no text parsing).  The CSV route
-    returns float64 exactly like the reference (pandas → torch.from_numpy)."""
+# Feature store.  The reference writes two CSV files (utils.py:265-284: text floats, ≈20 bytes per value,
+# float64 on reload, F8).  Beside them — the CSV pair stays readable by the reference — a binary sidecar:
+#   image_features.f32.npy   or   image_features.bf16.npy (the bf16 bit patterns as uint16)
+#   image_sqnorm.f32.npy     ‖row‖² of the rows as stored (what sbir_pairwise_topk takes as g_sqnorm)
+# so a gallery is stored and reloaded in its own type (cfg4's 10.24 GB bf16 gallery stays 10.24 GB) and the
+# scoring pass does not have to re-read it for the norms.
+_SIDECAR_F32 = "image_features.f32.npy"
+_SIDECAR_BF16 = "image_features.bf16.npy"
+_SIDECAR_SQNORM = "image_sqnorm.f32.npy"
+
+
+class GalleryFeatures:
+    """Gallery rows + their stored ‖row‖² travelling together (feature store → scoring pass).  Quacks
+    enough like the tensor the reference passes around (`.shape`, `.to(device)`, `len`) for
+    process_inference / run_inference; `rows` is the [N, D] tensor, `sqnorm` fp32 [N] or None."""
+
+    def __init__(self, rows: torch.Tensor, sqnorm: Optional[torch.Tensor] = None) -> None:
+        self.rows, self.sqnorm = rows, sqnorm
+
+    @property
+    def shape(self):
+        return self.rows.shape
+
+    @property
+    def dtype(self):
+        return self.rows.dtype
+
+    def __len__(self) -> int:
+        return self.rows.shape[0]
+
+    def to(self, *args, **kwargs) -> "GalleryFeatures":
+        rows = self.rows.to(*args, **kwargs)
+        sq = None
+        if self.sqnorm is not None and rows.dtype == self.rows.dtype:   # a dtype change invalidates stored norms
+            sq = self.sqnorm.to(device=rows.device)
+        return GalleryFeatures(rows, sq)
+
+
+def load_image_features(folder_name: str, root: Path = Path("data/image_features"), with_norms: bool = False):
+    """utils.py:258-263 → (image_paths, image_features).  Reads the reference's CSV pair; if the binary
+    sidecar written by save_image_features is present it is used instead (the gallery's own type, no text
+    parsing).  The CSV route returns float64 exactly like the reference (pandas → torch.from_numpy).
+    with_norms=True returns (image_paths, GalleryFeatures) carrying the stored ‖row‖² when the sidecar has them."""
     import pandas as pd
     path = Path(root) / folder_name
     image_paths = [Path(p[0]) for p in pd.read_csv(path / "image_paths.csv", header=None).values]
-    sidecar = path / "image_features.f32.npy"
-    if sidecar.is_file():
-        return image_paths, torch.from_numpy(np.load(sidecar))
-    image_features = pd.read_csv(path / "image_features.csv", header=None).values
-    return image_paths, torch.from_numpy(image_features)
+    feats = None
+    if (path / _SIDECAR_BF16).is_file():
+        feats = torch.from_numpy(np.load(path / _SIDECAR_BF16)).view(torch.bfloat16)
+    elif (path / _SIDECAR_F32).is_file():
+        feats = torch.from_numpy(np.load(path / _SIDECAR_F32))
+    if feats is None:
+        feats = torch.from_numpy(pd.read_csv(path / "image_features.csv", header=None).values)
+        return (image_paths, GalleryFeatures(feats)) if with_norms else (image_paths, feats)
+    if not with_norms:
+        return image_paths, feats
+    sq = torch.from_numpy(np.load(path / _SIDECAR_SQNORM)) if (path / _SIDECAR_SQNORM).is_file() else None
+    if sq is not None and sq.shape[0] != feats.shape[0]:
+        sq = None
+    return image_paths, GalleryFeatures(feats, sq)
 
 
-def save_image_features(model_name: str, dataset_name: str, inference_dataset, image_features: torch.Tensor,
-                        root: Path = Path("data/image_features"), write_csv: bool = True) -> str:
-    """utils.py:265-284: same folder naming and CSV files; additionally writes
-    image_features.f32.npy so reloading is exact fp32 and O(bytes) instead of text parsing."""
+def save_image_features(model_name: str, dataset_name: str, inference_dataset, image_features,
+                        root: Path = Path("data/image_features"), write_csv: bool = True, sqnorm: torch.Tensor = None) -> str:
+    """utils.py:265-284: same folder naming and the same two CSV files; additionally the binary sidecar
+    (rows in their own type, fp32 or bf16, and ‖row‖² when given or carried by a GalleryFeatures)."""
+    if isinstance(image_features, GalleryFeatures):
+        image_features, sqnorm = image_features.rows, (image_features.sqnorm if sqnorm is None else sqnorm)
     feature_path = Path(root)
     feature_path.mkdir(parents=True, exist_ok=True)
     date_time = datetime.now().strftime("%Y-%m-%d_%H-%M")
@@ -208,9 +258,15 @@ def save_image_features(model_name: str, dataset_name: str, inference_dataset, i
     feature_path.mkdir(parents=True, exist_ok=True)
     with open(feature_path / "image_paths.csv", "w") as f:
         csv.writer(f).writerows([[str(p)] for p in inference_dataset.image_paths])
-    feats = image_features.detach().float().cpu().numpy()
-    np.save(feature_path / "image_features.f32.npy", feats)
+    rows = image_features.detach().cpu().contiguous()
+    if rows.dtype == torch.bfloat16:
+        np.save(feature_path / _SIDECAR_BF16, rows.view(torch.uint16).numpy())
+    else:
+        rows = rows.float()
+        np.save(feature_path / _SIDECAR_F32, rows.numpy())
+    if sqnorm is not None:
+        np.save(feature_path / _SIDECAR_SQNORM, sqnorm.detach().float().cpu().numpy())
     if write_csv:
         with open(feature_path / "image_features.csv", "w") as f:
-            csv.writer(f).writerows(feats)
+            csv.writer(f).writerows(rows.float().numpy())
     return feature_path.name

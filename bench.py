@@ -105,15 +105,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------ data ----
-def make_shard(num_q, num_g, dim, dtype, row0, row1, device, seed=1234):
-    """Rows [row0,row1) of the seeded clustered gallery + ALL queries (SURVEY.md §8d generator,
-    evaluated on device in chunks with per-chunk seeds so every rank sees the same global data)."""
+def make_shard(num_q, num_g, dim, dtype, row0, row1, device, seed=1234, centroids=None):
+    """Rows [row0,row1) of the seeded clustered gallery + ALL queries: the SURVEY.md §8(d) generator
+    (class centroids ~N(0,I); gallery row j = centroid[j mod C] + noise_j; positives = randperm(N)[:Q];
+    query i = centroid of its positive + beta·noise_pos + N(0,I), beta 0.06 at 2048-d / 0.12 at 512-d),
+    evaluated on device in chunks with per-chunk seeds so every rank sees the same global data.
+    One stated deviation: §8(d) fixes C = 125 classes at its 1k × 10k calibration point (80 rows per class,
+    recall@1/10 ≈ 0.47/0.86); here C = max(125, N/80) keeps those 80 rows per class — and that recall
+    profile — at every gallery size.  With C = 125 at N = 10M every class has 80 000 rows, ~all positives rank in
+    the thousands and recall@10 ≈ 0, which exercises nothing of the rank path; `--centroids 125` runs it."""
     import torch
-    C = max(125, num_g // 80)
+    C = max(125, num_g // 80) if not centroids else int(centroids)
     beta = 0.06 if dim >= 2048 else 0.12
     gen = torch.Generator(device=device).manual_seed(seed)
     cent = torch.randn(C, dim, device=device, generator=gen)
-    pos = torch.randint(0, num_g, (num_q,), device=device, generator=gen)
+    if num_q <= num_g:
+        pos = torch.randperm(num_g, device=device, generator=gen)[:num_q].contiguous()
+    else:
+        pos = torch.randint(0, num_g, (num_q,), device=device, generator=gen)
     Q = torch.randn(num_q, dim, device=device, generator=gen)
     G = torch.empty(row1 - row0, dim, device=device, dtype=dtype)
     chunk = 1 << 18
@@ -133,6 +142,71 @@ def make_shard(num_q, num_g, dim, dtype, row0, row1, device, seed=1234):
             pi = pos[sel] - c0
             Q[sel] += cent[cls[pi]] + beta * noise[pi]
     return Q.to(dtype).contiguous(), G, pos
+
+
+# --------------------------------------------------------- in-run parity (untimed) ----
+def sampled_parity(Q, Gs, pos, r0, k, vals, idx, rank0, world, dist, n_sample=32):
+    """§8(d): results compared to the oracle IN THE SAME RUN, at the full size.  A sample of queries is
+    brute-forced on the device in fp64 with the reference formula ‖q − g + 1e-6‖₂ (utils.py:42) over ALL
+    gallery rows (every rank scans its shard; lists / counts are gathered), and the returned top-k indices
+    and ranks are compared.  Index differences are only accepted between distances closer than 1e-4 relative
+    (north_star); ranks must lie inside the band of fp32-level ties around d(q, pos) (12·2^-24 relative,
+    tests/test_gpu_parity.py) and are also counted for exact equality.  Torch is the CHECKER here, never timed."""
+    import torch
+    num_q, num_g_local = Q.shape[0], Gs.shape[0]
+    dev = Q.device
+    S = min(n_sample, num_q)
+    sel = torch.linspace(0, num_q - 1, S, device=dev).round().long()
+    qs = Q[sel].double()
+    ps = pos[sel]
+    # d(q, positive): the owner rank evaluates it, everyone gets it
+    mine = (ps >= r0) & (ps < r0 + num_g_local)
+    dpos = torch.zeros(S, dtype=torch.float64, device=dev)
+    if bool(mine.any()):
+        gp = Gs[(ps[mine] - r0)].double()
+        dpos[mine] = ((qs[mine] - gp + 1e-6) ** 2).sum(1).sqrt()
+    if world > 1:
+        dist.all_reduce(dpos)
+    tau = 12 * 2.0 ** -24 * dpos
+    kk = min(k, max(num_g_local, 1))
+    best_d = torch.full((S, k), float("inf"), dtype=torch.float64, device=dev)
+    best_i = torch.full((S, k), -1, dtype=torch.int64, device=dev)
+    lo = torch.zeros(S, dtype=torch.int64, device=dev)
+    hi = torch.zeros(S, dtype=torch.int64, device=dev)
+    chunk = 1 << 19
+    for c0 in range(0, num_g_local, chunk):
+        g = Gs[c0:c0 + chunk].double()
+        for s_ in range(S):
+            d = ((g - qs[s_] + 1e-6) ** 2).sum(1).sqrt()
+            lo[s_] += (d < dpos[s_] - tau[s_]).sum()
+            hi[s_] += (d <= dpos[s_] + tau[s_]).sum()
+            v, ix = torch.topk(d, min(kk, d.numel()), largest=False)
+            cat_d = torch.cat([best_d[s_], v])
+            cat_i = torch.cat([best_i[s_], ix + c0 + r0])
+            o = torch.argsort(cat_d, stable=True)[:k]
+            best_d[s_], best_i[s_] = cat_d[o], cat_i[o]
+        del g
+    if world > 1:
+        dist.all_reduce(lo)
+        dist.all_reduce(hi)
+        all_d = [torch.empty_like(best_d) for _ in range(world)]
+        all_i = [torch.empty_like(best_i) for _ in range(world)]
+        dist.all_gather(all_d, best_d)
+        dist.all_gather(all_i, best_i)
+        cat_d, cat_i = torch.cat(all_d, dim=1), torch.cat(all_i, dim=1)
+        o = torch.argsort(cat_d, dim=1, stable=True)[:, :k]
+        best_d, best_i = cat_d.gather(1, o), cat_i.gather(1, o)
+    hi = hi - 1  # the positive itself lies inside the band
+    ours_i, ours_v, ours_r = idx[sel], vals[sel].double(), rank0[sel]
+    differ = ours_i != best_i
+    rel = (ours_v - best_d).abs() / best_d.clamp_min(1e-30)
+    tie = differ & (rel <= 1e-4)
+    return {"checked": int(S), "oracle": "fp64 brute force of the reference formula over all gallery rows, on device, untimed",
+            "topk_entries": int(S * k), "topk_index_mismatches": int((differ & ~tie).sum().item()),
+            "topk_tie_swaps": int(tie.sum().item()), "max_rel_dist_err": float(rel[~differ].max().item()) if bool((~differ).any()) else None,
+            "rank_mismatches": int(((ours_r < lo) | (ours_r > hi)).sum().item()),
+            "rank_ambiguous_by_fp32_ties": int((lo != hi).sum().item()),
+            "mismatches": int((differ & ~tie).sum().item() + ((ours_r < lo) | (ours_r > hi)).sum().item())}
 
 
 # ----------------------------------------------------------------- CPU reference ----
@@ -187,6 +261,221 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------- measurement ----
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor throughput of THIS GPU, measured in the run (MEASURED_PEAKS.json carries bf16 only):
+    cuBLAS fp32 matmul 8192^3 with TF32 allowed, best of 10 (burst — the fp32 workloads' K1 launches take
+    milliseconds).  TFLOP/s."""
+    import torch
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def time_retrieval(step, steps, warmup, barrier, lib, dev, flush, sampler=None):
+    """W warm-up steps, then `steps` timed steps (CUDA events on the current stream, L2 flushed between steps
+    when `flush`), K1 launch times and launch count from the library's profiling hooks.
+    Returns (ms_per_step, k1_ms_per_step, launches_per_run, last output, clocks or None)."""
+    import torch
+    for _ in range(warmup):
+        out = step()
+    barrier()
+    lib.sbir_profile_enable(1)
+    k1_ms, k1_n, launches = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+    lib.sbir_profile_collect(ctypes.byref(k1_ms), ctypes.byref(k1_n), ctypes.byref(launches))  # reset counters
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    t_begin = time.time()
+    for a, b in evs:
+        if flush is not None:
+            flush.fill_(1)
+        a.record()
+        out = step()
+        b.record()
+    barrier()
+    clocks = sampler.stop(t_begin, time.time()) if sampler is not None else None
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    lib.sbir_profile_collect(ctypes.byref(k1_ms), ctypes.byref(k1_n), ctypes.byref(launches))
+    lib.sbir_profile_enable(0)
+    # K1 device time per step: fp32 workloads enqueue a second, device-gated K1 launch (the 3xTF32
+    # escalation pass) that returns at once when the first pass certified everything, so the sum of
+    # the K1 launches of a step is the time of the one that did the work
+    return ms_total / steps, k1_ms.value / max(1, steps), int(launches.value), out, clocks
+
+
+def k1_roofline(dim, num_q, rows, dtype_is_bf16, k1_ms, ms_per_step, peaks, tf32_peak, traffic=None):
+    flops = 2.0 * dim * num_q * rows
+    achieved = flops / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else None
+    if dtype_is_bf16:
+        peak = peaks["bf16_sustained"] if k1_ms > 100 else peaks["bf16"]
+        note = ("bf16 dense, sustained, " if k1_ms > 100 else "bf16 dense, burst, ") + peaks["source"]
+        burst = peaks["bf16"]
+    else:
+        peak = burst = tf32_peak
+        note = "tf32 dense, cuBLAS fp32 8192^3 with TF32 allowed, best of 10, measured in this run (kind::tf32 runs at half the bf16 rate)"
+    return {"bound": "tensor", "kernel": "dist_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_note": note,
+            "frac_of_burst_peak": (achieved / burst) if achieved else None,
+            "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_per_step if ms_per_step else None}
+
+
+def graph_us(fn, min_seconds=0.3):
+    """Device time of fn() in microseconds: captured once into a CUDA graph and replayed back to back (host
+    launch overhead excluded), long enough for the clock sampler to see it."""
+    import torch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    replays, total_ms, total_n = 50, 0.0, 0
+    t0 = time.time()
+    while True:
+        e0.record()
+        for _ in range(replays):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        total_n += replays
+        if time.time() - t0 > min_seconds:
+            break
+    return total_ms / total_n * 1e3
+
+
+def extra_retrieval_workload(name, lib, dev, local_rank, peaks, tf32_peak, centroids, reuse=None):
+    """One of the other BASELINE configs on this GPU, briefly: ms, pairs/s, roofline, clocks, sampled parity."""
+    import torch
+    from art_sbir_b200 import ops
+    num_q, num_g, dim, dtype_name, k, desc = WORKLOADS[name]
+    dtype = getattr(torch, dtype_name)
+    if reuse is not None:
+        Q, G, pos = reuse
+    else:
+        Q, G, pos = make_shard(num_q, num_g, dim, dtype, 0, num_g, dev, centroids=centroids)
+    torch.cuda.synchronize()
+    in_bytes = (Q.numel() + G.numel()) * Q.element_size()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if in_bytes < 400e6 else None
+
+    def step():
+        return ops.pairwise_topk(Q, G, k, "euclidean", pos_index=pos, return_uncertified=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    # enough steps for >= ~1 s of wall clock in the timed region, so the clock record is of THIS workload
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step(); step()
+    e0.record(); step(); e1.record(); torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1), 0.05) + (0.2 if flush is not None else 0.0)
+    steps = int(min(400, max(3, 1000.0 / est)))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    ms, k1_ms, launches, out, clocks = time_retrieval(step, steps, 3, barrier, lib, dev, flush, sampler)
+    vals, idx, rank0, unc = out
+    res = {"workload": name, "description": desc, "num_q": num_q, "num_g": num_g, "dim": dim, "k": k,
+           "dtype": "bf16" if dtype == torch.bfloat16 else "tf32 (fp32 in, fp32 accumulate, exact fp32/fp64 re-score)",
+           "steps": steps, "ms_per_step": ms, "value": num_q * num_g / (ms * 1e-3), "unit": "pairs/s",
+           "l2": "inputs larger than L2" if flush is None else "L2 flushed (512 MiB write) between timed steps",
+           "gpu_launches_per_step": launches / steps,
+           "roofline": k1_roofline(dim, num_q, num_g, dtype == torch.bfloat16, k1_ms, ms, peaks, tf32_peak),
+           "clocks": clocks, "uncertified_queries": int(unc.item()),
+           **{f"recall@{kk}": float((rank0 < kk).float().mean().item()) for kk in (1, 5, 10)},
+           "parity": sampled_parity(Q, G, pos, 0, k, vals, idx, rank0, 1, None)}
+    return res
+
+
+def cfg2_workload(lib, dev, local_rank):
+    """BASELINE cfg2: a/p/n [256, 2048] fp32, margin 0.2 — the reference's triplet loss fwd+bwd (train.py:169) and
+    batch-hard mining + loss + gradients, device time by CUDA-graph replay, next to torch's own kernels on the
+    same GPU; loss / mined indices / gradients checked against the oracle in the same run."""
+    import torch
+    from art_sbir_b200 import _binding as B, ops
+    from oracle import sbir_oracle as O
+    st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    g = torch.Generator().manual_seed(11)
+    a_h, p_h, n_h = (torch.randn(256, 2048, generator=g) for _ in range(3))
+    p_h = a_h + 0.9 * p_h
+    a, p, n = a_h.to(dev), p_h.to(dev), n_h.to(dev)
+    loss, per_row = torch.empty((), device=dev), torch.empty(256, device=dev)
+    ga, gp, gn = (torch.empty_like(a) for _ in range(3))
+    hard = torch.empty(256, 2, dtype=torch.int64, device=dev)
+    ws = torch.empty(lib.sbir_batch_hard_workspace_bytes(256, 2048), dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    t_begin = time.time()
+    res = {"workload": "cfg2", "description": "BASELINE cfg2: triplet step, batch 256 anchors/pos/neg 2048-d fp32, margin 0.2, 1 GPU",
+           "timing": "device time per call, CUDA-graph replay (>= 0.3 s of back-to-back replays each)"}
+    res["triplet_fwd_bwd_us"] = graph_us(lambda: B.check(lib.sbir_triplet_margin_loss(
+        a.data_ptr(), p.data_ptr(), n.data_ptr(), 256, 2048, 0.2, B.SBIR_EUCLIDEAN, loss.data_ptr(), per_row.data_ptr(),
+        ga.data_ptr(), gp.data_ptr(), gn.data_ptr(), st()), "triplet"))
+    res["triplet_GBps"] = 6 * a.numel() * 4 / res["triplet_fwd_bwd_us"] / 1e3
+    res["batch_hard_fwd_bwd_us"] = graph_us(lambda: B.check(lib.sbir_batch_hard_triplet_loss(
+        a.data_ptr(), p.data_ptr(), n.data_ptr(), 256, 2048, 0.2, B.SBIR_EUCLIDEAN, None, None, loss.data_ptr(), hard.data_ptr(),
+        ga.data_ptr(), gp.data_ptr(), gn.data_ptr(), ws.data_ptr(), ws.numel(), st()), "batch_hard"))
+    ta, tp, tn = (t.clone().requires_grad_(True) for t in (a, p, n))
+
+    def torch_triplet():
+        ta.grad = tp.grad = tn.grad = None
+        torch.nn.functional.triplet_margin_loss(ta, tp, tn, margin=0.2).backward()
+    res["torch_triplet_fwd_bwd_us"] = graph_us(torch_triplet)
+    eye = torch.zeros(256, 512, dtype=torch.bool, device=dev)
+    eye[torch.arange(256, device=dev), torch.arange(256, device=dev)] = True
+
+    def torch_batch_hard():  # the same definition (SURVEY §8a H8) with library ops: broadcast distance + masks + autograd
+        ta.grad = tp.grad = tn.grad = None
+        x = torch.cat([tp, tn])
+        dm = (ta[:, None, :] - x[None, :, :] + 1e-6).norm(dim=2)
+        hp = dm.masked_fill(~eye, float("-inf")).max(dim=1).values
+        hn = dm.masked_fill(eye, float("inf")).min(dim=1).values
+        torch.clamp_min(0.2 + hp - hn, 0).mean().backward()
+    res["torch_batch_hard_fwd_bwd_us"] = graph_us(torch_batch_hard)
+    res["clocks"] = sampler.stop(t_begin, time.time())
+    # parity in the same run (oracle = the reference's loss modules on CPU)
+    A, P, N = (t.clone().requires_grad_(True) for t in (a, p, n))
+    l_t = ops.triplet_margin_loss(A, P, N, 0.2, "euclidean")
+    l_t.backward()
+    ref_t = O.triplet_margin_loss(a_h, p_h, n_h, 0.2, "euclidean")
+    A2, P2, N2 = (t.clone().requires_grad_(True) for t in (a, p, n))
+    l_b, hidx = ops.batch_hard_triplet_loss(A2, P2, N2, 0.2, "euclidean", return_indices=True)
+    l_b.backward()
+    Ar, Pr, Nr = (t.clone().requires_grad_(True) for t in (a_h, p_h, n_h))
+    ref_b, hpi, hni = O.batch_hard_triplet_loss(Ar, Pr, Nr, 0.2, "euclidean")
+    ref_b.backward()
+    gerr = max(((x.grad.cpu() - y.grad).abs().max() / y.grad.abs().max()).item() for x, y in ((A2, Ar), (P2, Pr), (N2, Nr)))
+    res["parity"] = {"triplet_loss_rel_err": abs(l_t.item() - ref_t.item()) / abs(ref_t.item()),
+                     "batch_hard_loss_rel_err": abs(l_b.item() - ref_b.item()) / abs(ref_b.item()),
+                     "batch_hard_index_mismatches": int((hidx[:, 0].cpu() != hpi).sum() + (hidx[:, 1].cpu() != hni).sum()),
+                     "batch_hard_grad_max_err_rel_to_max": gerr}
+    return res
+
+
 # ------------------------------------------------------------------------ main ----
 def main():
     ap = argparse.ArgumentParser()
@@ -197,6 +486,9 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (extra_workloads)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled full-size oracle check")
+    ap.add_argument("--centroids", type=int, default=0, help="class centroids of the generator (0: max(125, N/80), see make_shard)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -226,7 +518,7 @@ def main():
     num_q, num_g, dim, dtype_name, k, desc = wl
     dtype = getattr(torch, dtype_name)
     r0, r1 = sharded.shard_bounds(num_g, world, rank)
-    Q, Gs, pos = make_shard(num_q, num_g, dim, dtype, r0, r1, dev)
+    Q, Gs, pos = make_shard(num_q, num_g, dim, dtype, r0, r1, dev, centroids=args.centroids)
     torch.cuda.synchronize()
 
     def step():
@@ -240,52 +532,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
         sampler.start()
         time.sleep(0.3)
-    for _ in range(args.warmup):
-        out = step()
-    barrier()
-    lib.sbir_profile_enable(1)
-    k1_ms, k1_n, launches = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
-    lib.sbir_profile_collect(ctypes.byref(k1_ms), ctypes.byref(k1_n), ctypes.byref(launches))  # reset counters
     # inputs smaller than L2 are evicted between timed steps by writing a 512 MiB buffer (untimed)
     in_bytes = (Q.numel() + Gs.numel()) * Q.element_size()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if in_bytes < 400e6 else None
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_begin = time.time()
-    for a, b in evs:
-        if flush is not None:
-            flush.fill_(1)
-        a.record()
-        out = step()
-        b.record()
-    barrier()
-    clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
-    lib.sbir_profile_collect(ctypes.byref(k1_ms), ctypes.byref(k1_n), ctypes.byref(launches))
-    lib.sbir_profile_enable(0)
-    # K1 device time per step: fp32 workloads enqueue a second, device-gated K1 launch (the 3xTF32
-    # escalation pass) that returns at once when the first pass certified everything, so the sum of
-    # the K1 launches of a step is the time of the one that did the work
-    t = torch.tensor([ms_total, k1_ms.value / max(1, args.steps), float(launches.value)], device=dev, dtype=torch.float64)
+    ms_step, k1_ms_step, launches, out, clocks = time_retrieval(step, args.steps, args.warmup, barrier, lib, dev, flush, sampler)
+    t = torch.tensor([ms_step, k1_ms_step, float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_total, k1_ms_per_launch, total_launches = tmax[0].item(), tmax[1].item(), int(tsum[2].item())
+        ms_per_step, k1_ms_per_launch, total_launches = tmax[0].item(), tmax[1].item(), int(tsum[2].item())
     else:
-        ms_total, k1_ms_per_launch, total_launches = t[0].item(), t[1].item(), int(t[2].item())
-    ms_per_step = ms_total / args.steps
+        ms_per_step, k1_ms_per_launch, total_launches = t[0].item(), t[1].item(), int(t[2].item())
     pairs = num_q * num_g
     value = pairs / (ms_per_step * 1e-3)
 
     vals, idx, rank0, unc = out
     recall = {f"recall@{kk}": float((rank0 < kk).float().mean().item()) for kk in (1, 5, 10)}
     uncert = int(unc.item()) if unc is not None else None
+    parity = None if args.no_parity else sampled_parity(Q, Gs, pos, r0, k, vals, idx, rank0, world, dist)
+
+    # ---- the other BASELINE configs, briefly, on rank 0's GPU (N = 1 only: they are single-GPU configs) ----
+    extras = []
+    peaks = measured_peaks()
+    tf32_peak = None
+    if world == 1 and not args.no_extra:
+        tf32_peak = measure_tf32_peak(dev)
+        if args.workload == "cfg4":
+            extras.append(extra_retrieval_workload("cfg4k100", lib, dev, local_rank, peaks, tf32_peak, args.centroids, reuse=(Q, Gs, pos)))
+        for name in ("cfg1", "cfg3", "cfg3k10"):
+            if name != args.workload:
+                extras.append(extra_retrieval_workload(name, lib, dev, local_rank, peaks, tf32_peak, args.centroids))
+        extras.append(cfg2_workload(lib, dev, local_rank))
+    elif dtype != torch.bfloat16:
+        tf32_peak = measure_tf32_peak(dev)
 
     # ---- e2e: pinned host buffers → C ABI / sharded API → host results ----
     e2e = None
@@ -337,24 +622,11 @@ def main():
             dist.destroy_process_group()
         return
 
-    peaks = measured_peaks()
-    flops_per_launch = 2.0 * dim * num_q * (r1 - r0)
-    achieved = flops_per_launch / (k1_ms_per_launch * 1e-3) / 1e12 if k1_ms_per_launch > 0 else None
-    if dtype == torch.bfloat16:
-        peak = peaks["bf16_sustained"] if k1_ms_per_launch > 100 else peaks["bf16"]
-        peak_note = ("bf16 dense, sustained, " if k1_ms_per_launch > 100 else "bf16 dense, burst, ") + peaks["source"]
-    else:
-        peak = 746.8  # cuBLAS TF32 8192^3 measured on this pool (profiles/r01_probe2_shared_thr_pool.log), MEASURED_PEAKS has no tf32 entry
-        peak_note = "tf32 dense, cuBLAS 8192^3 measured in round 1 (kind::tf32 runs at half the bf16 rate)"
     traffic_file = ROOT / "profiles" / f"k1_traffic_{args.workload}.json"
     # ncu capture of the single-GPU launch of this workload (profiles/); per-rank launches at N > 1
     # cover a shard and were not captured separately
     traffic = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch") if (traffic_file.is_file() and world == 1) else None
-    burst = peaks["bf16"] if dtype == torch.bfloat16 else peak
-    roofline = {"bound": "tensor", "kernel": "dist_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_note": peak_note,
-                "frac_of_burst_peak": (achieved / burst) if achieved else None,
-                "k1_ms_per_launch": k1_ms_per_launch, "k1_share_of_step": k1_ms_per_launch / ms_per_step}
+    roofline = k1_roofline(dim, num_q, r1 - r0, dtype == torch.bfloat16, k1_ms_per_launch, ms_per_step, peaks, tf32_peak, traffic)
 
     cpu = None
     if not args.no_cpu:
@@ -371,8 +643,11 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "num_q": num_q, "num_g": num_g, "dim": dim, "k": k,
                        "sharding": f"gallery rows over {world} GPU(s)", "l2": "inputs larger than L2" if flush is None else "L2 flushed (512 MiB write) between timed steps",
+                       "generator": "SURVEY §8(d) clustered generator, C = %s class centroids (80 gallery rows per class as at §8(d)'s 1k x 10k calibration point), positives = randperm"
+                                    % (args.centroids or max(125, num_g // 80)),
                        **recall, "uncertified_queries": uncert},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu,
+            "parity": parity, "tf32_peak_measured_tflops": tf32_peak, "extra_workloads": extras}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SBIR_B200_ABI_VERSION 1
+#define SBIR_B200_ABI_VERSION 2
 
 typedef enum sbir_status {
   SBIR_OK = 0,
@@ -59,6 +59,20 @@ int sbir_l2_normalize(const void* x, void* y, int64_t rows, int64_t dim, int dty
 /* out[i] = ||x[i,:]||_2^2 (fp32, accumulated in fp64). */
 int sbir_row_sqnorm(const void* x, int64_t rows, int64_t dim, int dtype, float* out,
                     void* stream);
+
+/* ---- N1: gallery feature build (inference.py:72-92, compute_image_features) ---
+ * The reference grows the gallery with torch.cat per batch of 50 encoder outputs (O(N²) copies),
+ * moves it to the host and dumps CSV text (inference.py:85-90).  Here every block of encoder
+ * output [rows, dim] (block_dtype fp32 or bf16, e.g. under autocast) is written straight into rows
+ * [row0, row0 + rows) of a PREALLOCATED device matrix gallery[gallery_rows, dim] in the gallery's
+ * own storage type (fp32 or bf16), L2-normalised first when normalize != 0 (H9's x / max(‖x‖,1e-8)),
+ * and gallery_sqnorm[row0 + i] = ‖stored row‖² (fp32; may be NULL).  The norms are those of the
+ * values AS STORED, which is what sbir_pairwise_topk takes as `g_sqnorm` to skip its own pass over
+ * the gallery.  With one encoder replica per GPU each rank appends only its own row range and the
+ * row-sharded layout of the multi-GPU path falls out for free. */
+int sbir_gallery_append(const void* block, int block_dtype, int64_t rows, int64_t dim, void* gallery,
+                        int gallery_dtype, int64_t gallery_rows, int64_t row0, float* gallery_sqnorm,
+                        int normalize, void* stream);
 
 /* ---- H1 / H2: row-wise distance, the reference's distance modules ----------
  * utils.euclidean_distance = nn.PairwiseDistance(p=2)  (utils.py:42; called at
@@ -98,12 +112,15 @@ int sbir_pairwise_distance_bwd(const float* x1, int64_t rows1, const float* x2, 
  * device-gated second pass in 3xTF32 precision takes over when many queries cannot
  * be certified; its operand copies are part of the workspace (3x the inputs, when
  * that is below 12 GiB).
+ * g_sqnorm (fp32 [num_g], may be NULL) = ‖g_j‖² of the gallery rows as stored, from
+ * sbir_gallery_append / sbir_row_sqnorm or the feature-store sidecar; when given, the pass reads
+ * num_g floats instead of the whole gallery to build its epilogue vector.
  * k <= 116; dim*sizeof(elem) must be a multiple of 16 bytes; pointers 16-byte aligned.
  * out_rank, pos_index, out_uncertified may be NULL. */
 size_t sbir_pairwise_topk_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int k,
                                           int dtype, int metric, int want_rank);
-int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
-                       int dtype, int metric, int k, int64_t index_offset,
+int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, const float* g_sqnorm,
+                       int64_t num_g, int64_t dim, int dtype, int metric, int k, int64_t index_offset,
                        const int64_t* pos_index, float* out_dist, int64_t* out_index,
                        int64_t* out_rank, int32_t* out_uncertified, void* workspace,
                        size_t workspace_bytes, void* stream);
@@ -117,8 +134,8 @@ int sbir_pairwise_topk(const void* q, int64_t num_q, const void* g, int64_t num_
 int sbir_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g,
                            int64_t dim, int dtype, int metric, const int64_t* pos_index_local,
                            double* out_pos_dist, void* stream);
-int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, int64_t num_g,
-                             int64_t dim, int dtype, int metric, int k, int64_t index_offset,
+int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, const float* g_sqnorm,
+                             int64_t num_g, int64_t dim, int dtype, int metric, int k, int64_t index_offset,
                              const double* pos_dist, const int64_t* pos_index_global, float* out_dist,
                              int64_t* out_index, int64_t* out_count_less,
                              int32_t* out_uncertified, void* workspace, size_t workspace_bytes,

@@ -396,6 +396,101 @@ def test_rowwise_distance_modules(ops):
             assert torch.allclose(X2.grad.cpu(), Y2.grad, rtol=1e-3, atol=1e-5 * Y2.grad.abs().max().item())
 
 
+@pytest.mark.parametrize("in_dtype,store_dtype,normalize", [("float32", "float32", False), ("float32", "bfloat16", False),
+                                                             ("bfloat16", "bfloat16", False), ("bfloat16", "float32", True),
+                                                             ("float32", "bfloat16", True), ("float32", "float32", True)])
+def test_gallery_append_builds_rows_and_norms_in_place(ops, in_dtype, store_dtype, normalize):
+    """N1 (inference.py:72-92): blocks of encoder output appended straight into the preallocated gallery in
+    its storage type, with ‖stored row‖²; ragged last block, a row length that is not a multiple of the
+    vector width, and the scoring pass fed with the stored norms must give the same answer as without."""
+    tin, tst = getattr(torch, in_dtype), getattr(torch, store_dtype)
+    for n, d, bs in ((1037, 512, 50), (130, 100, 64), (7, 36, 7)):
+        g = torch.Generator().manual_seed(n + d)
+        X = (torch.randn(n, d, generator=g) * 3).to(tin)
+        buf = ops.GalleryBuffer(n, d, tst, normalize=normalize)
+        for lo in range(0, n, bs):
+            buf.append(X[lo:lo + bs].cuda())
+        assert buf.filled == n
+        want = X.float()
+        if normalize:
+            want = O.l2_normalize(want)
+        want = want.to(tst)
+        got = buf.rows.cpu()
+        if normalize and store_dtype == "bfloat16":      # reciprocal-multiply before the bf16 rounding: within one bf16 ulp
+            assert torch.allclose(got.float(), want.float(), rtol=2 ** -7, atol=1e-30)
+        elif normalize:
+            assert torch.allclose(got.float(), want.float(), rtol=1e-6, atol=1e-9)    # norm and quotient: an fp32 ulp each
+        else:
+            assert torch.equal(got, want)
+        sq = (got.double() ** 2).sum(1)
+        assert torch.allclose(buf.sqnorm.cpu().double(), sq, rtol=2e-7)
+        with pytest.raises(ValueError):
+            buf.append(X[:1].cuda())                                             # full
+    Q, G, pos = O.synthetic_embeddings(200, 3000, 256, seed=4)
+    buf = ops.GalleryBuffer(3000, 256, tst)
+    for lo in range(0, 3000, 500):
+        buf.append(G[lo:lo + 500].to(tin).cuda())
+    q = Q.to(tst).cuda()
+    for lt in ("euclidean", "cosine"):
+        a = ops.pairwise_topk(q, buf.rows, 10, lt, pos_index=pos.cuda())
+        b = ops.pairwise_topk(q, buf.rows, 10, lt, pos_index=pos.cuda(), gallery_sqnorm=buf.sqnorm)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("loss_type", ["euclidean", "cosine"])
+def test_run_inference_computed_and_stored_routes_match_golden(ops, golden_dir, loss_type, tmp_path):
+    """inference.py:140-165 end to end with an identity encoder: (1) the gallery is BUILT by
+    compute_image_features (append kernel → preallocated buffer → feature store with sidecar), (2) the
+    second run LOADS it by folder name (sidecar rows + norms), (3) a third run reads the reference's own CSV
+    pair (float64, F8).  All three must reproduce the dict the unmodified reference produced."""
+    from art_sbir_b200 import inference as inf
+    z = np.load(golden_dir / f"retrieval_{loss_type}.npz")
+    ref = json.load(open(golden_dir / f"process_inference_{loss_type}.json"))
+    Q, G = torch.from_numpy(z["Q"]), torch.from_numpy(z["G"])
+    image_paths = [Path(str(p)) for p in z["image_paths"]]
+
+    class Sketches(torch.utils.data.Dataset):
+        sketch_paths = [Path(str(p)) for p in z["sketch_paths"]]
+        photo_paths = image_paths
+        transform = None
+        state_dict = {"dataset": "SketchyV1"}
+
+        def __len__(self):
+            return len(self.sketch_paths)
+
+        def __getitem__(self, i):
+            return (Q[i],)
+
+    class MemGallery(inf.InferenceDataset):
+        def load_image(self, idx):
+            return G[image_paths.index(self.image_paths[idx])]
+
+    def check(got, folder):
+        assert got["image_features"] == folder
+        for key in ("size", "count", "min", "25%", "50%", "75%", "max"):
+            assert got[key] == ref[key], key
+        assert got["topk_acc"] == ref["topk_acc"]
+        assert got["mean_reciprocal_rank"] == pytest.approx(ref["mean_reciprocal_rank"], rel=1e-12)
+        assert len(got["retrieval_samples"]) == len(ref["retrieval_samples"])
+        for a, b in zip(got["retrieval_samples"], ref["retrieval_samples"]):
+            (ka, va), (kb, vb) = next(iter(a.items())), next(iter(b.items()))
+            assert ka == kb and [p for p, _ in va] == [p for p, _ in vb]
+            assert np.allclose([d for _, d in va], [d for _, d in vb], rtol=DIST_RTOL)
+        json.dumps(got)
+
+    ds = Sketches()
+    got = inf.run_inference(torch.nn.Identity(), ds, None, loss_type, inference_dataset=MemGallery(image_paths), feature_root=tmp_path)
+    folder = got["image_features"]
+    assert folder.startswith("Identity_SketchyV1_") and (tmp_path / folder / "image_features.f32.npy").is_file()
+    assert (tmp_path / folder / "image_sqnorm.f32.npy").is_file() and (tmp_path / folder / "image_features.csv").is_file()
+    check(got, folder)
+    check(inf.run_inference(torch.nn.Identity(), ds, folder, loss_type, feature_root=tmp_path), folder)       # sidecar route
+    for side in ("image_features.f32.npy", "image_sqnorm.f32.npy"):
+        (tmp_path / folder / side).unlink()
+    check(inf.run_inference(torch.nn.Identity(), ds, folder, loss_type, feature_root=tmp_path), folder)       # reference CSV route
+
+
 @pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
 def test_l2_normalize(ops, dtype):
     tdt = getattr(torch, dtype)

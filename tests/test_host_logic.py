@@ -74,6 +74,26 @@ def test_feature_store_roundtrip(tmp_path):
     assert loaded.dtype == torch.float64 and torch.allclose(loaded.float(), feats, rtol=1e-6)
 
 
+def test_feature_store_keeps_bf16_rows_and_norms(tmp_path):
+    """N2: a bf16 gallery is stored and reloaded in its own type, with its stored ‖row‖² beside it; the
+    reference's CSV pair is still written (and still what the reference itself would read)."""
+    class DS:
+        image_paths = [Path(f"p/{c}.jpg") for c in "abcd"]
+    feats = torch.randn(4, 16).bfloat16()
+    sq = (feats.float() ** 2).sum(1)
+    name = U.save_image_features("ModifiedResNet", "KaggleV2", DS(), U.GalleryFeatures(feats, sq), root=tmp_path)
+    paths, loaded = U.load_image_features(name, root=tmp_path)
+    assert paths == DS.image_paths and loaded.dtype == torch.bfloat16 and torch.equal(loaded, feats)
+    paths, gal = U.load_image_features(name, root=tmp_path, with_norms=True)
+    assert isinstance(gal, U.GalleryFeatures) and torch.equal(gal.rows, feats) and torch.equal(gal.sqnorm, sq)
+    assert gal.shape == (4, 16) and len(gal) == 4
+    assert gal.to(torch.float32).sqnorm is None                     # norms belong to the rows as stored
+    for side in ("image_features.bf16.npy", "image_sqnorm.f32.npy"):
+        (tmp_path / name / side).unlink()
+    paths, gal = U.load_image_features(name, root=tmp_path, with_norms=True)        # CSV route (F8): float64, no norms
+    assert gal.rows.dtype == torch.float64 and gal.sqnorm is None and torch.equal(gal.rows.float(), feats.float())
+
+
 def test_shard_bounds_partition_the_gallery():
     for n, w in ((10, 3), (75000, 8), (7, 8), (0, 2)):
         spans = [sharded.shard_bounds(n, w, r) for r in range(w)]

@@ -593,7 +593,13 @@ def case_small():
         us = _graph_us(lambda: B.check(lib.sbir_batch_hard_triplet_loss(a.data_ptr(), p.data_ptr(), n.data_ptr(), 256, 2048, 0.2, metric, None, None,
                                                                        loss.data_ptr(), hard.data_ptr(), ga.data_ptr(), gp.data_ptr(), gn.data_ptr(),
                                                                        ws.data_ptr(), ws.numel(), st()), "batch_hard"))
-        res[f"cfg2 batch-hard fwd+bwd 256x512x2048 {name}"] = {"us": us}
+        torch.cuda.synchronize()
+        tw = ws[-(8 + 8 * 512) * 8:].view(torch.int64).cpu()
+        t = tw[:4].tolist()   # phase boundaries seen by CTA 0 (globaltimer ns)
+        st = tw[8:8 + 8 * 296].reshape(296, 8).double()
+        st = (st - float(t[0])) / 1e3                          # per-CTA stage stamps, us after CTA 0's start
+        res[f"cfg2 batch-hard fwd+bwd 256x512x2048 {name}"] = {"us": us, "phase_us(mine,select,grad)": [(t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3],
+                                                             "stage_median_us": st.median(0).values.tolist(), "stage_max_us": st.max(0).values.tolist(), "stage_min_us": st.min(0).values.tolist()}
     ta, tp, tn = (t.clone().requires_grad_(True) for t in (a, p, n))
 
     def torch_step():
