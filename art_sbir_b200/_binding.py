@@ -46,6 +46,8 @@ PROTOTYPES = {
     "sbir_release_host_staging": (c_int, []),
     "sbir_profile_enable": (c_int, [c_int]),
     "sbir_profile_collect": (c_int, [_P, _P, _P]),
+    "sbir_debug_set_option": (c_int, [c_char_p, c_int64]),
+    "sbir_debug_diag_build": (c_int, []),
     "sbir_debug_plan": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, c_int, _P]),
     "sbir_debug_k1_diag": (c_int, [_P, c_int]),
     "sbir_debug_dist_matrix_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
@@ -81,3 +83,8 @@ def check(status: int, what: str) -> None:
         msg = lib.sbir_status_string(status).decode()
         extra = f" (cudaError {lib.sbir_last_cuda_error()})" if status == 3 else ""
         raise RuntimeError(f"{what}: {msg}{extra}")
+
+
+def set_debug_option(name: str, value: int = 0) -> None:
+    """Process-wide tuning / test switch of the library (include/sbir_b200.h: sbir_debug_set_option)."""
+    check(load().sbir_debug_set_option(name.encode(), int(value)), f"sbir_debug_set_option({name})")

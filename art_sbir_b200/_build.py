@@ -28,6 +28,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags() -> list:
+    """SBIR_BUILD_DIAG=1 at BUILD time compiles the diagnostic switches / cycle counters of K1 in (-DSBIR_DIAG)."""
+    return NVCC_FLAGS + (["-DSBIR_DIAG"] if os.environ.get("SBIR_BUILD_DIAG") == "1" else [])
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():
@@ -40,7 +45,7 @@ def _digest() -> str:
     for f in sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "sbir_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -74,7 +79,7 @@ def _build_locked(digest: str, stamp: Path, verbose: bool) -> Path:
 
     def compile_one(src: str) -> tuple[str, str]:
         obj = BUILD_DIR / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *_flags(), "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

@@ -22,6 +22,10 @@ static std::mutex g_profile_mu;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_k1_events;
 static cudaEvent_t g_k1_open = nullptr;
 
+// ---- tuning / test switches (process-wide; set before launching, not thread-safe against running calls) ----
+static DebugOptions g_debug_options;
+const DebugOptions& debug_options() { return g_debug_options; }
+
 void count_kernel_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
 void profile_k1_begin(cudaStream_t st) {
   if (!g_profile_on.load(std::memory_order_relaxed)) return;
@@ -542,6 +546,29 @@ int sbir_batch_hard_triplet_loss(const float* a, const float* p, const float* n,
   return launch_batch_hard(a, p, n, batch, dim, margin, metric, anchor_label, cand_label, out_loss,
                            out_hard_index, grad_a, grad_p, grad_n, workspace, workspace_bytes,
                            static_cast<cudaStream_t>(stream));
+}
+
+int sbir_debug_set_option(const char* name, int64_t value) {
+  if (name == nullptr) return SBIR_ERR_INVALID_ARG;
+  DebugOptions& o = g_debug_options;
+  if (!std::strcmp(name, "k1_feed")) o.k1_feed = (int)value;
+  else if (!std::strcmp(name, "k1_pair")) o.k1_pair = (int)value;
+  else if (!std::strcmp(name, "k1_qres")) o.k1_qres = (int)value;
+  else if (!std::strcmp(name, "k1_chunk_mb")) o.k1_chunk_mb = (int)value;
+  else if (!std::strcmp(name, "k1_flags")) o.k1_flags = (int)value;
+  else if (!std::strcmp(name, "host_chunk_rows")) o.host_chunk_rows = value;
+  else if (!std::strcmp(name, "watchdog_cycles")) o.watchdog_cycles = value;
+  else if (!std::strcmp(name, "reset")) o = DebugOptions{};
+  else return SBIR_ERR_INVALID_ARG;
+  return SBIR_OK;
+}
+
+int sbir_debug_diag_build(void) {
+#ifdef SBIR_DIAG
+  return 1;
+#else
+  return 0;
+#endif
 }
 
 int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms, int32_t* out) {

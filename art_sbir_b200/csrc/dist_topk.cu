@@ -56,15 +56,10 @@ int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int
 // 2-4× sooner, so two warps share each TMEM lane quarter, each with its own list.  Lists of 64/128
 // entries make the epilogue the critical path at any width (one warp per scheduler issues one
 // dependent instruction every ~4 cycles): 8 warps, the second of each quarter feeding the first
-// (K1Config::kFeed).  SBIR_K1_FEED=0 falls back to 4 warps (A/B runs).
+// (K1Config::kFeed).  Option k1_feed = 0 falls back to 4 warps (A/B runs).
 static int epi_warps_for(int dtype, int cap) {
   if (cap <= 32) return dtype == SBIR_BF16 ? 8 : 4;
-  static int feed = -1;
-  if (feed < 0) {
-    const char* e = std::getenv("SBIR_K1_FEED");
-    feed = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return feed ? 8 : 4;
+  return debug_options().k1_feed == 0 ? 4 : 8;
 }
 
 // Single-CTA tiles or CTA pairs (cta_group::2, M = 256: each CTA loads its own query tile and HALF of the
@@ -72,10 +67,10 @@ static int epi_warps_for(int dtype, int cap) {
 // one MMA then waits for the slowest of 16 epilogue warps, so with small lists single-CTA tiles win
 // (cfg4: 816 vs 930 ms).  With the 128-entry lists of top-100 on fp32 rows only 3 single-CTA operand
 // stages fit and the mainloop starves (operand wait 300 of 680 cycles per k-block); the pair's 32 KB
-// stages fit 4: cfg3 K1 7.0 -> 6.2 ms.  SBIR_K1_PAIR=1 / 2 forces either form (A/B runs, tests).
+// stages fit 4: cfg3 K1 7.0 -> 6.2 ms.  Option k1_pair = 1 / 2 forces either form (A/B runs, tests).
 static int k1_pair_for(int dtype, int cap) {
-  const char* e = std::getenv("SBIR_K1_PAIR");
-  if (e != nullptr && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  const int forced = debug_options().k1_pair;
+  if (forced == 1 || forced == 2) return forced;
   return (dtype == SBIR_F32 && cap >= 64) ? 2 : 1;
 }
 
@@ -125,20 +120,16 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   const int64_t tile_bytes = (int64_t)kTileG * dim * (int64_t)es;
   // Resident-query form (dist_topk_kernel<..., kQRes>): bf16 rows of at most 1 KB — the query tile fits
   // 256 TMEM columns — on single-CTA tiles.  cfg4: 795 -> 765 ms (chunk 12 MB) -> 740 ms (48 MB).
-  // SBIR_K1_QRES=0 switches it off (A/B runs, tests).
+  // Option k1_qres = 0 switches it off (A/B runs, tests).
   {
-    const char* e = std::getenv("SBIR_K1_QRES");
-    p.qres = (!(e != nullptr && e[0] == '0') && dtype == SBIR_BF16 && p.pair == 1 && p.epi_warps == 8 && dim * 2 <= 1024 &&
+    p.qres = (debug_options().k1_qres != 0 && dtype == SBIR_BF16 && p.pair == 1 && p.epi_warps == 8 && dim * 2 <= 1024 &&
               dim % 8 == 0) ? 1 : 0;
   }
   // Chunk size: with the queries streamed through L2 as well, 12 MB keeps a chunk's gallery rows AND the
   // live query tiles resident; the resident-query form reads only gallery rows through L2, and longer
   // units mean fewer list hand-overs and query-tile loads (cfg4: 12 / 24 / 48 / 96 MB -> 787 / 765 / 740 / 736 ms).
   int64_t chunk_mb = p.qres ? 48 : 12;
-  if (const char* e = std::getenv("SBIR_K1_CHUNK_MB")) {  // experiments only
-    const int v = std::atoi(e);
-    if (v > 0) chunk_mb = v;
-  }
+  if (debug_options().k1_chunk_mb > 0) chunk_mb = debug_options().k1_chunk_mb;  // experiments / tests of the chunk hand-over
   int64_t tpc = (chunk_mb << 20) / (tile_bytes > 0 ? tile_bytes : 1);
   if (tpc < 1) tpc = 1;
   if (tpc > p.tiles_per_split) tpc = p.tiles_per_split;
@@ -192,10 +183,8 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.elems_per_kblock = (int)(kSwizzleBytes / elem_size(a.dtype));
   prm.q_raw = a.q;
   prm.dim_elems = (int)a.dim;
-  {
-    const char* fe = std::getenv("SBIR_K1_FLAGS");
-    prm.flags = fe ? std::atoi(fe) : 0;
-  }
+  prm.flags = debug_options().k1_flags;
+  prm.watchdog_cycles = debug_options().watchdog_cycles;
   prm.unit_counter = a.unit_counter;
   prm.chunk_done = a.chunk_done;
   prm.cand_val = a.cand_val;

@@ -49,6 +49,14 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+// Diagnostic switches (A/B runs, cycle counters) exist only in -DSBIR_DIAG builds (SBIR_BUILD_DIAG=1 at build
+// time); in the product build the flag word is the constant 0 and every diagnostic branch is compiled out.
+#ifdef SBIR_DIAG
+#define K1_DIAG_FLAGS(prm) ((prm).flags)
+#else
+#define K1_DIAG_FLAGS(prm) 0
+#endif
+
 namespace sbir {
 
 namespace {
@@ -195,6 +203,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr int kAccCols = Cfg::kAccCols;
   constexpr int kSubTiles = Cfg::kSubTiles;
   if (prm.gate != nullptr && *prm.gate == 0) return;  // uniform across the grid: nothing was set up yet
+  const long long wd = prm.watchdog_cycles;
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytesG = Cfg::kStageBytesG;
   constexpr int kStageBytes = Cfg::kStageBytes;
@@ -278,7 +287,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto next_unit_consumer = [&](int it) -> int {
     if constexpr (kDynamic) {
       const int slot = it % kSchedDepth;
-      mbar_wait(&sched_full_bar[slot], (uint32_t)(it / kSchedDepth) & 1u);
+      mbar_wait(&sched_full_bar[slot], (uint32_t)(it / kSchedDepth) & 1u, wd);
       return *reinterpret_cast<volatile int32_t*>(&sched_unit[slot]);
     } else {
       const int u = worker + it * num_workers;
@@ -302,7 +311,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         int unit;
         if constexpr (kDynamic) {
           const int slot = it % kSchedDepth;
-          mbar_wait(&sched_empty_bar[slot], ((uint32_t)(it / kSchedDepth) & 1u) ^ 1u);
+          mbar_wait(&sched_empty_bar[slot], ((uint32_t)(it / kSchedDepth) & 1u) ^ 1u, wd);
           uint32_t u = 0;
           if (issuer) u = atomicAdd(prm.unit_counter, 1u);
           u = __shfl_sync(kFullMask, u, 0);
@@ -320,7 +329,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int q_tile = uc.row_tile * kPair + cta_rank;
         for (int t = uc.t_begin * kSubTiles; t < uc.t_end * kSubTiles; ++t) {
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait(&empty_bar[stage], phase ^ 1, wd);
             if (!elect_one()) {
               // nothing to issue on this lane
             } else if constexpr (kQRes) {
@@ -366,7 +375,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const bool diag = (prm.flags & 64) != 0;
+      const bool diag = (K1_DIAG_FLAGS(prm) & 64) != 0;
       long long w_acc = 0, w_full = 0, w_issue = 0, w_commit = 0, n_kb = 0;
       const long long t_loop0 = clock64();
       for (int it = 0;; ++it) {
@@ -376,18 +385,18 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (unit < 0) break;
         const UnitCoord uc = decode_unit(unit, prm);
         if constexpr (kQRes) {
-          mbar_wait(q_ready_bar, (uint32_t)it & 1u);  // the epilogue warps stored this unit's query tile
+          mbar_wait(q_ready_bar, (uint32_t)it & 1u, wd);  // the epilogue warps stored this unit's query tile
           tc_fence_after();
         }
         for (int t = uc.t_begin * kSubTiles; t < uc.t_end * kSubTiles; ++t) {
           long long tw = diag ? clock64() : 0;
-          mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+          mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1, wd);  // epilogue drained this accumulator
           if (diag) w_acc += clock64() - tw;
           tc_fence_after();
           const uint32_t d_tmem = tmem_u + Cfg::kAccBase + acc * kAccCols;
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
             tw = diag ? clock64() : 0;
-            mbar_wait(&full_bar[stage], phase);
+            mbar_wait(&full_bar[stage], phase, wd);
             if (diag) w_full += clock64() - tw;
             tc_fence_after();
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_q + stage * kStageBytesQ));
@@ -504,7 +513,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (lane == 0) {
             const long long t0 = clock64();
             while (unit_ready[quarter] != it) {
-              if (clock64() - t0 > 4000000000LL) {
+              if (watchdog_expired(t0, wd)) {
                 printf("sbir: feeder start timed out (unit %d)\n", unit);
                 __trap();
               }
@@ -523,7 +532,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (lane == 0) {
             const long long t0 = clock64();
             while (ld_acquire(done_flag) < uc.chunk) {
-              if (clock64() - t0 > 4000000000LL) {
+              if (watchdog_expired(t0, wd)) {
                 printf("sbir: chunk hand-over timed out (unit %d)\n", unit);
                 __trap();
               }
@@ -532,7 +541,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           __syncwarp();
           (void)ld_acquire(done_flag);
           // latency-bound (one L2 round trip per batch of loads in flight): 16-32 loads per batch
-          if (prm.flags & 32) {  // A/B: four loads in flight
+          if (K1_DIAG_FLAGS(prm) & 32) {  // A/B: four loads in flight
 #pragma unroll 4
             for (int p = 0; p < kCap; ++p) {
               lv[p * kTileQ + row] = __ldcg(gval + p * kTileQ + row);
@@ -680,7 +689,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if constexpr (Cfg::kFeed) {
           const long long t0 = clock64();
           while (fq_pos - fq_head[row] >= (uint32_t)Cfg::kFeedDepth) {  // queue full: the owner drains it
-            if (clock64() - t0 > 4000000000LL) {
+            if (watchdog_expired(t0, wd)) {
               printf("sbir: feeder queue stuck (unit %d)\n", unit);
               __trap();
             }
@@ -729,16 +738,16 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const long long t0 = clock64();
             while (__shfl_sync(kFullMask, (int)mbar_try_wait(&acc_full_bar[acc], acc_phase), 0) == 0) {
               drain_feed();
-              if (clock64() - t0 > 4000000000LL) {
+              if (watchdog_expired(t0, wd)) {
                 printf("sbir: accumulator wait timed out (unit %d)\n", unit);
                 __trap();
               }
             }
           }
         }
-        const long long tw_e = (prm.flags & 64) ? clock64() : 0;
-        mbar_wait(&acc_full_bar[acc], acc_phase);
-        if ((prm.flags & 64) && ew == 0 && lane == 0 && blockIdx.x < 148)
+        const long long tw_e = (K1_DIAG_FLAGS(prm) & 64) ? clock64() : 0;
+        mbar_wait(&acc_full_bar[acc], acc_phase, wd);
+        if ((K1_DIAG_FLAGS(prm) & 64) && ew == 0 && lane == 0 && blockIdx.x < 148)
           g_k1_diag[blockIdx.x * 8 + 3] += (unsigned long long)(clock64() - tw_e);
         tc_fence_after();
         if constexpr (kSelect) {
@@ -750,7 +759,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         const float* gv = prm.gvec + (size_t)t * kAccCols + col_begin;
 #pragma unroll 1
-        for (int c = 0; c < ((prm.flags & 8) ? 0 : Cfg::kColsPerWarp / 32); ++c) {
+        for (int c = 0; c < ((K1_DIAG_FLAGS(prm) & 8) ? 0 : Cfg::kColsPerWarp / 32); ++c) {
           const uint32_t taddr = tmem_base + Cfg::kAccBase + lane_addr + acc * kAccCols + col_begin + c * 32;
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr, r);
@@ -777,7 +786,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               const float gmin = fminf(fmin3(gm4.x, gm4.y, gm4.z), gm4.w);
               const float bound = (kMetric == SBIR_EUCLIDEAN) ? fmaf(-2.f, smax, gmin) : fminf(0.f, __fmul_rn(smax, gmin));
               const float lim0 = kRank ? fmaxf(thr, hi) : thr;
-              if (!(prm.flags & 16) && !__any_sync(kFullMask, bound < lim0)) continue;
+              if (!(K1_DIAG_FLAGS(prm) & 16) && !__any_sync(kFullMask, bound < lim0)) continue;
             }
             float e[32];
             const float4* gv4 = reinterpret_cast<const float4*>(gv + c * 32);
@@ -893,7 +902,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               __threadfence_block();
               drain_feed();
               if (done) break;
-              if (clock64() - t0 > 4000000000LL) {
+              if (watchdog_expired(t0, wd)) {
                 printf("sbir: feeder hand-over timed out (unit %d)\n", unit);
                 __trap();
               }
@@ -940,13 +949,30 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& pr
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kPair;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // CTA pairs walk the units with a STATIC stride and wait on chunk hand-overs from other pairs, so every
+  // launched pair must be resident at the same time (the dynamic hand-out of single-CTA tiles needs no such
+  // guarantee: a unit is only ever waited for by CTAs that claimed a LATER unit, and its claimant is running).
+  // The grid is therefore clamped to what the device can hold (MIG slices, reduced shared memory carve-outs)
+  // and launched cooperatively: if the pairs cannot all be co-resident the launch FAILS with an error status
+  // instead of spinning into the watchdog.
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = kPair == 2 ? 1 : 0;
+  cfg.numAttrs = kPair == 2 ? 2 : 0;
+  if constexpr (kPair == 2) {
+    int max_clusters = 0;
+    SBIR_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    if (max_clusters < 1) return SBIR_ERR_UNSUPPORTED;
+    if (workers > max_clusters) {
+      workers = max_clusters;
+      cfg.gridDim = dim3((unsigned)(workers * kPair));
+    }
+  }
   profile_k1_begin(st);
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tq, tg, prm);
   profile_k1_end(st);

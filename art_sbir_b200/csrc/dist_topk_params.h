@@ -22,7 +22,8 @@ struct K1Params {
   const void* q_raw;   // query matrix in global memory (resident-query form: loaded into TMEM by the epilogue warps)
   int dim_elems;
   const int32_t* gate;     // optional: the kernel is a no-op unless *gate != 0 (escalation pass)
-  int flags;               // diagnostics (SBIR_K1_FLAGS): 8 = epilogue skips the accumulator (mainloop alone), 16 = no chunk screen
+  int flags;               // -DSBIR_DIAG builds only (k1_flags option): 8 = epilogue skips the accumulator (mainloop alone), 16 = no chunk screen, 64 = cycle counters
+  long long watchdog_cycles;  // bound on every spin / barrier wait (0 = none), see ptx.cuh
   uint32_t* unit_counter;  // [1] zeroed by the caller: next unit to hand out (kPair = 1)
   int32_t* chunk_done;     // [num_parts][q_tile_stride] zeroed: chunks finished per (partition, query tile)
   float* cand_val;         // [part][q_tile_stride][lists][cap][128]

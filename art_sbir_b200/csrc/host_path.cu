@@ -7,8 +7,10 @@
 // list warm-up happen once, not once per chunk; the first chunk is small (128 MB, doubling up to
 // 1 GiB) so that scoring starts early.  When the plan cuts the gallery into several partitions
 // (few queries) a multi-chunk gallery is scored chunk by chunk as shards and merged (K4).
-// Device / pinned staging buffers are cached per process and released by sbir_release_host_staging.
+// Device / pinned staging buffers, streams and events are cached PER DEVICE and released by
+// sbir_release_host_staging; an error return drains the cached streams first.
 #include <algorithm>
+#include <map>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -30,21 +32,39 @@ struct Staging {
   cudaStream_t compute = nullptr, copy = nullptr;
   std::vector<cudaEvent_t> events;
 };
-Staging g_staging;
+// One staging set PER DEVICE (streams, events and device memory belong to the device that was current when
+// they were created); calls on different devices of one process do not share anything but the mutex.
+std::map<int, Staging> g_staging_by_device;
 std::mutex g_staging_mu;
+thread_local Staging* tl_staging = nullptr;  // the current call's set (selected under the mutex)
+#define g_staging (*tl_staging)
 
-int ensure_staging(size_t bytes) {
+int select_staging() {
   int dev = 0;
   SBIR_CUDA_TRY(cudaGetDevice(&dev));
-  if (g_staging.device != dev || g_staging.bytes < bytes) {
+  Staging& s = g_staging_by_device[dev];
+  s.device = dev;
+  tl_staging = &s;
+  return SBIR_OK;
+}
+
+int ensure_staging(size_t bytes) {
+  if (g_staging.bytes < bytes) {
     if (g_staging.buf) cudaFree(g_staging.buf);
     g_staging.buf = nullptr;
     g_staging.bytes = 0;
     SBIR_CUDA_TRY(cudaMalloc(&g_staging.buf, bytes));
     g_staging.bytes = bytes;
-    g_staging.device = dev;
   }
   return SBIR_OK;
+}
+
+// An early error return must not leave copies / kernels in flight on the cached streams: the next call
+// would reuse the staging memory underneath them.
+void drain_staging() {
+  if (tl_staging == nullptr) return;
+  if (g_staging.copy) cudaStreamSynchronize(g_staging.copy);
+  if (g_staging.compute) cudaStreamSynchronize(g_staging.compute);
 }
 
 int ensure_streams() {
@@ -90,20 +110,29 @@ using namespace sbir;
 
 extern "C" int sbir_release_host_staging(void) {
   std::lock_guard<std::mutex> lock(g_staging_mu);
-  if (g_staging.buf) cudaFree(g_staging.buf);
-  g_staging.buf = nullptr;
-  g_staging.bytes = 0;
-  if (g_staging.pinned) cudaFreeHost(g_staging.pinned);
-  g_staging.pinned = nullptr;
-  g_staging.pinned_bytes = 0;
-  for (cudaEvent_t e : g_staging.events) cudaEventDestroy(e);
-  g_staging.events.clear();
-  if (g_staging.compute) cudaStreamDestroy(g_staging.compute);
-  if (g_staging.copy) cudaStreamDestroy(g_staging.copy);
-  g_staging.compute = g_staging.copy = nullptr;
-  g_staging.device = -1;
+  int prev = 0;
+  const bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
+  for (auto& kv : g_staging_by_device) {
+    Staging& s = kv.second;
+    if (cudaSetDevice(kv.first) != cudaSuccess) continue;
+    if (s.copy) cudaStreamSynchronize(s.copy);
+    if (s.compute) cudaStreamSynchronize(s.compute);
+    if (s.buf) cudaFree(s.buf);
+    if (s.pinned) cudaFreeHost(s.pinned);
+    for (cudaEvent_t e : s.events) cudaEventDestroy(e);
+    if (s.compute) cudaStreamDestroy(s.compute);
+    if (s.copy) cudaStreamDestroy(s.copy);
+  }
+  g_staging_by_device.clear();
+  tl_staging = nullptr;
+  if (have_prev) cudaSetDevice(prev);
   return SBIR_OK;
 }
+
+static int retrieve_host_locked(const void* q_host, int64_t num_q, const void* g_host, int64_t num_g,
+                                int64_t dim, int dtype, int metric, int k, const int64_t* pos_index_host,
+                                float* out_dist_host, int64_t* out_index_host, int64_t* out_rank_host,
+                                int32_t* out_uncertified_host);
 
 extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void* g_host, int64_t num_g,
                                   int64_t dim, int dtype, int metric, int k, const int64_t* pos_index_host,
@@ -115,6 +144,17 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   if (out_rank_host != nullptr && pos_index_host == nullptr) return SBIR_ERR_INVALID_ARG;
   if (dtype != SBIR_F32 && dtype != SBIR_BF16) return SBIR_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(g_staging_mu);
+  SBIR_TRY(select_staging());
+  const int status = retrieve_host_locked(q_host, num_q, g_host, num_g, dim, dtype, metric, k, pos_index_host, out_dist_host,
+                                          out_index_host, out_rank_host, out_uncertified_host);
+  if (status != SBIR_OK) drain_staging();
+  return status;
+}
+
+static int retrieve_host_locked(const void* q_host, int64_t num_q, const void* g_host, int64_t num_g,
+                                int64_t dim, int dtype, int metric, int k, const int64_t* pos_index_host,
+                                float* out_dist_host, int64_t* out_index_host, int64_t* out_rank_host,
+                                int32_t* out_uncertified_host) {
   const bool want_rank = out_rank_host != nullptr;
   const size_t es = elem_size(dtype);
   const size_t row_bytes = (size_t)dim * es;
@@ -133,7 +173,7 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
   std::vector<int64_t> chunk_end;
   {
     int64_t forced = 0;
-    if (const char* env = std::getenv("SBIR_HOST_CHUNK_ROWS")) forced = std::atoll(env);  // test hook: small chunks
+    forced = debug_options().host_chunk_rows;  // test hook: small chunks
     const int64_t unit = granule > 0 ? granule : kTileG;
     size_t target = granule > 0 ? (size_t(128) << 20) : (size_t(1) << 30);
     int64_t next = 0;
@@ -300,6 +340,12 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
 // to the pass as they arrive (same staging cache as sbir_retrieve_host).  Queries, the positives'
 // distances / global indices and the outputs are DEVICE buffers; work is ordered after `stream`
 // and the call returns when the outputs are complete.
+static int retrieve_host_shard_locked(const void* q_dev, int64_t num_q, const void* g_host, int64_t num_g,
+                                      int64_t dim, int dtype, int metric, int k, int64_t index_offset,
+                                      const double* pos_dist_dev, const int64_t* pos_index_global_dev,
+                                      float* out_dist_dev, int64_t* out_index_dev, int64_t* out_count_less_dev,
+                                      int32_t* out_uncertified_host, void* stream);
+
 extern "C" int sbir_retrieve_host_shard(const void* q_dev, int64_t num_q, const void* g_host, int64_t num_g,
                                         int64_t dim, int dtype, int metric, int k, int64_t index_offset,
                                         const double* pos_dist_dev, const int64_t* pos_index_global_dev,
@@ -311,6 +357,19 @@ extern "C" int sbir_retrieve_host_shard(const void* q_dev, int64_t num_q, const 
   if (out_count_less_dev != nullptr && pos_dist_dev == nullptr) return SBIR_ERR_INVALID_ARG;
   if (dtype != SBIR_F32 && dtype != SBIR_BF16) return SBIR_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(g_staging_mu);
+  SBIR_TRY(select_staging());
+  const int status = retrieve_host_shard_locked(q_dev, num_q, g_host, num_g, dim, dtype, metric, k, index_offset, pos_dist_dev,
+                                                pos_index_global_dev, out_dist_dev, out_index_dev, out_count_less_dev,
+                                                out_uncertified_host, stream);
+  if (status != SBIR_OK) drain_staging();
+  return status;
+}
+
+static int retrieve_host_shard_locked(const void* q_dev, int64_t num_q, const void* g_host, int64_t num_g,
+                                      int64_t dim, int dtype, int metric, int k, int64_t index_offset,
+                                      const double* pos_dist_dev, const int64_t* pos_index_global_dev,
+                                      float* out_dist_dev, int64_t* out_index_dev, int64_t* out_count_less_dev,
+                                      int32_t* out_uncertified_host, void* stream) {
   const bool want_rank = out_count_less_dev != nullptr;
   const size_t row_bytes = (size_t)dim * elem_size(dtype);
   int dev = 0, sms = 0;
@@ -325,10 +384,7 @@ extern "C" int sbir_retrieve_host_shard(const void* q_dev, int64_t num_q, const 
   std::vector<int64_t> chunk_end;
   if (granule > 0) {
     size_t target = size_t(128) << 20;
-    if (const char* env = std::getenv("SBIR_HOST_CHUNK_ROWS")) {  // test hook: small chunks
-      const long long v = std::atoll(env);
-      if (v > 0) target = (size_t)v * row_bytes;
-    }
+    if (debug_options().host_chunk_rows > 0) target = (size_t)debug_options().host_chunk_rows * row_bytes;  // test hook: small chunks
     int64_t next = 0;
     while (next < num_g) {
       const int64_t rows = std::max<int64_t>(granule, (int64_t)(target / row_bytes) / granule * granule);

@@ -6,6 +6,19 @@
 
 namespace sbir {
 
+// ---- api.cu: process-wide tuning / test switches, set through sbir_debug_set_option (never read from
+// the environment on the launch path).  0 / -1 = the library's own choice.
+struct DebugOptions {
+  int k1_feed = -1;               // owner+feeder epilogue for 64/128-entry lists: -1 auto, 0 off
+  int k1_pair = 0;                // CTA pairs: 0 auto, 1 never, 2 always
+  int k1_qres = -1;               // resident-query form: -1 auto, 0 off
+  int k1_chunk_mb = 0;            // gallery bytes per chunk step (MB): 0 auto
+  int k1_flags = 0;               // diagnostic bits, honoured by -DSBIR_DIAG builds only
+  long long host_chunk_rows = 0;  // upload chunk of the host-buffer entry points (rows): 0 auto
+  long long watchdog_cycles = 4000000000LL;  // bound on device-side waits: 0 = none
+};
+const DebugOptions& debug_options();
+
 // ---- rowops.cu ----------------------------------------------------------------
 // mode 0: ‖x‖² ; mode 1: −1/max(‖x‖,1e-8).  Rows [rows, rows_padded) get pad_value.
 // max_sqnorm_out is cleared first unless accumulate_max (then the running maximum is kept).

@@ -42,12 +42,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return done;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-// ~4e9 cycles (≈2 s at 1.9 GHz) is far beyond any legitimate wait in these kernels.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// ~4e9 cycles (≈2 s at 1.9 GHz) is far beyond any legitimate wait in these kernels; the limit is a
+// launch parameter (sbir_debug_set_option("watchdog_cycles", n); 0 = wait for ever) because tools that
+// slow kernels down by orders of magnitude (compute-sanitizer, cuda-gdb, time-sliced GPUs) need more.
+constexpr long long kDefaultWatchdogCycles = 4000000000LL;
+__device__ __forceinline__ bool watchdog_expired(long long t0, long long limit) {
+  return limit > 0 && clock64() - t0 > limit;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, long long limit = kDefaultWatchdogCycles) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (watchdog_expired(t0, limit)) {
       printf("sbir: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x,
              threadIdx.x, parity);
       __trap();

@@ -420,7 +420,7 @@ def cfg2_workload(lib, dev, local_rank):
     st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
     g = torch.Generator().manual_seed(11)
     a_h, p_h, n_h = (torch.randn(256, 2048, generator=g) for _ in range(3))
-    p_h = a_h + 0.9 * p_h
+    p_h, n_h = a_h + 0.9 * p_h, a_h + 0.9 * n_h      # positives and negatives equally far: about half the hinges active
     a, p, n = a_h.to(dev), p_h.to(dev), n_h.to(dev)
     loss, per_row = torch.empty((), device=dev), torch.empty(256, device=dev)
     ga, gp, gn = (torch.empty_like(a) for _ in range(3))
@@ -469,8 +469,8 @@ def cfg2_workload(lib, dev, local_rank):
     ref_b, hpi, hni = O.batch_hard_triplet_loss(Ar, Pr, Nr, 0.2, "euclidean")
     ref_b.backward()
     gerr = max(((x.grad.cpu() - y.grad).abs().max() / y.grad.abs().max()).item() for x, y in ((A2, Ar), (P2, Pr), (N2, Nr)))
-    res["parity"] = {"triplet_loss_rel_err": abs(l_t.item() - ref_t.item()) / abs(ref_t.item()),
-                     "batch_hard_loss_rel_err": abs(l_b.item() - ref_b.item()) / abs(ref_b.item()),
+    res["parity"] = {"triplet_loss_rel_err": abs(l_t.item() - ref_t.item()) / max(abs(ref_t.item()), 1e-12),
+                     "batch_hard_loss_rel_err": abs(l_b.item() - ref_b.item()) / max(abs(ref_b.item()), 1e-12),
                      "batch_hard_index_mismatches": int((hidx[:, 0].cpu() != hpi).sum() + (hidx[:, 1].cpu() != hni).sum()),
                      "batch_hard_grad_max_err_rel_to_max": gerr}
     return res

@@ -219,11 +219,19 @@ int sbir_profile_collect(double* k1_ms_sum, int64_t* k1_launches, int64_t* kerne
  * Writes the raw epilogue matrix E[num_q, num_g] (euclidean: ||g||²-2qg, cosine:
  * -q·g/max(||g||,eps)) computed by the tcgen05 tiles; used by tests to validate the
  * tensor-core path in isolation.  out_e is fp32 [num_q, num_g]. */
+/* Process-wide tuning / test switches — the library never reads the environment on the launch path.
+ * name ∈ { "k1_feed" (-1 auto | 0 off), "k1_pair" (0 auto | 1 single CTAs | 2 CTA pairs), "k1_qres" (-1 auto | 0 off),
+ *          "k1_chunk_mb" (0 auto), "host_chunk_rows" (0 auto), "watchdog_cycles" (device-side wait bound, default
+ *          4e9, 0 = none: for compute-sanitizer / cuda-gdb), "k1_flags" (diagnostic bits, honoured only by a
+ *          -DSBIR_DIAG build: sbir_debug_diag_build() == 1), "reset" (all defaults) }.
+ * Set between calls, not while one is running.  Unknown names return SBIR_ERR_INVALID_ARG. */
+int sbir_debug_set_option(const char* name, int64_t value);
+int sbir_debug_diag_build(void);
 /* Host-only: the work decomposition K1 would use (no device access).  out[12] = {cap,
  * lists_per_row, num_q_tiles, num_g_tiles, num_partitions, tiles_per_partition, num_chunks,
  * tiles_per_chunk, num_units, part_fastest, pair, q_tile_stride}. */
 int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms, int32_t* out);
-/* Profiling aid: when the environment variable SBIR_K1_FLAGS has bit 64 set, the distance kernel
+/* Profiling aid (-DSBIR_DIAG builds): when option k1_flags has bit 64 set, the distance kernel
  * records per CTA (8 uint64 each, 148 CTAs) the cycles its MMA issuer waited for a free
  * accumulator [0] and for operands [1], its whole loop [2], and the cycles epilogue warp 0 waited
  * for finished accumulators [3].  Copies up to n values to the host buffer `out` and clears them. */

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported(sbir_lib):
 def test_binding_covers_header_exactly(sbir_lib):
     from art_sbir_b200 import _binding
     assert sorted(_binding.PROTOTYPES) == _declared_symbols()
-    assert sbir_lib.sbir_abi_version() == 1
+    assert sbir_lib.sbir_abi_version() == _binding.ABI_VERSION == 2
 
 
 def test_header_compiles_as_plain_c(tmp_path):
@@ -59,9 +59,9 @@ def test_status_strings_and_argument_checks(sbir_lib):
     # bad enum / sizes are rejected before any CUDA call
     assert lib.sbir_l2_normalize(None, None, 4, 8, 7, 1e-8, None) == 1
     assert lib.sbir_pairwise_distance(None, 3, None, 2, 8, 0, 0, None, None) == 1      # 3 vs 2 rows do not broadcast
-    assert lib.sbir_pairwise_topk(None, 4, None, 4, 8, 0, 0, 0, 0, None, None, None, None, None, None, 0, None) == 1  # k = 0
-    assert lib.sbir_pairwise_topk(None, 4, None, 4, 8, 0, 0, 500, 0, None, None, None, None, None, None, 0, None) == 2  # k too large
-    assert lib.sbir_pairwise_topk(None, 4, None, 4, 8, 0, 5, 10, 0, None, None, None, None, None, None, 0, None) == 1  # bad metric
+    assert lib.sbir_pairwise_topk(None, 4, None, None, 4, 8, 0, 0, 0, 0, None, None, None, None, None, None, 0, None) == 1  # k = 0
+    assert lib.sbir_pairwise_topk(None, 4, None, None, 4, 8, 0, 0, 500, 0, None, None, None, None, None, None, 0, None) == 2  # k too large
+    assert lib.sbir_pairwise_topk(None, 4, None, None, 4, 8, 0, 5, 10, 0, None, None, None, None, None, None, 0, None) == 1  # bad metric
     assert lib.sbir_triplet_margin_loss(None, None, None, 4, 8, 0.2, 0, None, None, None, None, None, None) == 1
     assert lib.sbir_pairwise_topk_workspace_bytes(1000, 10000, 2048, 10, 0, 0, 1) > 0
     assert lib.sbir_pairwise_topk_workspace_bytes(1000, 10000, 2048, 1000, 0, 0, 1) == 0
@@ -71,9 +71,42 @@ def test_status_strings_and_argument_checks(sbir_lib):
     assert lib.sbir_retrieve_host_shard(None, 4, None, 4, 8, 0, 0, 10, 0, None, None, None, None, None, None, None) == 1
     assert lib.sbir_retrieve_host_shard(None, 4, None, 4, 8, 9, 0, 10, 0, None, None, None, None, None, None, None) == 1  # bad dtype
     assert lib.sbir_debug_k1_diag(None, 8) == 1
+    # gallery append: the block must fit the preallocated matrix; bad dtypes / NULL buffers are rejected up front
+    assert lib.sbir_gallery_append(None, 0, 4, 8, None, 0, 3, 0, None, 0, None) == 1        # 4 rows into a 3-row gallery
+    assert lib.sbir_gallery_append(None, 0, 2, 8, None, 0, 3, 2, None, 0, None) == 1        # rows [2, 4) of 3
+    assert lib.sbir_gallery_append(None, 7, 2, 8, None, 0, 3, 0, None, 0, None) == 1        # bad block dtype
+    assert lib.sbir_gallery_append(None, 0, 2, 8, None, 0, 3, 0, None, 0, None) == 1        # NULL buffers
+    assert lib.sbir_gallery_append(None, 0, 0, 8, None, 1, 3, 3, None, 1, None) == 0        # empty block: no-op
+    # tuning / test switches: set through the ABI, never read from the environment on the launch path
+    assert lib.sbir_debug_set_option(b"k1_chunk_mb", 1) == 0 and lib.sbir_debug_set_option(b"reset", 0) == 0
+    assert lib.sbir_debug_set_option(b"no_such_option", 1) == 1 and lib.sbir_debug_set_option(None, 1) == 1
+    assert lib.sbir_debug_diag_build() == 0                                                   # product build: diagnostics compiled out
     # empty problems are a no-op success
     assert lib.sbir_l2_normalize(None, None, 0, 8, 0, 1e-8, None) == 0
-    assert lib.sbir_pairwise_topk(None, 0, None, 4, 8, 0, 0, 10, 0, None, None, None, None, None, None, 0, None) == 0
+    assert lib.sbir_pairwise_topk(None, 0, None, None, 4, 8, 0, 0, 10, 0, None, None, None, None, None, None, 0, None) == 0
+
+
+def test_launch_path_reads_no_environment_variables():
+    """VERDICT r1 #10: tuning switches must not be getenv() calls on the launch path."""
+    for src in (ROOT / "art_sbir_b200" / "csrc").glob("*"):
+        assert "getenv" not in src.read_text(), src
+
+
+def test_debug_options_change_the_plan_and_reset(sbir_lib):
+    out = (ctypes.c_int32 * 12)()
+    from art_sbir_b200 import _binding
+    try:
+        assert sbir_lib.sbir_debug_plan(100_000, 10_000_000, 512, 10, 1, 148, out) == 0
+        auto_chunks = out[6]
+        _binding.set_debug_option("k1_chunk_mb", 12)
+        assert sbir_lib.sbir_debug_plan(100_000, 10_000_000, 512, 10, 1, 148, out) == 0
+        assert out[6] > auto_chunks                                   # smaller chunk steps -> more of them
+        _binding.set_debug_option("k1_pair", 2)
+        assert sbir_lib.sbir_debug_plan(12_500, 75_000, 2048, 10, 0, 148, out) == 0 and out[10] == 2
+    finally:
+        _binding.set_debug_option("reset")
+    assert sbir_lib.sbir_debug_plan(100_000, 10_000_000, 512, 10, 1, 148, out) == 0 and out[6] == auto_chunks
+    assert sbir_lib.sbir_debug_plan(12_500, 75_000, 2048, 10, 0, 148, out) == 0 and out[10] == 1
 
 
 def test_product_refuses_cpu_tensors_and_never_imports_the_oracle():

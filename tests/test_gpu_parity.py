@@ -29,6 +29,14 @@ def ops(sbir_lib):
     return _ops
 
 
+@pytest.fixture
+def dbg(sbir_lib):
+    """Library tuning / test switches (sbir_debug_set_option), restored to their defaults afterwards."""
+    from art_sbir_b200 import _binding
+    yield _binding.set_debug_option
+    _binding.set_debug_option("reset")
+
+
 def assert_topk_matches(vals, idx, ref_vals, ref_idx, dist_rows):
     """dist_rows[i] = oracle distances of query i to every gallery row (for tie analysis)."""
     vals, idx = vals.cpu(), idx.cpu()
@@ -296,17 +304,17 @@ def test_large_lists_on_hit_dense_data_with_duplicates(ops, dtype, lt, k):
     assert int(unc.item()) <= nq // 50 + 4
 
 
-def test_resident_query_form_matches_default_kernel(ops, monkeypatch):
+def test_resident_query_form_matches_default_kernel(ops, dbg):
     """Resident-query form (default for bf16 rows of at most 1 KB and small lists): the query tile lives
     in tensor memory and is the MMA's A operand from there (tcgen05.mma with A in TMEM), gallery
-    half-tiles stream through shared memory.  SBIR_K1_QRES=0 selects the all-shared-memory form:
+    half-tiles stream through shared memory.  option k1_qres = 0 selects the all-shared-memory form:
     identical results, ragged shapes included."""
     for nq, ng, d, lt, k in ((257, 3001, 512, "euclidean", 10), (1000, 20000, 192, "cosine", 20), (130, 700, 64, "euclidean", 1)):
         Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=nq, beta=0.3 if d < 512 else None)
         q, g, p = Q.bfloat16().cuda(), G.bfloat16().cuda(), pos.cuda()
-        monkeypatch.setenv("SBIR_K1_QRES", "0")
+        dbg("k1_qres", 0)
         v0, i0, r0 = ops.pairwise_topk(q, g, k, lt, pos_index=p)
-        monkeypatch.delenv("SBIR_K1_QRES", raising=False)
+        dbg("k1_qres", -1)
         v1, i1, r1 = ops.pairwise_topk(q, g, k, lt, pos_index=p)
         assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(r0, r1)
 
@@ -665,12 +673,12 @@ def test_topk_merge_against_a_sort(ops, lists, nq, k):
 
 
 @pytest.mark.parametrize("chunk_rows", [0, 4096])
-def test_retrieve_host_equals_device_path(ops, sbir_lib, chunk_rows, monkeypatch):
+def test_retrieve_host_equals_device_path(ops, sbir_lib, chunk_rows, dbg):
     """Host-buffer entry point == device path, also when the gallery is uploaded and scored in
-    several chunks (SBIR_HOST_CHUNK_ROWS forces 5 chunks here; production chunks are 1 GiB)."""
+    several chunks (option host_chunk_rows forces 5 chunks here; production chunks are 1 GiB)."""
     from art_sbir_b200 import _binding as B
     if chunk_rows:
-        monkeypatch.setenv("SBIR_HOST_CHUNK_ROWS", str(chunk_rows))
+        dbg("host_chunk_rows", chunk_rows)
     nq, ng, d, k = 300, 20000, 512, 10
     Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=8)
     q, g = Q.bfloat16().pin_memory(), G.bfloat16().pin_memory()
@@ -686,14 +694,14 @@ def test_retrieve_host_equals_device_path(ops, sbir_lib, chunk_rows, monkeypatch
     sbir_lib.sbir_release_host_staging()
 
 
-def test_retrieve_host_streams_chunks_into_one_pass(ops, sbir_lib, monkeypatch):
+def test_retrieve_host_streams_chunks_into_one_pass(ops, sbir_lib, dbg):
     """With enough query tiles for a single gallery partition the uploaded chunks are FED to one
     retrieval pass (the distance kernel continues the same candidate lists from launch to launch).
-    Small chunk steps (SBIR_K1_CHUNK_MB) and 8192-row uploads force four feeds here; the result must
+    Small chunk steps (option k1_chunk_mb) and 8192-row uploads force four feeds here; the result must
     equal the device path bit for bit, ranks included, for top-10 and top-100."""
     from art_sbir_b200 import _binding as B
-    monkeypatch.setenv("SBIR_K1_CHUNK_MB", "1")
-    monkeypatch.setenv("SBIR_HOST_CHUNK_ROWS", "8192")
+    dbg("k1_chunk_mb", 1)
+    dbg("host_chunk_rows", 8192)
     nq, ng, d = 24000, 30000, 64
     Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=12, beta=0.3)
     pos[::97] = -1                                        # some queries without a positive
@@ -712,14 +720,14 @@ def test_retrieve_host_streams_chunks_into_one_pass(ops, sbir_lib, monkeypatch):
     sbir_lib.sbir_release_host_staging()
 
 
-def test_retrieve_host_streamed_fp32_with_escalation(ops, sbir_lib, monkeypatch):
+def test_retrieve_host_streamed_fp32_with_escalation(ops, sbir_lib, dbg):
     """Streamed feeds followed by the device-gated escalation pass: collapsed fp32 embeddings (a large
     common component) uploaded in several chunks — the first pass (fed chunk by chunk) cannot certify
     them, the centred 3xTF32 pass over the now-resident gallery must, and the host entry point must
     return what the device path returns."""
     from art_sbir_b200 import _binding as B
-    monkeypatch.setenv("SBIR_K1_CHUNK_MB", "1")
-    monkeypatch.setenv("SBIR_HOST_CHUNK_ROWS", "4096")
+    dbg("k1_chunk_mb", 1)
+    dbg("host_chunk_rows", 4096)
     nq, ng, d, k = 24000, 14000, 64, 10
     Q0, G0, pos = O.synthetic_embeddings(nq, ng, d, seed=15, beta=0.3)
     base = 3.0 * torch.rand(1, d, generator=torch.Generator().manual_seed(2))
@@ -744,13 +752,13 @@ def test_retrieve_host_streamed_fp32_with_escalation(ops, sbir_lib, monkeypatch)
     sbir_lib.sbir_release_host_staging()
 
 
-def test_sharded_host_path_equals_single_pass(ops, sbir_lib, monkeypatch):
+def test_sharded_host_path_equals_single_pass(ops, sbir_lib, dbg):
     """sbir_retrieve_host_shard: each rank's shard comes from HOST memory in chunks fed to one pass.
     Two and three shards scored one after the other on this GPU + K4 merge must equal the
     single-GPU device path; sharded_retrieve_host (world size 1) as well."""
     from art_sbir_b200 import _binding as B, sharded
-    monkeypatch.setenv("SBIR_K1_CHUNK_MB", "1")
-    monkeypatch.setenv("SBIR_HOST_CHUNK_ROWS", "8192")
+    dbg("k1_chunk_mb", 1)
+    dbg("host_chunk_rows", 8192)
     nq, ng, d, k = 24000, 41000, 64, 10
     Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=14, beta=0.3)
     pos[::101] = -1

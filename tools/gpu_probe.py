@@ -13,6 +13,12 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def B_set(name, value):
+    """Library tuning / diagnostic switch (k1_flags needs a build with SBIR_BUILD_DIAG=1)."""
+    from art_sbir_b200 import _binding
+    _binding.set_debug_option(name, value)
+
+
 def _data(nq, ng, d, dtype, seed=0):
     import torch
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -315,7 +321,7 @@ def case_mainloop():
         res = {}
         for rep in range(2):
             for flags in (0, 8):
-                os.environ["SBIR_K1_FLAGS"] = str(flags)
+                B_set("k1_flags", int(flags))
                 ops.pairwise_topk(q, g, k, "euclidean")
                 torch.cuda.synchronize()
                 lib.sbir_profile_enable(1)
@@ -330,7 +336,7 @@ def case_mainloop():
                 res.setdefault("full" if flags == 0 else "mainloop_only", []).append(
                     {"k1_ms": round(k1, 3), "tflops": round(2 * d * nq * ng / k1 / 1e9, 1)})
         out[f"{nq}x{ng}x{d} {dt}"] = res
-    os.environ.pop("SBIR_K1_FLAGS", None)
+    B_set("k1_flags", 0)
     return out
 
 
@@ -348,7 +354,7 @@ def case_ab():
         res = {}
         for rep in range(3):
             for flags in (0, 16):
-                os.environ["SBIR_K1_FLAGS"] = str(flags)
+                B_set("k1_flags", int(flags))
                 ops.pairwise_topk(q, g, k, "euclidean", pos_index=p)
                 torch.cuda.synchronize()
                 lib.sbir_profile_enable(1)
@@ -361,7 +367,7 @@ def case_ab():
                 lib.sbir_profile_enable(0)
                 res.setdefault(flags, []).append(round(ms.value / max(1, n.value), 3))
         out[f"{nq}x{ng}x{d} {dt} k={k} rank={rank}"] = res
-    os.environ.pop("SBIR_K1_FLAGS", None)
+    B_set("k1_flags", 0)
     return out
 
 
@@ -534,10 +540,10 @@ def case_k100():
                           (20000, 1000000, 512, "bfloat16")]:
         q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
         for chunk in ("12", "100000"):
-            os.environ["SBIR_K1_CHUNK_MB"] = chunk
+            B_set("k1_chunk_mb", int(chunk))
             for k in (10, 100):
                 out[f"{nq}x{ng}x{d} {dt} k={k} chunkMB={chunk}"] = _k1_ms(q, g, k)
-    os.environ.pop("SBIR_K1_CHUNK_MB", None)
+    B_set("k1_chunk_mb", 0)
     return out
 
 
@@ -596,10 +602,10 @@ def case_small():
         torch.cuda.synchronize()
         tw = ws[-(8 + 8 * 512) * 8:].view(torch.int64).cpu()
         t = tw[:4].tolist()   # phase boundaries seen by CTA 0 (globaltimer ns)
-        st = tw[8:8 + 8 * 296].reshape(296, 8).double()
-        st = (st - float(t[0])) / 1e3                          # per-CTA stage stamps, us after CTA 0's start
+        stg = tw[8:8 + 8 * 296].reshape(296, 8).double()
+        stg = (stg - float(t[0])) / 1e3                          # per-CTA stage stamps, us after CTA 0's start
         res[f"cfg2 batch-hard fwd+bwd 256x512x2048 {name}"] = {"us": us, "phase_us(mine,select,grad)": [(t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3],
-                                                             "stage_median_us": st.median(0).values.tolist(), "stage_max_us": st.max(0).values.tolist(), "stage_min_us": st.min(0).values.tolist()}
+                                                             "stage_median_us": stg.median(0).values.tolist(), "stage_max_us": stg.max(0).values.tolist(), "stage_min_us": stg.min(0).values.tolist()}
     ta, tp, tn = (t.clone().requires_grad_(True) for t in (a, p, n))
 
     def torch_step():
@@ -632,9 +638,9 @@ def case_k100_mainloop():
         q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
         for k in (10, 100):
             for flags in ("0", "8"):
-                os.environ["SBIR_K1_FLAGS"] = flags
+                B_set("k1_flags", int(flags))
                 out[f"{nq}x{ng}x{d} {dt} k={k} flags={flags}"] = _k1_ms(q, g, k)
-    os.environ.pop("SBIR_K1_FLAGS", None)
+    B_set("k1_flags", 0)
     return out
 
 
@@ -649,10 +655,10 @@ def case_ab2():
         res = {}
         for rnd in range(5):
             for flags in ("0", "32", "8"):
-                os.environ["SBIR_K1_FLAGS"] = flags
+                B_set("k1_flags", int(flags))
                 res.setdefault(flags, []).append(_k1_ms(q, g, k, iters=3)[0])
         out[f"{nq}x{ng}x{d} {dt} k={k}"] = {f: [round(statistics.median(v), 3), round(min(v), 3)] for f, v in res.items()}
-    os.environ.pop("SBIR_K1_FLAGS", None)
+    B_set("k1_flags", 0)
     return out
 
 
@@ -674,7 +680,7 @@ def case_diag():
     for nq, ng, d, dt, k in shapes:
         q, g, pos = _clustered(nq, ng, d, getattr(torch, dt))
         for flags in ("64", "72"):   # 72 = 64 + 8: epilogue switched off (mainloop alone)
-            os.environ["SBIR_K1_FLAGS"] = flags
+            B_set("k1_flags", int(flags))
             ops.pairwise_topk(q, g, k, "euclidean")
             torch.cuda.synchronize()
             lib.sbir_debug_k1_diag(buf, 148 * 8)
@@ -689,7 +695,7 @@ def case_diag():
                 "wait_operands_frac": round(a[:, 1].mean() / loop, 3), "epi_wait_acc_full_frac": round(a[:, 3].mean() / loop, 3),
                 "per_kblock_clk": {"loop": round(loop / a[:, 7].mean(), 1), "wait_operands": round(a[:, 1].mean() / a[:, 7].mean(), 1),
                                    "issue_4_mma": round(a[:, 5].mean() / a[:, 7].mean(), 1), "commit": round(a[:, 6].mean() / a[:, 7].mean(), 1)}}
-    os.environ.pop("SBIR_K1_FLAGS", None)
+    B_set("k1_flags", 0)
     return out
 
 
