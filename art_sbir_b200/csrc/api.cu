@@ -1,5 +1,6 @@
 // api.cu — the extern "C" boundary declared in include/sbir_b200.h: argument checking,
 // workspace layout, and the launch sequences.  No kernel code lives here.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstring>
@@ -62,9 +63,32 @@ int num_sms_cached() {
 bool dtype_ok(int d) { return d == SBIR_F32 || d == SBIR_BF16; }
 bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 
+// fp32 embeddings are selected on their bf16-rounded copies (kind::f16 tiles: twice the kind::tf32 rate; the
+// certificate uses measured rounding-residual norms, rowops.cu: convert_bf16_norm_kernel) when the copies fit
+// the workspace budget and bf16 rows satisfy TMA's 16-byte pitch.  Option k1_sel_bf16 = 0 keeps kind::tf32.
+bool select_on_bf16(int64_t num_q, int64_t num_g, int64_t dim, int dtype) {
+  if (dtype != SBIR_F32 || debug_options().k1_sel_bf16 == 0) return false;
+  if (dim % 8 != 0 || num_g <= 0) return false;
+  return ((size_t)num_q + (size_t)num_g) * (size_t)dim * 2 <= (size_t(16) << 30);
+}
+
 TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int want_rank) {
   TopkLayout L{};
-  L.plan = make_k1_plan(num_q, num_g, dim, k, dtype, num_sms_cached());
+  L.sel_bf16 = select_on_bf16(num_q, num_g, dim, dtype);
+  // fp32 embeddings keep their wider candidate slack (k + 16) whichever tensor path selects them
+  L.plan = topk_primary_plan(num_q, num_g, dim, k, dtype, 0);
+  // 3xTF32 escalation copies ([rows, 3·dim] fp32) — only when they stay below 12 GiB
+  const size_t split_bytes = ((size_t)num_q + (size_t)num_g) * (size_t)dim * 3 * sizeof(float);
+  L.precise = dtype == SBIR_F32 && num_g > 0 && split_bytes <= (size_t(12) << 30);
+  if (L.precise) {
+    L.plan3 = make_k1_plan(num_q, num_g, 3 * dim, k, dtype, num_sms_cached(), 16);
+    // the escalation pass re-uses the candidate / list-state buffers: they are sized for the larger of the two
+    // plans; the passes must agree on the per-list capacity (finalize's certificate compares like with like)
+    L.precise = L.plan3.cap == L.plan.cap;
+  }
+  auto lists_of = [](const K1Plan& p) { return (size_t)p.num_splits * p.q_tile_stride * p.lists_per_row; };
+  const size_t lists = L.precise ? std::max(lists_of(L.plan), lists_of(L.plan3)) : lists_of(L.plan);
+  const size_t parts = L.precise ? (size_t)std::max(L.plan.num_splits, L.plan3.num_splits) : (size_t)L.plan.num_splits;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + (bytes ? bytes : 1), 256); return r; };
   const size_t nq = (size_t)(num_q > 0 ? num_q : 1);
@@ -72,25 +96,21 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   L.off_gmax = take(sizeof(float));
   L.off_gmin = take((size_t)L.plan.num_g_tiles * (kTileG / 8) * sizeof(float));
   L.off_qsq = take(nq * sizeof(float));
-  const size_t cand = (size_t)L.plan.num_splits * L.plan.q_tile_stride * L.plan.lists_per_row * L.plan.cap * kTileQ;
+  const size_t cand = lists * L.plan.cap * kTileQ;
   L.off_cand_val = take(cand * sizeof(float));
   L.off_cand_idx = take(cand * sizeof(int32_t));
   L.off_flags = take(nq * sizeof(int32_t));
   L.off_uncert = take(sizeof(int32_t));
   L.off_shared_thr = take((size_t)L.plan.q_tile_stride * kTileQ * sizeof(int32_t));
-  const size_t rows = (size_t)L.plan.num_splits * L.plan.q_tile_stride * L.plan.lists_per_row * kTileQ;
-  L.off_row_max = take(rows * sizeof(float));
-  L.off_row_maxpos = take(rows * sizeof(int32_t));
-  L.sched_bytes = 256 + (size_t)L.plan.num_splits * L.plan.q_tile_stride * sizeof(int32_t);
+  L.off_row_max = take(lists * kTileQ * sizeof(float));
+  L.off_row_maxpos = take(lists * kTileQ * sizeof(int32_t));
+  L.sched_bytes = 256 + parts * L.plan.q_tile_stride * sizeof(int32_t);
   L.off_sched = take(L.sched_bytes);
-  // 3xTF32 escalation copies ([rows, 3·dim] fp32) — only when they stay below 12 GiB
-  const size_t split_bytes = ((size_t)num_q + (size_t)num_g) * (size_t)dim * 3 * sizeof(float);
-  L.precise = dtype == SBIR_F32 && num_g > 0 && split_bytes <= (size_t(12) << 30);
-  if (L.precise) {
-    L.plan3 = make_k1_plan(num_q, num_g, 3 * dim, k, dtype, num_sms_cached());
-    // identical list geometry (it depends on the query/gallery tile counts, k and dtype only)
-    L.precise = L.plan3.num_splits == L.plan.num_splits && L.plan3.cap == L.plan.cap &&
-                L.plan3.lists_per_row == L.plan.lists_per_row && L.plan3.tiles_per_split == L.plan.tiles_per_split;
+  if (L.sel_bf16) {
+    L.off_qb = take((size_t)num_q * dim * 2);
+    L.off_gb = take((size_t)num_g * dim * 2);
+    L.off_qres = take(nq * sizeof(float));
+    L.off_gres = L.off_gmax + 16;  // the residual maxima share gmax's 256-byte block (cleared together)
   }
   if (L.precise) {
     L.off_gate = take(256);
@@ -116,6 +136,12 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
 }
 
 }  // namespace
+
+K1Plan topk_primary_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms) {
+  const bool sel = select_on_bf16(num_q, num_g, dim, dtype);
+  return make_k1_plan(num_q, num_g, dim, k, sel ? SBIR_BF16 : dtype, num_sms > 0 ? num_sms : num_sms_cached(),
+                      dtype == SBIR_F32 ? 16 : 6);
+}
 
 // ---- one retrieval pass in three phases (kernels.h: TopkPass) ----
 // begin: argument checks, workspace carve-up, counters zeroed, query norms.
@@ -160,6 +186,7 @@ int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, co
   P.padded = (int64_t)L.plan.num_g_tiles * kTileG;
   float* cand_val = reinterpret_cast<float*>(ws + L.off_cand_val);
   int32_t* cand_idx = reinterpret_cast<int32_t*>(ws + L.off_cand_idx);
+  // scalars the kernels accumulate into (external uncertified counter, running maxima): one 4-byte and one 256-byte memset
   SBIR_CUDA_TRY(cudaMemsetAsync(P.uncert, 0, sizeof(int32_t), st));
 
   if (num_g == 0) {
@@ -213,20 +240,29 @@ int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, co
   fa.out_dist = out_dist; fa.out_index = out_index;
   fa.uncertified = P.uncert; fa.flags = P.flags;
 
-  // Pass 1 runs the tensor-core tiles on the embeddings as they are (fp32 -> kind::tf32, bf16 -> kind::f16).
-  const float kappa = k1_kappa(dtype, dim);
-  ra.kappa = kappa; ra.gate = nullptr;
-  fa.kappa = kappa; fa.gate = nullptr;
-  ka.q = q; ka.g = g; ka.dim = dim; ka.gate = nullptr;
-  SBIR_TRY(launch_row_norm(q, num_q, num_q, dim, dtype, 0, 0.f, P.qsq, nullptr, st));
-  SBIR_CUDA_TRY(cudaMemsetAsync(P.gmax, 0, sizeof(float), st));
-  if (want_rank) {
-    SBIR_CUDA_TRY(cudaMemsetAsync(ra.cnt_less, 0, (size_t)num_q * sizeof(int32_t), st));
-    SBIR_CUDA_TRY(cudaMemsetAsync(ra.dropped, 0, (size_t)num_q * sizeof(int32_t), st));
-    SBIR_CUDA_TRY(cudaMemsetAsync(ra.pool_count, 0, sizeof(uint32_t), st));
+  // Pass 1 runs the tensor-core tiles on the embeddings as they are (bf16 -> kind::f16; fp32 -> kind::tf32), or —
+  // fp32 embeddings, normally — on their bf16-rounded copies (kind::f16 at twice the rate; L.sel_bf16).
+  ka.gate = nullptr; ka.dim = dim;
+  ra.gate = nullptr; fa.gate = nullptr;
+  SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_gmax, 0, 256, st));  // gmax and, in the same 256-byte block, the bf16 residual maxima
+  SBIR_TRY(launch_pass_reset(want_rank ? ra.cnt_less : nullptr, ra.dropped, num_q, want_rank ? ra.pool_count : nullptr,
+                             ws + L.off_sched, L.sched_bytes, reinterpret_cast<int32_t*>(ws + L.off_shared_thr),
+                             (int64_t)L.plan.q_tile_stride * kTileQ, nullptr, st));
+  if (L.sel_bf16) {
+    float* qres = reinterpret_cast<float*>(ws + L.off_qres);
+    float* gres = reinterpret_cast<float*>(ws + L.off_gres);
+    const float kappa = k1_accum_kappa(dim, 2);  // bf16 products are exact in the fp32 accumulator
+    ra.kappa = kappa; fa.kappa = kappa;
+    ra.q_res = qres; ra.g_res = gres; fa.q_res = qres; fa.g_res = gres;
+    ka.q = ws + L.off_qb; ka.g = ws + L.off_gb; ka.dtype = SBIR_BF16;
+    SBIR_TRY(launch_convert_bf16_norm(static_cast<const float*>(q), num_q, num_q, dim, ws + L.off_qb, 0, 0.f, P.qsq, nullptr, qres,
+                                      nullptr, st));
+  } else {
+    const float kappa = k1_kappa(dtype, dim);
+    ra.kappa = kappa; fa.kappa = kappa;
+    ka.q = q; ka.g = g;
+    SBIR_TRY(launch_row_norm(q, num_q, num_q, dim, dtype, 0, 0.f, P.qsq, nullptr, st));
   }
-  SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_sched, 0, L.sched_bytes, st));
-  SBIR_TRY(launch_fill_i32(ka.shared_thr, (int64_t)L.plan.q_tile_stride * kTileQ, 0x7f800000, st));
   return SBIR_OK;
 }
 
@@ -251,7 +287,11 @@ int topk_pass_feed(TopkPass& P, int64_t row_end) {
   const int64_t pad_end = last ? P.padded : row_end;  // the padding rows of the last tile belong to the last feed
   const int vec_mode = P.metric == SBIR_EUCLIDEAN ? 0 : 1;
   const float vec_pad = P.metric == SBIR_EUCLIDEAN ? INFINITY : nanf("");
-  if (P.g_sqnorm != nullptr)  // gallery built by sbir_gallery_append / reloaded with its sidecar: N floats instead of N·dim elements
+  if (L.sel_bf16)  // fp32 rows -> bf16 selection operands + exact norms + rounding-residual maxima, one pass over the rows
+    SBIR_TRY(launch_convert_bf16_norm(static_cast<const float*>(P.g) + (size_t)row0 * P.dim, row_end - row0, pad_end - row0, P.dim,
+                                      P.ws + L.off_gb + (size_t)row0 * P.dim * 2, vec_mode, vec_pad, P.gvec + row0, P.gmax, nullptr,
+                                      reinterpret_cast<float*>(P.ws + L.off_gres), st));
+  else if (P.g_sqnorm != nullptr)  // gallery built by sbir_gallery_append / reloaded with its sidecar: N floats instead of N·dim elements
     SBIR_TRY(launch_gvec_from_sqnorm(P.g_sqnorm + row0, row_end - row0, pad_end - row0, vec_mode, vec_pad, P.gvec + row0, P.gmax,
                                      st, /*accumulate_max=*/true));
   else
@@ -260,7 +300,7 @@ int topk_pass_feed(TopkPass& P, int64_t row_end) {
   SBIR_TRY(launch_chunk_min(P.gvec + row0, (pad_end - row0) / 8, P.gmin + row0 / 8, st));
   // the rank band uses the largest gallery norm seen so far (it only widens from feed to feed)
   if (P.want_rank) SBIR_TRY(launch_rank_band(P.ra, st));
-  SBIR_CUDA_TRY(cudaMemsetAsync(P.ws + L.off_sched, 0, 256, st));  // unit counter of this launch
+  if (row0 != 0) SBIR_CUDA_TRY(cudaMemsetAsync(P.ws + L.off_sched, 0, 256, st));  // unit counter of this launch (begin zeroed the first one)
   P.ka.chunk_begin = (row0 == 0) ? 0 : (int)(row0 / granule);
   P.ka.chunk_end = last ? 0 : (int)(row_end / granule);
   SBIR_TRY(launch_k1(P.ka, L.plan, st));
@@ -280,7 +320,7 @@ int topk_pass_finish(TopkPass& P) {
   const bool want_rank = P.want_rank;
   const int64_t num_q = P.num_q, num_g = P.num_g, dim = P.dim;
   SBIR_TRY(launch_finalize_topk(fa, L.plan, st));
-  if (want_rank) SBIR_TRY(launch_rank_finalize(ra, st));
+  if (want_rank) SBIR_TRY(launch_rank_resolve(ra, st));
 
   // One whole-gallery scoring pass: (rank band) -> K1 -> finalize (+ rank pool resolution).  `gate`
   // makes every kernel of the pass a no-op unless the device flag is set.
@@ -288,19 +328,15 @@ int topk_pass_finish(TopkPass& P) {
                       const int32_t* gate) -> int {
     ra.kappa = kappa; ra.gate = gate;
     fa.kappa = kappa; fa.gate = gate;
-    ka.q = kq; ka.g = kg; ka.dim = kdim; ka.gate = gate;
+    ra.q_res = nullptr; ra.g_res = nullptr; fa.q_res = nullptr; fa.g_res = nullptr;  // no bf16 rounding in this pass
+    ka.q = kq; ka.g = kg; ka.dim = kdim; ka.dtype = SBIR_F32; ka.gate = gate;
     ka.chunk_begin = 0; ka.chunk_end = 0;
-    if (want_rank) {
-      SBIR_CUDA_TRY(cudaMemsetAsync(ra.cnt_less, 0, (size_t)num_q * sizeof(int32_t), st));
-      SBIR_CUDA_TRY(cudaMemsetAsync(ra.dropped, 0, (size_t)num_q * sizeof(int32_t), st));
-      SBIR_CUDA_TRY(cudaMemsetAsync(ra.pool_count, 0, sizeof(uint32_t), st));
-      SBIR_TRY(launch_rank_band(ra, st));
-    }
-    SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_sched, 0, L.sched_bytes, st));
-    SBIR_TRY(launch_fill_i32(ka.shared_thr, (int64_t)L.plan.q_tile_stride * kTileQ, 0x7f800000, st));
+    SBIR_TRY(launch_pass_reset(want_rank ? ra.cnt_less : nullptr, ra.dropped, num_q, want_rank ? ra.pool_count : nullptr,
+                               ws + L.off_sched, L.sched_bytes, ka.shared_thr, (int64_t)L.plan.q_tile_stride * kTileQ, gate, st));
+    if (want_rank) SBIR_TRY(launch_rank_band(ra, st));
     SBIR_TRY(launch_k1(ka, plan, st));
     SBIR_TRY(launch_finalize_topk(fa, plan, st));
-    if (want_rank) SBIR_TRY(launch_rank_finalize(ra, st));
+    if (want_rank) SBIR_TRY(launch_rank_resolve(ra, st));
     return SBIR_OK;
   };
 
@@ -343,7 +379,7 @@ int topk_pass_finish(TopkPass& P) {
   fa.gate = nullptr;
   ra.gate = nullptr;
   SBIR_TRY(launch_topk_fallback(fa, st));
-  if (want_rank) SBIR_TRY(launch_rank_fallback(ra, st));
+  if (want_rank) SBIR_TRY(launch_rank_output(ra, st));
   P.done = true;
   return SBIR_OK;
 }
@@ -554,6 +590,7 @@ int sbir_debug_set_option(const char* name, int64_t value) {
   if (!std::strcmp(name, "k1_feed")) o.k1_feed = (int)value;
   else if (!std::strcmp(name, "k1_pair")) o.k1_pair = (int)value;
   else if (!std::strcmp(name, "k1_qres")) o.k1_qres = (int)value;
+  else if (!std::strcmp(name, "k1_sel_bf16")) o.k1_sel_bf16 = (int)value;
   else if (!std::strcmp(name, "k1_chunk_mb")) o.k1_chunk_mb = (int)value;
   else if (!std::strcmp(name, "k1_flags")) o.k1_flags = (int)value;
   else if (!std::strcmp(name, "host_chunk_rows")) o.host_chunk_rows = value;
@@ -574,7 +611,7 @@ int sbir_debug_diag_build(void) {
 int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms, int32_t* out) {
   if (num_q <= 0 || num_g <= 0 || dim <= 0 || k <= 0 || k > kMaxK || !dtype_ok(dtype) || num_sms <= 0 || out == nullptr)
     return SBIR_ERR_INVALID_ARG;
-  const K1Plan p = make_k1_plan(num_q, num_g, dim, k, dtype, num_sms);
+  const K1Plan p = topk_primary_plan(num_q, num_g, dim, k, dtype, num_sms);
   const int32_t v[12] = {p.cap, p.lists_per_row, p.num_q_tiles, p.num_g_tiles, p.num_splits, p.tiles_per_split,
                          p.num_chunks, p.tiles_per_chunk, p.num_units, p.part_fastest, p.pair, p.q_tile_stride};
   for (int i = 0; i < 12; ++i) out[i] = v[i];

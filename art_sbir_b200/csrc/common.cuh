@@ -216,14 +216,20 @@ __device__ __forceinline__ double e_of_distance(double d, int metric, float qsq)
   if (metric == SBIR_EUCLIDEAN) return d * d - (double)qsq;
   return (d - 1.0) * (double)fmaxf(sqrtf(qsq), kCosineEps);
 }
-__device__ __forceinline__ double e_margin(int metric, float qsq, float gsq_max, float kappa, int dim) {
+// q_res = ‖q − bf16(q)‖, g_res_abs / g_res_rel = max_j ‖g_j − bf16(g_j)‖ (absolute / relative to max(‖g_j‖,eps)):
+// non-zero when fp32 embeddings were SELECTED on their bf16-rounded copies (rowops.cu: convert_bf16_norm_kernel);
+// then q·g − qh·gh = qh·gl + ql·g is bounded by Cauchy-Schwarz on the measured residual norms.
+__device__ __forceinline__ double e_margin(int metric, float qsq, float gsq_max, float kappa, int dim, float q_res = 0.f,
+                                           float g_res_abs = 0.f, float g_res_rel = 0.f) {
+  const double nq = sqrt((double)qsq);
   if (metric == SBIR_EUCLIDEAN) {
     const double s = (double)qsq + (double)gsq_max;
+    const double split = 2.0 * (1.01 * nq * (double)g_res_abs + (double)q_res * sqrt((double)gsq_max) + (double)q_res * (double)g_res_abs);
     // tensor-core rounding of 2·q·g  +  the reference's +1e-6 per component  +  fp32 epilogue rounding
-    return (double)kappa * s + 4e-6 * sqrt((double)dim * s) + 1e-12 * (double)dim + 4e-7 * s + 1e-30;
+    return (double)kappa * s + split + 4e-6 * sqrt((double)dim * s) + 1e-12 * (double)dim + 4e-7 * s + 1e-30;
   }
-  const double nq = sqrt((double)qsq);
-  return (double)kappa * nq + 1e-6 * nq + 1e-30;
+  const double split = 1.01 * nq * (double)g_res_rel + (double)q_res * (1.0 + (double)g_res_rel);
+  return (double)kappa * nq + split + 1e-6 * nq + 1e-30;
 }
 
 // Total order used everywhere a ranked list is produced: ascending distance, ties by

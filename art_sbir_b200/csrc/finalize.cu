@@ -5,6 +5,7 @@
 //   * rank of the positive = count(d < d_pos) (inference.py:49-52) from the fused counters
 //     plus exact resolution of the uncertain band,
 //   * K4 merge of per-shard top-k lists (after the all-gather), retrieval metrics (H5).
+#include <algorithm>
 #include <climits>
 
 #include "common.cuh"
@@ -38,6 +39,13 @@ __device__ __forceinline__ void bitonic_sort_smem(Key* key, int32_t* idx, int n)
 
 constexpr int kFinThreads = 128;
 
+// bound on |approximate e − exact e| for query q in the pass described by p (FinParams / RankParams)
+template <typename Params>
+__device__ __forceinline__ double query_margin(const Params& p, int q) {
+  return e_margin(p.metric, p.qsq[q], p.gsq_max[0], p.kappa, p.dim, p.q_res ? p.q_res[q] : 0.f, p.g_res ? p.g_res[0] : 0.f,
+                  p.g_res ? p.g_res[1] : 0.f);
+}
+
 struct FinParams {
   const void* q;
   const void* g;
@@ -49,6 +57,8 @@ struct FinParams {
   const float* qsq;
   const float* gsq_max;
   float kappa;
+  const float* q_res;   // [num_q] ‖q − bf16(q)‖ or NULL (bf16 selection of fp32 embeddings, see e_margin)
+  const float* g_res;   // [2] max ‖g − bf16(g)‖ absolute / relative, or NULL
   float* out_dist;
   long long* out_index;
   int32_t* uncertified;
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinPar
   // kernel's time goes to (k=100, 2048-d fp32: 1 MB per query), so the cut is worth a third of it.
   int RS = R;
   if (p.k <= R) {
-    const double lim = (double)sv[p.k - 1] + 2.0 * e_margin(p.metric, p.qsq[q], p.gsq_max[0], p.kappa, p.dim);
+    const double lim = (double)sv[p.k - 1] + 2.0 * query_margin(p, q);
     int lo = p.k, hi = R;  // sv[0..R) ascending: first position whose value exceeds lim
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_topk_kernel(const FinPar
       const double tau = (double)sv[R - 1];
       const float qsq = p.qsq[q];
       const double ek = e_of_distance(ex[p.k - 1], p.metric, qsq);
-      const double m = e_margin(p.metric, qsq, p.gsq_max[0], p.kappa, p.dim);
+      const double m = query_margin(p, q);
       if (!(ek + m < tau)) flag = 1;
     }
     p.flags[q] = flag;
@@ -222,6 +232,8 @@ struct RankParams {
   const float* qsq;
   const float* gsq_max;
   float kappa;
+  const float* q_res;
+  const float* g_res;
   double* pos_dist;
   float* rank_lo;
   float* rank_hi;
@@ -279,7 +291,7 @@ __global__ void __launch_bounds__(kRankWarps * 32) rank_band_kernel(const RankPa
     } else {
       const float qsq = p.qsq[q];
       const double c = e_of_distance(dpos, p.metric, qsq);
-      const double m = e_margin(p.metric, qsq, p.gsq_max[0], p.kappa, p.dim);
+      const double m = query_margin(p, q);
       p.rank_lo[q] = __double2float_rd(c - m);
       p.rank_hi[q] = __double2float_ru(c + m);
     }
@@ -304,40 +316,50 @@ __global__ void __launch_bounds__(kRankWarps * 32) rank_resolve_kernel(const Ran
   }
 }
 
-__global__ void __launch_bounds__(256) rank_finalize_kernel(const RankParams p) {
-  if (p.gate != nullptr && *p.gate == 0) return;
-  const int q = blockIdx.x * 256 + threadIdx.x;
-  if (q >= p.num_q) return;
-  const double dpos = p.pos_dist[q];
-  if (dpos != dpos) p.out_rank[q] = p.missing_rank;
-  else if (p.dropped[q] > 0) p.out_rank[q] = -1;  // resolved by rank_fallback_kernel
-  else p.out_rank[q] = p.cnt_less[q];
-}
-
-// Exact brute-force count for queries whose uncertain band overflowed.
+// Rank output, once, after the last scoring pass: the fused counters (+ the resolved band) give the rank;
+// queries without a positive get `missing_rank`; queries whose uncertain band overflowed the pool are
+// counted exactly by brute force.  A few blocks per SM walk the queries.
 template <typename T, bool kVec>
-__global__ void __launch_bounds__(kFbThreads) rank_fallback_kernel(const RankParams p) {
+__global__ void __launch_bounds__(kFbThreads) rank_output_kernel(const RankParams p) {
   __shared__ int red[kFbWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int q = blockIdx.x; q < p.num_q; q += gridDim.x) {
-  if (p.out_rank[q] != -1) continue;  // uniform across the block (read before anyone writes it)
-  __syncthreads();
-  const double dpos = p.pos_dist[q];
-  const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
-  int cnt = 0;
-  for (int j = warp; j < p.num_g; j += kFbWarps) {
-    const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)j * p.dim,
-                                                  p.dim, p.metric, lane);
-    cnt += ranks_before_positive(d, j, p, q) ? 1 : 0;
+    const double dpos = p.pos_dist[q];
+    if (dpos != dpos || p.dropped[q] <= 0) {  // uniform across the block
+      if (threadIdx.x == 0) p.out_rank[q] = (dpos != dpos) ? p.missing_rank : (long long)p.cnt_less[q];
+      continue;
+    }
+    __syncthreads();
+    const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
+    int cnt = 0;
+    for (int j = warp; j < p.num_g; j += kFbWarps) {
+      const double d = warp_exact_distance<T, kVec>(qrow, reinterpret_cast<const T*>(p.g) + (size_t)j * p.dim,
+                                                    p.dim, p.metric, lane);
+      cnt += ranks_before_positive(d, j, p, q) ? 1 : 0;
+    }
+    if (lane == 0) red[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long r = 0;
+      for (int w = 0; w < kFbWarps; ++w) r += red[w];
+      p.out_rank[q] = r;
+    }
   }
-  if (lane == 0) red[warp] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    long long r = 0;
-    for (int w = 0; w < kFbWarps; ++w) r += red[w];
-    p.out_rank[q] = r;
-  }
-  }
+}
+
+// Start of a (device-gated) scoring pass: counters, scheduler state and shared thresholds back to their
+// initial values in ONE launch (memsets cannot be gated on a device flag).
+__global__ void __launch_bounds__(256) pass_reset_kernel(int32_t* __restrict__ cnt_less, int32_t* __restrict__ dropped, long long num_q,
+                                                         uint32_t* __restrict__ pool_count, uint32_t* __restrict__ sched,
+                                                         long long sched_words, int32_t* __restrict__ shared_thr, long long num_thr,
+                                                         const int32_t* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (cnt_less != nullptr)
+    for (long long i = i0; i < num_q; i += stride) { cnt_less[i] = 0; dropped[i] = 0; }
+  for (long long i = i0; i < sched_words; i += stride) sched[i] = 0u;
+  for (long long i = i0; i < num_thr; i += stride) shared_thr[i] = 0x7f800000;
+  if (i0 == 0 && pool_count != nullptr) *pool_count = 0u;
 }
 
 template <typename T, bool kVec>
@@ -718,6 +740,7 @@ FinParams make_fin_params(const FinalizeArgs& a, const K1Plan* plan) {
     p.m_pow2 = m < 2 ? 2 : m;
   }
   p.qsq = a.qsq; p.gsq_max = a.gsq_max; p.kappa = a.kappa;
+  p.q_res = a.q_res; p.g_res = a.g_res;
   p.out_dist = a.out_dist; p.out_index = reinterpret_cast<long long*>(a.out_index);
   p.uncertified = a.uncertified; p.flags = a.flags;
   p.gate = a.gate;
@@ -733,6 +756,7 @@ RankParams make_rank_params(const RankArgs& a) {
   p.pos_tie = reinterpret_cast<const long long*>(a.pos_tie);
   p.tie_offset = a.tie_offset;
   p.qsq = a.qsq; p.gsq_max = a.gsq_max; p.kappa = a.kappa;
+  p.q_res = a.q_res; p.g_res = a.g_res;
   p.pos_dist = a.pos_dist; p.rank_lo = a.rank_lo; p.rank_hi = a.rank_hi;
   p.cnt_less = a.cnt_less;
   p.pool_count = a.pool_count; p.pool_cap = a.pool_cap; p.pool_q = a.pool_q; p.pool_idx = a.pool_idx;
@@ -788,23 +812,33 @@ int launch_rank_band(const RankArgs& a, cudaStream_t st) {
   return SBIR_OK;
 }
 
-int launch_rank_finalize(const RankArgs& a, cudaStream_t st) {
+int launch_rank_resolve(const RankArgs& a, cudaStream_t st) {
   if (a.num_q <= 0) return SBIR_OK;
   const RankParams p = make_rank_params(a);
   const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
   SBIR_DISPATCH_T(a.dtype, vec, rank_resolve_kernel, 148 * 8, kRankWarps * 32, 0, st, p);
   SBIR_CHECK_LAUNCH();
-  rank_finalize_kernel<<<(unsigned)((a.num_q + 255) / 256), 256, 0, st>>>(p);
-  SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }
 
-int launch_rank_fallback(const RankArgs& a, cudaStream_t st) {
+int launch_rank_output(const RankArgs& a, cudaStream_t st) {
   if (a.num_q <= 0) return SBIR_OK;
   const RankParams p = make_rank_params(a);
   const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
   const unsigned grid = (unsigned)(a.num_q < 148 * 8 ? a.num_q : 148 * 8);
-  SBIR_DISPATCH_T(a.dtype, vec, rank_fallback_kernel, grid, kFbThreads, 0, st, p);
+  SBIR_DISPATCH_T(a.dtype, vec, rank_output_kernel, grid, kFbThreads, 0, st, p);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_pass_reset(int32_t* cnt_less, int32_t* dropped, int64_t num_q, uint32_t* pool_count, void* sched, size_t sched_bytes,
+                      int32_t* shared_thr, int64_t num_thr, const int32_t* gate, cudaStream_t st) {
+  const long long n = std::max<long long>(std::max<long long>(num_q, (long long)(sched_bytes / 4)), num_thr);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  pass_reset_kernel<<<(unsigned)blocks, 256, 0, st>>>(cnt_less, dropped, (long long)num_q, pool_count, static_cast<uint32_t*>(sched),
+                                                       (long long)(sched_bytes / 4), shared_thr, (long long)num_thr, gate);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }

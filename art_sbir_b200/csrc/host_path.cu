@@ -163,11 +163,7 @@ static int retrieve_host_locked(const void* q_host, int64_t num_q, const void* g
   // distance kernel's chunk-step boundaries (`granule` rows; 0 = the plan has several gallery
   // partitions and cannot be fed in pieces).
   const int64_t granule = [&]() -> int64_t {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
-    const K1Plan plan = make_k1_plan(num_q, num_g, dim, k, dtype, sms);  // the plan topk_pass_begin will make
+    const K1Plan plan = topk_primary_plan(num_q, num_g, dim, k, dtype);  // the plan topk_pass_begin will make
     return plan.num_splits == 1 ? (int64_t)plan.tiles_per_chunk * kTileG : 0;
   }();
   std::vector<int64_t> chunk_end;
@@ -372,13 +368,9 @@ static int retrieve_host_shard_locked(const void* q_dev, int64_t num_q, const vo
                                       int32_t* out_uncertified_host, void* stream) {
   const bool want_rank = out_count_less_dev != nullptr;
   const size_t row_bytes = (size_t)dim * elem_size(dtype);
-  int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-    sms = 148;
   int64_t granule = 0;
   if (num_g > 0) {
-    const K1Plan plan = make_k1_plan(num_q, num_g, dim, k, dtype, sms);
+    const K1Plan plan = topk_primary_plan(num_q, num_g, dim, k, dtype);
     granule = plan.num_splits == 1 ? (int64_t)plan.tiles_per_chunk * kTileG : 0;
   }
   std::vector<int64_t> chunk_end;

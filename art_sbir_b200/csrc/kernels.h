@@ -12,6 +12,7 @@ struct DebugOptions {
   int k1_feed = -1;               // owner+feeder epilogue for 64/128-entry lists: -1 auto, 0 off
   int k1_pair = 0;                // CTA pairs: 0 auto, 1 never, 2 always
   int k1_qres = -1;               // resident-query form: -1 auto, 0 off
+  int k1_sel_bf16 = -1;           // fp32 embeddings selected on bf16 copies (kind::f16): -1 auto, 0 off (kind::tf32)
   int k1_chunk_mb = 0;            // gallery bytes per chunk step (MB): 0 auto
   int k1_flags = 0;               // diagnostic bits, honoured by -DSBIR_DIAG builds only
   long long host_chunk_rows = 0;  // upload chunk of the host-buffer entry points (rows): 0 auto
@@ -25,6 +26,11 @@ const DebugOptions& debug_options();
 int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t dim, int dtype,
                     int mode, float pad_value, float* out, float* max_sqnorm_out, cudaStream_t st,
                     bool accumulate_max = false);
+// fp32 rows → bf16 selection operands + epilogue vector (exact fp32 norms, as launch_row_norm) + the norm of the
+// rounding residual per row (res_row, queries) / its running maxima (res_max[0] abs, res_max[1] relative; gallery).
+// max_sq and res_max ACCUMULATE (clear them before the first call).
+int launch_convert_bf16_norm(const float* x, int64_t rows, int64_t rows_padded, int64_t dim, void* y_bf16, int mode,
+                             float pad_value, float* vec, float* max_sq, float* res_row, float* res_max, cudaStream_t st);
 // The same vector from stored ‖g‖² (gallery built by sbir_gallery_append / reloaded with its sidecar).
 int launch_gvec_from_sqnorm(const float* sqnorm, int64_t rows, int64_t rows_padded, int mode, float pad_value,
                             float* out, float* max_out, cudaStream_t st, bool accumulate_max = false);
@@ -68,7 +74,10 @@ struct K1Plan {
   int q_tile_stride;  // query-tile stride of candidate slots / shared thresholds (num_q_tiles rounded up to even)
   int lists_per_query() const { return num_splits * lists_per_row; }
 };
-K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms);
+K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms, int slack = 0);
+// The plan of the first scoring pass of sbir_pairwise_topk for these inputs (api.cu: fp32 embeddings may be selected
+// on bf16 copies, which changes tile bytes and chunking).
+K1Plan topk_primary_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms = 0);
 
 struct K1Args {
   const void* q;
@@ -117,6 +126,8 @@ struct FinalizeArgs {
   const float* qsq;        // [num_q] ‖q‖² (fp32)
   const float* gsq_max;    // [1] max ‖g‖²
   float kappa;             // error bound of the tensor-core dot product, relative to ‖q‖·‖g‖
+  const float* q_res;      // [num_q] ‖q − bf16(q)‖ when fp32 embeddings were selected on bf16 copies, else NULL
+  const float* g_res;      // [2] max ‖g − bf16(g)‖ (absolute, relative) in that case, else NULL
   float* out_dist;         // [num_q][k]
   int64_t* out_index;      // [num_q][k]
   int32_t* uncertified;    // [1] counter (may be NULL)
@@ -139,6 +150,8 @@ struct RankArgs {
   const float* qsq;
   const float* gsq_max;
   float kappa;
+  const float* q_res;        // see FinalizeArgs
+  const float* g_res;
   double* pos_dist;          // [num_q] workspace
   float* rank_lo;            // [num_q]
   float* rank_hi;            // [num_q]
@@ -153,8 +166,11 @@ struct RankArgs {
   const int32_t* gate;       // optional device flag (escalation pass)
 };
 int launch_rank_band(const RankArgs& a, cudaStream_t st);
-int launch_rank_finalize(const RankArgs& a, cudaStream_t st);   // pool resolution + rank (or -1 = needs brute force)
-int launch_rank_fallback(const RankArgs& a, cudaStream_t st);   // exact brute force for the -1 entries
+int launch_rank_resolve(const RankArgs& a, cudaStream_t st);    // exact comparison of the pooled (query, row) pairs of a pass
+int launch_rank_output(const RankArgs& a, cudaStream_t st);     // once at the end: rank from the counters / missing / exact brute force
+// (device-gated) start of a scoring pass: counters, scheduler words and shared thresholds reset in one launch
+int launch_pass_reset(int32_t* cnt_less, int32_t* dropped, int64_t num_q, uint32_t* pool_count, void* sched, size_t sched_bytes,
+                      int32_t* shared_thr, int64_t num_thr, const int32_t* gate, cudaStream_t st);
 // Escalation (fp32 inputs): after the TF32 pass, gate[0] = 1 iff more than `max_bad` queries failed
 // the top-k certificate or overflowed the rank pool; then the 3xTF32 pass re-does everything.
 int launch_escalate_decide(const int32_t* flags, const int32_t* dropped, int64_t num_q, int64_t max_bad,
@@ -187,6 +203,8 @@ struct TopkLayout {
   K1Plan plan;
   size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert, off_shared_thr;
   size_t off_row_max, off_row_maxpos, off_sched, sched_bytes, off_gmin;
+  bool sel_bf16;       // fp32 inputs selected on bf16-rounded copies (kind::f16 tiles) — off_qb / off_gb / off_qres / off_gres
+  size_t off_qb, off_gb, off_qres, off_gres;
   bool precise;        // fp32 inputs small enough for the 3xTF32 escalation workspace
   K1Plan plan3;        // plan of the escalation pass (dim' = 3·dim), same partitions / lists as `plan`
   size_t off_gate, off_q3, off_g3;  // off_sched: unit counter + chunk_done (zeroed together)

@@ -197,6 +197,80 @@ __global__ void __launch_bounds__(kRowThreads) row_norm_kernel(const T* __restri
     atomicMax(reinterpret_cast<int*>(max_out), __float_as_int(local_max));
 }
 
+// ------------------------------------ bf16 selection operands of fp32 embeddings ----
+// fp32 embeddings are SELECTED on the kind::f16 tensor path (twice the kind::tf32 rate): this kernel
+// writes the bf16-rounded copy xh of every row together with everything the exactness certificate needs —
+// the K1 epilogue vector from the EXACT fp32 row (‖x‖² or −1/max(‖x‖,eps), padded like row_norm_kernel), the
+// running maximum of ‖x‖², and the norm of the rounding residual xl = x − xh (exact in fp32): per row
+// (queries) or as running maxima over the rows (gallery: res_max[0] = max ‖xl‖, res_max[1] = max ‖xl‖/max(‖x‖,eps)).
+// Since q·g − qh·gh = qh·gl + ql·g, |q·g − qh·gh| ≤ ‖q‖·‖gl‖ + ‖ql‖·‖g‖ (+ ‖ql‖‖gl‖): a bound from MEASURED
+// residual norms (≈ 0.85·2^-9 relative per operand on real data), i.e. about 2^-8·‖q‖‖g‖ — twice kind::tf32's
+// band, which is why the plan only takes this path when the candidate lists have room for it (api.cu).
+template <bool kVec>
+__global__ void __launch_bounds__(kRowThreads) convert_bf16_norm_kernel(const float* __restrict__ x, int64_t rows,
+                                                                       int64_t rows_padded, int dim,
+                                                                       __nv_bfloat16* __restrict__ y, int mode, float pad_value,
+                                                                       float* __restrict__ vec, float* __restrict__ max_sq,
+                                                                       float* __restrict__ res_row, float* __restrict__ res_max) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float local_max = 0.f, local_res = 0.f, local_rel = 0.f;
+  for (int64_t r = warp0; r < rows_padded; r += nwarps) {
+    if (r >= rows) {
+      if (lane == 0) vec[r] = pad_value;
+      continue;
+    }
+    const float* xr = x + r * dim;
+    __nv_bfloat16* yr = y + r * dim;
+    double sq = 0.0, rs = 0.0;
+    if constexpr (kVec) {
+      const int nvec = dim / 4;
+#pragma unroll 4
+      for (int i = lane; i < nvec; i += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + i);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 h[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          h[c] = __float2bfloat16_rn(e[c]);
+          const float l = __fsub_rn(e[c], __bfloat162float(h[c]));  // exact
+          sq += (double)e[c] * (double)e[c];
+          rs += (double)l * (double)l;
+        }
+        *reinterpret_cast<uint2*>(yr + (size_t)i * 4) = *reinterpret_cast<const uint2*>(h);
+      }
+    } else {
+      for (int i = lane; i < dim; i += 32) {
+        const float e = xr[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(e);
+        const float l = __fsub_rn(e, __bfloat162float(h));
+        yr[i] = h;
+        sq += (double)e * (double)e;
+        rs += (double)l * (double)l;
+      }
+    }
+    sq = warp_sum(sq);
+    rs = warp_sum(rs);
+    const float sqf = (float)sq;
+    const float res = __double2float_ru(sqrt(rs)) * 1.000001f;  // rounded up: it is used as a bound
+    local_max = fmaxf(local_max, sqf);
+    local_res = fmaxf(local_res, res);
+    local_rel = fmaxf(local_rel, __fdiv_ru(res, clamped_norm(sq)) * 1.000001f);
+    if (lane == 0) {
+      vec[r] = (mode == 0) ? sqf : -1.0f / clamped_norm(sq);
+      if (res_row != nullptr) res_row[r] = res;
+    }
+  }
+  if (lane == 0) {
+    if (max_sq != nullptr && local_max > 0.f) atomicMax(reinterpret_cast<int*>(max_sq), __float_as_int(local_max));
+    if (res_max != nullptr) {
+      if (local_res > 0.f) atomicMax(reinterpret_cast<int*>(res_max), __float_as_int(local_res));
+      if (local_rel > 0.f) atomicMax(reinterpret_cast<int*>(res_max + 1), __float_as_int(local_rel));
+    }
+  }
+}
+
 // ------------------------------------------- gallery append (N1) / gvec from norms ----
 // One block of encoder output (fp32 or bf16 [rows, dim]) written straight into rows
 // [row0, row0 + rows) of the preallocated gallery matrix in ITS storage type (fp32 or bf16),
@@ -546,6 +620,18 @@ int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t di
   if (dtype == SBIR_F32)
     return launch_norm<float>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
   return launch_norm<__nv_bfloat16>(x, rows, rows_padded, dim, mode, pad_value, out, max_out, vec, st);
+}
+
+int launch_convert_bf16_norm(const float* x, int64_t rows, int64_t rows_padded, int64_t dim, void* y_bf16, int mode,
+                             float pad_value, float* vec, float* max_sq, float* res_row, float* res_max, cudaStream_t st) {
+  if (rows_padded <= 0) return SBIR_OK;
+  const bool vec_ok = rows_vectorizable(x, dim, SBIR_F32) && reinterpret_cast<uintptr_t>(y_bf16) % 8 == 0;
+  const int grid = row_grid(rows_padded);
+  __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
+  if (vec_ok) convert_bf16_norm_kernel<true><<<grid, kRowThreads, 0, st>>>(x, rows, rows_padded, (int)dim, y, mode, pad_value, vec, max_sq, res_row, res_max);
+  else convert_bf16_norm_kernel<false><<<grid, kRowThreads, 0, st>>>(x, rows, rows_padded, (int)dim, y, mode, pad_value, vec, max_sq, res_row, res_max);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
 }
 
 int launch_gvec_from_sqnorm(const float* sqnorm, int64_t rows, int64_t rows_padded, int mode, float pad_value,

@@ -111,21 +111,32 @@ def _plan(lib, nq, ng, d, k, dtype, sms=148):
     return dict(zip(keys, list(out)))
 
 
+@pytest.mark.parametrize("sel_bf16", [-1, 0])
 @pytest.mark.parametrize("nq,ng,d,k,dtype", [
     (100_000, 10_000_000, 512, 10, 1), (12_500, 75_000, 2048, 100, 0), (12_500, 75_000, 2048, 10, 0),
     (1_000, 10_000, 2048, 10, 0), (1, 513, 1024, 10, 0), (300, 9001, 512, 10, 1), (5, 7, 64, 3, 0),
-    (257, 3001, 512, 50, 1), (100_000, 1_250_000, 512, 10, 1)])
-def test_k1_plan_covers_every_tile_exactly_once(sbir_lib, nq, ng, d, k, dtype):
+    (257, 3001, 512, 50, 1), (100_000, 1_250_000, 512, 10, 1), (40, 900, 36, 5, 0)])
+def test_k1_plan_covers_every_tile_exactly_once(sbir_lib, nq, ng, d, k, dtype, sel_bf16):
     """The unit grid (query tile x partition x chunk) must tile the Q x G problem exactly: every
     (query tile, gallery tile) pair belongs to one unit, chunks of a partition are contiguous and
-    ordered, capacities hold k plus slack, and the gallery chunk of a unit stays L2-sized."""
-    p = _plan(sbir_lib, nq, ng, d, k, dtype)
+    ordered, capacities hold k plus slack, and the gallery chunk of a unit stays L2-sized.  fp32
+    embeddings are planned for their bf16 selection copies (kind::f16 tiles) unless option
+    k1_sel_bf16 = 0 keeps them on kind::tf32 (or their rows do not give bf16 copies a 16-byte pitch)."""
+    from art_sbir_b200 import _binding
+    try:
+        _binding.set_debug_option("k1_sel_bf16", sel_bf16)
+        p = _plan(sbir_lib, nq, ng, d, k, dtype)
+        ws = sbir_lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, dtype, 0, 1)
+    finally:
+        _binding.set_debug_option("reset")
+    tiles_bf16 = dtype == 1 or (sel_bf16 != 0 and d % 8 == 0)          # element type the tensor-core tiles read
     assert p["q_tiles"] == -(-nq // 128) and p["g_tiles"] == -(-ng // 256)
-    assert p["cap"] in (16, 32, 64, 128) and p["cap"] >= k + 6 and p["cap"] * p["lists"] * p["parts"] <= 4096
+    slack = 6 if dtype == 1 else 16
+    assert p["cap"] in (16, 32, 64, 128) and p["cap"] >= min(k + slack, 128) and p["cap"] * p["lists"] * p["parts"] <= 4096
     assert p["q_tile_stride"] >= p["q_tiles"] and p["q_tile_stride"] % 2 == 0
     # rows of the unit grid: query tiles, or PAIRS of them when the plan uses CTA pairs
-    # (chosen for fp32 embeddings with the 64/128-entry lists of large k)
-    assert p["pair"] == (2 if (dtype == 0 and p["cap"] >= 64 and p["q_tiles"] >= 2) else 1)
+    # (chosen for kind::tf32 tiles with the 64/128-entry lists of large k)
+    assert p["pair"] == (2 if (not tiles_bf16 and p["cap"] >= 64 and p["q_tiles"] >= 2) else 1)
     assert p["units"] == p["chunks"] * p["parts"] * -(-p["q_tiles"] // p["pair"])
     covered = []
     for part in range(p["parts"]):
@@ -136,70 +147,31 @@ def test_k1_plan_covers_every_tile_exactly_once(sbir_lib, nq, ng, d, k, dtype):
             t1 = min(t0 + p["tiles_per_chunk"], e)
             covered.extend(range(t0, t1))
     assert covered == list(range(p["g_tiles"]))                       # each gallery tile once, in order
-    es = 2 if dtype == 1 else 4
-    # ~12 MB chunks; 48 MB for the resident-query form (bf16 rows of at most 1 KB: only gallery rows go through L2)
-    limit = (49 << 20) if (dtype == 1 and d * 2 <= 1024) else (13 << 20)
+    es = 2 if tiles_bf16 else 4
+    # ~12 MB chunks; 48 MB for the resident-query form (bf16 tiles of rows of at most 1 KB: only gallery rows go through L2)
+    limit = (49 << 20) if (tiles_bf16 and d * 2 <= 1024) else (13 << 20)
     assert p["tiles_per_chunk"] == 1 or p["tiles_per_chunk"] * 256 * d * es <= limit
     # few query tiles -> partitions supply the parallelism; many -> a single partition
     if p["q_tiles"] >= 2 * 148:
         assert p["parts"] == 1
-    ws = sbir_lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, dtype, 0, 1)
     assert ws > 0 and ws >= p["parts"] * p["q_tile_stride"] * p["lists"] * p["cap"] * 128 * 8
+    if dtype == 0 and tiles_bf16:
+        assert ws >= (nq + ng) * d * 2                                # room for the bf16 selection copies
 
 
-def test_positive_lookup_is_stateless_across_galleries():
-    """Two galleries of equal length evaluated in one process (and a list mutated in place) must
-    each resolve against their own contents, like the reference's stateless scan (utils.py:22-25)."""
-    a, b, c = Path("p/a.jpg"), Path("p/b.jpg"), Path("p/c.jpg")
-    assert U.find_image_index([a, b, c], "b") == 1
-    assert U.find_image_index([b, a, c], "b") == 0
-    paths = [a, b, c]
-    assert inf.positive_indices(["s/b-1.png", "s/c-2.png"], paths, verbose=False).tolist() == [1, 2]
-    paths[0], paths[1] = paths[1], paths[0]                      # same object, same length, new order
-    assert inf.positive_indices(["s/b-1.png", "s/c-2.png"], paths, verbose=False).tolist() == [0, 2]
-    assert U.find_image_index(paths, "b", U.build_stem_index(paths)) == 0
-    # stems with more than three '-' parts stay a LIST in the reference (inference.py:33-37): never found
-    key = inf.sketch_key("s/1-2-3-4.png", paths)
-    assert isinstance(key, list) and O.find_image_index(paths, key) == -1
-    assert U.find_image_index(paths, key) == -1 and U.find_image_index(paths, key, U.build_stem_index(paths)) == -1
-    assert inf.positive_indices(["s/1-2-3-4.png", "s/a-1.png"], paths, verbose=False).tolist() == [-1, 1]
-
-
-def test_topk_larger_than_gallery_raises_like_torch():
-    paths = [Path("p/a.jpg"), Path("p/b.jpg")]
-    with pytest.raises(RuntimeError, match="selected index k out of range"):
-        inf.get_topk_images(10, paths, torch.zeros(1, 8), torch.zeros(2, 8), "euclidean")
-    with pytest.raises(RuntimeError, match="selected index k out of range"):        # what the reference's call raises
-        O.get_topk_images(10, paths, torch.zeros(1, 8), torch.zeros(2, 8), "euclidean")
-
-
-def test_run_inference_needs_the_second_sketch_set_for_kaggle_and_mixed():
-    class DS:
-        state_dict = {"dataset": "KaggleDatasetV2"}
-    with pytest.raises(ValueError, match="second_dataset"):
-        inf.run_inference(torch.nn.Identity(), DS(), folder_name="unused")
-
-
-def test_shard_offsets_are_derived_or_checked():
-    assert sharded._resolve_offsets(10, None, None, 1, 0, "cpu", None) == (0, 10)
-    assert sharded._resolve_offsets(10, 5, 20, 1, 0, "cpu", None) == (5, 20)
-    with pytest.raises(ValueError, match="outside the gallery"):
-        sharded._resolve_offsets(10, 15, 20, 1, 0, "cpu", None)
-
-
-def test_ops_validate_operand_pairs_before_taking_pointers():
-    from art_sbir_b200 import ops
-    q = torch.zeros(3, 8)
-    # shape / k / per-query checks run on whatever device the tensors live on; _dev is the CUDA gate
-    import unittest.mock as mock
-    with mock.patch.object(ops, "_dev", lambda t, name: t.contiguous()):
-        with pytest.raises(ValueError, match=r"expected \[Q,D\]"):
-            ops._check_retrieval_args(q, torch.zeros(5, 9))
-        with pytest.raises(ValueError, match="k must be in"):
-            ops._check_retrieval_args(q, torch.zeros(5, 8), 500)
-        with pytest.raises(ValueError, match="one entry per query"):
-            ops._check_retrieval_args(q, torch.zeros(5, 8), 3, (("pos_index", torch.zeros(4, dtype=torch.int64)),))
-        a, b = ops._check_retrieval_args(q, torch.zeros(5, 8, dtype=torch.bfloat16), 3)
-        assert a.dtype == b.dtype == torch.float32                                  # mixed dtypes are scored in fp32
-        a, b = ops._check_retrieval_args(q.double(), torch.zeros(5, 8, dtype=torch.float64), 3)
-        assert a.dtype == b.dtype == torch.float32                                  # F8: CSV-loaded float64 galleries
+def test_bf16_selection_error_bound_from_residual_norms():
+    """The certificate for fp32 embeddings selected on bf16 copies (common.cuh: e_margin) bounds
+    |q·g − qh·gh| by ‖q‖·‖gl‖ + ‖ql‖·‖g‖ (+ ‖ql‖‖gl‖) with the MEASURED residual norms: checked here in fp64 on
+    zero-mean, all-positive and wide-dynamic-range data.  It is about the size of the element-wise worst case
+    2^-8·‖q‖‖g‖ (bf16 rounds each operand by at most 2^-9), i.e. roughly twice kind::tf32's band."""
+    g = torch.Generator().manual_seed(1)
+    for make in (lambda n: torch.randn(n, 512, generator=g), lambda n: torch.rand(n, 512, generator=g) * 3 + 1,
+                 lambda n: torch.randn(n, 512, generator=g) * torch.logspace(-3, 3, 512)):
+        Q, G = make(64).double(), make(512).double()
+        Qh, Gh = Q.float().bfloat16().double(), G.float().bfloat16().double()
+        err = (Q @ G.T - Qh @ Gh.T).abs()
+        qn, gn = Q.norm(dim=1), G.norm(dim=1)
+        qr, gr = (Q - Qh).norm(dim=1), (G - Gh).norm(dim=1)
+        bound = 1.01 * qn[:, None] * gr.max() + qr[:, None] * gn.max() + qr[:, None] * gr.max()
+        assert (err <= bound).all()
+        assert 0.5 < (bound / (2.0 ** -8 * qn[:, None] * gn.max())).max() < 1.25   # vs the element-wise worst case

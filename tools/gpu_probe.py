@@ -251,6 +251,24 @@ def case_time():
             _time_topk(12500, 75000, 2048, "bfloat16", 10, rank=True)]
 
 
+def case_sel():
+    """fp32 embeddings: selection on bf16 copies (kind::f16) vs kind::tf32 — time, uncertified queries."""
+    out = []
+    for shape in ((12500, 75000, 2048, 10), (12500, 75000, 2048, 100), (12500, 75000, 2048, 30), (1000, 10000, 2048, 10),
+                  (20000, 200000, 1024, 10), (20000, 200000, 1024, 100), (20000, 1000000, 512, 10)):
+        for sel in (0, -1):
+            B_set("k1_sel_bf16", sel)
+            r = _time_topk(shape[0], shape[1], shape[2], "float32", shape[3], rank=True)
+            r["sel_bf16"] = sel
+            out.append(r)
+            r = _time_topk(shape[0], shape[1], shape[2], "float32", shape[3], rank=True, clustered=False) if shape[0] <= 1000 else None
+            if r:
+                r["sel_bf16"] = sel
+                out.append(r)
+    B_set("reset", 0)
+    return out
+
+
 def _bench(fn, iters=20, warm=3):
     import torch
     for _ in range(warm):
