@@ -34,7 +34,7 @@ PROTOTYPES = {
     "sbir_positive_distance": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P]),
     "sbir_pairwise_topk_shard": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P,
                                          _P, _P, _P, _P, c_size_t, _P]),
-    "sbir_topk_merge": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P]),
+    "sbir_topk_merge": (c_int, [_P, _P, c_int, c_int64, c_int64, c_int64, c_int, _P, _P, _P]),
     "sbir_retrieval_metrics": (c_int, [_P, c_int64, c_int, _P, _P]),
     "sbir_triplet_margin_loss": (c_int, [_P, _P, _P, c_int64, c_int64, c_float, c_int, _P, _P, _P, _P, _P, _P]),
     "sbir_batch_hard_workspace_bytes": (c_size_t, [c_int64, c_int64]),

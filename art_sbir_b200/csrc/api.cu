@@ -66,15 +66,25 @@ bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 // fp32 embeddings are selected on their bf16-rounded copies (kind::f16 tiles: twice the kind::tf32 rate; the
 // certificate uses measured rounding-residual norms, rowops.cu: convert_bf16_norm_kernel) when the copies fit
 // the workspace budget and bf16 rows satisfy TMA's 16-byte pitch.  Option k1_sel_bf16 = 0 keeps kind::tf32.
-bool select_on_bf16(int64_t num_q, int64_t num_g, int64_t dim, int dtype) {
-  if (dtype != SBIR_F32 || debug_options().k1_sel_bf16 == 0) return false;
+// The bf16 rounding band is about twice kind::tf32's, so the candidate lists must have room for it: measured on
+// the clustered 12.5k x 75k x 2048 workload, k = 10 (32-entry lists) and k = 30 (64) certify every query and run
+// 6.1 -> 3.8 ms / 6.5 -> 4.3 ms, while k = 100 (128-entry lists, 28 entries of slack) leaves queries uncertified and
+// falls into the 3xTF32 escalation pass (7.9 -> 39 ms) — hence "capacity >= 2k".  Problems of a few 1e10 FLOP (the
+// reference's own 1k x 10k evaluation) are launch-bound and stay on the path with fewer kernels and lists.
+bool select_on_bf16(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype) {
+  const int opt = debug_options().k1_sel_bf16;
+  if (dtype != SBIR_F32 || opt == 0) return false;
   if (dim % 8 != 0 || num_g <= 0) return false;
-  return ((size_t)num_q + (size_t)num_g) * (size_t)dim * 2 <= (size_t(16) << 30);
+  if (((size_t)num_q + (size_t)num_g) * (size_t)dim * 2 > (size_t(16) << 30)) return false;
+  if (opt > 0) return true;  // forced (tests, A/B runs)
+  const int want = k + 16;
+  const int cap = want <= 16 ? 16 : want <= 32 ? 32 : want <= 64 ? 64 : 128;
+  return cap >= 2 * k && 2.0 * (double)dim * (double)num_q * (double)num_g >= 4e11;
 }
 
 TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int want_rank) {
   TopkLayout L{};
-  L.sel_bf16 = select_on_bf16(num_q, num_g, dim, dtype);
+  L.sel_bf16 = select_on_bf16(num_q, num_g, dim, k, dtype);
   // fp32 embeddings keep their wider candidate slack (k + 16) whichever tensor path selects them
   L.plan = topk_primary_plan(num_q, num_g, dim, k, dtype, 0);
   // 3xTF32 escalation copies ([rows, 3·dim] fp32) — only when they stay below 12 GiB
@@ -138,7 +148,7 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
 }  // namespace
 
 K1Plan topk_primary_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms) {
-  const bool sel = select_on_bf16(num_q, num_g, dim, dtype);
+  const bool sel = select_on_bf16(num_q, num_g, dim, k, dtype);
   return make_k1_plan(num_q, num_g, dim, k, sel ? SBIR_BF16 : dtype, num_sms > 0 ? num_sms : num_sms_cached(),
                       dtype == SBIR_F32 ? 16 : 6);
 }
@@ -541,13 +551,16 @@ int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, const 
                    static_cast<cudaStream_t>(stream));
 }
 
-int sbir_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
-                    float* out_dist, int64_t* out_index, void* stream) {
-  if (num_lists < 0 || num_q < 0 || k <= 0) return SBIR_ERR_INVALID_ARG;
+int sbir_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t list_stride_dist, int64_t list_stride_index,
+                    int64_t num_q, int k, float* out_dist, int64_t* out_index, void* stream) {
+  if (num_lists < 0 || num_q < 0 || k <= 0 || list_stride_dist < 0 || list_stride_index < 0) return SBIR_ERR_INVALID_ARG;
+  if ((list_stride_dist > 0 && list_stride_dist < num_q * k) || (list_stride_index > 0 && list_stride_index < num_q * k))
+    return SBIR_ERR_INVALID_ARG;
   if (num_q == 0) return SBIR_OK;
   if (out_dist == nullptr || out_index == nullptr) return SBIR_ERR_INVALID_ARG;
   if (num_lists > 0 && (dist == nullptr || index == nullptr)) return SBIR_ERR_INVALID_ARG;
-  return launch_topk_merge(dist, index, num_lists, num_q, k, out_dist, out_index, static_cast<cudaStream_t>(stream));
+  return launch_topk_merge(dist, index, num_lists, num_q, k, out_dist, out_index, static_cast<cudaStream_t>(stream), list_stride_dist,
+                           list_stride_index);
 }
 
 int sbir_retrieval_metrics(const int64_t* rank0, int64_t num_q, int k, double* out, void* stream) {
@@ -612,9 +625,10 @@ int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   if (num_q <= 0 || num_g <= 0 || dim <= 0 || k <= 0 || k > kMaxK || !dtype_ok(dtype) || num_sms <= 0 || out == nullptr)
     return SBIR_ERR_INVALID_ARG;
   const K1Plan p = topk_primary_plan(num_q, num_g, dim, k, dtype, num_sms);
-  const int32_t v[12] = {p.cap, p.lists_per_row, p.num_q_tiles, p.num_g_tiles, p.num_splits, p.tiles_per_split,
-                         p.num_chunks, p.tiles_per_chunk, p.num_units, p.part_fastest, p.pair, p.q_tile_stride};
-  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  const int32_t v[13] = {p.cap, p.lists_per_row, p.num_q_tiles, p.num_g_tiles, p.num_splits, p.tiles_per_split,
+                         p.num_chunks, p.tiles_per_chunk, p.num_units, p.part_fastest, p.pair, p.q_tile_stride,
+                         (dtype == SBIR_BF16 || select_on_bf16(num_q, num_g, dim, k, dtype)) ? 1 : 0};
+  for (int i = 0; i < 13; ++i) out[i] = v[i];
   return SBIR_OK;
 }
 

@@ -399,8 +399,8 @@ __device__ __forceinline__ bool merge_before(float da, float db, const long long
 __device__ __forceinline__ int small_div(int x, float inv_d) { return __float2int_rz(((float)x + 0.5f) * inv_d); }
 
 __global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(
-    const float* __restrict__ dist, const long long* __restrict__ index, int num_lists, int num_q,
-    int k, int qb, float* __restrict__ out_dist, long long* __restrict__ out_index) {
+    const float* __restrict__ dist, const long long* __restrict__ index, int num_lists, size_t stride_d, size_t stride_i,
+    int num_q, int k, int qb, float* __restrict__ out_dist, long long* __restrict__ out_index) {
   extern __shared__ __align__(16) uint8_t merge_smem[];
   const int half_lists = (num_lists + 1) / 2;
   // ping [qb][num_lists][k], pong [qb][half_lists][k]; indices first (8-byte aligned), then distances
@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(
     const size_t src = (size_t)q0 * k + x;
 #pragma unroll 4
     for (int l = 0; l < num_lists; ++l) {
-      d_ping[dst + l * k] = __ldg(dist + (size_t)l * num_q * k + src);
-      i_ping[dst + l * k] = __ldg(index + (size_t)l * num_q * k + src);
+      d_ping[dst + l * k] = __ldg(dist + (size_t)l * stride_d + src);
+      i_ping[dst + l * k] = __ldg(index + (size_t)l * stride_i + src);
     }
   }
   __syncthreads();
@@ -476,27 +476,26 @@ __global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(
 // one warp per query, binary searches straight in global memory.
 constexpr int kMergeWarps = 4;
 __global__ void __launch_bounds__(kMergeWarps * 32) topk_merge_generic_kernel(
-    const float* __restrict__ dist, const long long* __restrict__ index, int num_lists, int num_q,
-    int k, float* __restrict__ out_dist, long long* __restrict__ out_index) {
+    const float* __restrict__ dist, const long long* __restrict__ index, int num_lists, size_t stride_d, size_t stride_i,
+    int num_q, int k, float* __restrict__ out_dist, long long* __restrict__ out_index) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * kMergeWarps + (threadIdx.x >> 5);
   if (q >= num_q) return;
   const int total = num_lists * k;
   for (int x = lane; x < total; x += 32) {
     const int l = x / k, i = x % k;
-    const size_t base = ((size_t)l * num_q + q) * k;
-    const float dx = dist[base + i];
-    const long long ix = index[base + i];
+    const float dx = dist[(size_t)l * stride_d + (size_t)q * k + i];
+    const long long ix = index[(size_t)l * stride_i + (size_t)q * k + i];
     if (ix < 0) continue;
     int pos = i;
     for (int l2 = 0; l2 < num_lists; ++l2) {
       if (l2 == l) continue;
-      const size_t b2 = ((size_t)l2 * num_q + q) * k;
+      const size_t b2d = (size_t)l2 * stride_d + (size_t)q * k, b2i = (size_t)l2 * stride_i + (size_t)q * k;
       int lo = 0, hi = k;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const float dm = dist[b2 + mid];
-        const long long im = index[b2 + mid];
+        const float dm = dist[b2d + mid];
+        const long long im = index[b2i + mid];
         const bool before = im >= 0 && (dm < dx || (dm == dx && im < ix));
         if (before) lo = mid + 1; else hi = mid;
       }
@@ -907,8 +906,10 @@ int launch_positive_distance(const void* q, int64_t num_q, const void* g, int64_
 }
 
 int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
-                      float* out_dist, int64_t* out_index, cudaStream_t st) {
+                      float* out_dist, int64_t* out_index, cudaStream_t st, int64_t list_stride_dist, int64_t list_stride_index) {
   if (num_q <= 0 || k <= 0) return SBIR_OK;
+  const size_t stride_d = list_stride_dist > 0 ? (size_t)list_stride_dist : (size_t)num_q * k;
+  const size_t stride_i = list_stride_index > 0 ? (size_t)list_stride_index : (size_t)num_q * k;
   const size_t n = (size_t)num_q * k;
   const size_t per_q = ((size_t)num_lists + (num_lists + 1) / 2) * k * 12;  // gathered lists + one round of merged lists
   if (num_lists > 0 && per_q <= 96 * 1024) {
@@ -921,7 +922,7 @@ int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, in
       SBIR_CUDA_TRY(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((num_q + qb - 1) / qb);
     topk_merge_kernel<<<grid, kMergeThreads, smem, st>>>(dist, reinterpret_cast<const long long*>(index), num_lists,
-                                                         (int)num_q, k, qb, out_dist,
+                                                         stride_d, stride_i, (int)num_q, k, qb, out_dist,
                                                          reinterpret_cast<long long*>(out_index));
     SBIR_CHECK_LAUNCH();
     return SBIR_OK;
@@ -931,7 +932,7 @@ int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, in
   if (num_lists <= 0) return SBIR_OK;
   const unsigned grid = (unsigned)((num_q + kMergeWarps - 1) / kMergeWarps);
   topk_merge_generic_kernel<<<grid, kMergeWarps * 32, 0, st>>>(dist, reinterpret_cast<const long long*>(index), num_lists,
-                                                               (int)num_q, k, out_dist,
+                                                               stride_d, stride_i, (int)num_q, k, out_dist,
                                                                reinterpret_cast<long long*>(out_index));
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;

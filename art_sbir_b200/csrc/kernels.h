@@ -12,7 +12,7 @@ struct DebugOptions {
   int k1_feed = -1;               // owner+feeder epilogue for 64/128-entry lists: -1 auto, 0 off
   int k1_pair = 0;                // CTA pairs: 0 auto, 1 never, 2 always
   int k1_qres = -1;               // resident-query form: -1 auto, 0 off
-  int k1_sel_bf16 = -1;           // fp32 embeddings selected on bf16 copies (kind::f16): -1 auto, 0 off (kind::tf32)
+  int k1_sel_bf16 = -1;           // fp32 embeddings selected on bf16 copies (kind::f16): -1 auto, 0 never (kind::tf32), 1 always
   int k1_chunk_mb = 0;            // gallery bytes per chunk step (MB): 0 auto
   int k1_flags = 0;               // diagnostic bits, honoured by -DSBIR_DIAG builds only
   long long host_chunk_rows = 0;  // upload chunk of the host-buffer entry points (rows): 0 auto
@@ -191,8 +191,10 @@ int launch_center_split_tf32(const float* x, int64_t rows, int64_t rows_padded, 
 int launch_positive_distance(const void* q, int64_t num_q, const void* g, int64_t num_g, int64_t dim,
                              int dtype, int metric, const int64_t* pos_index, double* out,
                              cudaStream_t st);
+// list l starts at dist + l·list_stride_dist / index + l·list_stride_index (elements; 0 = dense, num_q·k)
 int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
-                      float* out_dist, int64_t* out_index, cudaStream_t st);
+                      float* out_dist, int64_t* out_index, cudaStream_t st, int64_t list_stride_dist = 0,
+                      int64_t list_stride_index = 0);
 int launch_fill_i32(int32_t* out, int64_t n, int32_t value, cudaStream_t st);
 int launch_fill_i64(int64_t* out, int64_t n, int64_t value, cudaStream_t st);
 int launch_retrieval_metrics(const int64_t* rank0, int64_t num_q, int k, double* out, cudaStream_t st);

@@ -282,13 +282,27 @@ def pairwise_topk_shard(queries, gallery_shard, k, loss_type, index_offset, pos_
 
 
 def topk_merge(dist: torch.Tensor, index: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Merge [L, Q, k] ascending lists into the k best per query (K4)."""
-    dist, index = _dev(dist.float(), "dist"), _dev(index.to(torch.int64), "index")
+    """Merge [L, Q, k] ascending lists into the k best per query (K4).  The L lists may be views into a
+    larger buffer (e.g. the packed all-gather messages of sharded._exchange): only each [Q, k] block must be
+    dense; the list stride is passed to the kernel, nothing is copied."""
+    if dist.dtype != torch.float32 or index.dtype != torch.int64:
+        dist, index = dist.float(), index.to(torch.int64)
+    if not dist.is_cuda or not index.is_cuda:
+        raise RuntimeError("topk_merge takes CUDA tensors: the sbir_b200 path has no CPU fallback")
     L, nq, k = dist.shape
+
+    def dense_blocks(t):
+        return t.stride(2) == 1 and t.stride(1) == k and (L <= 1 or t.stride(0) >= nq * k)
+    if not dense_blocks(dist):
+        dist = dist.contiguous()
+    if not dense_blocks(index):
+        index = index.contiguous()
+    sd = dist.stride(0) if L > 1 else 0
+    si = index.stride(0) if L > 1 else 0
     out_d = torch.empty((nq, k), dtype=torch.float32, device=dist.device)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=dist.device)
     with torch.cuda.device(dist.device):
-        B.check(B.load().sbir_topk_merge(dist.data_ptr(), index.data_ptr(), L, nq, k, out_d.data_ptr(),
+        B.check(B.load().sbir_topk_merge(dist.data_ptr(), index.data_ptr(), L, sd, si, nq, k, out_d.data_ptr(),
                                          out_i.data_ptr(), _stream()), "sbir_topk_merge")
     return out_d, out_i
 

@@ -6,9 +6,8 @@ exchange step:
 
     d(q, pos)      owner shard computes it, all-reduce(sum) of (value, has) pairs  [Q] fp64
     local K1       per-shard top-k with global indices + local count(d < d_pos)
-    all-gather     [Q, k] (dist, index) per shard            — Q·k·12 bytes per rank
-    all-reduce     int64 [Q] counts (sum)
-    K4 merge       k best of the P·k gathered candidates, ties by global index
+    all-gather     ONE packed message per rank: [Q,k] dist + [Q,k] index + [Q] count — Q·(12k + 8) bytes
+    K4 merge       k best of the P·k gathered candidates, ties by global index; counts summed locally
 
 so the result is identical to the single-GPU result for any number of shards.
 """
@@ -92,20 +91,35 @@ def sharded_pairwise_topk(queries: torch.Tensor, gallery_shard: torch.Tensor, k:
 
 
 def _exchange(vals, idx, cnt, pos_dist, num_gallery_total, world, group, merge_fn):
-    """The path's one exchange step: all-gather of the per-shard lists + K4 merge, all-reduce of the counts."""
+    """The path's one exchange step.  Every rank contributes ONE packed message — its [Q,k] distances (fp32),
+    [Q,k] global indices (int64) and [Q] local counts (int64), Q·(12k + 8) bytes — to ONE all-gather; the
+    gathered buffer is read in place by K4 (views of the [world, Q, k] blocks) and the counts are summed
+    locally.  (Round 1 issued two all-gathers and an all-reduce here; with ≤ 13 MB per rank the step is
+    latency-bound, so the number of collectives is what matters.)"""
     if world > 1:
-        # gathered straight into the [world, Q, k] layout K4 reads (no per-rank list, no stack copy)
-        all_vals = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
-        all_idx = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
+        nq, k = vals.shape
+        dev = vals.device
+        has_cnt = cnt is not None
+        nbytes = nq * k * 12 + (nq * 8 if has_cnt else 0)
+        nbytes_pad = (nbytes + 15) // 16 * 16
+        # int64 indices first (8-byte aligned views), then the counts, then the fp32 distances
+        mine = torch.empty(nbytes_pad, dtype=torch.uint8, device=dev)
+        o_idx, o_cnt, o_val = 0, nq * k * 8, nq * k * 8 + (nq * 8 if has_cnt else 0)
+        mine[o_idx:o_idx + nq * k * 8].view(torch.int64).copy_(idx.reshape(-1))
+        if has_cnt:
+            mine[o_cnt:o_cnt + nq * 8].view(torch.int64).copy_(cnt)
+        mine[o_val:o_val + nq * k * 4].view(torch.float32).copy_(vals.reshape(-1))
+        gathered = torch.empty((world, nbytes_pad), dtype=torch.uint8, device=dev)
         if dist.get_backend(group) == "nccl":
-            dist.all_gather_into_tensor(all_vals, vals.contiguous(), group=group)
-            dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=group)
+            dist.all_gather_into_tensor(gathered, mine, group=group)
         else:  # gloo (CPU tests of the plumbing): list form
-            dist.all_gather(list(all_vals.unbind(0)), vals.contiguous(), group=group)
-            dist.all_gather(list(all_idx.unbind(0)), idx.contiguous(), group=group)
+            dist.all_gather(list(gathered.unbind(0)), mine, group=group)
+        # strided [world, Q, k] views of the gathered messages (list stride = message size): K4 reads them in place
+        all_idx = gathered[:, o_idx:o_idx + nq * k * 8].view(torch.int64).unflatten(1, (nq, k))
+        all_vals = gathered[:, o_val:o_val + nq * k * 4].view(torch.float32).unflatten(1, (nq, k))
         vals, idx = merge_fn(all_vals, all_idx)
-        if cnt is not None:
-            dist.all_reduce(cnt, group=group)
+        if has_cnt:
+            cnt = gathered[:, o_cnt:o_cnt + nq * 8].view(torch.int64).sum(dim=0)
     rank_out = None
     if pos_dist is not None:
         rank_out = torch.where(pos_dist != pos_dist, torch.full_like(cnt, num_gallery_total), cnt)

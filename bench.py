@@ -319,12 +319,20 @@ def time_retrieval(step, steps, warmup, barrier, lib, dev, flush, sampler=None):
     return ms_total / steps, k1_ms.value / max(1, steps), int(launches.value), out, clocks
 
 
-def k1_roofline(dim, num_q, rows, dtype_is_bf16, k1_ms, ms_per_step, peaks, tf32_peak, traffic=None):
+def tiles_are_bf16(lib, num_q, num_g, dim, k, dtype_is_bf16):
+    """Element type the distance kernel's tensor-core tiles read for this problem (bf16 embeddings, or fp32
+    embeddings selected on their bf16 copies — sbir_debug_plan out[12]): decides which measured peak applies."""
+    out = (ctypes.c_int32 * 13)()
+    lib.sbir_debug_plan(num_q, num_g, dim, k, 1 if dtype_is_bf16 else 0, 148, out)
+    return bool(out[12])
+
+
+def k1_roofline(dim, num_q, rows, tile_bf16, k1_ms, ms_per_step, peaks, tf32_peak, traffic=None):
     flops = 2.0 * dim * num_q * rows
     achieved = flops / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else None
-    if dtype_is_bf16:
+    if tile_bf16:
         peak = peaks["bf16_sustained"] if k1_ms > 100 else peaks["bf16"]
-        note = ("bf16 dense, sustained, " if k1_ms > 100 else "bf16 dense, burst, ") + peaks["source"]
+        note = ("bf16 dense (kind::f16 tiles), sustained, " if k1_ms > 100 else "bf16 dense (kind::f16 tiles), burst, ") + peaks["source"]
         burst = peaks["bf16"]
     else:
         peak = burst = tf32_peak
@@ -399,11 +407,12 @@ def extra_retrieval_workload(name, lib, dev, local_rank, peaks, tf32_peak, centr
     ms, k1_ms, launches, out, clocks = time_retrieval(step, steps, 3, barrier, lib, dev, flush, sampler)
     vals, idx, rank0, unc = out
     res = {"workload": name, "description": desc, "num_q": num_q, "num_g": num_g, "dim": dim, "k": k,
-           "dtype": "bf16" if dtype == torch.bfloat16 else "tf32 (fp32 in, fp32 accumulate, exact fp32/fp64 re-score)",
+           "dtype": "bf16" if dtype == torch.bfloat16 else "f32 (selected on tensor-core tiles, exact fp32/fp64 re-score)",
            "steps": steps, "ms_per_step": ms, "value": num_q * num_g / (ms * 1e-3), "unit": "pairs/s",
            "l2": "inputs larger than L2" if flush is None else "L2 flushed (512 MiB write) between timed steps",
            "gpu_launches_per_step": launches / steps,
-           "roofline": k1_roofline(dim, num_q, num_g, dtype == torch.bfloat16, k1_ms, ms, peaks, tf32_peak),
+           "tensor_tiles": "bf16 (kind::f16)" if tiles_are_bf16(lib, num_q, num_g, dim, k, dtype == torch.bfloat16) else "tf32 (kind::tf32)",
+           "roofline": k1_roofline(dim, num_q, num_g, tiles_are_bf16(lib, num_q, num_g, dim, k, dtype == torch.bfloat16), k1_ms, ms, peaks, tf32_peak),
            "clocks": clocks, "uncertified_queries": int(unc.item()),
            **{f"recall@{kk}": float((rank0 < kk).float().mean().item()) for kk in (1, 5, 10)},
            "parity": sampled_parity(Q, G, pos, 0, k, vals, idx, rank0, 1, None)}
@@ -569,8 +578,6 @@ def main():
             if name != args.workload:
                 extras.append(extra_retrieval_workload(name, lib, dev, local_rank, peaks, tf32_peak, args.centroids))
         extras.append(cfg2_workload(lib, dev, local_rank))
-    elif dtype != torch.bfloat16:
-        tf32_peak = measure_tf32_peak(dev)
 
     # ---- e2e: pinned host buffers → C ABI / sharded API → host results ----
     e2e = None
@@ -626,7 +633,10 @@ def main():
     # ncu capture of the single-GPU launch of this workload (profiles/); per-rank launches at N > 1
     # cover a shard and were not captured separately
     traffic = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch") if (traffic_file.is_file() and world == 1) else None
-    roofline = k1_roofline(dim, num_q, r1 - r0, dtype == torch.bfloat16, k1_ms_per_launch, ms_per_step, peaks, tf32_peak, traffic)
+    tile_bf16 = tiles_are_bf16(lib, num_q, r1 - r0, dim, k, dtype == torch.bfloat16)
+    if not tile_bf16 and tf32_peak is None:
+        tf32_peak = measure_tf32_peak(dev)
+    roofline = k1_roofline(dim, num_q, r1 - r0, tile_bf16, k1_ms_per_launch, ms_per_step, peaks, tf32_peak, traffic)
 
     cpu = None
     if not args.no_cpu:
@@ -639,7 +649,7 @@ def main():
     line = {"metric": "query x gallery pairs/sec (distance + top-%d + rank)" % k, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16" if dtype == torch.bfloat16 else "tf32 (fp32 in, fp32 accumulate, exact fp32/fp64 re-score)",
+            "dtype": "bf16" if dtype == torch.bfloat16 else "f32 (selected on tensor-core tiles, exact fp32/fp64 re-score)",
             "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "num_q": num_q, "num_g": num_g, "dim": dim, "k": k,
                        "sharding": f"gallery rows over {world} GPU(s)", "l2": "inputs larger than L2" if flush is None else "L2 flushed (512 MiB write) between timed steps",

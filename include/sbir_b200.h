@@ -142,10 +142,13 @@ int sbir_pairwise_topk_shard(const void* q, int64_t num_q, const void* g, const 
                              void* stream);
 
 /* ---- K4: merge of per-shard top-K lists (after the NCCL all-gather) ---------
- * dist/index are [num_lists, num_q, k], each list ascending; writes the k smallest
+ * dist/index hold num_lists lists of [num_q, k], each ascending; list l starts at
+ * dist + l*list_stride_dist and index + l*list_stride_index (in elements; 0 = dense, num_q*k), so the
+ * packed per-rank messages of ONE all-gather are merged where they landed.  Writes the k smallest
  * of the union per query, ascending, ties by ascending index. */
-int sbir_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t num_q, int k,
-                    float* out_dist, int64_t* out_index, void* stream);
+int sbir_topk_merge(const float* dist, const int64_t* index, int num_lists, int64_t list_stride_dist,
+                    int64_t list_stride_index, int64_t num_q, int k, float* out_dist, int64_t* out_index,
+                    void* stream);
 
 /* ---- H5: retrieval metrics (inference.py:95-98,113-134) ---------------------
  * rank0 is the 0-based rank per query.  Writes, as fp64:
@@ -221,15 +224,17 @@ int sbir_profile_collect(double* k1_ms_sum, int64_t* k1_launches, int64_t* kerne
  * tensor-core path in isolation.  out_e is fp32 [num_q, num_g]. */
 /* Process-wide tuning / test switches — the library never reads the environment on the launch path.
  * name ∈ { "k1_feed" (-1 auto | 0 off), "k1_pair" (0 auto | 1 single CTAs | 2 CTA pairs), "k1_qres" (-1 auto | 0 off),
+ *          "k1_sel_bf16" (fp32 embeddings selected on bf16 copies: -1 auto | 0 never | 1 always),
  *          "k1_chunk_mb" (0 auto), "host_chunk_rows" (0 auto), "watchdog_cycles" (device-side wait bound, default
  *          4e9, 0 = none: for compute-sanitizer / cuda-gdb), "k1_flags" (diagnostic bits, honoured only by a
  *          -DSBIR_DIAG build: sbir_debug_diag_build() == 1), "reset" (all defaults) }.
  * Set between calls, not while one is running.  Unknown names return SBIR_ERR_INVALID_ARG. */
 int sbir_debug_set_option(const char* name, int64_t value);
 int sbir_debug_diag_build(void);
-/* Host-only: the work decomposition K1 would use (no device access).  out[12] = {cap,
+/* Host-only: the work decomposition K1 would use (no device access).  out[13] = {cap,
  * lists_per_row, num_q_tiles, num_g_tiles, num_partitions, tiles_per_partition, num_chunks,
- * tiles_per_chunk, num_units, part_fastest, pair, q_tile_stride}. */
+ * tiles_per_chunk, num_units, part_fastest, pair, q_tile_stride, tile_dtype (1: the tensor-core tiles read bf16 —
+ * bf16 embeddings, or fp32 embeddings selected on their bf16 copies; 0: kind::tf32 on fp32)}. */
 int sbir_debug_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms, int32_t* out);
 /* Profiling aid (-DSBIR_DIAG builds): when option k1_flags has bit 64 set, the distance kernel
  * records per CTA (8 uint64 each, 148 CTAs) the cycles its MMA issuer waited for a free

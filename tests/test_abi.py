@@ -93,7 +93,7 @@ def test_launch_path_reads_no_environment_variables():
 
 
 def test_debug_options_change_the_plan_and_reset(sbir_lib):
-    out = (ctypes.c_int32 * 12)()
+    out = (ctypes.c_int32 * 13)()
     from art_sbir_b200 import _binding
     try:
         assert sbir_lib.sbir_debug_plan(100_000, 10_000_000, 512, 10, 1, 148, out) == 0

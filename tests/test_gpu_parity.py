@@ -319,6 +319,46 @@ def test_resident_query_form_matches_default_kernel(ops, dbg):
         assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(r0, r1)
 
 
+@pytest.mark.parametrize("nq,ng,d,lt,k", [(130, 1000, 512, "euclidean", 1), (200, 2500, 1024, "cosine", 10), (64, 1500, 2048, "euclidean", 30),
+                                           (300, 5000, 96, "euclidean", 10), (1000, 20000, 192, "cosine", 20), (37, 300, 64, "euclidean", 100)])
+def test_fp32_selected_on_bf16_copies_matches_tf32_selection_and_oracle(ops, dbg, nq, ng, d, lt, k):
+    """fp32 embeddings selected on their bf16-rounded copies (kind::f16 tiles at twice the kind::tf32 rate; certificate
+    and rank band from measured rounding residuals).  Large problems take this path on their own; here it is forced
+    on small shapes: results must be bit-identical to the kind::tf32 selection (both are re-scored exactly) and
+    match the oracle — including k = 100 on a tiny gallery, where the wider band cannot be certified and the
+    escalation / brute-force fallbacks have to deliver the exact answer."""
+    Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=nq + ng + 1, beta=0.3 if d < 512 else None, num_classes=max(4, ng // 80))
+    pos[::7] = -1
+    q, g, p = Q.cuda(), G.cuda(), pos.cuda()
+    dbg("k1_sel_bf16", 0)
+    v0, i0, r0, u0 = ops.pairwise_topk(q, g, k, lt, pos_index=p, return_uncertified=True)
+    dbg("k1_sel_bf16", 1)
+    v1, i1, r1, u1 = ops.pairwise_topk(q, g, k, lt, pos_index=p, return_uncertified=True)
+    assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(r0, r1)
+    ref_v, ref_i = O.pairwise_topk_batched(Q, G, k, lt)
+    dist_rows = [O.distances(Q[i:i + 1], G, lt) for i in range(nq)]
+    assert_topk_matches(v1, i1, ref_v, ref_i, dist_rows)
+    assert_ranks_match_up_to_fp32_ties(r1, Q, G, pos, lt)
+    if k <= 30:
+        assert int(u1.item()) <= nq // 50 + 4                 # lists with room for the bf16 band certify (almost) everything
+
+
+def test_fp32_bf16_selection_on_collapsed_embeddings(ops, dbg):
+    """Forced bf16 selection on embeddings with a large common component: the measured residual norms make the band
+    cover everything, nothing certifies, and the centred 3xTF32 escalation pass must still produce exact results."""
+    nq, ng, d = 200, 8000, 256
+    Q0, G0, pos = O.synthetic_embeddings(nq, ng, d, seed=9, beta=0.12)
+    base = 3.0 * torch.rand(1, d, generator=torch.Generator().manual_seed(1))
+    Q, G = (base + 0.02 * Q0).contiguous(), (base + 0.02 * G0).contiguous()
+    dbg("k1_sel_bf16", 0)
+    want = ops.pairwise_topk(Q.cuda(), G.cuda(), 10, "euclidean", pos_index=pos.cuda())
+    dbg("k1_sel_bf16", 1)
+    got = ops.pairwise_topk(Q.cuda(), G.cuda(), 10, "euclidean", pos_index=pos.cuda(), return_uncertified=True)
+    for a, b in zip(want, got[:3]):
+        assert torch.equal(a, b)
+    assert int(got[3].item()) <= nq // 50 + 4
+
+
 def test_cancellation_heavy_fp32_escalates_to_3xtf32(ops):
     """Embeddings whose norms dwarf their distances (post-ReLU-like: a large common component) and
     positives unrelated to the queries: the TF32 error band covers much of the distance
@@ -804,7 +844,8 @@ def _device_clustered(nq, ng, d, dtype, seed=1234):
 
 
 @pytest.mark.parametrize("nq,ng,d,dtype,k", [(1000, 10000, 2048, torch.float32, 10),      # BASELINE cfg1
-                                              (12500, 75000, 2048, torch.float32, 100),    # BASELINE cfg3
+                                              (12500, 75000, 2048, torch.float32, 100),    # BASELINE cfg3 (kind::tf32 tiles)
+                                              (12500, 75000, 2048, torch.float32, 10),     # cfg3 shape, top-10: fp32 selected on bf16 copies
                                               (4096, 400000, 512, torch.bfloat16, 10)])    # cfg4-shaped slice
 def test_full_size_properties(ops, nq, ng, d, dtype, k):
     Q, G, pos = _device_clustered(nq, ng, d, dtype)

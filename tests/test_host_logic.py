@@ -104,14 +104,14 @@ def test_shard_bounds_partition_the_gallery():
 
 def _plan(lib, nq, ng, d, k, dtype, sms=148):
     import ctypes
-    out = (ctypes.c_int32 * 12)()
+    out = (ctypes.c_int32 * 13)()
     assert lib.sbir_debug_plan(nq, ng, d, k, dtype, sms, out) == 0
     keys = ("cap", "lists", "q_tiles", "g_tiles", "parts", "tiles_per_part", "chunks", "tiles_per_chunk", "units",
-            "part_fastest", "pair", "q_tile_stride")
+            "part_fastest", "pair", "q_tile_stride", "tile_bf16")
     return dict(zip(keys, list(out)))
 
 
-@pytest.mark.parametrize("sel_bf16", [-1, 0])
+@pytest.mark.parametrize("sel_bf16", [-1, 0, 1])
 @pytest.mark.parametrize("nq,ng,d,k,dtype", [
     (100_000, 10_000_000, 512, 10, 1), (12_500, 75_000, 2048, 100, 0), (12_500, 75_000, 2048, 10, 0),
     (1_000, 10_000, 2048, 10, 0), (1, 513, 1024, 10, 0), (300, 9001, 512, 10, 1), (5, 7, 64, 3, 0),
@@ -129,7 +129,11 @@ def test_k1_plan_covers_every_tile_exactly_once(sbir_lib, nq, ng, d, k, dtype, s
         ws = sbir_lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, dtype, 0, 1)
     finally:
         _binding.set_debug_option("reset")
-    tiles_bf16 = dtype == 1 or (sel_bf16 != 0 and d % 8 == 0)          # element type the tensor-core tiles read
+    # element type the tensor-core tiles read: fp32 embeddings go through bf16 selection copies when forced, or
+    # (auto) when the lists have room for the wider rounding band (capacity >= 2k) and the problem is not launch-bound
+    auto = p["cap"] >= 2 * k and 2.0 * d * nq * ng >= 4e11
+    tiles_bf16 = dtype == 1 or (d % 8 == 0 and (sel_bf16 == 1 or (sel_bf16 == -1 and auto)))
+    assert p["tile_bf16"] == int(tiles_bf16)
     assert p["q_tiles"] == -(-nq // 128) and p["g_tiles"] == -(-ng // 256)
     slack = 6 if dtype == 1 else 16
     assert p["cap"] in (16, 32, 64, 128) and p["cap"] >= min(k + slack, 128) and p["cap"] * p["lists"] * p["parts"] <= 4096

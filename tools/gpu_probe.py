@@ -256,7 +256,7 @@ def case_sel():
     out = []
     for shape in ((12500, 75000, 2048, 10), (12500, 75000, 2048, 100), (12500, 75000, 2048, 30), (1000, 10000, 2048, 10),
                   (20000, 200000, 1024, 10), (20000, 200000, 1024, 100), (20000, 1000000, 512, 10)):
-        for sel in (0, -1):
+        for sel in (0, 1):
             B_set("k1_sel_bf16", sel)
             r = _time_topk(shape[0], shape[1], shape[2], "float32", shape[3], rank=True)
             r["sel_bf16"] = sel
@@ -602,7 +602,7 @@ def case_small():
         d = torch.sort(torch.rand(lists, nq, k, device="cuda"), dim=2).values.contiguous()
         i = torch.randint(0, 10_000_000, (lists, nq, k), device="cuda")
         od, oi = torch.empty(nq, k, device="cuda"), torch.empty(nq, k, dtype=torch.int64, device="cuda")
-        us = _graph_us(lambda: B.check(lib.sbir_topk_merge(d.data_ptr(), i.data_ptr(), lists, nq, k, od.data_ptr(), oi.data_ptr(), st()), "merge"))
+        us = _graph_us(lambda: B.check(lib.sbir_topk_merge(d.data_ptr(), i.data_ptr(), lists, 0, 0, nq, k, od.data_ptr(), oi.data_ptr(), st()), "merge"))
         res[f"topk_merge {lists}x{nq}x{k}"] = {"us": us, "GB/s": (d.numel() * 12 + nq * k * 12) / us / 1e3}
     a, p, n = (torch.randn(256, 2048, device="cuda") for _ in range(3))
     loss, per_row = torch.empty((), device="cuda"), torch.empty(256, device="cuda")
@@ -618,7 +618,7 @@ def case_small():
                                                                        loss.data_ptr(), hard.data_ptr(), ga.data_ptr(), gp.data_ptr(), gn.data_ptr(),
                                                                        ws.data_ptr(), ws.numel(), st()), "batch_hard"))
         torch.cuda.synchronize()
-        tw = ws[-(8 + 8 * 512) * 8:].view(torch.int64).cpu()
+        tw = ws[-((8 + 8 * 512) * 8 + 255) // 256 * 256:].view(torch.int64).cpu()
         t = tw[:4].tolist()   # phase boundaries seen by CTA 0 (globaltimer ns)
         stg = tw[8:8 + 8 * 296].reshape(296, 8).double()
         stg = (stg - float(t[0])) / 1e3                          # per-CTA stage stamps, us after CTA 0's start
