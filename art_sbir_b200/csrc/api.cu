@@ -66,6 +66,15 @@ bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 // fp32 embeddings are selected on their bf16-rounded copies (kind::f16 tiles: twice the kind::tf32 rate; the
 // certificate uses measured rounding-residual norms, rowops.cu: convert_bf16_norm_kernel) when the copies fit
 // the workspace budget and bf16 rows satisfy TMA's 16-byte pitch.  Option k1_sel_bf16 = 0 keeps kind::tf32.
+// Rows whose byte length is not a multiple of 16 (TMA's pitch granularity; the reference accepts any width): the
+// tensor-core tiles then read zero-padded copies of the operands kept in the workspace (`kdim` columns), while every
+// exact kernel — norms, re-scoring, rank resolution, fallbacks — keeps reading the caller's rows.  Zero columns add
+// nothing to q·g or the norms, so the tiles compute the same values.
+int64_t tile_dim(int64_t dim, int dtype) {
+  const int64_t per16 = 16 / (int64_t)elem_size(dtype);
+  return (dim + per16 - 1) / per16 * per16;
+}
+
 // The bf16 rounding band is about twice kind::tf32's, so the candidate lists must have room for it: measured on
 // the clustered 12.5k x 75k x 2048 workload, k = 10 (32-entry lists) and k = 30 (64) certify every query and run
 // 6.1 -> 3.8 ms / 6.5 -> 4.3 ms, while k = 100 (128-entry lists, 28 entries of slack) leaves queries uncertified and
@@ -74,7 +83,7 @@ bool metric_ok(int m) { return m == SBIR_EUCLIDEAN || m == SBIR_COSINE; }
 bool select_on_bf16(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype) {
   const int opt = debug_options().k1_sel_bf16;
   if (dtype != SBIR_F32 || opt == 0) return false;
-  if (dim % 8 != 0 || num_g <= 0) return false;
+  if (dim % 8 != 0 || num_g <= 0) return false;  // (padded rows stay on their own element type)
   if (((size_t)num_q + (size_t)num_g) * (size_t)dim * 2 > (size_t(16) << 30)) return false;
   if (opt > 0) return true;  // forced (tests, A/B runs)
   const int want = k + 16;
@@ -84,14 +93,16 @@ bool select_on_bf16(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype)
 
 TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int want_rank) {
   TopkLayout L{};
+  L.kdim = tile_dim(dim, dtype);
+  L.padded_rows = L.kdim != dim;
   L.sel_bf16 = select_on_bf16(num_q, num_g, dim, k, dtype);
   // fp32 embeddings keep their wider candidate slack (k + 16) whichever tensor path selects them
   L.plan = topk_primary_plan(num_q, num_g, dim, k, dtype, 0);
   // 3xTF32 escalation copies ([rows, 3·dim] fp32) — only when they stay below 12 GiB
-  const size_t split_bytes = ((size_t)num_q + (size_t)num_g) * (size_t)dim * 3 * sizeof(float);
+  const size_t split_bytes = ((size_t)num_q + (size_t)num_g) * (size_t)L.kdim * 3 * sizeof(float);
   L.precise = dtype == SBIR_F32 && num_g > 0 && split_bytes <= (size_t(12) << 30);
   if (L.precise) {
-    L.plan3 = make_k1_plan(num_q, num_g, 3 * dim, k, dtype, num_sms_cached(), 16);
+    L.plan3 = make_k1_plan(num_q, num_g, 3 * L.kdim, k, dtype, num_sms_cached(), 16);
     // the escalation pass re-uses the candidate / list-state buffers: they are sized for the larger of the two
     // plans; the passes must agree on the per-list capacity (finalize's certificate compares like with like)
     L.precise = L.plan3.cap == L.plan.cap;
@@ -122,12 +133,16 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
     L.off_qres = take(nq * sizeof(float));
     L.off_gres = L.off_gmax + 16;  // the residual maxima share gmax's 256-byte block (cleared together)
   }
+  if (L.padded_rows) {
+    L.off_qpad = take((size_t)num_q * L.kdim * elem_size(dtype));
+    L.off_gpad = take((size_t)num_g * L.kdim * elem_size(dtype));
+  }
   if (L.precise) {
     L.off_gate = take(256);
-    L.off_q3 = take((size_t)num_q * dim * 3 * sizeof(float));
-    L.off_g3 = take((size_t)num_g * dim * 3 * sizeof(float));
-    L.off_mu = take((size_t)dim * sizeof(float));
-    L.off_colpart = take(col_mean_workspace_bytes(dim));
+    L.off_q3 = take((size_t)num_q * L.kdim * 3 * sizeof(float));
+    L.off_g3 = take((size_t)num_g * L.kdim * 3 * sizeof(float));
+    L.off_mu = take((size_t)L.kdim * sizeof(float));
+    L.off_colpart = take(col_mean_workspace_bytes(L.kdim));
   }
   if (want_rank) {
     L.off_pos_dist = take(nq * sizeof(double));
@@ -149,7 +164,7 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
 
 K1Plan topk_primary_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int num_sms) {
   const bool sel = select_on_bf16(num_q, num_g, dim, k, dtype);
-  return make_k1_plan(num_q, num_g, dim, k, sel ? SBIR_BF16 : dtype, num_sms > 0 ? num_sms : num_sms_cached(),
+  return make_k1_plan(num_q, num_g, tile_dim(dim, dtype), k, sel ? SBIR_BF16 : dtype, num_sms > 0 ? num_sms : num_sms_cached(),
                       dtype == SBIR_F32 ? 16 : 6);
 }
 
@@ -177,8 +192,11 @@ int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, co
   if (num_g > 0 && g == nullptr) return SBIR_ERR_INVALID_ARG;
   const bool want_rank = out_rank != nullptr && (pos_index != nullptr || pos_dist_in != nullptr);
   if (out_rank != nullptr && !want_rank) return SBIR_ERR_INVALID_ARG;
-  if ((dim * (int64_t)elem_size(dtype)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) % 16 != 0) return SBIR_ERR_UNSUPPORTED;
+  // rows of any width are accepted (odd widths go through zero-padded tile copies); only when the rows themselves
+  // are 16-byte multiples must the base pointers be 16-byte aligned too (TMA reads them in place)
+  if ((dim * (int64_t)elem_size(dtype)) % 16 == 0 && (reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) % 16 != 0)
+    return SBIR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) % elem_size(dtype) != 0) return SBIR_ERR_UNSUPPORTED;
 
   P.L = topk_layout(num_q, num_g, dim, k, dtype, want_rank ? 1 : 0);
   const TopkLayout& L = P.L;
@@ -252,8 +270,13 @@ int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, co
 
   // Pass 1 runs the tensor-core tiles on the embeddings as they are (bf16 -> kind::f16; fp32 -> kind::tf32), or —
   // fp32 embeddings, normally — on their bf16-rounded copies (kind::f16 at twice the rate; L.sel_bf16).
-  ka.gate = nullptr; ka.dim = dim;
+  ka.gate = nullptr; ka.dim = L.kdim;
   ra.gate = nullptr; fa.gate = nullptr;
+  P.kq = q; P.kg = g;  // what the tensor-core tiles (and the escalation pass's operand split) read
+  if (L.padded_rows) {
+    P.kq = ws + L.off_qpad; P.kg = ws + L.off_gpad;
+    SBIR_TRY(launch_pad_rows(q, num_q, dim, dtype, ws + L.off_qpad, L.kdim, st));
+  }
   SBIR_CUDA_TRY(cudaMemsetAsync(ws + L.off_gmax, 0, 256, st));  // gmax and, in the same 256-byte block, the bf16 residual maxima
   SBIR_TRY(launch_pass_reset(want_rank ? ra.cnt_less : nullptr, ra.dropped, num_q, want_rank ? ra.pool_count : nullptr,
                              ws + L.off_sched, L.sched_bytes, reinterpret_cast<int32_t*>(ws + L.off_shared_thr),
@@ -268,9 +291,9 @@ int topk_pass_begin(TopkPass& P, const void* q, int64_t num_q, const void* g, co
     SBIR_TRY(launch_convert_bf16_norm(static_cast<const float*>(q), num_q, num_q, dim, ws + L.off_qb, 0, 0.f, P.qsq, nullptr, qres,
                                       nullptr, st));
   } else {
-    const float kappa = k1_kappa(dtype, dim);
+    const float kappa = k1_kappa(dtype, L.kdim);
     ra.kappa = kappa; fa.kappa = kappa;
-    ka.q = q; ka.g = g;
+    ka.q = P.kq; ka.g = P.kg;
     SBIR_TRY(launch_row_norm(q, num_q, num_q, dim, dtype, 0, 0.f, P.qsq, nullptr, st));
   }
   return SBIR_OK;
@@ -295,6 +318,9 @@ int topk_pass_feed(TopkPass& P, int64_t row_end) {
   }
   const size_t row_bytes = (size_t)P.dim * elem_size(P.dtype);
   const int64_t pad_end = last ? P.padded : row_end;  // the padding rows of the last tile belong to the last feed
+  if (L.padded_rows)
+    SBIR_TRY(launch_pad_rows(static_cast<const uint8_t*>(P.g) + (size_t)row0 * row_bytes, row_end - row0, P.dim, P.dtype,
+                             P.ws + L.off_gpad + (size_t)row0 * L.kdim * elem_size(P.dtype), L.kdim, st));
   const int vec_mode = P.metric == SBIR_EUCLIDEAN ? 0 : 1;
   const float vec_pad = P.metric == SBIR_EUCLIDEAN ? INFINITY : nanf("");
   if (L.sel_bf16)  // fp32 rows -> bf16 selection operands + exact norms + rounding-residual maxima, one pass over the rows
@@ -356,8 +382,9 @@ int topk_pass_finish(TopkPass& P) {
   // operands split into TF32 hi/lo parts concatenated along K ([qh|qh|ql]·[gh|gl|gh] = 3xTF32,
   // error ~2^-20): same kernel, 3x the MMA work, far cheaper than brute-forcing every query.
   if (L.precise) {
-    const void* q = P.q;
-    const void* g = P.g;
+    const void* q = P.kq;      // zero-padded copies when the rows are not 16-byte multiples (kdim columns)
+    const void* g = P.kg;
+    const int64_t dim = L.kdim;
     const int metric = P.metric;
     float* gvec = P.gvec; float* gmax = P.gmax; float* gmin = P.gmin; float* qsq = P.qsq;
     const int64_t padded = P.padded;

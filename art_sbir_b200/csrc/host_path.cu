@@ -4,7 +4,7 @@
 // compute stream, so PCIe transfer overlaps the tensor-core work.  Normally the chunks are FED
 // to one retrieval pass (api.cu: topk_pass_begin / feed / finish): the distance kernel is launched
 // per uploaded chunk and continues the same candidate lists, so re-scoring, rank resolution and
-// list warm-up happen once, not once per chunk; the first chunk is small (128 MB, doubling up to
+// list warm-up happen once, not once per chunk; the first chunk is small (32 MB, doubling up to
 // 1 GiB) so that scoring starts early.  When the plan cuts the gallery into several partitions
 // (few queries) a multi-chunk gallery is scored chunk by chunk as shards and merged (K4).
 // Device / pinned staging buffers, streams and events are cached PER DEVICE and released by
@@ -171,7 +171,7 @@ static int retrieve_host_locked(const void* q_host, int64_t num_q, const void* g
     int64_t forced = 0;
     forced = debug_options().host_chunk_rows;  // test hook: small chunks
     const int64_t unit = granule > 0 ? granule : kTileG;
-    size_t target = granule > 0 ? (size_t(128) << 20) : (size_t(1) << 30);
+    size_t target = granule > 0 ? (size_t(32) << 20) : (size_t(1) << 30);
     int64_t next = 0;
     while (next < num_g) {
       int64_t rows = forced > 0 ? forced : (int64_t)(target / row_bytes);
@@ -375,7 +375,7 @@ static int retrieve_host_shard_locked(const void* q_dev, int64_t num_q, const vo
   }
   std::vector<int64_t> chunk_end;
   if (granule > 0) {
-    size_t target = size_t(128) << 20;
+    size_t target = size_t(32) << 20;
     if (debug_options().host_chunk_rows > 0) target = (size_t)debug_options().host_chunk_rows * row_bytes;  // test hook: small chunks
     int64_t next = 0;
     while (next < num_g) {

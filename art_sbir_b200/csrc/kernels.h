@@ -31,6 +31,8 @@ int launch_row_norm(const void* x, int64_t rows, int64_t rows_padded, int64_t di
 // max_sq and res_max ACCUMULATE (clear them before the first call).
 int launch_convert_bf16_norm(const float* x, int64_t rows, int64_t rows_padded, int64_t dim, void* y_bf16, int mode,
                              float pad_value, float* vec, float* max_sq, float* res_row, float* res_max, cudaStream_t st);
+// dst[r, 0:dim] = src[r, :], dst[r, dim:dim_pad] = 0 (rows whose byte length is not a 16-byte multiple, api.cu)
+int launch_pad_rows(const void* src, int64_t rows, int64_t dim, int dtype, void* dst, int64_t dim_pad, cudaStream_t st);
 // The same vector from stored ‖g‖² (gallery built by sbir_gallery_append / reloaded with its sidecar).
 int launch_gvec_from_sqnorm(const float* sqnorm, int64_t rows, int64_t rows_padded, int mode, float pad_value,
                             float* out, float* max_out, cudaStream_t st, bool accumulate_max = false);
@@ -205,6 +207,9 @@ struct TopkLayout {
   K1Plan plan;
   size_t off_gvec, off_gmax, off_qsq, off_cand_val, off_cand_idx, off_flags, off_uncert, off_shared_thr;
   size_t off_row_max, off_row_maxpos, off_sched, sched_bytes, off_gmin;
+  int64_t kdim;        // columns of the rows the tensor-core tiles read (dim rounded up to a 16-byte multiple)
+  bool padded_rows;    // kdim != dim: zero-padded operand copies at off_qpad / off_gpad
+  size_t off_qpad, off_gpad;
   bool sel_bf16;       // fp32 inputs selected on bf16-rounded copies (kind::f16 tiles) — off_qb / off_gb / off_qres / off_gres
   size_t off_qb, off_gb, off_qres, off_gres;
   bool precise;        // fp32 inputs small enough for the 3xTF32 escalation workspace
@@ -225,6 +230,8 @@ struct TopkPass {
   cudaStream_t st;
   const void* q;
   const void* g;
+  const void* kq;         // operands of the tensor-core tiles: q / g, or their zero-padded copies (TopkLayout::padded_rows)
+  const void* kg;
   const float* g_sqnorm;  // optional stored ‖g‖² of the gallery rows (else computed from the rows)
   int64_t num_q, num_g, dim, padded, fed_rows;
   int dtype, metric;

@@ -634,6 +634,29 @@ int launch_convert_bf16_norm(const float* x, int64_t rows, int64_t rows_padded, 
   return SBIR_OK;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) pad_rows_kernel(const T* __restrict__ src, long long rows, int dim, T* __restrict__ dst, int dim_pad) {
+  const long long n = rows * dim_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / dim_pad;
+    const int c = (int)(i - r * dim_pad);
+    dst[i] = c < dim ? src[r * dim + c] : T(0.f);
+  }
+}
+
+int launch_pad_rows(const void* src, int64_t rows, int64_t dim, int dtype, void* dst, int64_t dim_pad, cudaStream_t st) {
+  if (rows <= 0) return SBIR_OK;
+  long long blocks = ((long long)rows * dim_pad + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (dtype == SBIR_F32)
+    pad_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, (long long)rows, (int)dim, (float*)dst, (int)dim_pad);
+  else
+    pad_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)src, (long long)rows, (int)dim,
+                                                                     (__nv_bfloat16*)dst, (int)dim_pad);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
 int launch_gvec_from_sqnorm(const float* sqnorm, int64_t rows, int64_t rows_padded, int mode, float pad_value,
                             float* out, float* max_out, cudaStream_t st, bool accumulate_max) {
   if (rows_padded <= 0) return SBIR_OK;
