@@ -185,8 +185,6 @@ static int retrieve_host_locked(const void* q_host, int64_t num_q, const void* g
   }
   const int num_chunks = (int)chunk_end.size();
   const bool streamed = granule > 0 || num_chunks == 1;  // one pass fed chunk by chunk (or all at once)
-  int64_t max_rows = 0;
-  for (int c = 0; c < num_chunks; ++c) max_rows = std::max(max_rows, chunk_end[c] - (c ? chunk_end[c - 1] : 0));
 
   // Device layout: Q | G (whole gallery, chunks land in place) | gathered positives |
   // per-chunk top-k lists (shard mode) | merged outputs | rank accumulators | workspace.
@@ -209,9 +207,16 @@ static int retrieve_host_locked(const void* q_host, int64_t num_q, const void* g
     off_rank = take((size_t)num_q * sizeof(int64_t));
     off_cnt = take((size_t)num_q * sizeof(int64_t));
   }
-  const size_t ws_bytes = streamed
-      ? sbir_pairwise_topk_workspace_bytes(num_q, num_g, dim, k, dtype, metric, want_rank ? 1 : 0)
-      : sbir_pairwise_topk_workspace_bytes(num_q, max_rows, dim, k, dtype, metric, want_rank ? 1 : 0);
+  // shard mode scores every uploaded chunk as a gallery of its own: the workspace must fit the LARGEST layout, which
+  // is not necessarily the one of the longest chunk (a short last chunk may be planned with more partitions)
+  size_t ws_bytes = 0;
+  if (streamed) {
+    ws_bytes = sbir_pairwise_topk_workspace_bytes(num_q, num_g, dim, k, dtype, metric, want_rank ? 1 : 0);
+  } else {
+    for (int c = 0; c < num_chunks; ++c)
+      ws_bytes = std::max(ws_bytes, sbir_pairwise_topk_workspace_bytes(num_q, chunk_end[c] - (c ? chunk_end[c - 1] : 0), dim, k, dtype,
+                                                                        metric, want_rank ? 1 : 0));
+  }
   if (ws_bytes == 0) return SBIR_ERR_UNSUPPORTED;
   const size_t off_ws = take(ws_bytes);
   SBIR_TRY(ensure_staging(o));

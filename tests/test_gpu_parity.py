@@ -753,6 +753,26 @@ def test_retrieve_host_equals_device_path(ops, sbir_lib, chunk_rows, dbg):
     sbir_lib.sbir_release_host_staging()
 
 
+def test_retrieve_host_shard_mode_with_a_short_last_chunk(ops, sbir_lib, dbg):
+    """Several gallery partitions (few query tiles per worker) cannot be fed in pieces: the uploaded chunks are
+    scored as shards and merged (K4).  The short last chunk is planned with MORE partitions than the long ones —
+    the workspace must fit the largest layout (regression: it used to be sized for the longest chunk)."""
+    from art_sbir_b200 import _binding as B
+    dbg("host_chunk_rows", 4096)
+    nq, ng, d, k = 20000, 9000, 64, 10
+    Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=18, beta=0.3)
+    q, g = Q.bfloat16().pin_memory(), G.bfloat16().pin_memory()
+    od = torch.empty(nq, k).pin_memory()
+    oi = torch.empty(nq, k, dtype=torch.int64).pin_memory()
+    orank = torch.empty(nq, dtype=torch.int64).pin_memory()
+    unc = ctypes.c_int32(-1)
+    B.check(sbir_lib.sbir_retrieve_host(q.data_ptr(), nq, g.data_ptr(), ng, d, B.SBIR_BF16, B.SBIR_EUCLIDEAN, k, pos.data_ptr(),
+                                        od.data_ptr(), oi.data_ptr(), orank.data_ptr(), ctypes.byref(unc)), "sbir_retrieve_host")
+    v, i, r = ops.pairwise_topk(q.cuda(), g.cuda(), k, "euclidean", pos_index=pos.cuda())
+    assert torch.equal(i.cpu(), oi) and torch.equal(v.cpu(), od) and torch.equal(r.cpu(), orank)
+    sbir_lib.sbir_release_host_staging()
+
+
 def test_retrieve_host_streams_chunks_into_one_pass(ops, sbir_lib, dbg):
     """With enough query tiles for a single gallery partition the uploaded chunks are FED to one
     retrieval pass (the distance kernel continues the same candidate lists from launch to launch).
