@@ -43,6 +43,7 @@ PROTOTYPES = {
     "sbir_retrieve_host": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "sbir_retrieve_host_shard": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P, _P,
                                          _P, _P, _P]),
+    "sbir_gather_rows_host": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int]),
     "sbir_release_host_staging": (c_int, []),
     "sbir_profile_enable": (c_int, [c_int]),
     "sbir_profile_collect": (c_int, [_P, _P, _P]),

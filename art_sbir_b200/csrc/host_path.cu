@@ -108,6 +108,36 @@ __global__ void missing_rank_kernel(long long* rank, const double* pos_dist, lon
 
 using namespace sbir;
 
+// Host utility of the sharded host path: dst[i, :] = src[index[i], :] (zero row where the index is outside
+// [0, num_rows)), with a few threads — the rows of the positives a rank owns are gathered from its host-resident shard
+// before they are uploaded (under torchrun the Python process runs single-threaded: the same gather through torch
+// indexing took tens of milliseconds per call at cfg4).
+extern "C" int sbir_gather_rows_host(const void* src, int64_t num_rows, int64_t row_bytes, const int64_t* index, int64_t n,
+                                     void* dst, int threads) {
+  if (num_rows < 0 || row_bytes <= 0 || n < 0) return SBIR_ERR_INVALID_ARG;
+  if (n == 0) return SBIR_OK;
+  if (index == nullptr || dst == nullptr || (num_rows > 0 && src == nullptr)) return SBIR_ERR_INVALID_ARG;
+  auto work = [&](int64_t i0, int64_t i1) {
+    for (int64_t i = i0; i < i1; ++i) {
+      const int64_t r = index[i];
+      uint8_t* out = static_cast<uint8_t*>(dst) + (size_t)i * (size_t)row_bytes;
+      if (r >= 0 && r < num_rows) std::memcpy(out, static_cast<const uint8_t*>(src) + (size_t)r * (size_t)row_bytes, (size_t)row_bytes);
+      else std::memset(out, 0, (size_t)row_bytes);
+    }
+  };
+  int nt = threads > 0 ? threads : 8;
+  const int64_t by_size = ((int64_t)n * row_bytes) >> 20;  // one thread per MiB moved, at least one
+  if (nt > by_size) nt = (int)std::max<int64_t>(1, by_size);
+  if (nt <= 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+    for (auto& th : pool) th.join();
+  }
+  return SBIR_OK;
+}
+
 extern "C" int sbir_release_host_staging(void) {
   std::lock_guard<std::mutex> lock(g_staging_mu);
   int prev = 0;

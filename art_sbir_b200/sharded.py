@@ -126,6 +126,19 @@ def _exchange(vals, idx, cnt, pos_dist, num_gallery_total, world, group, merge_f
     return vals, idx, rank_out
 
 
+_pinned_cache = {}
+
+
+def _pinned_rows(rows: int, dim: int, dtype: torch.dtype) -> torch.Tensor:
+    """Pinned host staging for gathered rows, kept between calls (pinning 100 MB costs more than the gather)."""
+    key = (dim, dtype)
+    buf = _pinned_cache.get(key)
+    if buf is None or buf.shape[0] < rows:
+        buf = torch.empty((rows, dim), dtype=dtype).pin_memory()
+        _pinned_cache[key] = buf
+    return buf
+
+
 def sharded_retrieve_host(queries_host: torch.Tensor, gallery_shard_host: torch.Tensor, k: int,
                           loss_type: str = "euclidean", pos_index: Optional[torch.Tensor] = None,
                           shard_offset: Optional[int] = None, num_gallery_total: Optional[int] = None, group=None,
@@ -153,14 +166,21 @@ def sharded_retrieve_host(queries_host: torch.Tensor, gallery_shard_host: torch.
     nq, d = q.shape
     pos_dist = pos_g = None
     if pos_index is not None:
-        pos_cpu = pos_index.to("cpu", torch.int64)
-        mine = (pos_cpu >= shard_offset) & (pos_cpu < shard_offset + n_local)
-        sel = mine.nonzero().flatten()
-        rows = g_host[pos_cpu[sel] - shard_offset].to(dev) if sel.numel() else torch.empty(0, d, dtype=q.dtype, device=dev)
-        local = torch.full((nq,), -1, dtype=torch.int64)
-        local[sel] = torch.arange(sel.numel())
+        pos_cpu = pos_index.to("cpu", torch.int64).contiguous()
+        # rows of the positives this rank owns, gathered from the host shard by a few C threads into pinned memory
+        # (a zero row for every query whose positive lives elsewhere), then one upload
+        local = pos_cpu - shard_offset
+        mine = (local >= 0) & (local < n_local)
+        own = local[mine].contiguous()                         # shard rows of the positives this rank owns
+        n_own = own.numel()
+        rows_host = _pinned_rows(max(n_own, 1), d, g_host.dtype)
+        if n_own:
+            B.check(B.load().sbir_gather_rows_host(g_host.data_ptr(), n_local, d * g_host.element_size(), own.data_ptr(), n_own,
+                                                   rows_host.data_ptr(), 0), "sbir_gather_rows_host")
+        rows = rows_host[:max(n_own, 1)].to(dev, non_blocking=True)
+        ident = torch.where(mine, torch.cumsum(mine, 0) - 1, torch.full((nq,), -1, dtype=torch.int64)).to(dev)
         mine_d = mine.to(dev)
-        d_local = ops.positive_distance(q, rows, local.to(dev), loss_type) if sel.numel() else torch.zeros(nq, dtype=torch.float64, device=dev)
+        d_local = ops.positive_distance(q, rows, ident, loss_type)
         pair = torch.stack([torch.where(mine_d, d_local, torch.zeros_like(d_local)), mine_d.to(torch.float64)])
         if world > 1:
             dist.all_reduce(pair, group=group)

@@ -207,6 +207,11 @@ int sbir_retrieve_host_shard(const void* q_dev, int64_t num_q, const void* g_hos
                              const double* pos_dist_dev, const int64_t* pos_index_global_dev,
                              float* out_dist_dev, int64_t* out_index_dev, int64_t* out_count_less_dev,
                              int32_t* out_uncertified_host, void* stream);
+/* Host utility for the sharded host path: dst[i, :] = src[index[i], :] for i < n (row_bytes each; a zero row where
+ * index[i] is outside [0, num_rows)), with `threads` host threads (0: up to 8, one per MiB moved).  Used to collect
+ * the rows of the positives a rank owns from its host-resident shard before they are uploaded. */
+int sbir_gather_rows_host(const void* src, int64_t num_rows, int64_t row_bytes, const int64_t* index,
+                          int64_t n, void* dst, int threads);
 /* Frees the cached staging memory of sbir_retrieve_host / sbir_retrieve_host_shard. */
 int sbir_release_host_staging(void);
 

@@ -868,6 +868,70 @@ def test_sharded_host_path_equals_single_pass(ops, sbir_lib, dbg):
     sbir_lib.sbir_release_host_staging()
 
 
+# ---------------------------------------------------- buffer overrun guards (memcheck substitute) ----
+@pytest.mark.parametrize("nq,ng,d,dtype,lt,k,opts", [
+    (300, 6000, 128, "float32", "euclidean", 10, {"k1_sel_bf16": 0}),        # kind::tf32, 32-entry lists
+    (300, 6000, 128, "float32", "euclidean", 100, {"k1_sel_bf16": 0}),       # CTA pairs, 128-entry lists
+    (300, 6000, 128, "float32", "cosine", 10, {"k1_sel_bf16": 1}),           # fp32 selected on bf16 copies
+    (300, 6000, 128, "bfloat16", "euclidean", 10, {}),                       # resident-query form
+    (300, 6000, 128, "bfloat16", "cosine", 100, {}),                         # owner + feeder warps
+    (20000, 9000, 64, "bfloat16", "euclidean", 10, {"k1_chunk_mb": 1}),      # chunk hand-overs
+    (130, 2000, 66, "float32", "euclidean", 5, {}),                          # padded tile copies
+    (200, 8000, 256, "float32", "euclidean", 10, {"collapsed": 1})])         # escalation pass + fallbacks
+def test_no_kernel_writes_outside_its_buffers(ops, sbir_lib, dbg, nq, ng, d, dtype, lt, k, opts):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_compute_sanitizer_closed.txt), so out-of-bounds WRITES
+    are hunted with guard bands instead: the workspace and every output buffer of the C-ABI call sit between 64 KB
+    bands of a known byte pattern inside one allocation, sized EXACTLY as the ABI reports; after the pass every band
+    must be intact and the results must still be the reference's.  Covers every operand form of the distance kernel,
+    both finalize forms, the rank pool, the padded-row copies and the escalation pass."""
+    from art_sbir_b200 import _binding as B
+    opts = dict(opts)
+    collapsed = opts.pop("collapsed", 0)
+    for key, val in opts.items():
+        dbg(key, val)
+    tdt = getattr(torch, dtype)
+    Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=nq + k, beta=0.3 if d < 512 else None)
+    if collapsed:
+        base = 3.0 * torch.rand(1, d, generator=torch.Generator().manual_seed(1))
+        Q, G = (base + 0.02 * Q).contiguous(), (base + 0.02 * G).contiguous()
+    q, g, p = Q.to(tdt).cuda(), G.to(tdt).cuda(), pos.cuda()
+    dt, metric = (B.SBIR_BF16 if tdt == torch.bfloat16 else B.SBIR_F32), ops.metric_id(lt)
+    ws_bytes = sbir_lib.sbir_pairwise_topk_workspace_bytes(nq, ng, d, k, dt, metric, 1)
+    GUARD, PAT = 1 << 16, 0xA5
+    sizes = [ws_bytes, nq * k * 4, nq * k * 8, nq * 8, 4]                      # workspace, dist, index, rank, uncertified
+    offs, o = [], GUARD
+    for sz in sizes:
+        offs.append(o)
+        o += (sz + 255) // 256 * 256 + GUARD
+    arena = torch.full((o,), PAT, dtype=torch.uint8, device="cuda")
+    base_ptr = arena.data_ptr()
+    assert base_ptr % 256 == 0
+    B.check(sbir_lib.sbir_pairwise_topk(q.data_ptr(), nq, g.data_ptr(), None, ng, d, dt, metric, k, 0, p.data_ptr(),
+                                        base_ptr + offs[1], base_ptr + offs[2], base_ptr + offs[3], base_ptr + offs[4],
+                                        base_ptr + offs[0], ws_bytes, torch.cuda.current_stream().cuda_stream), "sbir_pairwise_topk")
+    torch.cuda.synchronize()
+    host = arena.cpu()
+    prev_end = 0
+    for off, sz in zip(offs, sizes):
+        assert (host[prev_end:off] == PAT).all(), f"guard band before offset {off} was overwritten"
+        prev_end = off + sz
+    assert (host[prev_end:] == PAT).all(), "guard band behind the last buffer was overwritten"
+    vals = host[offs[1]:offs[1] + nq * k * 4].view(torch.float32).reshape(nq, k)
+    idx = host[offs[2]:offs[2] + nq * k * 8].view(torch.int64).reshape(nq, k)
+    rank = host[offs[3]:offs[3] + nq * 8].view(torch.int64)
+    v2, i2, r2 = ops.pairwise_topk(q, g, k, lt, pos_index=p)                    # the ordinary route: same bits
+    assert torch.equal(vals, v2.cpu()) and torch.equal(idx, i2.cpu()) and torch.equal(rank, r2.cpu())
+    sel = torch.arange(0, nq, max(1, nq // 40))
+    Qo, Go = Q.to(tdt).float(), G.to(tdt).float()
+    if collapsed:   # ground truth = the reference formula element by element in fp32, long sum in fp64
+        dd = ((Qo[sel, None, :] - Go[None, :, :]) + torch.tensor(1e-6)).double().pow(2).sum(-1).sqrt().float()
+        assert torch.equal(idx[sel], torch.topk(dd, k, dim=1, largest=False).indices)
+    else:
+        ref_v, ref_i = O.pairwise_topk_batched(Qo[sel], Go, k, lt)
+        dist_rows = [O.distances(Qo[i:i + 1], Go, lt) for i in sel.tolist()]
+        assert_topk_matches(vals[sel], idx[sel], ref_v, ref_i, dist_rows)
+
+
 # ------------------------------------------------------------ BASELINE-size property checks ----
 def _device_clustered(nq, ng, d, dtype, seed=1234):
     gen = torch.Generator(device="cuda").manual_seed(seed)
