@@ -636,9 +636,25 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         same = bool(torch.equal(oi, idx.cpu()) and torch.equal(orank, rank0.cpu()))
-        e2e = {"value": pairs / dt.item(), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt.item() * 1e3, "steps": es, "matches_device_path": same}
         lib.sbir_release_host_staging()
+        # context for the e2e number (untimed): how long the SAME host->device bytes take as plain pinned copies with all
+        # ranks copying at once — the floor the host path cannot go below on this box, next to the device-only step time
+        sink_q, sink_g = torch.empty_like(qh, device=dev), torch.empty_like(gh, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            sink_q.copy_(qh, non_blocking=True)
+            sink_g.copy_(gh, non_blocking=True)
+        barrier()
+        ct = torch.tensor([(time.perf_counter() - t0) / 2], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        del sink_q, sink_g
+        e2e = {"value": pairs / dt.item(), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt.item() * 1e3, "steps": es, "matches_device_path": same,
+               "h2d_copy_only_ms": ct.item() * 1e3,
+               "h2d_copy_only_GBps_per_rank": (qh.numel() * qh.element_size() + gh.numel() * gh.element_size()) / ct.item() / 1e9,
+               "note": "the upload is streamed into the pass: e2e ~ max(device step, plain pinned H2D copy of the same bytes with all ranks copying at once) + prologue"}
 
     if rank != 0:
         if world > 1:

@@ -269,6 +269,20 @@ def case_sel():
     return out
 
 
+def case_shard():
+    """K1 efficiency on the per-GPU shard sizes of cfg4 (one GPU, no collectives): is the 8-GPU loss inherent to
+    1.25M-row shards (list warm-up, tails), and does the chunk size matter there?"""
+    out = []
+    for ng in (1_250_000, 2_500_000):
+        for mb in (0, 24, 96):
+            B_set("k1_chunk_mb", mb)
+            r = _time_topk(100_000, ng, 512, "bfloat16", 10, rank=True)
+            r["chunk_mb"] = mb or 48
+            out.append(r)
+    B_set("reset", 0)
+    return out
+
+
 def _bench(fn, iters=20, warm=3):
     import torch
     for _ in range(warm):
