@@ -210,22 +210,34 @@ def sampled_parity(Q, Gs, pos, r0, k, vals, idx, rank0, world, dist, n_sample=32
 
 
 # ----------------------------------------------------------------- CPU reference ----
-def cpu_reference_sample(num_g_sample, dim, nq_sample, seconds_hint=20.0):
-    """The reference's per-query path (inference.py:44,49: PairwiseDistance broadcast +
-    topk(len(G))) via the oracle port, fp32, all host threads, on a bounded sample."""
+def workload_config(name, world, centroids=0):
+    """The `config` object of the JSON line: the WORKLOAD only (no results, no timing details), identical in the
+    b200 arm and in the reference arm."""
+    num_q, num_g, dim, dtype_name, k, desc = WORKLOADS[name]
+    return {"workload": name, "description": desc, "num_q": num_q, "num_g": num_g, "dim": dim, "k": k, "metric_fn": "euclidean",
+            "input_dtype": dtype_name, "sharding": f"gallery rows over {world} GPU(s)",
+            "generator": "SURVEY 8(d) clustered generator, C = %s class centroids (80 gallery rows per class as at 8(d)'s 1k x 10k "
+                         "calibration point), positives = randperm" % (centroids or max(125, num_g // 80))}
+
+
+def cpu_reference_sample(num_g_sample, dim, nq_sample, seconds_hint=20.0, dtype_name="float32"):
+    """The reference's per-query path (inference.py:44,49,52: PairwiseDistance broadcast + topk(len(G)) + nonzero) via
+    the oracle port, all host threads, on a bounded SAMPLE OF THE SAME WORKLOAD: clustered embeddings from the same
+    generator family (oracle.synthetic_embeddings, 80 gallery rows per class), rounded to the workload's input type and
+    evaluated in fp32 as the reference would (its CPU ops take fp32; bf16 inputs = fp32 math on bf16-rounded values)."""
     import torch
     from oracle import sbir_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    g = torch.Generator().manual_seed(1234)
-    G = torch.randn(num_g_sample, dim, generator=g)
-    Q = torch.randn(nq_sample, dim, generator=g)
-    O.ranking_position(Q[:1], G, 0, "euclidean")  # warm-up (allocator, threads)
+    Q, G, pos = O.synthetic_embeddings(nq_sample, num_g_sample, dim, seed=1234, num_classes=max(125, num_g_sample // 80))
+    tdt = getattr(torch, dtype_name)
+    Q, G = Q.to(tdt).float(), G.to(tdt).float()
+    O.ranking_position(Q[:1], G, int(pos[0]), "euclidean")  # warm-up (allocator, threads)
     t0 = time.perf_counter()
     done = 0
     for i in range(nq_sample):
-        # what the reference does for EVERY query (inference.py:113 → :44,:49,:52); its full sort
+        # what the reference does for EVERY query (inference.py:113 -> :44,:49,:52); its full sort
         # subsumes the top-10 (get_topk_images, :62-65, only runs for 10 sampled queries)
-        O.ranking_position(Q[i:i + 1], G, i % num_g_sample, "euclidean")
+        O.ranking_position(Q[i:i + 1], G, int(pos[i]), "euclidean")
         done += 1
         if time.perf_counter() - t0 > seconds_hint:
             break
@@ -235,26 +247,29 @@ def cpu_reference_sample(num_g_sample, dim, nq_sample, seconds_hint=20.0):
 
 def run_reference(args, wl):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the
-    reference is pure Python/torch and /root/reference does not exist on the GPU box)."""
+    reference is pure Python/torch and /root/reference does not exist on the GPU box), on this arm's
+    `config`, `metric`, `unit`; every step is a bounded sample of that workload."""
     num_q, num_g, dim, dtype, k, desc = wl
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     ng_s = min(num_g, 500_000 if dim <= 512 else 75_000)
     times, pairs = [], 0
     per_step_q = 4
     for s in range(args.warmup + args.steps):
-        v, done, dt, threads = cpu_reference_sample(ng_s, dim, per_step_q, seconds_hint=30.0)
+        v, done, dt, threads = cpu_reference_sample(ng_s, dim, per_step_q, seconds_hint=30.0, dtype_name=dtype)
         if s >= args.warmup:
             times.append(dt)
             pairs += done * ng_s
     value = pairs / sum(times)
-    sample = f"{per_step_q} queries x {ng_s} gallery rows per step ({dim}-d fp32), PairwiseDistance + topk(N) per query (inference.py:44,49,52)"
+    sample = (f"{per_step_q} queries x {ng_s} gallery rows per step of the same clustered workload ({dim}-d, {dtype}-rounded, fp32 math), "
+              "PairwiseDistance + topk(N) + nonzero per query (inference.py:44,49,52)")
     line = {"impl": "reference", "metric": "query x gallery pairs/sec (distance + top-%d + rank)" % k, "value": value,
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "sampled": sample},
+            "config": workload_config(args.workload, world, args.centroids),
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -673,21 +688,20 @@ def main():
     cpu = None
     if not args.no_cpu:
         ng_s = min(num_g, 500_000 if dim <= 512 else 75_000)
-        v, done, dt, threads = cpu_reference_sample(ng_s, dim, 4096, seconds_hint=12.0)
+        v, done, dt, threads = cpu_reference_sample(ng_s, dim, 4096, seconds_hint=12.0, dtype_name=dtype_name)
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-               "sample": f"{done} queries x {ng_s} gallery rows, {dim}-d fp32, reference per-query loop "
-                         f"(PairwiseDistance + topk(N), inference.py:44,49,52), {dt:.1f} s"}
+               "sample": f"{done} queries x {ng_s} gallery rows of the same clustered workload ({dim}-d, {dtype_name}-rounded, fp32 math), "
+                         f"reference per-query loop (PairwiseDistance + topk(N) + nonzero, inference.py:44,49,52), {dt:.1f} s"}
 
     line = {"metric": "query x gallery pairs/sec (distance + top-%d + rank)" % k, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if dtype == torch.bfloat16 else "f32 (selected on tensor-core tiles, exact fp32/fp64 re-score)",
             "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "num_q": num_q, "num_g": num_g, "dim": dim, "k": k,
-                       "sharding": f"gallery rows over {world} GPU(s)", "l2": "inputs larger than L2" if flush is None else "L2 flushed (512 MiB write) between timed steps",
-                       "generator": "SURVEY §8(d) clustered generator, C = %s class centroids (80 gallery rows per class as at §8(d)'s 1k x 10k calibration point), positives = randperm"
-                                    % (args.centroids or max(125, num_g // 80)),
-                       **recall, "uncertified_queries": uncert},
+            "config": workload_config(args.workload, world, args.centroids),
+            "timing": {"l2": "inputs larger than L2" if flush is None else "L2 flushed (512 MiB write) between timed steps",
+                       "method": "CUDA events on the launching stream around each of K steps after W warm-up steps, barrier + synchronize on both sides, max over ranks"},
+            "results": {**recall, "uncertified_queries": uncert},
             "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity, "tf32_peak_measured_tflops": tf32_peak, "extra_workloads": extras}
     print(json.dumps(line), flush=True)
