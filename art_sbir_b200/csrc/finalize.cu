@@ -618,6 +618,78 @@ __global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(
   }
 }
 
+// Tournament form (at most 32 lists — the shard counts of one box): the same coalesced gather of the block's runs
+// into shared memory, then a GROUP of G = next_pow2(num_lists) lanes per query holds the heads of that query's lists
+// and pops the minimum k times (3·log2(G) shuffles per pop); a warp merges 32/G queries side by side and the rows leave
+// as one contiguous run.  ~60 instructions per query at 8 lists × k = 10 instead of ~600 for the merge-path rounds
+// (which Nsight showed instruction-bound: issue slots 69 % busy, 1.7 TB/s), so the kernel is bound by its loads.
+template <int G>
+__global__ void __launch_bounds__(kMergeThreads, 8) topk_merge_tournament_kernel(
+    const float* __restrict__ dist, const long long* __restrict__ index, int num_lists, size_t stride_d, size_t stride_i,
+    int num_q, int k, int qb, float* __restrict__ out_dist, long long* __restrict__ out_index) {
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  // lists [qb][num_lists][k] and merged rows [qb][k]; indices first (8-byte aligned), then distances
+  long long* i_in = reinterpret_cast<long long*>(merge_smem);
+  long long* i_out = i_in + (size_t)qb * num_lists * k;
+  float* d_in = reinterpret_cast<float*>(i_out + (size_t)qb * k);
+  float* d_out = d_in + (size_t)qb * num_lists * k;
+  const int q0 = blockIdx.x * qb;
+  const int nq = min(qb, num_q - q0);
+  const int run = nq * k;  // contiguous entries per list for this block
+  const float inv_k = 1.0f / (float)k;
+  for (int x = threadIdx.x; x < run; x += kMergeThreads) {
+    const int qi = small_div(x, inv_k), i = x - qi * k;
+    const int dst = qi * num_lists * k + i;
+    const size_t src = (size_t)q0 * k + x;
+#pragma unroll 4
+    for (int l = 0; l < num_lists; ++l) {
+      d_in[dst + l * k] = __ldg(dist + (size_t)l * stride_d + src);
+      i_in[dst + l * k] = __ldg(index + (size_t)l * stride_i + src);
+    }
+  }
+  __syncthreads();
+  constexpr int kGroups = 32 / G;                   // queries per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / G, p = lane % G;           // query slot of the warp, list of this lane
+  for (int qi0 = warp * kGroups; qi0 < nq; qi0 += (kMergeThreads / 32) * kGroups) {
+    const int qi = qi0 + sub;
+    const bool live = qi < nq && p < num_lists;
+    const int base = live ? (qi * num_lists + p) * k : 0;
+    int h = 0;                                      // head of this lane's list
+    float hd = live ? d_in[base] : INFINITY;
+    long long hi = live ? i_in[base] : -1LL;
+    for (int o = 0; o < k; ++o) {
+      // minimum of the group's heads in the (distance, valid-before-padding, index) order
+      float bd = hd;
+      long long bi = hi;
+      int bl = p;
+#pragma unroll
+      for (int s = G >> 1; s > 0; s >>= 1) {
+        const float od = __shfl_xor_sync(kFullMask, bd, s);
+        const long long oi = __shfl_xor_sync(kFullMask, bi, s);
+        const int ol = __shfl_xor_sync(kFullMask, bl, s);
+        const bool other_first = (od != bd) ? (od < bd) : ((oi >= 0 && (bi < 0 || oi < bi)) || (oi == bi && ol < bl));
+        if (other_first) { bd = od; bi = oi; bl = ol; }
+      }
+      if (qi < nq && p == 0) {
+        d_out[qi * k + o] = bi >= 0 ? bd : INFINITY;
+        i_out[qi * k + o] = bi >= 0 ? bi : -1LL;
+      }
+      if (live && bl == p && bi >= 0) {             // this lane's head won: advance
+        ++h;
+        hd = h < k ? d_in[base + h] : INFINITY;
+        hi = h < k ? i_in[base + h] : -1LL;
+      }
+    }
+  }
+  __syncthreads();
+  const size_t obase = (size_t)q0 * k;
+  for (int x = threadIdx.x; x < run; x += kMergeThreads) {
+    out_dist[obase + x] = d_out[x];
+    out_index[obase + x] = i_out[x];
+  }
+}
+
 // Generic form for list sets that do not fit in shared memory (hundreds of lists × large k):
 // one warp per query, binary searches straight in global memory.
 constexpr int kMergeWarps = 4;
@@ -1063,6 +1135,32 @@ int launch_topk_merge(const float* dist, const int64_t* index, int num_lists, in
   const size_t stride_d = list_stride_dist > 0 ? (size_t)list_stride_dist : (size_t)num_q * k;
   const size_t stride_i = list_stride_index > 0 ? (size_t)list_stride_index : (size_t)num_q * k;
   const size_t n = (size_t)num_q * k;
+  if (num_lists > 0 && num_lists <= 32 && (size_t)(num_lists + 1) * k * 12 <= 48 * 1024) {
+    // tournament form: G lanes per query; a block of 4 warps takes qb queries per pass through shared memory
+    int G = 1;
+    while (G < num_lists) G <<= 1;
+    const size_t per_q = (size_t)(num_lists + 1) * k * 12;
+    int qb = (kMergeThreads / 32) * (32 / G);                    // one pass of the block
+    while ((size_t)qb * 2 * per_q <= 16 * 1024) qb *= 2;         // ~16 KB of shared memory per block
+    while (qb > 1 && (size_t)qb * per_q > 48 * 1024) qb /= 2;
+    const size_t smem = (size_t)qb * per_q;
+    const unsigned grid = (unsigned)((num_q + qb - 1) / qb);
+    const long long* idx = reinterpret_cast<const long long*>(index);
+    long long* oidx = reinterpret_cast<long long*>(out_index);
+#define SBIR_TOURNAMENT(GG) \
+  topk_merge_tournament_kernel<GG><<<grid, kMergeThreads, smem, st>>>(dist, idx, num_lists, stride_d, stride_i, (int)num_q, k, qb, out_dist, oidx)
+    switch (G) {
+      case 1: SBIR_TOURNAMENT(1); break;
+      case 2: SBIR_TOURNAMENT(2); break;
+      case 4: SBIR_TOURNAMENT(4); break;
+      case 8: SBIR_TOURNAMENT(8); break;
+      case 16: SBIR_TOURNAMENT(16); break;
+      default: SBIR_TOURNAMENT(32); break;
+    }
+#undef SBIR_TOURNAMENT
+    SBIR_CHECK_LAUNCH();
+    return SBIR_OK;
+  }
   const size_t per_q = ((size_t)num_lists + (num_lists + 1) / 2) * k * 12;  // gathered lists + one round of merged lists
   if (num_lists > 0 && per_q <= 96 * 1024) {
     // ~16 KB of shared memory per block (a dozen blocks per SM keep loads in flight while others merge)

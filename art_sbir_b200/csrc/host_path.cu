@@ -31,17 +31,19 @@ struct Staging {
   int device = -1;
   cudaStream_t compute = nullptr, copy = nullptr;
   std::vector<cudaEvent_t> events;
+  std::mutex call_mu;  // one host-buffer call at a time PER DEVICE (calls on different devices run concurrently)
 };
 // One staging set PER DEVICE (streams, events and device memory belong to the device that was current when
 // they were created); calls on different devices of one process do not share anything but the mutex.
-std::map<int, Staging> g_staging_by_device;
-std::mutex g_staging_mu;
+std::map<int, Staging> g_staging_by_device;   // nodes are never moved: pointers / mutexes inside stay valid
+std::mutex g_staging_mu;                      // guards the map itself only
 thread_local Staging* tl_staging = nullptr;  // the current call's set (selected under the mutex)
 #define g_staging (*tl_staging)
 
 int select_staging() {
   int dev = 0;
   SBIR_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_staging_mu);
   Staging& s = g_staging_by_device[dev];
   s.device = dev;
   tl_staging = &s;
@@ -139,11 +141,12 @@ extern "C" int sbir_gather_rows_host(const void* src, int64_t num_rows, int64_t 
 }
 
 extern "C" int sbir_release_host_staging(void) {
-  std::lock_guard<std::mutex> lock(g_staging_mu);
+  std::lock_guard<std::mutex> map_lock(g_staging_mu);
   int prev = 0;
   const bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
   for (auto& kv : g_staging_by_device) {
     Staging& s = kv.second;
+    std::lock_guard<std::mutex> lock(s.call_mu);  // waits for a call in flight on that device
     if (cudaSetDevice(kv.first) != cudaSuccess) continue;
     if (s.copy) cudaStreamSynchronize(s.copy);
     if (s.compute) cudaStreamSynchronize(s.compute);
@@ -152,9 +155,10 @@ extern "C" int sbir_release_host_staging(void) {
     for (cudaEvent_t e : s.events) cudaEventDestroy(e);
     if (s.compute) cudaStreamDestroy(s.compute);
     if (s.copy) cudaStreamDestroy(s.copy);
+    s.buf = nullptr; s.bytes = 0; s.pinned = nullptr; s.pinned_bytes = 0;
+    s.events.clear();
+    s.compute = s.copy = nullptr;
   }
-  g_staging_by_device.clear();
-  tl_staging = nullptr;
   if (have_prev) cudaSetDevice(prev);
   return SBIR_OK;
 }
@@ -173,8 +177,8 @@ extern "C" int sbir_retrieve_host(const void* q_host, int64_t num_q, const void*
     return SBIR_ERR_INVALID_ARG;
   if (out_rank_host != nullptr && pos_index_host == nullptr) return SBIR_ERR_INVALID_ARG;
   if (dtype != SBIR_F32 && dtype != SBIR_BF16) return SBIR_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(g_staging_mu);
   SBIR_TRY(select_staging());
+  std::lock_guard<std::mutex> lock(g_staging.call_mu);
   const int status = retrieve_host_locked(q_host, num_q, g_host, num_g, dim, dtype, metric, k, pos_index_host, out_dist_host,
                                           out_index_host, out_rank_host, out_uncertified_host);
   if (status != SBIR_OK) drain_staging();
@@ -387,8 +391,8 @@ extern "C" int sbir_retrieve_host_shard(const void* q_dev, int64_t num_q, const 
   if (num_g > 0 && g_host == nullptr) return SBIR_ERR_INVALID_ARG;
   if (out_count_less_dev != nullptr && pos_dist_dev == nullptr) return SBIR_ERR_INVALID_ARG;
   if (dtype != SBIR_F32 && dtype != SBIR_BF16) return SBIR_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lock(g_staging_mu);
   SBIR_TRY(select_staging());
+  std::lock_guard<std::mutex> lock(g_staging.call_mu);
   const int status = retrieve_host_shard_locked(q_dev, num_q, g_host, num_g, dim, dtype, metric, k, index_offset, pos_dist_dev,
                                                 pos_index_global_dev, out_dist_dev, out_index_dev, out_count_less_dev,
                                                 out_uncertified_host, stream);
