@@ -360,6 +360,7 @@ batch_hard_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     __syncthreads();
     BH_STAMP(2);
     const int nband = s_nband;
+    if (P.timing && threadIdx.x == 0) P.timing[8 + blockIdx.x * 8 + 5] = (unsigned long long)nband;  // diagnostics: band size
     // Exact re-scoring, one warp per band entry.  The arrival order of the entries does not matter: the
     // winner is chosen by the total order (fp32 distance, candidate index).  If the band overflows the
     // list (degenerate data: everything within rounding of everything), every candidate is re-scored.
@@ -452,7 +453,6 @@ batch_hard_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     BH_STAMP(4);
   }
   __threadfence();
-  BH_STAMP(5);
   grid.sync();
   BH_STAMP(6);
 
@@ -644,7 +644,11 @@ int launch_batch_hard(const float* a, const float* p, const float* n, int64_t ba
   P.sel = reinterpret_cast<int*>(ws + L.off_sel);
   P.pair_d = reinterpret_cast<double*>(ws + L.off_pair_d);
   P.pair_stat = reinterpret_cast<float*>(ws + L.off_pair_stat);
-  P.timing = reinterpret_cast<unsigned long long*>(ws + L.off_timing);
+#ifdef SBIR_DIAG
+  P.timing = reinterpret_cast<unsigned long long*>(ws + L.off_timing);  // stage stamps: diagnostic builds only (SBIR_BUILD_DIAG=1)
+#else
+  P.timing = nullptr;
+#endif
   P.out_loss = out_loss;
   P.out_hard_index = reinterpret_cast<long long*>(out_hard_index);
   P.ga = ga; P.gp = gp; P.gn = gn;

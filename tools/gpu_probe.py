@@ -634,9 +634,17 @@ def case_small():
         torch.cuda.synchronize()
         tw = ws[-(((8 + 8 * 512) * 8 + 255) // 256 * 256):].view(torch.int64).cpu().numpy()
         t = [int(x) for x in tw[:4]]                                         # phase boundaries seen by CTA 0 (globaltimer ns)
-        stg = (tw[8:8 + 8 * 296].reshape(296, 8) - t[0]) / 1e3                # per-CTA stage stamps, us after CTA 0's start
-        ok = stg[:256]                                                       # CTAs that own an anchor pass every stage
+        if t[0] == 0:                                                        # product build: stamps exist only with SBIR_BUILD_DIAG=1
+            res[f"cfg2 batch-hard fwd+bwd 256x512x2048 {name}"] = {"us": us}
+            continue
+        raw = tw[8:8 + 8 * 296].reshape(296, 8)
+        stg = (raw - t[0]) / 1e3                                              # per-CTA stage stamps, us after CTA 0's start
+        ok = stg[:256].copy()                                                # CTAs that own an anchor pass every stage
         import numpy as np
+        ok[:, 5] = raw[:256, 5]                                              # slot 5 carries the band size, not a stamp
+        slow = np.argsort(-(ok[:, 4] - ok[:, 0]))[:8]
+        res[f"cfg2 batch-hard slowest CTAs {name} (cta, scan_us, band_us, exact_us, select+grad_us, band_entries)"] = [
+            [int(c), round(ok[c, 1] - ok[c, 0], 2), round(ok[c, 2] - ok[c, 1], 2), round(ok[c, 3] - ok[c, 2], 2), round(ok[c, 4] - ok[c, 3], 2), int(ok[c, 5])] for c in slow]
         res[f"cfg2 batch-hard fwd+bwd 256x512x2048 {name}"] = {
             "us": us, "phase_us(mine,select,grad)": [(t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3],
             "stage_median_us": np.median(ok, 0).round(2).tolist(), "stage_max_us": ok.max(0).round(2).tolist(),
