@@ -75,20 +75,21 @@ int64_t tile_dim(int64_t dim, int dtype) {
   return (dim + per16 - 1) / per16 * per16;
 }
 
-// The bf16 rounding band is about twice kind::tf32's, so the candidate lists must have room for it: measured on
-// the clustered 12.5k x 75k x 2048 workload, k = 10 (32-entry lists) and k = 30 (64) certify every query and run
-// 6.1 -> 3.8 ms / 6.5 -> 4.3 ms, while k = 100 (128-entry lists, 28 entries of slack) leaves queries uncertified and
-// falls into the 3xTF32 escalation pass (7.9 -> 39 ms) — hence "capacity >= 2k".  Problems of a few 1e10 FLOP (the
-// reference's own 1k x 10k evaluation) are launch-bound and stay on the path with fewer kernels and lists.
+// The bf16 rounding band is about twice kind::tf32's: measured on the clustered 12.5k x 75k x 2048 workload, k = 10
+// (32-entry lists) and k = 30 (64) certify every query and run 6.1 -> 3.8 ms / 6.5 -> 4.3 ms, while k = 100 (128-entry
+// lists, 28 entries of slack) leaves 0.6 % of the queries uncertified.  Those are caught by TIERS behind the pass
+// (topk_pass_finish): a few certificate failures are re-selected on kind::tf32 tiles as a small batch of their own;
+// more (or overflowing rank pools) trigger one kind::tf32 pass over all queries; only then the 3xTF32 pass and the
+// brute-force fallbacks.  Problems of a few 1e10 FLOP (the reference's own 1k x 10k evaluation) are launch-bound and
+// stay on the path with fewer kernels and lists.
 bool select_on_bf16(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype) {
   const int opt = debug_options().k1_sel_bf16;
   if (dtype != SBIR_F32 || opt == 0) return false;
   if (dim % 8 != 0 || num_g <= 0) return false;  // (padded rows stay on their own element type)
   if (((size_t)num_q + (size_t)num_g) * (size_t)dim * 2 > (size_t(16) << 30)) return false;
   if (opt > 0) return true;  // forced (tests, A/B runs)
-  const int want = k + 16;
-  const int cap = want <= 16 ? 16 : want <= 32 ? 32 : want <= 64 ? 64 : 128;
-  return cap >= 2 * k && 2.0 * (double)dim * (double)num_q * (double)num_g >= 4e11;
+  (void)k;
+  return 2.0 * (double)dim * (double)num_q * (double)num_g >= 4e11;
 }
 
 TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype, int want_rank) {
@@ -108,8 +109,18 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
     L.precise = L.plan3.cap == L.plan.cap;
   }
   auto lists_of = [](const K1Plan& p) { return (size_t)p.num_splits * p.q_tile_stride * p.lists_per_row; };
-  const size_t lists = L.precise ? std::max(lists_of(L.plan), lists_of(L.plan3)) : lists_of(L.plan);
-  const size_t parts = L.precise ? (size_t)std::max(L.plan.num_splits, L.plan3.num_splits) : (size_t)L.plan.num_splits;
+  size_t lists = lists_of(L.plan), parts = (size_t)L.plan.num_splits;
+  if (L.precise) { lists = std::max(lists, lists_of(L.plan3)); parts = std::max(parts, (size_t)L.plan3.num_splits); }
+  if (L.sel_bf16) {
+    // tiers: the kind::tf32 plan for all queries shares the candidate / list-state buffers; the subset pass has its own
+    L.plan_tf32 = make_k1_plan(num_q, num_g, L.kdim, k, SBIR_F32, num_sms_cached(), 16);
+    int64_t max_bad = num_q / 50;
+    if (max_bad < 4) max_bad = 4;
+    L.sub_q = (max_bad + kTileQ - 1) / kTileQ * kTileQ;
+    L.plan_sub = make_k1_plan(L.sub_q, num_g, L.kdim, k, SBIR_F32, num_sms_cached(), 16);
+    if (L.plan_tf32.cap != L.plan.cap || L.plan_sub.cap != L.plan.cap) L.sel_bf16 = false;  // (cannot happen: same k and slack)
+  }
+  if (L.sel_bf16) { lists = std::max(lists, lists_of(L.plan_tf32)); parts = std::max(parts, (size_t)L.plan_tf32.num_splits); }
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + (bytes ? bytes : 1), 256); return r; };
   const size_t nq = (size_t)(num_q > 0 ? num_q : 1);
@@ -128,6 +139,22 @@ TopkLayout topk_layout(int64_t num_q, int64_t num_g, int64_t dim, int k, int dty
   L.sched_bytes = 256 + parts * L.plan.q_tile_stride * sizeof(int32_t);
   L.off_sched = take(L.sched_bytes);
   if (L.sel_bf16) {
+    const size_t sq = (size_t)L.sub_q;
+    L.off_tier_gates = take(256);                       // gate_sub, gate_full, fq_count
+    L.off_fq = take(sq * sizeof(int32_t));
+    L.off_qsub = take(sq * (size_t)dim * sizeof(float));
+    L.off_qsq_sub = take(sq * sizeof(float));
+    L.off_sub_dist = take(sq * (size_t)k * sizeof(float));
+    L.off_sub_index = take(sq * (size_t)k * sizeof(int64_t));
+    L.off_sub_flags = take(sq * sizeof(int32_t));
+    const size_t sub_lists = lists_of(L.plan_sub);
+    L.off_sub_cand_val = take(sub_lists * L.plan_sub.cap * kTileQ * sizeof(float));
+    L.off_sub_cand_idx = take(sub_lists * L.plan_sub.cap * kTileQ * sizeof(int32_t));
+    L.off_sub_row_max = take(sub_lists * kTileQ * sizeof(float));
+    L.off_sub_row_maxpos = take(sub_lists * kTileQ * sizeof(int32_t));
+    L.sub_sched_bytes = 256 + (size_t)L.plan_sub.num_splits * L.plan_sub.q_tile_stride * sizeof(int32_t);
+    L.off_sub_sched = take(L.sub_sched_bytes);
+    L.off_sub_thr = take((size_t)L.plan_sub.q_tile_stride * kTileQ * sizeof(int32_t));
     L.off_qb = take((size_t)num_q * dim * 2);
     L.off_gb = take((size_t)num_g * dim * 2);
     L.off_qres = take(nq * sizeof(float));
@@ -375,6 +402,47 @@ int topk_pass_finish(TopkPass& P) {
     if (want_rank) SBIR_TRY(launch_rank_resolve(ra, st));
     return SBIR_OK;
   };
+
+  // Tiers behind the bf16 selection of fp32 embeddings (device-gated, no host synchronisation): its rounding band is
+  // twice kind::tf32's, so a query may fail the certificate here that kind::tf32 tiles would certify.
+  if (L.sel_bf16) {
+    int32_t* gates = reinterpret_cast<int32_t*>(ws + L.off_tier_gates);
+    int32_t* gate_sub = gates, *gate_full = gates + 1, *fq_count = gates + 2;
+    int32_t* fq = reinterpret_cast<int32_t*>(ws + L.off_fq);
+    float* q_sub = reinterpret_cast<float*>(ws + L.off_qsub);
+    float* qsq_sub = reinterpret_cast<float*>(ws + L.off_qsq_sub);
+    float* sub_dist = reinterpret_cast<float*>(ws + L.off_sub_dist);
+    int64_t* sub_index = reinterpret_cast<int64_t*>(ws + L.off_sub_index);
+    int32_t* sub_flags = reinterpret_cast<int32_t*>(ws + L.off_sub_flags);
+    int64_t max_bad = num_q / 50;
+    if (max_bad < 4) max_bad = 4;
+    SBIR_TRY(launch_tier_decide(P.flags, want_rank ? ra.dropped : nullptr, num_q, max_bad, fq, fq_count, gate_sub, gate_full, P.uncert, st));
+    // (a) a few certificate failures: those queries alone, on kind::tf32 tiles against the whole gallery
+    SBIR_TRY(launch_gather_sub(static_cast<const float*>(P.q), dim, fq, fq_count, L.sub_q, q_sub, P.qsq, qsq_sub, gate_sub, st));
+    K1Args ks{};
+    ks.q = q_sub; ks.g = P.kg; ks.num_q = L.sub_q; ks.num_g = num_g; ks.dim = L.kdim;
+    ks.dtype = SBIR_F32; ks.metric = P.metric; ks.mode = kModeTopk;
+    ks.gvec = P.gvec; ks.gmin = P.gmin; ks.gate = gate_sub;
+    ks.cand_val = reinterpret_cast<float*>(ws + L.off_sub_cand_val);
+    ks.cand_idx = reinterpret_cast<int32_t*>(ws + L.off_sub_cand_idx);
+    ks.row_max = reinterpret_cast<float*>(ws + L.off_sub_row_max);
+    ks.row_maxpos = reinterpret_cast<int32_t*>(ws + L.off_sub_row_maxpos);
+    ks.unit_counter = reinterpret_cast<uint32_t*>(ws + L.off_sub_sched);
+    ks.chunk_done = reinterpret_cast<int32_t*>(ws + L.off_sub_sched + 256);
+    ks.shared_thr = reinterpret_cast<int32_t*>(ws + L.off_sub_thr);
+    SBIR_TRY(launch_pass_reset(nullptr, nullptr, 0, nullptr, ws + L.off_sub_sched, L.sub_sched_bytes, ks.shared_thr,
+                               (int64_t)L.plan_sub.q_tile_stride * kTileQ, gate_sub, st));
+    SBIR_TRY(launch_k1(ks, L.plan_sub, st));
+    FinalizeArgs fs = fa;
+    fs.q = q_sub; fs.num_q = L.sub_q; fs.cand_val = ks.cand_val; fs.cand_idx = ks.cand_idx; fs.qsq = qsq_sub;
+    fs.kappa = k1_kappa(SBIR_F32, L.kdim); fs.q_res = nullptr; fs.g_res = nullptr;
+    fs.out_dist = sub_dist; fs.out_index = sub_index; fs.uncertified = nullptr; fs.flags = sub_flags; fs.gate = gate_sub;
+    SBIR_TRY(launch_finalize_topk(fs, L.plan_sub, st));
+    SBIR_TRY(launch_scatter_sub(fq, fq_count, L.sub_q, fa.k, sub_dist, sub_index, sub_flags, fa.out_dist, fa.out_index, P.flags,
+                                P.uncert, gate_sub, st));
+    // (b) more than that, or rank pools overflowed: one kind::tf32 pass over all queries
+    SBIR_TRY(run_pass(P.kq, P.kg, L.kdim, L.plan_tf32, k1_kappa(SBIR_F32, L.kdim), gate_full));
+  }
 
   // Pass 2 (fp32 only, device-gated): when more than 2 % of the queries could not be certified or
   // overflowed the rank pool — embeddings whose norms dwarf their distances, positives deep in an

@@ -755,6 +755,97 @@ __global__ void __launch_bounds__(1024) escalate_decide_kernel(const int32_t* __
   }
 }
 
+// ---- tiers behind the bf16 selection of fp32 embeddings (api.cu) ----
+// After the kind::f16 pass: how many queries are unresolved (top-k certificate failed / rank pool overflowed)?
+//   none                                  -> nothing to do
+//   a few certificate failures only       -> gate_sub: those queries (listed in `fq`, ascending) are re-selected on
+//                                            kind::tf32 tiles as a small batch of their own
+//   more, or rank pools overflowed        -> gate_full: one kind::tf32 pass over all queries
+// One block; the list is built by an ordered scan so the subset's row order is deterministic.
+__global__ void __launch_bounds__(1024) tier_decide_kernel(const int32_t* __restrict__ flags, const int32_t* __restrict__ dropped,
+                                                           int num_q, int max_sub, int32_t* __restrict__ fq, int32_t* __restrict__ fq_count,
+                                                           int32_t* __restrict__ gate_sub, int32_t* __restrict__ gate_full,
+                                                           int32_t* __restrict__ uncertified) {
+  __shared__ int s_flag, s_drop, s_base;
+  __shared__ int s_warp[32];
+  if (threadIdx.x == 0) { s_flag = 0; s_drop = 0; s_base = 0; }
+  __syncthreads();
+  int nf = 0, nd = 0;
+  for (int i = threadIdx.x; i < num_q; i += 1024) {
+    nf += (flags[i] & 1) ? 1 : 0;
+    nd += (dropped != nullptr && dropped[i] > 0) ? 1 : 0;
+  }
+  if (nf) atomicAdd(&s_flag, nf);
+  if (nd) atomicAdd(&s_drop, nd);
+  __syncthreads();
+  const int total_flag = s_flag, total_drop = s_drop;
+  const bool sub = total_flag > 0 && total_flag <= max_sub && total_drop == 0;
+  const bool full = (total_flag > 0 || total_drop > 0) && !sub;
+  if (threadIdx.x == 0) {
+    gate_sub[0] = sub ? 1 : 0;
+    gate_full[0] = full ? 1 : 0;
+    fq_count[0] = sub ? total_flag : 0;
+    if (full && uncertified != nullptr) uncertified[0] = 0;  // the full pass counts again
+  }
+  if (!sub) return;
+  // ordered compaction: chunks of 1024 queries, ballot + warp prefix inside a chunk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < num_q; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const bool f = i < num_q && (flags[i] & 1);
+    const unsigned m = __ballot_sync(kFullMask, f);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (f) fq[before + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += s_warp[w];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+}
+
+// q_sub[i, :] = q[fq[i], :] for i < count (zero rows behind), qsq_sub likewise.  One warp per row.
+__global__ void __launch_bounds__(256) gather_sub_kernel(const float* __restrict__ q, int dim, const int32_t* __restrict__ fq,
+                                                         const int32_t* __restrict__ fq_count, int sub_q, float* __restrict__ q_sub,
+                                                         const float* __restrict__ qsq, float* __restrict__ qsq_sub,
+                                                         const int32_t* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= sub_q) return;
+  const int n = *fq_count;
+  const bool have = r < n;
+  const float* src = have ? q + (size_t)fq[r] * dim : nullptr;
+  for (int c = lane; c < dim; c += 32) q_sub[(size_t)r * dim + c] = have ? src[c] : 0.f;
+  if (lane == 0) qsq_sub[r] = have ? qsq[fq[r]] : 0.f;
+}
+
+// results of the subset pass back into the caller's rows; certificate flags and the uncertified counter follow
+__global__ void __launch_bounds__(256) scatter_sub_kernel(const int32_t* __restrict__ fq, const int32_t* __restrict__ fq_count, int k,
+                                                          const float* __restrict__ sub_dist, const long long* __restrict__ sub_index,
+                                                          const int32_t* __restrict__ sub_flags, float* __restrict__ out_dist,
+                                                          long long* __restrict__ out_index, int32_t* __restrict__ flags,
+                                                          int32_t* __restrict__ uncertified, const int32_t* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  const int n = *fq_count;
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    const int q = fq[r];
+    for (int i = threadIdx.x; i < k; i += 256) {
+      out_dist[(size_t)q * k + i] = sub_dist[(size_t)r * k + i];
+      out_index[(size_t)q * k + i] = sub_index[(size_t)r * k + i];
+    }
+    if (threadIdx.x == 0 && (sub_flags[r] & 1) == 0) {
+      flags[q] = 0;
+      if (uncertified != nullptr) atomicSub(uncertified, 1);
+    }
+  }
+}
+
 // 3xTF32 operand split (see kernels.h).  float4 in, three float4 out per vector.
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, long long rows, int dim,
                                                          int gallery_layout, float* __restrict__ out,
@@ -1062,6 +1153,30 @@ int launch_pass_reset(int32_t* cnt_less, int32_t* dropped, int64_t num_q, uint32
   if (blocks < 1) blocks = 1;
   pass_reset_kernel<<<(unsigned)blocks, 256, 0, st>>>(cnt_less, dropped, (long long)num_q, pool_count, static_cast<uint32_t*>(sched),
                                                        (long long)(sched_bytes / 4), shared_thr, (long long)num_thr, gate);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_tier_decide(const int32_t* flags, const int32_t* dropped, int64_t num_q, int64_t max_sub, int32_t* fq, int32_t* fq_count,
+                       int32_t* gate_sub, int32_t* gate_full, int32_t* uncertified, cudaStream_t st) {
+  tier_decide_kernel<<<1, 1024, 0, st>>>(flags, dropped, (int)num_q, (int)max_sub, fq, fq_count, gate_sub, gate_full, uncertified);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_gather_sub(const float* q, int64_t dim, const int32_t* fq, const int32_t* fq_count, int64_t sub_q, float* q_sub,
+                      const float* qsq, float* qsq_sub, const int32_t* gate, cudaStream_t st) {
+  gather_sub_kernel<<<(unsigned)((sub_q + 7) / 8), 256, 0, st>>>(q, (int)dim, fq, fq_count, (int)sub_q, q_sub, qsq, qsq_sub, gate);
+  SBIR_CHECK_LAUNCH();
+  return SBIR_OK;
+}
+
+int launch_scatter_sub(const int32_t* fq, const int32_t* fq_count, int64_t sub_q, int k, const float* sub_dist, const int64_t* sub_index,
+                       const int32_t* sub_flags, float* out_dist, int64_t* out_index, int32_t* flags, int32_t* uncertified,
+                       const int32_t* gate, cudaStream_t st) {
+  scatter_sub_kernel<<<(unsigned)(sub_q < 1 ? 1 : sub_q), 256, 0, st>>>(fq, fq_count, k, sub_dist, reinterpret_cast<const long long*>(sub_index),
+                                                                      sub_flags, out_dist, reinterpret_cast<long long*>(out_index), flags,
+                                                                      uncertified, gate);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
 }

@@ -173,6 +173,15 @@ int launch_rank_output(const RankArgs& a, cudaStream_t st);     // once at the e
 // (device-gated) start of a scoring pass: counters, scheduler words and shared thresholds reset in one launch
 int launch_pass_reset(int32_t* cnt_less, int32_t* dropped, int64_t num_q, uint32_t* pool_count, void* sched, size_t sched_bytes,
                       int32_t* shared_thr, int64_t num_thr, const int32_t* gate, cudaStream_t st);
+// Tiers behind the bf16 selection of fp32 embeddings (finalize.cu: tier_decide_kernel): a few certificate failures ->
+// those queries re-selected on kind::tf32 tiles as a batch of their own (fq / gather / scatter); more -> gate_full.
+int launch_tier_decide(const int32_t* flags, const int32_t* dropped, int64_t num_q, int64_t max_sub, int32_t* fq, int32_t* fq_count,
+                       int32_t* gate_sub, int32_t* gate_full, int32_t* uncertified, cudaStream_t st);
+int launch_gather_sub(const float* q, int64_t dim, const int32_t* fq, const int32_t* fq_count, int64_t sub_q, float* q_sub,
+                      const float* qsq, float* qsq_sub, const int32_t* gate, cudaStream_t st);
+int launch_scatter_sub(const int32_t* fq, const int32_t* fq_count, int64_t sub_q, int k, const float* sub_dist, const int64_t* sub_index,
+                       const int32_t* sub_flags, float* out_dist, int64_t* out_index, int32_t* flags, int32_t* uncertified,
+                       const int32_t* gate, cudaStream_t st);
 // Escalation (fp32 inputs): after the TF32 pass, gate[0] = 1 iff more than `max_bad` queries failed
 // the top-k certificate or overflowed the rank pool; then the 3xTF32 pass re-does everything.
 int launch_escalate_decide(const int32_t* flags, const int32_t* dropped, int64_t num_q, int64_t max_bad,
@@ -210,6 +219,11 @@ struct TopkLayout {
   int64_t kdim;        // columns of the rows the tensor-core tiles read (dim rounded up to a 16-byte multiple)
   bool padded_rows;    // kdim != dim: zero-padded operand copies at off_qpad / off_gpad
   size_t off_qpad, off_gpad;
+  // tiers behind the bf16 selection (sel_bf16): kind::tf32 plans for all queries / for a subset of `sub_q` rows
+  K1Plan plan_tf32, plan_sub;
+  int64_t sub_q;
+  size_t off_tier_gates, off_fq, off_qsub, off_qsq_sub, off_sub_dist, off_sub_index, off_sub_flags;
+  size_t off_sub_cand_val, off_sub_cand_idx, off_sub_row_max, off_sub_row_maxpos, off_sub_sched, sub_sched_bytes, off_sub_thr;
   bool sel_bf16;       // fp32 inputs selected on bf16-rounded copies (kind::f16 tiles) — off_qb / off_gb / off_qres / off_gres
   size_t off_qb, off_gb, off_qres, off_gres;
   bool precise;        // fp32 inputs small enough for the 3xTF32 escalation workspace

@@ -362,6 +362,20 @@ def test_fp32_selected_on_bf16_copies_matches_tf32_selection_and_oracle(ops, dbg
         assert int(u1.item()) <= nq // 50 + 4                 # lists with room for the bf16 band certify (almost) everything
 
 
+def test_bf16_selection_tiers_at_cfg3_top100(ops, dbg):
+    """BASELINE cfg3 (12.5k x 75k x 2048 fp32, top-100): with 128-entry lists the bf16 selection band leaves ~0.6 % of the
+    queries uncertified; the tier behind the pass re-selects exactly those on kind::tf32 tiles as a small batch.  Results
+    must be bit-identical to the all-kind::tf32 pass, with nothing left to brute force."""
+    Q, G, pos = _device_clustered(12500, 75000, 2048, torch.float32)
+    dbg("k1_sel_bf16", 0)
+    want = ops.pairwise_topk(Q, G, 100, "euclidean", pos_index=pos, return_uncertified=True)
+    dbg("k1_sel_bf16", 1)
+    got = ops.pairwise_topk(Q, G, 100, "euclidean", pos_index=pos, return_uncertified=True)
+    for a, b in zip(want[:3], got[:3]):
+        assert torch.equal(a, b)
+    assert int(want[3].item()) == 0 and int(got[3].item()) == 0
+
+
 def test_fp32_bf16_selection_on_collapsed_embeddings(ops, dbg):
     """Forced bf16 selection on embeddings with a large common component: the measured residual norms make the band
     cover everything, nothing certifies, and the centred 3xTF32 escalation pass must still produce exact results."""

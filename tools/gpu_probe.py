@@ -256,7 +256,7 @@ def case_sel():
     out = []
     for shape in ((12500, 75000, 2048, 10), (12500, 75000, 2048, 100), (12500, 75000, 2048, 30), (1000, 10000, 2048, 10),
                   (20000, 200000, 1024, 10), (20000, 200000, 1024, 100), (20000, 1000000, 512, 10)):
-        for sel in (0, 1):
+        for sel in (0, -1):
             B_set("k1_sel_bf16", sel)
             r = _time_topk(shape[0], shape[1], shape[2], "float32", shape[3], rank=True)
             r["sel_bf16"] = sel
