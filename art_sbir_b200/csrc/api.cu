@@ -698,6 +698,7 @@ int sbir_debug_set_option(const char* name, int64_t value) {
   if (!std::strcmp(name, "k1_feed")) o.k1_feed = (int)value;
   else if (!std::strcmp(name, "k1_pair")) o.k1_pair = (int)value;
   else if (!std::strcmp(name, "k1_qres")) o.k1_qres = (int)value;
+  else if (!std::strcmp(name, "k1_pair_coop")) o.k1_pair_coop = (int)value;
   else if (!std::strcmp(name, "k1_sel_bf16")) o.k1_sel_bf16 = (int)value;
   else if (!std::strcmp(name, "k1_chunk_mb")) o.k1_chunk_mb = (int)value;
   else if (!std::strcmp(name, "k1_flags")) o.k1_flags = (int)value;

@@ -201,6 +201,7 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.dim_elems = (int)a.dim;
   prm.flags = debug_options().k1_flags;
   prm.watchdog_cycles = debug_options().watchdog_cycles;
+  prm.pair_cooperative = debug_options().k1_pair_coop != 0 ? 1 : 0;
   prm.unit_counter = a.unit_counter;
   prm.chunk_done = a.chunk_done;
   prm.cand_val = a.cand_val;

@@ -963,7 +963,7 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& pr
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = kPair == 2 ? 2 : 0;
+  cfg.numAttrs = kPair == 2 ? (prm.pair_cooperative ? 2 : 1) : 0;  // option k1_pair_coop = 0: Nsight Compute cannot replay cooperative cluster launches
   if constexpr (kPair == 2) {
     int max_clusters = 0;
     SBIR_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
@@ -974,7 +974,14 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tg, const K1Params& pr
     }
   }
   profile_k1_begin(st);
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tq, tg, prm);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tq, tg, prm);
+  if (e != cudaSuccess && kPair == 2) {
+    // Some environments reject the cooperative flavour of a cluster launch (Nsight Compute's kernel replay does);
+    // the grid is already clamped to what fits, which is the practical guarantee on an otherwise idle device.
+    (void)cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, tq, tg, prm);
+  }
   profile_k1_end(st);
   if (e != cudaSuccess) {
     set_last_cuda_error((int)e);

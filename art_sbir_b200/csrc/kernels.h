@@ -12,6 +12,7 @@ struct DebugOptions {
   int k1_feed = -1;               // owner+feeder epilogue for 64/128-entry lists: -1 auto, 0 off
   int k1_pair = 0;                // CTA pairs: 0 auto, 1 never, 2 always
   int k1_qres = -1;               // resident-query form: -1 auto, 0 off
+  int k1_pair_coop = 1;           // CTA-pair launches cooperative (1) or plain cluster launches (0: profilers that cannot replay them)
   int k1_sel_bf16 = -1;           // fp32 embeddings selected on bf16 copies (kind::f16): -1 auto, 0 never (kind::tf32), 1 always
   int k1_chunk_mb = 0;            // gallery bytes per chunk step (MB): 0 auto
   int k1_flags = 0;               // diagnostic bits, honoured by -DSBIR_DIAG builds only

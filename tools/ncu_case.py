@@ -5,7 +5,9 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from art_sbir_b200 import ops  # noqa: E402
+from art_sbir_b200 import _binding, ops  # noqa: E402
+
+_binding.set_debug_option("k1_pair_coop", 0)   # Nsight Compute cannot replay cooperative cluster launches
 from tools.gpu_probe import _clustered  # noqa: E402
 
 nq, ng, d, dtype, k = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), getattr(torch, sys.argv[4]), int(sys.argv[5])
