@@ -430,7 +430,7 @@ def extra_retrieval_workload(name, lib, dev, local_rank, peaks, tf32_peak, centr
     step(); step()
     e0.record(); step(); e1.record(); torch.cuda.synchronize()
     est = max(e0.elapsed_time(e1), 0.05) + (0.2 if flush is not None else 0.0)
-    steps = int(min(400, max(3, 1000.0 / est)))
+    steps = int(min(2000, max(3, 1000.0 / est)))
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)

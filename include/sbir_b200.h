@@ -108,14 +108,22 @@ int sbir_pairwise_distance_bwd(const float* x1, int64_t rows1, const float* x2, 
  * per-query selection, the K(+slack) survivors are re-scored with the exact
  * reference formula, and `out_uncertified[0]` counts queries whose selection could
  * not be proven exact (they are then recomputed by the brute-force exact kernel, so
- * results are exact either way; the counter is diagnostic).  For fp32 inputs a
- * device-gated second pass in 3xTF32 precision takes over when many queries cannot
- * be certified; its operand copies are part of the workspace (3x the inputs, when
- * that is below 12 GiB).
+ * results are exact either way; the counter is diagnostic).  Tile element types: bf16
+ * embeddings -> kind::f16; fp32 embeddings -> kind::tf32, or (problems of >= 4e11 FLOP
+ * whose rows are multiples of 8 elements) kind::f16 on bf16-rounded copies kept in the
+ * workspace, certified with measured rounding residuals.  Behind that pass, device-gated
+ * tiers take over what it cannot certify: a few queries are re-selected on kind::tf32
+ * tiles as a small batch, more trigger a kind::tf32 pass over all queries, and when more
+ * than 2 % are still unresolved a 3xTF32 pass (operand copies in the workspace: 3x the
+ * inputs, when that is below 12 GiB; euclidean: centred on the gallery mean).
+ * Rows may have ANY width: rows whose byte length is not a multiple of 16 are scored
+ * through zero-padded tile copies in the workspace (exact kernels read the caller's rows);
+ * when the rows ARE 16-byte multiples, q and g must be 16-byte aligned.
  * g_sqnorm (fp32 [num_g], may be NULL) = ‖g_j‖² of the gallery rows as stored, from
  * sbir_gallery_append / sbir_row_sqnorm or the feature-store sidecar; when given, the pass reads
- * num_g floats instead of the whole gallery to build its epilogue vector.
- * k <= 116; dim*sizeof(elem) must be a multiple of 16 bytes; pointers 16-byte aligned.
+ * num_g floats instead of the whole gallery to build its epilogue vector (ignored when fp32
+ * rows are converted to bf16 selection copies: that pass reads the rows anyway).
+ * k <= 116.
  * out_rank, pos_index, out_uncertified may be NULL. */
 size_t sbir_pairwise_topk_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int k,
                                           int dtype, int metric, int want_rank);
