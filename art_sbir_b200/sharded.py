@@ -28,6 +28,42 @@ def shard_bounds(num_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def weighted_shard_bounds(num_rows: int, weights, rank: int, align: int = 1) -> Tuple[int, int]:
+    """Contiguous row range of `rank` when rank r gets a share of the gallery proportional to weights[r]
+    (its measured scoring speed, see `rank_speed_weights`).  The GPUs of one chassis do not run a power-capped
+    tensor kernel at the same clock, and the exchange step waits for the slowest shard, so equal shards leave the
+    faster GPUs idle; cuts are rounded to `align` rows, cover [0, num_rows) exactly, and equal weights reproduce an
+    even split.  Any partition gives the same result (module docstring), so this is purely a speed choice."""
+    w = [max(float(x), 0.0) for x in weights]
+    total = sum(w)
+    if not w or total <= 0.0:
+        raise ValueError("weights must hold one non-negative number per rank, not all zero")
+    if not 0 <= rank < len(w):
+        raise ValueError(f"rank {rank} outside the {len(w)} weights")
+    align = max(1, int(align))
+    cuts, acc = [0], 0.0
+    for r in range(len(w) - 1):
+        acc += w[r]
+        cut = int(round(num_rows * acc / total / align)) * align
+        cuts.append(min(max(cut, cuts[-1]), num_rows))
+    cuts.append(num_rows)
+    return cuts[rank], cuts[rank + 1]
+
+
+def rank_speed_weights(rows_local: int, busy_ms_local: float, device=None, group=None):
+    """Gallery rows per millisecond of every rank (all-gathered, the same list everywhere): `busy_ms_local` is the
+    time this rank's GPU spent scoring `rows_local` rows with nobody to wait for — the distance kernel's own time,
+    not the step time, which the exchange step equalises across ranks."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    mine = torch.tensor([float(rows_local) / max(float(busy_ms_local), 1e-9)], dtype=torch.float64,
+                        device=device if device is not None else "cpu")
+    if world == 1:
+        return [float(mine.item())]
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [float(t.item()) for t in out]
+
+
 def _resolve_offsets(n_local: int, shard_offset: Optional[int], num_gallery_total: Optional[int], world: int,
                      rank: int, dev, group) -> Tuple[int, int]:
     """First global row of this rank's shard and the gallery length.  Whatever the caller left out is

@@ -528,6 +528,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (extra_workloads)")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled full-size oracle check")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal gallery shards (default: shard sizes follow each GPU's measured speed)")
     ap.add_argument("--centroids", type=int, default=0, help="class centroids of the generator (0: max(125, N/80), see make_shard)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -572,6 +573,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- N > 1: speed-weighted shards.  The GPUs of one chassis settle at different clocks under the power cap
+    # and the exchange step waits for the slowest shard, so (untimed, before the measurement) every rank times the
+    # distance kernel on an equal shard and the gallery is re-cut in proportion (sharded.weighted_shard_bounds);
+    # the data generator is row-deterministic, so the global problem — and the result — is unchanged.
+    balance = None
+    if world > 1 and not args.no_balance:
+        balance = {"rounds": []}
+        for _ in range(2):
+            _, cal_k1, _, _, _ = time_retrieval(step, 4, 3, barrier, lib, dev, None)
+            speeds = sharded.rank_speed_weights(r1 - r0, cal_k1, dev)
+            balance["rounds"].append({"rows_per_ms_per_rank": [round(x, 1) for x in speeds]})
+            if max(speeds) / min(speeds) < 1.01:
+                break
+            n0, n1 = sharded.weighted_shard_bounds(num_g, speeds, rank, align=256)
+            if (n0, n1) != (r0, r1):
+                del Q, Gs, pos
+                torch.cuda.empty_cache()
+                r0, r1 = n0, n1
+                Q, Gs, pos = make_shard(num_q, num_g, dim, dtype, r0, r1, dev, centroids=args.centroids)
+                torch.cuda.synchronize()
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler is not None:
         sampler.start()
@@ -587,8 +609,14 @@ def main():
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_per_step, k1_ms_per_launch, total_launches = tmax[0].item(), tmax[1].item(), int(tsum[2].item())
+        mine = torch.tensor([ms_step, k1_ms_step, float(r1 - r0)], device=dev, dtype=torch.float64)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = {"step_ms": [round(t[0].item(), 3) for t in every], "k1_ms": [round(t[1].item(), 3) for t in every],
+                    "gallery_rows": [int(t[2].item()) for t in every]}
     else:
         ms_per_step, k1_ms_per_launch, total_launches = t[0].item(), t[1].item(), int(t[2].item())
+        per_rank = None
     pairs = num_q * num_g
     value = pairs / (ms_per_step * 1e-3)
 
@@ -683,7 +711,12 @@ def main():
     tile_bf16 = tiles_are_bf16(lib, num_q, r1 - r0, dim, k, dtype == torch.bfloat16)
     if not tile_bf16 and tf32_peak is None:
         tf32_peak = measure_tf32_peak(dev)
-    roofline = k1_roofline(dim, num_q, r1 - r0, tile_bf16, k1_ms_per_launch, ms_per_step, peaks, tf32_peak, traffic)
+    # N > 1: the roofline line describes the rank whose distance kernel ran longest (its own shard rows)
+    slow_rows = r1 - r0 if per_rank is None else per_rank["gallery_rows"][max(range(world), key=lambda r: per_rank["k1_ms"][r])]
+    roofline = k1_roofline(dim, num_q, slow_rows, tile_bf16, k1_ms_per_launch, ms_per_step, peaks, tf32_peak, traffic)
+    if per_rank is not None:
+        per_rank["k1_tflops"] = [round(2.0 * dim * num_q * n / (t * 1e-3) / 1e12, 1) if t > 0 else None
+                                 for n, t in zip(per_rank["gallery_rows"], per_rank["k1_ms"])]
 
     cpu = None
     if not args.no_cpu:
@@ -700,7 +733,11 @@ def main():
             "data": "synthetic",
             "config": workload_config(args.workload, world, args.centroids),
             "timing": {"l2": "inputs larger than L2" if flush is None else "L2 flushed (512 MiB write) between timed steps",
-                       "method": "CUDA events on the launching stream around each of K steps after W warm-up steps, barrier + synchronize on both sides, max over ranks"},
+                       "method": "CUDA events on the launching stream around each of K steps after W warm-up steps, barrier + synchronize on both sides, max over ranks",
+                       "per_rank": per_rank,
+                       "shards": None if world == 1 else ("equal" if balance is None else
+                                                          {"rule": "rows proportional to each GPU's measured distance-kernel speed (untimed calibration passes before the measurement; same global problem, same result)",
+                                                           **balance})},
             "results": {**recall, "uncertified_queries": uncert},
             "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity, "tf32_peak_measured_tflops": tf32_peak, "extra_workloads": extras}

@@ -102,6 +102,26 @@ def test_shard_bounds_partition_the_gallery():
         assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
 
 
+def test_weighted_shard_bounds_follow_the_weights():
+    """Speed-weighted sharding (sharded.weighted_shard_bounds): a partition of [0, N) in rank order whose shares
+    follow the weights to within the alignment; equal weights reproduce the even split."""
+    for n, w, align in ((10_000_000, [1.0, 1.1, 0.9, 1.0, 1.05, 0.95, 1.0, 1.0], 256), (101, [3, 1, 0], 1), (7, [1] * 8, 1),
+                        (1000, [1e-3, 1e3], 16), (0, [1, 2], 1)):
+        spans = [sharded.weighted_shard_bounds(n, w, r, align) for r in range(len(w))]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] and spans[i][0] <= spans[i][1] for i in range(len(w) - 1))
+        tot = float(sum(w))
+        for (a, b), wi in zip(spans, w):
+            assert abs((b - a) - n * wi / tot) <= align + 1
+    even = [sharded.weighted_shard_bounds(75_000, [2.5] * 8, r) for r in range(8)]
+    assert even == [sharded.shard_bounds(75_000, 8, r) for r in range(8)]
+    with pytest.raises(ValueError):
+        sharded.weighted_shard_bounds(10, [0, 0], 0)
+    with pytest.raises(ValueError):
+        sharded.weighted_shard_bounds(10, [1, 1], 2)
+    assert sharded.rank_speed_weights(1000, 4.0) == [250.0]      # no process group: this rank alone
+
+
 def _plan(lib, nq, ng, d, k, dtype, sms=148):
     import ctypes
     out = (ctypes.c_int32 * 13)()

@@ -49,14 +49,21 @@ def _cpu_merge(dist_lists, idx_lists):
     return d.gather(1, order)[:, :k], ix.gather(1, order)[:, :k]
 
 
-def _worker(rank, world, port, loss_type, ret):
+def _worker(rank, world, port, loss_type, ret, weighted=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from art_sbir_b200 import sharded
         Q, G, pos = O.synthetic_embeddings(12, 101, 32, seed=5, beta=0.3, num_classes=4)
         pos[3] = -1
-        a, b = sharded.shard_bounds(G.shape[0], world, rank)
+        if weighted:
+            # speed-weighted shards: every rank reports (rows, busy ms) of a calibration pass, all ranks derive the same cuts
+            speeds = sharded.rank_speed_weights(100, 1.0 + 0.5 * rank)
+            assert speeds == [100.0 / (1.0 + 0.5 * r) for r in range(world)]
+            a, b = sharded.weighted_shard_bounds(G.shape[0], speeds, rank)
+            ret[f"span{rank}"] = (a, b)
+        else:
+            a, b = sharded.shard_bounds(G.shape[0], world, rank)
         vals, idx, rk = sharded.sharded_pairwise_topk(Q, G[a:b], 5, loss_type, pos_index=pos, local_fn=_oracle_local,
                                                       pos_dist_fn=_oracle_pos_dist, merge_fn=_cpu_merge)
         ret[rank] = (vals, idx, rk)
@@ -86,3 +93,24 @@ def test_sharded_equals_unsharded(world, loss_type):
         assert torch.allclose(vals, want_v, rtol=1e-6)
         assert torch.equal(rk, want_r)
         assert rk[3].item() == G.shape[0]
+
+
+def test_speed_weighted_shards_give_the_same_result():
+    """Uneven shards cut from all-gathered per-rank speeds (what bench.py --gpus N does before timing):
+    faster ranks hold more rows, the spans tile the gallery, and the result is the unsharded one."""
+    world = 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), "euclidean", ret, True), nprocs=world, join=True)
+    spans = [ret[f"span{r}"] for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == 101 and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    sizes = [b - a for a, b in spans]
+    assert sizes[0] > sizes[1] > sizes[2] > 0
+    Q, G, pos = O.synthetic_embeddings(12, 101, 32, seed=5, beta=0.3, num_classes=4)
+    pos[3] = -1
+    want_v, want_i = O.pairwise_topk_batched(Q, G, 5, "euclidean")
+    want_r = O.rank_of_positive_batched(Q, G, pos, "euclidean")
+    for r in range(world):
+        vals, idx, rk = ret[r]
+        assert torch.equal(idx, want_i) and torch.equal(rk, want_r)
+        assert torch.allclose(vals, want_v, rtol=1e-6)
