@@ -58,7 +58,11 @@ int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int
 // dependent instruction every ~4 cycles): 8 warps, the second of each quarter feeding the first
 // (K1Config::kFeed).  Option k1_feed = 0 falls back to 4 warps (A/B runs).
 static int epi_warps_for(int dtype, int cap) {
-  if (cap <= 32) return dtype == SBIR_BF16 ? 8 : 4;
+  if (cap <= 32) {
+    const int forced = debug_options().k1_epi;  // A/B runs: kind::tf32 tiles with two lists per row (single-CTA tiles only)
+    if (forced == 8 && dtype == SBIR_F32 && debug_options().k1_pair != 2) return 8;
+    return dtype == SBIR_BF16 ? 8 : 4;
+  }
   return debug_options().k1_feed == 0 ? 4 : 8;
 }
 

@@ -673,6 +673,45 @@ def case_small():
     return res
 
 
+def case_cfg1():
+    """Small retrievals (the reference's own 1k x 10k evaluation): A/B of the tile / epilogue forms.
+    Device time by CUDA-graph replay, K1's own time from the library's profiling hooks, results compared with the default form."""
+    import ctypes
+    import torch
+    from art_sbir_b200 import _binding as B, ops
+    lib = B.load()
+    out = {}
+    for nq, ng, d, k in ((1000, 10000, 2048, 10), (1000, 10000, 2048, 100), (2000, 40000, 2048, 10), (1000, 10000, 512, 10)):
+        q, g, pos = _clustered(nq, ng, d, torch.float32)
+        base = None
+        for name, opts in (("default", {}), ("epi8", {"k1_epi": 8}), ("sel_bf16", {"k1_sel_bf16": 1}), ("sel_tf32", {"k1_sel_bf16": 0})):
+            B_set("reset", 0)
+            for o, v in opts.items():
+                B_set(o, v)
+            try:
+                r = ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos, return_uncertified=True)
+                torch.cuda.synchronize()
+                us = _graph_us(lambda: ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos))
+                lib.sbir_profile_enable(1)
+                k1_ms, k1_n, launches = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+                lib.sbir_profile_collect(ctypes.byref(k1_ms), ctypes.byref(k1_n), ctypes.byref(launches))
+                for _ in range(5):
+                    ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
+                torch.cuda.synchronize()
+                lib.sbir_profile_collect(ctypes.byref(k1_ms), ctypes.byref(k1_n), ctypes.byref(launches))
+                lib.sbir_profile_enable(0)
+                rec = {"us": round(us, 1), "k1_us": round(k1_ms.value / 5 * 1e3, 1), "launches": launches.value // 5, "uncertified": int(r[3].item())}
+                if base is None:
+                    base = r
+                else:
+                    rec["same_as_default"] = bool(torch.equal(r[1], base[1]) and torch.equal(r[2], base[2]) and torch.equal(r[0], base[0]))
+            except Exception as e:  # noqa: BLE001
+                rec = {"error": str(e)[:200]}
+            out[f"{nq}x{ng}x{d} k={k} {name}"] = rec
+    B_set("reset", 0)
+    return out
+
+
 def case_k100_mainloop():
     """k=100 (cap 128: 3 operand stages) with the epilogue switched off: is it the mainloop?"""
     import torch
