@@ -58,11 +58,10 @@ int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t dim, int
 // dependent instruction every ~4 cycles): 8 warps, the second of each quarter feeding the first
 // (K1Config::kFeed).  Option k1_feed = 0 falls back to 4 warps (A/B runs).
 static int epi_warps_for(int dtype, int cap) {
-  if (cap <= 32) {
-    const int forced = debug_options().k1_epi;  // A/B runs: kind::tf32 tiles with two lists per row (single-CTA tiles only)
-    if (forced == 8 && dtype == SBIR_F32 && debug_options().k1_pair != 2) return 8;
-    return dtype == SBIR_BF16 ? 8 : 4;
-  }
+  // (kind::tf32 tiles with 8 warps / two lists per row were measured on the small shapes where the epilogue sets the time:
+  // 1k x 10k x 2048 K1 180 vs 177 us — the cost there is the ~cap*ln(columns/cap) cold-list insertions per row and list,
+  // which a second list per row does not reduce; profiles/r02_probe_cfg1_ab.log)
+  if (cap <= 32) return dtype == SBIR_BF16 ? 8 : 4;
   return debug_options().k1_feed == 0 ? 4 : 8;
 }
 

@@ -1025,13 +1025,6 @@ int dispatch_mode_cap(int mode, int cap, int pair, bool qres, const CUtensorMap&
     SBIR_K1_CASE(kModeTopkRank, 16)
     SBIR_K1_CASE(kModeTopkRank, 32)
     SBIR_K1_CASE(kModeDump, 16)
-  } else if constexpr (kTF32) {
-    // kind::tf32 with two lists per row (8 epilogue warps, single-CTA tiles): small problems, where every unit
-    // starts on cold lists and the epilogue — not the mainloop — sets the time (option k1_epi, dist_topk.cu)
-    SBIR_K1_CASE1(kModeTopk, 16)
-    SBIR_K1_CASE1(kModeTopk, 32)
-    SBIR_K1_CASE1(kModeTopkRank, 16)
-    SBIR_K1_CASE1(kModeTopkRank, 32)
   }
   SBIR_K1_CASE(kModeTopk, 64)
   SBIR_K1_CASE(kModeTopk, 128)

@@ -10,7 +10,6 @@ namespace sbir {
 // the environment on the launch path).  0 / -1 = the library's own choice.
 struct DebugOptions {
   int k1_feed = -1;               // owner+feeder epilogue for 64/128-entry lists: -1 auto, 0 off
-  int k1_epi = 0;                 // epilogue warps of small lists (cap <= 32): 0 auto, 4, 8 (two lists per row)
   int k1_pair = 0;                // CTA pairs: 0 auto, 1 never, 2 always
   int k1_qres = -1;               // resident-query form: -1 auto, 0 off
   int k1_pair_coop = 1;           // CTA-pair launches cooperative (1) or plain cluster launches (0: profilers that cannot replay them)

@@ -684,7 +684,7 @@ def case_cfg1():
     for nq, ng, d, k in ((1000, 10000, 2048, 10), (1000, 10000, 2048, 100), (2000, 40000, 2048, 10), (1000, 10000, 512, 10)):
         q, g, pos = _clustered(nq, ng, d, torch.float32)
         base = None
-        for name, opts in (("default", {}), ("epi8", {"k1_epi": 8}), ("sel_bf16", {"k1_sel_bf16": 1}), ("sel_tf32", {"k1_sel_bf16": 0})):
+        for name, opts in (("default", {}), ("sel_bf16", {"k1_sel_bf16": 1}), ("sel_tf32", {"k1_sel_bf16": 0})):
             B_set("reset", 0)
             for o, v in opts.items():
                 B_set(o, v)
@@ -709,6 +709,22 @@ def case_cfg1():
                 rec = {"error": str(e)[:200]}
             out[f"{nq}x{ng}x{d} k={k} {name}"] = rec
     B_set("reset", 0)
+    return out
+
+
+def case_qorder():
+    """Does finalize's candidate re-scoring (gathers of 8 KB gallery rows) profit from L2 when queries with overlapping
+    candidate sets run next to each other?  cfg3 with the queries in generator order vs grouped by class of their positive."""
+    import torch
+    from art_sbir_b200 import ops
+    out = {}
+    for k in (100, 10):
+        q, g, pos = _clustered(12500, 75000, 2048, torch.float32)
+        C = max(125, 75000 // 80)
+        for name, order in (("generator order", None), ("grouped by class", torch.argsort(pos % C, stable=True)), ("random order", torch.randperm(12500, device="cuda"))):
+            qq, pp = (q, pos) if order is None else (q[order].contiguous(), pos[order].contiguous())
+            us = _graph_us(lambda: ops.pairwise_topk(qq, g, k, "euclidean", pos_index=pp), replays=20)
+            out[f"cfg3 k={k} {name}"] = round(us, 1)
     return out
 
 
