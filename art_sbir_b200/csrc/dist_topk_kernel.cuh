@@ -600,6 +600,24 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (ej < thr) {
           lv[maxpos * kTileQ + row] = ej;
           li[maxpos * kTileQ + row] = gidx_e;
+          if (own_max == INFINITY) {
+            // The list is not full yet (its entries are finite, free slots hold +inf): slots fill in order —
+            // maxpos is the fill count — and there is no maximum to search for until the last one is taken.
+            // A cold list takes ~cap·(1 + ln(columns/cap)) insertions per row; this spares the first cap of them
+            // the scan (1k x 10k evaluation: a quarter of all insertions).
+            if (maxpos + 1 < kCap) {
+              ++maxpos;
+              return;
+            }
+            if constexpr (Cfg::kTwoLevel) {  // full from here on: group maxima of the (now all finite) entries
+              for (int u = 0; u < kCap / 8; ++u) {
+                float gm = -INFINITY;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) gm = fmaxf(gm, lv[(u * 8 + v) * kTileQ + row]);
+                lg[u * kTileQ + row] = gm;
+              }
+            }
+          }
           float mx = -INFINITY;
           int mp = 0;
           if constexpr (Cfg::kTwoLevel) {
