@@ -174,18 +174,27 @@ struct UnitCoord {
   int row_tile, part, chunk, t_begin, t_end;
 };
 __device__ __forceinline__ UnitCoord decode_unit(int unit, const K1Params& p) {
-  const int per_step = p.num_parts * p.num_row_tiles;
+  // L2 bands: the rows of the unit grid are walked in bands of `band_rows` query tiles, and a band scans all
+  // chunk steps of the launch before the next band starts, so that what is live at any time — the band's query
+  // tiles and parked lists plus one or two gallery chunks — fits L2 (one band = the plain chunk-major order).
+  const int band_units = p.band_rows * p.num_steps * p.num_parts;  // units of a full band
+  const int band = unit / band_units;
+  const int row0 = band * p.band_rows;
+  const int rows = min(p.band_rows, p.num_row_tiles - row0);
+  const int per_step = p.num_parts * rows;
+  const int in_band = unit - band * band_units;
   UnitCoord c;
-  const int step = unit / per_step;
+  const int step = in_band / per_step;
   c.chunk = p.chunk_begin + step;
-  const int r = unit - step * per_step;
+  const int r = in_band - step * per_step;
   if (p.part_fastest) {
     c.row_tile = r / p.num_parts;
     c.part = r - c.row_tile * p.num_parts;
   } else {
-    c.part = r / p.num_row_tiles;
-    c.row_tile = r - c.part * p.num_row_tiles;
+    c.part = r / rows;
+    c.row_tile = r - c.part * rows;
   }
+  c.row_tile += row0;
   const int part_begin = c.part * p.tiles_per_part;
   const int part_end = min(part_begin + p.tiles_per_part, p.num_g_tiles);
   c.t_begin = part_begin + c.chunk * p.tiles_per_chunk;

@@ -17,6 +17,8 @@ struct K1Params {
   int num_row_tiles;   // query tiles (kPair = 1) or query-tile pairs (kPair = 2): rows of the unit grid
   int num_parts, tiles_per_part, num_chunks, tiles_per_chunk, num_units, part_fastest;
   int chunk_begin;     // first chunk step of this launch (streamed galleries: later launches continue the lists)
+  int num_steps;       // chunk steps this launch covers
+  int band_rows;       // rows of the unit grid per L2 band (decode_unit); num_row_tiles = one band
   int q_tile_stride;   // query-tile stride of candidate slots (num_q_tiles rounded up to even)
   int elems_per_kblock;
   const void* q_raw;   // query matrix in global memory (resident-query form: loaded into TMEM by the epilogue warps)

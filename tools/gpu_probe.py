@@ -728,6 +728,39 @@ def case_qorder():
     return out
 
 
+def case_bands():
+    """cfg4 (and its 8-GPU shard) with the query tiles walked in L2 bands: time per pass for band count x chunk size."""
+    import torch
+    from art_sbir_b200 import ops
+    out = []
+    for ng in (10_000_000, 1_250_000):
+        q, g, pos = _clustered(100_000, ng, 512, torch.bfloat16)
+        base = None
+        for bands, chunk in ((-1, 0), (0, 0), (2, 0), (3, 0), (4, 0), (3, 24), (4, 24), (6, 24), (2, 96)):
+            B_set("reset", 0)
+            B_set("k1_bands", bands)
+            if chunk:
+                B_set("k1_chunk_mb", chunk)
+            r = ops.pairwise_topk(q, g, 10, "euclidean", pos_index=pos, return_uncertified=True)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            for i in range(3):
+                ops.pairwise_topk(q, g, 10, "euclidean", pos_index=pos)
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+            rec = {"gallery": ng, "bands": bands, "chunk_mb": chunk or 48, "ms": [round(x, 2) for x in ms], "uncertified": int(r[3].item())}
+            if base is None:
+                base = r
+            else:
+                rec["same_result"] = bool(torch.equal(r[0], base[0]) and torch.equal(r[1], base[1]) and torch.equal(r[2], base[2]))
+            out.append(rec)
+        del q, g, pos
+    B_set("reset", 0)
+    return out
+
+
 def case_k100_mainloop():
     """k=100 (cap 128: 3 operand stages) with the epilogue switched off: is it the mainloop?"""
     import torch
