@@ -160,27 +160,14 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   const int64_t q_tile_bytes = (int64_t)kTileQ * p.pair * dim * (int64_t)es;
   p.part_fastest = (p.num_splits > 1 && q_tile_bytes * workers > (24LL << 20)) ? 1 : 0;
   p.num_units = p.num_chunks * p.num_splits * row_tiles;
-  // L2 bands (decode_unit).  Chunk-major order re-reads EVERY query tile and parked list once per chunk step; when
-  // those exceed what L2 holds beside the gallery chunks in flight (cfg4: 102 MB of queries + 26 MB of lists + 48-96 MB of
-  // chunks against 126 MB) they come from DRAM every step and evict the chunk the other CTAs are reading (ncu, round 1/2:
-  // 72 GB of DRAM traffic for 10.35 GB of inputs).  Bands keep a slice of the queries L2-resident for a whole scan of the
-  // gallery; the gallery is then read `bands` times, which is the cheaper side as soon as there are many chunk steps.
+  // L2 bands (decode_unit, option k1_bands): walking the query tiles in bands that scan the whole gallery one after the
+  // other was built to keep a band's queries L2-resident.  Measured on cfg4 (profiles/r02_probe_l2_bands.log): it is
+  // 0.5-1.5 % SLOWER and reads MORE from DRAM (1 band 58 GB, 2 bands 80 GB, 3 bands 95 GB per launch) — the re-reads are
+  // gallery-chunk lines evicted by the streaming traffic, not the queries, and every band repeats them.  Off unless forced.
   p.band_q = row_tiles;
   {
-    const int64_t q_bytes = (int64_t)row_tiles * p.pair * kTileQ * (dim * (int64_t)es + (int64_t)p.cap * p.lists_per_row * p.num_splits * 8);
-    const int64_t chunk_bytes = (int64_t)p.tiles_per_chunk * tile_bytes * p.num_splits;
-    const int64_t budget = (96LL << 20) - 3 * chunk_bytes / 2;   // ~1.5 chunks are live across a step boundary
-    int64_t bands = 1;
     const int forced = debug_options().k1_bands;
-    if (forced > 0) {
-      bands = forced < row_tiles ? forced : row_tiles;
-    } else if (forced == 0 && p.num_chunks >= 8 && budget > (8LL << 20) && q_bytes > budget) {
-      bands = (q_bytes + budget - 1) / budget;
-      // a band still gives every worker a unit or two per chunk step (the CTAs then sit on at most two steps)
-      const int64_t max_bands = row_tiles * (int64_t)p.num_splits / (3LL * workers / 2);
-      if (bands > max_bands) bands = max_bands;
-    }
-    if (bands > 1) p.band_q = (int)((row_tiles + bands - 1) / bands);
+    if (forced > 1) p.band_q = (int)((row_tiles + forced - 1) / (forced < row_tiles ? forced : row_tiles));
   }
   return p;
 }
@@ -228,6 +215,7 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.flags = debug_options().k1_flags;
   prm.watchdog_cycles = debug_options().watchdog_cycles;
   prm.pair_cooperative = debug_options().k1_pair_coop != 0 ? 1 : 0;
+  prm.l2_hints = (qres && debug_options().k1_l2_hints != 0 && prm.num_chunks > 1) ? 1 : 0;
   prm.unit_counter = a.unit_counter;
   prm.chunk_done = a.chunk_done;
   prm.cand_val = a.cand_val;

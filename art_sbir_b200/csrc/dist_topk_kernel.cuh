@@ -213,6 +213,10 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr int kSubTiles = Cfg::kSubTiles;
   if (prm.gate != nullptr && *prm.gate == 0) return;  // uniform across the grid: nothing was set up yet
   const long long wd = prm.watchdog_cycles;
+  // L2 policies of the resident-query form (prm.l2_hints): the gallery chunk every CTA streams during a chunk step is
+  // kept (evict_last); query tiles on their way to TMEM and parked lists are touched once per step (evict_first).
+  [[maybe_unused]] const uint64_t pol_keep = l2_policy_evict_last();
+  [[maybe_unused]] const uint64_t pol_stream = l2_policy_evict_first();
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytesG = Cfg::kStageBytesG;
   constexpr int kStageBytes = Cfg::kStageBytes;
@@ -344,8 +348,12 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             } else if constexpr (kQRes) {
               // only the gallery half-tile's k-slice: the query tile is already in tensor memory
               mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-              tma_load_2d(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
-                          kb * prm.elems_per_kblock, t * kAccCols);
+              if (prm.l2_hints)
+                tma_load_2d_hint(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
+                                 kb * prm.elems_per_kblock, t * kAccCols, pol_keep);
+              else
+                tma_load_2d(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
+                            kb * prm.elems_per_kblock, t * kAccCols);
             } else if constexpr (kPair == 2) {
               // the leader's barrier collects the bytes of both CTAs' loads
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
@@ -484,7 +492,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
               uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
-              if (q_valid && j * 32 + v * 4 < row_words) t4 = __ldg(src + j * 8 + v);
+              if (q_valid && j * 32 + v * 4 < row_words) t4 = prm.l2_hints ? ld_stream_v4(src + j * 8 + v, pol_stream) : __ldg(src + j * 8 + v);
               w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
             }
             tmem_st_32x32b_x32(tmem_base + lane_addr + j * 32, w);
@@ -564,8 +572,13 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             [[maybe_unused]] int32_t ti[kBatch];
 #pragma unroll
             for (int p = 0; p < kBatch; ++p) {
-              tv[p] = __ldcg(gval + (p0 + p) * kTileQ + row);
-              if constexpr (Cfg::kIdxInSmem) ti[p] = __ldcg(gidx + (p0 + p) * kTileQ + row);
+              if (kQRes && prm.l2_hints) {
+                tv[p] = ld_cg_hint(gval + (p0 + p) * kTileQ + row, pol_stream);
+                if constexpr (Cfg::kIdxInSmem) ti[p] = ld_cg_hint(gidx + (p0 + p) * kTileQ + row, pol_stream);
+              } else {
+                tv[p] = __ldcg(gval + (p0 + p) * kTileQ + row);
+                if constexpr (Cfg::kIdxInSmem) ti[p] = __ldcg(gidx + (p0 + p) * kTileQ + row);
+              }
             }
 #pragma unroll
             for (int p = 0; p < kBatch; ++p) {
@@ -940,8 +953,13 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           // whichever SM it lands — or finalize.cu picks it up from there.
 #pragma unroll 4
           for (int p = 0; p < kCap; ++p) {
-            gval[p * kTileQ + row] = lv[p * kTileQ + row];
-            if constexpr (Cfg::kIdxInSmem) gidx[p * kTileQ + row] = li[p * kTileQ + row];
+            if (kQRes && prm.l2_hints) {
+              st_hint(gval + p * kTileQ + row, lv[p * kTileQ + row], pol_stream);
+              if constexpr (Cfg::kIdxInSmem) st_hint(gidx + p * kTileQ + row, li[p * kTileQ + row], pol_stream);
+            } else {
+              gval[p * kTileQ + row] = lv[p * kTileQ + row];
+              if constexpr (Cfg::kIdxInSmem) gidx[p * kTileQ + row] = li[p * kTileQ + row];
+            }
           }
           prm.row_max[list_slot * kTileQ + row] = own_max;
           prm.row_maxpos[list_slot * kTileQ + row] = maxpos;

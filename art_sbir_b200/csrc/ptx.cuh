@@ -86,6 +86,42 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
       : "memory");
 }
 
+// L2 eviction policies (descriptor operands of the .L2::cache_hint forms).  evict_last: lines that every CTA re-reads
+// during a chunk step (the gallery chunk); evict_first: data touched once per step (query tiles going to TMEM, parked lists).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4* ptr, uint64_t policy) {  // read-only, no L1 allocation
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ float ld_cg_hint(const float* ptr, uint64_t policy) {
+  float v;
+  asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(policy) : "memory");
+  return v;
+}
+__device__ __forceinline__ int32_t ld_cg_hint(const int32_t* ptr, uint64_t policy) {
+  int32_t v;
+  asm volatile("ld.global.cg.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_hint(float* ptr, float v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_hint(int32_t* ptr, int32_t v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(ptr), "r"(v), "l"(policy) : "memory");
+}
+
 // ----------------------------------------------------------------- tcgen05 ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

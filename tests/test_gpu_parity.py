@@ -338,6 +338,26 @@ def test_resident_query_form_matches_default_kernel(ops, dbg):
         assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(r0, r1)
 
 
+def test_l2_bands_of_query_tiles_give_the_same_result(ops, dbg):
+    """Unit order with the query tiles walked in L2 bands (option k1_bands; every band scans all chunk steps before the
+    next one starts): a different schedule of the same units, so results are identical — also with chunk hand-overs,
+    several gallery partitions, CTA pairs (static unit stride) and a last band that is shorter than the others."""
+    cases = ((20000, 9000, 64, torch.bfloat16, "euclidean", 10, 1), (1500, 40000, 128, torch.float32, "cosine", 100, 1),
+             (3000, 30000, 96, torch.float32, "euclidean", 10, 1), (700, 5000, 512, torch.bfloat16, "euclidean", 20, 0))
+    for nq, ng, d, dtype, lt, k, chunk_mb in cases:
+        Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=nq + 1, beta=0.3)
+        q, g, p = Q.to(dtype).cuda(), G.to(dtype).cuda(), pos.cuda()
+        dbg("reset", 0)
+        if chunk_mb:
+            dbg("k1_chunk_mb", chunk_mb)
+        dbg("k1_bands", -1)
+        v0, i0, r0 = ops.pairwise_topk(q, g, k, lt, pos_index=p)
+        for bands in (2, 3, 5):
+            dbg("k1_bands", bands)
+            v1, i1, r1 = ops.pairwise_topk(q, g, k, lt, pos_index=p)
+            assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(r0, r1), (nq, ng, d, lt, k, bands)
+
+
 @pytest.mark.parametrize("nq,ng,d,lt,k", [(130, 1000, 512, "euclidean", 1), (200, 2500, 1024, "cosine", 10), (64, 1500, 2048, "euclidean", 30),
                                            (300, 5000, 96, "euclidean", 10), (1000, 20000, 192, "cosine", 20), (37, 300, 64, "euclidean", 100)])
 def test_fp32_selected_on_bf16_copies_matches_tf32_selection_and_oracle(ops, dbg, nq, ng, d, lt, k):

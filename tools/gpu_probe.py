@@ -761,6 +761,36 @@ def case_bands():
     return out
 
 
+def case_l2hints():
+    """cfg4 (and its 8-GPU shard, and cfg4 with K = 100) with and without the L2 eviction hints of the resident-query form."""
+    import torch
+    from art_sbir_b200 import ops
+    out = []
+    for ng, k in ((10_000_000, 10), (1_250_000, 10), (10_000_000, 100)):
+        q, g, pos = _clustered(100_000, ng, 512, torch.bfloat16)
+        base = None
+        for hints in (0, -1, 0, -1):
+            B_set("reset", 0)
+            B_set("k1_l2_hints", hints)
+            r = ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos, return_uncertified=True)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            for i in range(3):
+                ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            rec = {"gallery": ng, "k": k, "l2_hints": hints, "ms": [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(3)], "uncertified": int(r[3].item())}
+            if base is None:
+                base = r
+            else:
+                rec["same_result"] = bool(torch.equal(r[0], base[0]) and torch.equal(r[1], base[1]) and torch.equal(r[2], base[2]))
+            out.append(rec)
+        del q, g, pos
+    B_set("reset", 0)
+    return out
+
+
 def case_k100_mainloop():
     """k=100 (cap 128: 3 operand stages) with the epilogue switched off: is it the mainloop?"""
     import torch
