@@ -215,7 +215,12 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.flags = debug_options().k1_flags;
   prm.watchdog_cycles = debug_options().watchdog_cycles;
   prm.pair_cooperative = debug_options().k1_pair_coop != 0 ? 1 : 0;
-  prm.l2_hints = (qres && debug_options().k1_l2_hints != 0 && prm.num_chunks > 1) ? 1 : 0;
+  // L2 eviction hints of the resident-query form, bits: 1 gallery chunk evict_last, 2 query tiles evict_first, 4 parked
+  // lists evict_first (option k1_l2_hints).  OFF by default: measured on cfg4 (profiles/r02_probe_l2_hints.log) they cut the
+  // DRAM traffic of a launch from 64 GB to 46 GB (all three; the query-tile hint alone: 53 GB) but cost 0.6-1.2 % of time —
+  // the query tiles that survive in L2 from one chunk step to the next are what keeps a unit's start short, and DRAM
+  // runs at ~1 % of its bandwidth either way.  Time is the metric, so the traffic stays.
+  prm.l2_hints = (qres && prm.num_chunks > 1 && debug_options().k1_l2_hints > 0) ? debug_options().k1_l2_hints : 0;
   prm.unit_counter = a.unit_counter;
   prm.chunk_done = a.chunk_done;
   prm.cand_val = a.cand_val;

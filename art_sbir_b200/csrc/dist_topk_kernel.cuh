@@ -348,7 +348,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             } else if constexpr (kQRes) {
               // only the gallery half-tile's k-slice: the query tile is already in tensor memory
               mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-              if (prm.l2_hints)
+              if (prm.l2_hints & 1)
                 tma_load_2d_hint(smem_g + stage * kStageBytesG, &tmap_g, &full_bar[stage],
                                  kb * prm.elems_per_kblock, t * kAccCols, pol_keep);
               else
@@ -492,7 +492,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
               uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
-              if (q_valid && j * 32 + v * 4 < row_words) t4 = prm.l2_hints ? ld_stream_v4(src + j * 8 + v, pol_stream) : __ldg(src + j * 8 + v);
+              if (q_valid && j * 32 + v * 4 < row_words) t4 = (prm.l2_hints & 2) ? ld_stream_v4(src + j * 8 + v, pol_stream) : __ldg(src + j * 8 + v);
               w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
             }
             tmem_st_32x32b_x32(tmem_base + lane_addr + j * 32, w);
@@ -572,7 +572,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             [[maybe_unused]] int32_t ti[kBatch];
 #pragma unroll
             for (int p = 0; p < kBatch; ++p) {
-              if (kQRes && prm.l2_hints) {
+              if (kQRes && (prm.l2_hints & 4)) {
                 tv[p] = ld_cg_hint(gval + (p0 + p) * kTileQ + row, pol_stream);
                 if constexpr (Cfg::kIdxInSmem) ti[p] = ld_cg_hint(gidx + (p0 + p) * kTileQ + row, pol_stream);
               } else {
@@ -953,7 +953,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           // whichever SM it lands — or finalize.cu picks it up from there.
 #pragma unroll 4
           for (int p = 0; p < kCap; ++p) {
-            if (kQRes && prm.l2_hints) {
+            if (kQRes && (prm.l2_hints & 4)) {
               st_hint(gval + p * kTileQ + row, lv[p * kTileQ + row], pol_stream);
               if constexpr (Cfg::kIdxInSmem) st_hint(gidx + p * kTileQ + row, li[p * kTileQ + row], pol_stream);
             } else {
