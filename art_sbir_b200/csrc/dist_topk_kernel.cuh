@@ -274,7 +274,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(&sched_full_bar[s], 1);
       mbar_init(&sched_empty_bar[s], 1 + kEpiWarps);  // MMA issuer + every epilogue warp
     }
-    mbar_init(q_ready_bar, 4);  // one arrival per TMEM lane quarter
+    mbar_init(q_ready_bar, kEpiWarps);  // every epilogue warp stores its share of the query tile
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -340,6 +340,17 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (unit < 0) break;
         const UnitCoord uc = decode_unit(unit, prm);
         const int q_tile = uc.row_tile * kPair + cta_rank;
+        if constexpr (kQRes) {
+          // The unit was claimed a ring of operand stages ahead of its first MMA: pull its query tile (contiguous
+          // rows) into L2 now, so that the epilogue warps' loads into tensor memory — the one step between two
+          // units that nothing overlaps — do not wait for DRAM.
+          if (issuer) {
+            const int rows_q = min(kTileQ, prm.num_q - q_tile * kTileQ);
+            if (rows_q > 0)
+              l2_prefetch_bulk(static_cast<const uint8_t*>(prm.q_raw) + (size_t)q_tile * kTileQ * prm.dim_elems * 2,
+                               (uint32_t)rows_q * (uint32_t)prm.dim_elems * 2u);
+          }
+        }
         for (int t = uc.t_begin * kSubTiles; t < uc.t_end * kSubTiles; ++t) {
           for (int kb = 0; kb < prm.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1, wd);
@@ -469,6 +480,35 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     int acc = 0;
     uint32_t acc_phase = 0;
 
+    // Resident-query form: store the query tile of unit `u` into tensor memory.  Every thread stores ITS row (TMEM lane =
+    // query row, column j = 32-bit word j of the row, i.e. two bf16 per column, K-major); the two warps of a lane quarter
+    // take alternate k-blocks, and the MMA issuer is released once all eight have arrived.  May only run after every MMA
+    // of the previous unit has completed (its last accumulator was seen full).
+    [[maybe_unused]] bool q_preloaded = false;
+    [[maybe_unused]] auto load_q_tile = [&](int u) {
+      if constexpr (kQRes) {
+        const UnitCoord un = decode_unit(u, prm);
+        const int qn = (un.row_tile * kPair + cta_rank) * kTileQ + row;
+        const bool valid = qn < prm.num_q;
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(prm.q_raw) + (size_t)qn * prm.dim_elems * 2);
+        const int row_words = prm.dim_elems / 2;
+        for (int j = half; j < prm.num_k_blocks; j += Cfg::kColSplit) {
+          uint32_t w[32];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && j * 32 + v * 4 < row_words) t4 = (prm.l2_hints & 2) ? ld_stream_v4(src + j * 8 + v, pol_stream) : __ldg(src + j * 8 + v);
+            w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
+          }
+          tmem_st_32x32b_x32(tmem_base + lane_addr + j * 32, w);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_ready_bar);
+      }
+    };
+
     for (int it = 0;; ++it) {
       const int unit = next_unit_consumer(it);
       __syncwarp();  // every lane has read the ring slot
@@ -480,28 +520,10 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const bool q_valid = q < prm.num_q;
 
       if constexpr (kQRes) {
-        // Every MMA of the previous unit has completed (its last accumulator was seen full), so the
-        // query tile in TMEM can be replaced: this thread stores ITS row (TMEM lane = query row,
-        // column j = 32-bit word j of the row, i.e. two bf16 per column, K-major) — one warp per
-        // lane quarter — and the MMA issuer is released once all four quarters are in.
-        if (half == 0) {
-          const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(prm.q_raw) + (size_t)q * prm.dim_elems * 2);
-          const int row_words = prm.dim_elems / 2;
-          for (int j = 0; j < prm.num_k_blocks; ++j) {
-            uint32_t w[32];
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
-              if (q_valid && j * 32 + v * 4 < row_words) t4 = (prm.l2_hints & 2) ? ld_stream_v4(src + j * 8 + v, pol_stream) : __ldg(src + j * 8 + v);
-              w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
-            }
-            tmem_st_32x32b_x32(tmem_base + lane_addr + j * 32, w);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(q_ready_bar);
-        }
+        // The unit's query tile normally went into tensor memory while the previous unit's last accumulator was still
+        // being worked on (load_q_tile below); only the first unit of this CTA, or one after an empty unit, loads it here.
+        if (!q_preloaded) load_q_tile(unit);
+        q_preloaded = false;
       }
 
       // This thread's list: entry p lives at [p * kTileQ + row] (conflict-free / coalesced).
@@ -790,6 +812,18 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if ((K1_DIAG_FLAGS(prm) & 64) && ew == 0 && lane == 0 && blockIdx.x < 148)
           g_k1_diag[blockIdx.x * 8 + 3] += (unsigned long long)(clock64() - tw_e);
         tc_fence_after();
+        if constexpr (kQRes) {
+          // Last accumulator of the unit: every MMA that reads the query tile has completed, so the NEXT unit's tile
+          // goes into tensor memory first and the MMA issuer starts on it while this accumulator's epilogue, the list
+          // parking and the next unit's list reload run — the tensor pipe no longer idles through them between units.
+          if (t == uc.t_end * kSubTiles - 1) {
+            const int next = next_unit_consumer(it + 1);   // published by the scheduler when it finished feeding this unit
+            if (next >= 0) {
+              load_q_tile(next);
+              q_preloaded = true;
+            }
+          }
+        }
         if constexpr (kSelect) {
           // Another partition (or the other column half) scanning the same query may already
           // hold `cap` candidates below some value: nothing at or above it can reach the final

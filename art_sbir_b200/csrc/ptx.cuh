@@ -86,6 +86,11 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
       : "memory");
 }
 
+// Asynchronous bulk prefetch of `bytes` (multiple of 16) contiguous global bytes into L2.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+
 // L2 eviction policies (descriptor operands of the .L2::cache_hint forms).  evict_last: lines that every CTA re-reads
 // during a chunk step (the gallery chunk); evict_first: data touched once per step (query tiles going to TMEM, parked lists).
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
