@@ -698,6 +698,7 @@ int sbir_debug_set_option(const char* name, int64_t value) {
   if (!std::strcmp(name, "k1_feed")) o.k1_feed = (int)value;
   else if (!std::strcmp(name, "k1_bands")) o.k1_bands = (int)value;
   else if (!std::strcmp(name, "k1_l2_hints")) o.k1_l2_hints = (int)value;
+  else if (!std::strcmp(name, "k1_q_early")) o.k1_q_early = (int)value;
   else if (!std::strcmp(name, "k1_pair")) o.k1_pair = (int)value;
   else if (!std::strcmp(name, "k1_qres")) o.k1_qres = (int)value;
   else if (!std::strcmp(name, "k1_pair_coop")) o.k1_pair_coop = (int)value;

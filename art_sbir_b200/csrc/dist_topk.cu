@@ -215,6 +215,7 @@ int launch_k1(const K1Args& a, const K1Plan& plan, cudaStream_t st) {
   prm.flags = debug_options().k1_flags;
   prm.watchdog_cycles = debug_options().watchdog_cycles;
   prm.pair_cooperative = debug_options().k1_pair_coop != 0 ? 1 : 0;
+  prm.q_early = debug_options().k1_q_early != 0 ? 1 : 0;
   // L2 eviction hints of the resident-query form, bits: 1 gallery chunk evict_last, 2 query tiles evict_first, 4 parked
   // lists evict_first (option k1_l2_hints).  OFF by default: measured on cfg4 (profiles/r02_probe_l2_hints.log) they cut the
   // DRAM traffic of a launch from 64 GB to 46 GB (all three; the query-tile hint alone: 53 GB) but cost 0.6-1.2 % of time —

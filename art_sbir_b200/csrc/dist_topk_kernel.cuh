@@ -816,7 +816,7 @@ dist_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           // Last accumulator of the unit: every MMA that reads the query tile has completed, so the NEXT unit's tile
           // goes into tensor memory first and the MMA issuer starts on it while this accumulator's epilogue, the list
           // parking and the next unit's list reload run — the tensor pipe no longer idles through them between units.
-          if (t == uc.t_end * kSubTiles - 1) {
+          if (prm.q_early && t == uc.t_end * kSubTiles - 1) {
             const int next = next_unit_consumer(it + 1);   // published by the scheduler when it finished feeding this unit
             if (next >= 0) {
               load_q_tile(next);

@@ -25,6 +25,7 @@ struct K1Params {
   int dim_elems;
   const int32_t* gate;     // optional: the kernel is a no-op unless *gate != 0 (escalation pass)
   int flags;               // -DSBIR_DIAG builds only (k1_flags option): 8 = epilogue skips the accumulator (mainloop alone), 16 = no chunk screen, 64 = cycle counters
+  int q_early;             // resident-query form: next unit's query tile stored while the current unit's last accumulator is worked on (option k1_q_early = 0: A/B)
   int l2_hints;            // resident-query form: L2 eviction hints (gallery chunk evict_last, query tiles / parked lists evict_first)
   int pair_cooperative;    // CTA-pair launches carry the cooperative attribute (co-residency guaranteed or the launch fails)
   long long watchdog_cycles;  // bound on every spin / barrier wait (0 = none), see ptx.cuh

@@ -12,6 +12,7 @@ struct DebugOptions {
   int k1_feed = -1;               // owner+feeder epilogue for 64/128-entry lists: -1 auto, 0 off
   int k1_bands = 0;               // L2 bands of query tiles (make_k1_plan): 0 auto, -1 never, n forced
   int k1_l2_hints = 0;            // resident-query form: L2 eviction hints (bits 1 gallery evict_last, 2 query tiles / 4 parked lists evict_first); 0 off (default: they cost time)
+  int k1_q_early = 1;             // resident-query form: early store of the next unit's query tile (0: at the unit's start, A/B)
   int k1_pair = 0;                // CTA pairs: 0 auto, 1 never, 2 always
   int k1_qres = -1;               // resident-query form: -1 auto, 0 off
   int k1_pair_coop = 1;           // CTA-pair launches cooperative (1) or plain cluster launches (0: profilers that cannot replay them)

@@ -766,12 +766,16 @@ def case_l2hints():
     import torch
     from art_sbir_b200 import ops
     out = []
-    for ng, k in ((10_000_000, 10),):
+    opt = "k1_l2_hints"
+    import sys
+    if len(sys.argv) > 2:
+        opt = sys.argv[2]          # e.g. k1_q_early: values 0 / 1 alternate
+    for ng, k in ((10_000_000, 10), (1_250_000, 10), (10_000_000, 100)):
         q, g, pos = _clustered(100_000, ng, 512, torch.bfloat16)
         base = None
-        for hints in (0, 1, 2, 4, 3, 5, 6, 7, 0, 1, 2, 4, 3, 5, 6, 7):
+        for hints in ((0, 1, 2, 4, 3, 5, 6, 7, 0, 1, 2, 4, 3, 5, 6, 7) if opt == "k1_l2_hints" else (0, 1, 0, 1)):
             B_set("reset", 0)
-            B_set("k1_l2_hints", hints)
+            B_set(opt, hints)
             r = ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos, return_uncertified=True)
             torch.cuda.synchronize()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -780,7 +784,7 @@ def case_l2hints():
                 ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
                 ev[i + 1].record()
             torch.cuda.synchronize()
-            rec = {"gallery": ng, "k": k, "l2_hints": hints, "ms": [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(3)], "uncertified": int(r[3].item())}
+            rec = {"gallery": ng, "k": k, opt: hints, "ms": [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(3)], "uncertified": int(r[3].item())}
             if base is None:
                 base = r
             else:
