@@ -175,6 +175,24 @@ def _pinned_rows(rows: int, dim: int, dtype: torch.dtype) -> torch.Tensor:
     return buf
 
 
+def _upload_replicated(x_host: torch.Tensor, dev, world: int, rank: int, group) -> torch.Tensor:
+    """A host matrix every rank holds (the queries) → the device.  With several ranks on one box the ranks share the
+    host's memory and PCIe bandwidth (8 ranks copying at once: ≈23 GB/s each), so uploading the same 100 MB eight times
+    puts ≈4 ms in front of the first scoring launch; instead every rank uploads ITS 1/world of the rows and the slices
+    are all-gathered over NVLink."""
+    n = x_host.shape[0]
+    if world == 1 or n < 4096 or dist.get_backend(group) != "nccl":
+        return x_host.to(dev, non_blocking=True).contiguous()
+    per = (n + world - 1) // world
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    mine = torch.zeros((per,) + tuple(x_host.shape[1:]), dtype=x_host.dtype, device=dev)
+    if hi > lo:
+        mine[:hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+    full = torch.empty((world * per,) + tuple(x_host.shape[1:]), dtype=x_host.dtype, device=dev)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:n]
+
+
 def sharded_retrieve_host(queries_host: torch.Tensor, gallery_shard_host: torch.Tensor, k: int,
                           loss_type: str = "euclidean", pos_index: Optional[torch.Tensor] = None,
                           shard_offset: Optional[int] = None, num_gallery_total: Optional[int] = None, group=None,
@@ -198,7 +216,7 @@ def sharded_retrieve_host(queries_host: torch.Tensor, gallery_shard_host: torch.
     if queries_host.dtype != gallery_shard_host.dtype or queries_host.dtype not in (torch.float32, torch.bfloat16):
         queries_host, gallery_shard_host = queries_host.float(), gallery_shard_host.float()
     g_host = gallery_shard_host.contiguous()
-    q = queries_host.to(dev, non_blocking=True).contiguous()
+    q = _upload_replicated(queries_host, dev, world, rank, group)
     nq, d = q.shape
     pos_dist = pos_g = None
     if pos_index is not None:
