@@ -9,7 +9,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "art_sbir_b200" / "lib" / "libsbir_b200.so"
-OPS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "ELECT", "HMMA", "HGMMA", "UBLKCP",
+OPS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "ELECT", "HMMA", "HGMMA", "UBLKCP", "UBLKPF",
        "LDGSTS", "ATOMG", "BAR.SYNC", "MEMBAR", "DFMA", "FMNMX3"]
 
 
