@@ -70,10 +70,15 @@ static int epi_warps_for(int dtype, int cap) {
 // one MMA then waits for the slowest of 16 epilogue warps, so with small lists single-CTA tiles win
 // (cfg4: 816 vs 930 ms).  With the 128-entry lists of top-100 on fp32 rows only 3 single-CTA operand
 // stages fit and the mainloop starves (operand wait 300 of 680 cycles per k-block); the pair's 32 KB
-// stages fit 4: cfg3 K1 7.0 -> 6.2 ms.  Option k1_pair = 1 / 2 forces either form (A/B runs, tests).
-static int k1_pair_for(int dtype, int cap) {
+// stages fit 4: cfg3 K1 7.0 -> 6.2 ms.  bf16 tiles of rows of 4 KB and more (2048-d: fp32 embeddings selected on their
+// bf16 copies) run the all-shared-memory form, which re-reads the 512 KB query tile for every gallery tile and is L2-bound
+// (12.5k x 75k x 2048: 46 GB of operands in 3 ms = 15 TB/s); a pair moves a third less: K1 3.27 -> 2.97 ms, pass 4.03-4.10 ->
+// 3.81-3.84 ms (top-10), 6.7-6.9 -> 6.65-6.75 ms (top-100); 1024-d rows: no difference (profiles/r02_probe_pair_wide_rows.log).
+// Option k1_pair = 1 / 2 forces either form (A/B runs, tests).
+static int k1_pair_for(int dtype, int cap, int64_t dim) {
   const int forced = debug_options().k1_pair;
   if (forced == 1 || forced == 2) return forced;
+  if (dtype == SBIR_BF16 && dim * 2 >= 4096) return 2;
   return (dtype == SBIR_F32 && cap >= 64) ? 2 : 1;
 }
 
@@ -102,7 +107,7 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   if (p.num_q_tiles < 1) p.num_q_tiles = 1;
   if (p.num_g_tiles < 1) p.num_g_tiles = 1;
   p.q_tile_stride = (p.num_q_tiles + 1) & ~1;
-  p.pair = (p.num_q_tiles >= 2 && num_sms >= 2) ? k1_pair_for(dtype, p.cap) : 1;
+  p.pair = (p.num_q_tiles >= 2 && num_sms >= 2) ? k1_pair_for(dtype, p.cap, dim) : 1;
   const int row_tiles = (p.num_q_tiles + p.pair - 1) / p.pair;  // rows of the unit grid
   const int workers = num_sms / p.pair;                           // CTAs or CTA pairs
   const size_t es = dtype == SBIR_BF16 ? 2 : 4;

@@ -321,10 +321,15 @@ __global__ void __launch_bounds__(kFbThreads) topk_fallback_kernel(const FinPara
   __shared__ int32_t mi[1024];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = p.k;
-  // a few blocks per SM walk the queries: when nothing is flagged (the normal case) the launch costs
-  // a couple of microseconds instead of one empty block per query
-  for (int q = blockIdx.x; q < p.num_q; q += gridDim.x) {
-  if ((p.flags[q] & 1) == 0) continue;
+  // A few blocks per SM walk the queries in runs of 32: every warp reads the run's flags with one coalesced load (the
+  // same 32 words in all warps, so the ballot is block-uniform) and the block brute-forces the flagged ones.  With
+  // nothing flagged — the normal case — 100k queries cost three load round trips per block (one dependent load per
+  // query and block took 80 us).
+  for (int base = blockIdx.x * 32; base < p.num_q; base += gridDim.x * 32) {
+  unsigned todo = __ballot_sync(kFullMask, base + lane < p.num_q && (p.flags[base + lane] & 1) != 0);
+  while (todo != 0u) {
+  const int q = base + __ffs(todo) - 1;
+  todo &= todo - 1;
   __syncthreads();  // shared lists of the previous flagged query fully consumed
   for (int i = lane; i < k; i += 32) {
     wd[warp][i] = INFINITY;
@@ -362,6 +367,7 @@ __global__ void __launch_bounds__(kFbThreads) topk_fallback_kernel(const FinPara
     const bool have = mi[i] != INT_MAX;
     p.out_dist[(size_t)q * k + i] = have ? (float)md[i] : INFINITY;
     p.out_index[(size_t)q * k + i] = have ? (long long)mi[i] + p.index_offset : -1LL;
+  }
   }
   }
 }
@@ -469,12 +475,20 @@ template <typename T, bool kVec>
 __global__ void __launch_bounds__(kFbThreads) rank_output_kernel(const RankParams p) {
   __shared__ int red[kFbWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int q = blockIdx.x; q < p.num_q; q += gridDim.x) {
-    const double dpos = p.pos_dist[q];
-    if (dpos != dpos || p.dropped[q] <= 0) {  // uniform across the block
-      if (threadIdx.x == 0) p.out_rank[q] = (dpos != dpos) ? p.missing_rank : (long long)p.cnt_less[q];
-      continue;
+  // runs of 32 queries, read by every warp with coalesced loads (block-uniform ballot, see topk_fallback_kernel): warp 0
+  // writes the ranks the counters settled, the block counts the overflowed ones exactly
+  for (int base = blockIdx.x * 32; base < p.num_q; base += gridDim.x * 32) {
+    const int qi = base + lane;
+    bool brute = false;
+    if (qi < p.num_q) {
+      const double dp = p.pos_dist[qi];
+      brute = dp == dp && p.dropped[qi] > 0;
+      if (!brute && warp == 0) p.out_rank[qi] = (dp != dp) ? p.missing_rank : (long long)p.cnt_less[qi];
     }
+    unsigned todo = __ballot_sync(kFullMask, brute);
+    while (todo != 0u) {
+    const int q = base + __ffs(todo) - 1;
+    todo &= todo - 1;
     __syncthreads();
     const T* qrow = reinterpret_cast<const T*>(p.q) + (size_t)q * p.dim;
     int cnt = 0;
@@ -489,6 +503,7 @@ __global__ void __launch_bounds__(kFbThreads) rank_output_kernel(const RankParam
       long long r = 0;
       for (int w = 0; w < kFbWarps; ++w) r += red[w];
       p.out_rank[q] = r;
+    }
     }
   }
 }
@@ -1110,7 +1125,8 @@ int launch_topk_fallback(const FinalizeArgs& a, cudaStream_t st) {
   if (a.num_q <= 0) return SBIR_OK;
   const FinParams p = make_fin_params(a, nullptr);
   const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
-  const unsigned grid = (unsigned)(a.num_q < 148 * 8 ? a.num_q : 148 * 8);
+  const int64_t runs = (a.num_q + 31) / 32;
+  const unsigned grid = (unsigned)(runs < 148 * 8 ? runs : 148 * 8);
   SBIR_DISPATCH_T(a.dtype, vec, topk_fallback_kernel, grid, kFbThreads, 0, st, p);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;
@@ -1139,7 +1155,8 @@ int launch_rank_output(const RankArgs& a, cudaStream_t st) {
   if (a.num_q <= 0) return SBIR_OK;
   const RankParams p = make_rank_params(a);
   const bool vec = rows_vectorizable(a.q, a.dim, a.dtype) && rows_vectorizable(a.g, a.dim, a.dtype);
-  const unsigned grid = (unsigned)(a.num_q < 148 * 8 ? a.num_q : 148 * 8);
+  const int64_t runs = (a.num_q + 31) / 32;
+  const unsigned grid = (unsigned)(runs < 148 * 8 ? runs : 148 * 8);
   SBIR_DISPATCH_T(a.dtype, vec, rank_output_kernel, grid, kFbThreads, 0, st, p);
   SBIR_CHECK_LAUNCH();
   return SBIR_OK;

@@ -117,11 +117,13 @@ def test_debug_options_change_the_plan_and_reset(sbir_lib):
         assert sbir_lib.sbir_debug_plan(100_000, 10_000_000, 512, 10, 1, 148, out) == 0
         assert out[6] > auto_chunks                                   # smaller chunk steps -> more of them
         _binding.set_debug_option("k1_pair", 2)
-        assert sbir_lib.sbir_debug_plan(12_500, 75_000, 2048, 10, 0, 148, out) == 0 and out[10] == 2
+        assert sbir_lib.sbir_debug_plan(12_500, 75_000, 1024, 10, 0, 148, out) == 0 and out[10] == 2
     finally:
         _binding.set_debug_option("reset")
     assert sbir_lib.sbir_debug_plan(100_000, 10_000_000, 512, 10, 1, 148, out) == 0 and out[6] == auto_chunks
-    assert sbir_lib.sbir_debug_plan(12_500, 75_000, 2048, 10, 0, 148, out) == 0 and out[10] == 1
+    assert sbir_lib.sbir_debug_plan(12_500, 75_000, 1024, 10, 0, 148, out) == 0 and out[10] == 1
+    # bf16 tiles of rows >= 4 KB (2048-d fp32 embeddings selected on their bf16 copies) take CTA pairs on their own
+    assert sbir_lib.sbir_debug_plan(12_500, 75_000, 2048, 10, 0, 148, out) == 0 and out[10] == 2 and out[12] == 1
 
 
 def test_product_refuses_cpu_tensors_and_never_imports_the_oracle():

@@ -338,6 +338,28 @@ def test_resident_query_form_matches_default_kernel(ops, dbg):
         assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(r0, r1)
 
 
+def test_cta_pairs_match_single_cta_tiles_on_bf16_tiles(ops, dbg):
+    """CTA pairs (cta_group::2, M = 256; the default for bf16 tiles of rows >= 4 KB, i.e. 2048-d fp32 embeddings selected on
+    their bf16 copies) against single-CTA tiles: same candidates, same certificate, identical results — small and large
+    lists, both metrics, an odd number of query tiles, bf16 embeddings and bf16-selected fp32 embeddings."""
+    cases = ((700, 5000, 2048, torch.float32, "euclidean", 10), (300, 4000, 2048, torch.float32, "cosine", 100),
+             (900, 6000, 256, torch.bfloat16, "euclidean", 10), (385, 3000, 2048, torch.bfloat16, "cosine", 30))
+    for nq, ng, d, dtype, lt, k in cases:
+        Q, G, pos = O.synthetic_embeddings(nq, ng, d, seed=nq + 7, beta=0.3 if d < 512 else None)
+        q, g, p = Q.to(dtype).cuda(), G.to(dtype).cuda(), pos.cuda()
+        dbg("reset", 0)
+        if dtype == torch.float32:
+            dbg("k1_sel_bf16", 1)
+        dbg("k1_pair", 1)
+        v0, i0, r0 = ops.pairwise_topk(q, g, k, lt, pos_index=p)
+        dbg("k1_pair", 2)
+        v1, i1, r1 = ops.pairwise_topk(q, g, k, lt, pos_index=p)
+        assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(r0, r1), (nq, ng, d, lt, k)
+        want_v, want_i = O.pairwise_topk_batched(Q.to(dtype).float(), G.to(dtype).float(), k, lt)
+        assert torch.equal(i1.cpu(), want_i) or (i1.cpu() != want_i).float().mean() < 0.01   # ties only (checked in detail elsewhere)
+        assert torch.allclose(v1.cpu(), want_v.float(), rtol=2e-5, atol=1e-6)
+
+
 def test_l2_bands_of_query_tiles_give_the_same_result(ops, dbg):
     """Unit order with the query tiles walked in L2 bands (option k1_bands; every band scans all chunk steps before the
     next one starts): a different schedule of the same units, so results are identical — also with chunk hand-overs,

@@ -159,8 +159,10 @@ def test_k1_plan_covers_every_tile_exactly_once(sbir_lib, nq, ng, d, k, dtype, s
     assert p["cap"] in (16, 32, 64, 128) and p["cap"] >= min(k + slack, 128) and p["cap"] * p["lists"] * p["parts"] <= 4096
     assert p["q_tile_stride"] >= p["q_tiles"] and p["q_tile_stride"] % 2 == 0
     # rows of the unit grid: query tiles, or PAIRS of them when the plan uses CTA pairs
-    # (chosen for kind::tf32 tiles with the 64/128-entry lists of large k)
-    assert p["pair"] == (2 if (not tiles_bf16 and p["cap"] >= 64 and p["q_tiles"] >= 2) else 1)
+    # (chosen for kind::tf32 tiles with the 64/128-entry lists of large k, and for bf16 tiles of rows of 4 KB and more —
+    # the all-shared-memory form is L2-bound there and a pair moves a third fewer operand bytes)
+    want_pair = (not tiles_bf16 and p["cap"] >= 64) or (tiles_bf16 and d * 2 >= 4096)
+    assert p["pair"] == (2 if (want_pair and p["q_tiles"] >= 2) else 1)
     assert p["units"] == p["chunks"] * p["parts"] * -(-p["q_tiles"] // p["pair"])
     covered = []
     for part in range(p["parts"]):
