@@ -581,20 +581,27 @@ def main():
     # (two calibration rounds rank the GPUs differently), so a static cut gains nothing (102.1 vs 102.1 ms, profiles/).
     balance = None
     if world > 1 and args.balance:
-        balance = {"rounds": []}
-        for _ in range(2):
+        balance = {"rounds": [], "damping": 0.6}
+        for _ in range(3):
             _, cal_k1, _, _, _ = time_retrieval(step, 4, 3, barrier, lib, dev, None)
-            speeds = sharded.rank_speed_weights(r1 - r0, cal_k1, dev)
-            balance["rounds"].append({"rows_per_ms_per_rank": [round(x, 1) for x in speeds]})
-            if max(speeds) / min(speeds) < 1.01:
+            mine = torch.tensor([float(r1 - r0), cal_k1], device=dev, dtype=torch.float64)
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            rows = [t[0].item() for t in every]
+            ms = [t[1].item() for t in every]
+            balance["rounds"].append({"gallery_rows": [int(x) for x in rows], "k1_ms": [round(x, 3) for x in ms]})
+            if max(ms) / min(ms) < 1.015:
                 break
-            n0, n1 = sharded.weighted_shard_bounds(num_g, speeds, rank, align=256)
-            if (n0, n1) != (r0, r1):
-                del Q, Gs, pos
-                torch.cuda.empty_cache()
-                r0, r1 = n0, n1
-                Q, Gs, pos = make_shard(num_q, num_g, dim, dtype, r0, r1, dev, centroids=args.centroids)
-                torch.cuda.synchronize()
+            # A GPU that finishes early idles (and cools) until the exchange step, so its measured speed overstates what it
+            # sustains at full duty: move only part of the way towards equal kernel times, and re-measure.
+            mean_ms = sum(ms) / world
+            weights = [n * (mean_ms / t) ** 0.6 for n, t in zip(rows, ms)]
+            n0, n1 = sharded.weighted_shard_bounds(num_g, weights, rank, align=256)
+            del Q, Gs, pos
+            torch.cuda.empty_cache()
+            r0, r1 = n0, n1
+            Q, Gs, pos = make_shard(num_q, num_g, dim, dtype, r0, r1, dev, centroids=args.centroids)
+            torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler is not None:
