@@ -239,7 +239,8 @@ int sbir_profile_collect(double* k1_ms_sum, int64_t* k1_launches, int64_t* kerne
  * name ∈ { "k1_feed" (-1 auto | 0 off), "k1_pair" (0 auto | 1 single CTAs | 2 CTA pairs), "k1_qres" (-1 auto | 0 off),
  *          "k1_sel_bf16" (fp32 embeddings selected on bf16 copies: -1 auto | 0 never | 1 always),
  *          "k1_pair_coop" (1: CTA-pair launches are cooperative, 0: plain cluster launches — Nsight Compute cannot replay
- *          cooperative cluster launches), "k1_bands" (query tiles walked in n L2 bands: 0 / -1 off, n forced), "k1_l2_hints" (L2 eviction
+ *          cooperative cluster launches), "k1_bands" (query tiles walked in n L2 bands: 0 / -1 off, n forced), "k1_q_early" (resident-query form: 1 = the next
+ *          unit's query tile is stored while the current unit's last accumulator is worked on (default), 0 = at the unit's start), "k1_l2_hints" (L2 eviction
  *          hints of the resident-query form, bits 1|2|4; 0 = off, the default), "k1_chunk_mb" (0 auto), "host_chunk_rows" (0 auto), "watchdog_cycles" (device-side wait bound, default
  *          4e9, 0 = none: for compute-sanitizer / cuda-gdb), "k1_flags" (diagnostic bits, honoured only by a
  *          -DSBIR_DIAG build: sbir_debug_diag_build() == 1), "reset" (all defaults) }.
