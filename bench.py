@@ -528,8 +528,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (extra_workloads)")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled full-size oracle check")
-    ap.add_argument("--balance", action="store_true", help="N > 1: cut the gallery by each GPU's measured distance-kernel speed instead of equally (sharded.weighted_shard_bounds; "
-                    "measured on 8 GPUs: no gain — the per-GPU differences are power-cap jitter from pass to pass, not a property of the GPU)")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal gallery shards (default: a few untimed calibration rounds cut the gallery by each GPU's "
+                    "sustained distance-kernel speed, sharded.weighted_shard_bounds)")
     ap.add_argument("--centroids", type=int, default=0, help="class centroids of the generator (0: max(125, N/80), see make_shard)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -574,13 +574,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- N > 1, --balance: speed-weighted shards.  The exchange step waits for the slowest shard, so (untimed, before
-    # the measurement) every rank times the distance kernel on an equal shard and the gallery is re-cut in proportion
-    # (sharded.weighted_shard_bounds); the data generator is row-deterministic, so the global problem — and the result —
-    # is unchanged.  Off by default: on 8 GPUs the per-rank kernel times differ by ~6 % within a step but NOT persistently
-    # (two calibration rounds rank the GPUs differently), so a static cut gains nothing (102.1 vs 102.1 ms, profiles/).
+    # ---- N > 1: speed-weighted shards.  The exchange step waits for the slowest shard, and under the power cap the GPUs of
+    # one chassis do not sustain the same clock (8 GPUs, equal shards: per-rank kernel times 92-103 ms on one box, 93-99 ms
+    # on another).  Untimed, before the measurement, every rank times its distance kernel and the gallery is re-cut towards
+    # equal kernel times (sharded.weighted_shard_bounds) — damped and re-measured up to three times, because a GPU that
+    # finishes early idles until the exchange and overstates what it sustains at full duty.  The data generator is
+    # row-deterministic, so the global problem — and the result — is unchanged; `timing.shards` records every round.
+    # Measured A/B on 8 GPUs (profiles/r02_bench_cfg4_n8_{equal,weighted}_shards*.json): 105.0 -> 101.3 ms on a box with
+    # a persistent 12 % spread, 102.1 -> 102.1 ms on one whose 6 % spread was jitter.
     balance = None
-    if world > 1 and args.balance:
+    if world > 1 and not args.no_balance:
         balance = {"rounds": [], "damping": 0.6}
         for _ in range(3):
             _, cal_k1, _, _, _ = time_retrieval(step, 4, 3, barrier, lib, dev, None)
