@@ -50,6 +50,19 @@ def weighted_shard_bounds(num_rows: int, weights, rank: int, align: int = 1) -> 
     return cuts[rank], cuts[rank + 1]
 
 
+def rebalanced_weights(rows, busy_ms, damping: float = 0.6):
+    """Next shard weights from the current cut and the time every rank's GPU spent scoring it: each shard moves
+    `damping` of the way (in log space) towards the size that would equalise the kernel times.  Damped because the
+    measurement is biased — a GPU that finishes early idles until the exchange step and, under a power cap, clocks
+    higher than it can sustain at full duty — so re-measure and repeat; 1.0 is the full correction."""
+    rows = [float(r) for r in rows]
+    ms = [max(float(t), 1e-9) for t in busy_ms]
+    if len(rows) != len(ms) or not rows:
+        raise ValueError("one row count and one time per rank")
+    mean_ms = sum(ms) / len(ms)
+    return [r * (mean_ms / t) ** float(damping) for r, t in zip(rows, ms)]
+
+
 def rank_speed_weights(rows_local: int, busy_ms_local: float, device=None, group=None):
     """Gallery rows per millisecond of every rank (all-gathered, the same list everywhere): `busy_ms_local` is the
     time this rank's GPU spent scoring `rows_local` rows with nobody to wait for — the distance kernel's own time,

@@ -597,8 +597,7 @@ def main():
                 break
             # A GPU that finishes early idles (and cools) until the exchange step, so its measured speed overstates what it
             # sustains at full duty: move only part of the way towards equal kernel times, and re-measure.
-            mean_ms = sum(ms) / world
-            weights = [n * (mean_ms / t) ** 0.6 for n, t in zip(rows, ms)]
+            weights = sharded.rebalanced_weights(rows, ms, damping=0.6)
             n0, n1 = sharded.weighted_shard_bounds(num_g, weights, rank, align=256)
             del Q, Gs, pos
             torch.cuda.empty_cache()

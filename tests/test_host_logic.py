@@ -120,6 +120,16 @@ def test_weighted_shard_bounds_follow_the_weights():
     with pytest.raises(ValueError):
         sharded.weighted_shard_bounds(10, [1, 1], 2)
     assert sharded.rank_speed_weights(1000, 4.0) == [250.0]      # no process group: this rank alone
+    # damped re-cut towards equal kernel times: the slow rank gives rows away, less than the full correction would take
+    rows, ms = [1000, 1000, 1000, 1000], [10.0, 10.0, 10.0, 12.0]
+    w = sharded.rebalanced_weights(rows, ms, damping=0.6)
+    full = sharded.rebalanced_weights(rows, ms, damping=1.0)
+    assert w[3] < w[0] == w[1] == w[2] and full[3] < w[3] < rows[3]
+    cut = [sharded.weighted_shard_bounds(4000, w, r) for r in range(4)]
+    assert cut[-1][1] == 4000 and (cut[3][1] - cut[3][0]) < 1000 < (cut[0][1] - cut[0][0])
+    assert sharded.rebalanced_weights([5, 7], [3.0, 3.0]) == [5.0, 7.0]      # equal times: nothing moves
+    with pytest.raises(ValueError):
+        sharded.rebalanced_weights([1, 2], [1.0])
 
 
 def _plan(lib, nq, ng, d, k, dtype, sms=148):
