@@ -747,7 +747,7 @@ def main():
                        "method": "CUDA events on the launching stream around each of K steps after W warm-up steps, barrier + synchronize on both sides, max over ranks",
                        "per_rank": per_rank,
                        "shards": None if world == 1 else ("equal" if balance is None else
-                                                          {"rule": "rows proportional to each GPU's measured distance-kernel speed (untimed calibration passes before the measurement; same global problem, same result)",
+                                                          {"rule": "gallery re-cut towards equal distance-kernel times in damped, re-measured rounds (untimed, before the measurement; stops below 1.5 % spread; same global problem, same result)",
                                                            **balance})},
             "results": {**recall, "uncertified_queries": uncert},
             "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline, "cpu_baseline": cpu,
