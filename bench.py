@@ -530,6 +530,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled full-size oracle check")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal gallery shards (default: a few untimed calibration rounds cut the gallery by each GPU's "
                     "sustained distance-kernel speed, sharded.weighted_shard_bounds)")
+    ap.add_argument("--balance-threshold", type=float, default=1.015, help="N > 1: stop re-cutting once max/min of the per-rank kernel times is below this")
     ap.add_argument("--centroids", type=int, default=0, help="class centroids of the generator (0: max(125, N/80), see make_shard)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -593,7 +594,7 @@ def main():
             rows = [t[0].item() for t in every]
             ms = [t[1].item() for t in every]
             balance["rounds"].append({"gallery_rows": [int(x) for x in rows], "k1_ms": [round(x, 3) for x in ms]})
-            if max(ms) / min(ms) < 1.015:
+            if max(ms) / min(ms) < args.balance_threshold:
                 break
             # A GPU that finishes early idles (and cools) until the exchange step, so its measured speed overstates what it
             # sustains at full duty: move only part of the way towards equal kernel times, and re-measure.
