@@ -762,20 +762,20 @@ def case_bands():
 
 
 def case_l2hints():
-    """cfg4 (and its 8-GPU shard, and cfg4 with K = 100) with and without the L2 eviction hints of the resident-query form."""
+    """cfg4, its 8-GPU shard and cfg4 with K = 100: A/B of one library option inside one process (same box, same thermal
+    state).  `python tools/gpu_probe.py l2hints` sweeps the L2 eviction hints of the resident-query form (k1_l2_hints bits);
+    `python tools/gpu_probe.py l2hints <option>` alternates 0 / 1 of another switch, e.g. k1_q_early."""
     import torch
     from art_sbir_b200 import ops
+    opt = sys.argv[2] if len(sys.argv) > 2 else "k1_l2_hints"
+    values = (0, 1, 2, 4, 3, 5, 6, 7, 0, 1, 2, 4, 3, 5, 6, 7) if opt == "k1_l2_hints" else (0, 1, 0, 1)
     out = []
-    opt = "k1_l2_hints"
-    import sys
-    if len(sys.argv) > 2:
-        opt = sys.argv[2]          # e.g. k1_q_early: values 0 / 1 alternate
     for ng, k in ((10_000_000, 10), (1_250_000, 10), (10_000_000, 100)):
         q, g, pos = _clustered(100_000, ng, 512, torch.bfloat16)
         base = None
-        for hints in ((0, 1, 2, 4, 3, 5, 6, 7, 0, 1, 2, 4, 3, 5, 6, 7) if opt == "k1_l2_hints" else (0, 1, 0, 1)):
+        for value in values:
             B_set("reset", 0)
-            B_set(opt, hints)
+            B_set(opt, value)
             r = ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos, return_uncertified=True)
             torch.cuda.synchronize()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -784,34 +784,7 @@ def case_l2hints():
                 ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos)
                 ev[i + 1].record()
             torch.cuda.synchronize()
-            rec = {"gallery": ng, "k": k, opt: hints, "ms": [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(3)], "uncertified": int(r[3].item())}
-            if base is None:
-                base = r
-            else:
-                rec["same_result"] = bool(torch.equal(r[0], base[0]) and torch.equal(r[1], base[1]) and torch.equal(r[2], base[2]))
-            out.append(rec)
-        del q, g, pos
-    B_set("reset", 0)
-    return out
-
-
-def case_pairsel():
-    """Wide fp32 rows selected on bf16 copies run the all-shared-memory form (the query tile does not fit tensor memory),
-    which re-reads the query tile for every gallery tile: single-CTA tiles vs CTA pairs (each CTA loads half the gallery tile)."""
-    import torch
-    from art_sbir_b200 import ops
-    out = []
-    for nq, ng, d, k in ((12500, 75000, 2048, 10), (12500, 75000, 2048, 100), (20000, 200000, 1024, 10), (20000, 200000, 2048, 10), (12500, 75000, 2048, 30)):
-        q, g, pos = _clustered(nq, ng, d, torch.float32)
-        base = None
-        for pair in (0, 2, 0, 2):
-            B_set("reset", 0)
-            B_set("k1_pair", pair)
-            r = ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos, return_uncertified=True)
-            torch.cuda.synchronize()
-            us = _graph_us(lambda: ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos), replays=20)
-            k1 = _k1_ms(q, g, k, pos)
-            rec = {"shape": [nq, ng, d, k], "k1_pair": pair, "us": round(us, 1), "k1": k1, "uncertified": int(r[3].item())}
+            rec = {"gallery": ng, "k": k, opt: value, "ms": [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(3)], "uncertified": int(r[3].item())}
             if base is None:
                 base = r
             else:
