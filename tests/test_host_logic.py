@@ -211,3 +211,26 @@ def test_bf16_selection_error_bound_from_residual_norms():
         bound = 1.01 * qn[:, None] * gr.max() + qr[:, None] * gn.max() + qr[:, None] * gr.max()
         assert (err <= bound).all()
         assert 0.5 < (bound / (2.0 ** -8 * qn[:, None] * gn.max())).max() < 1.25   # vs the element-wise worst case
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's CPU arm: the oracle port of the reference's per-query loop on the host cores)
+    prints ONE JSON line with the same metric / unit / config as the b200 arm, `impl: reference`, a cpu_baseline describing
+    the run and an e2e object with zero copied bytes — and needs no GPU and no CUDA library."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"]["workload"] == "cfg4" and d["config"]["num_g"] == 10_000_000 and d["config"]["k"] == 10
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
