@@ -152,7 +152,9 @@ K1Plan make_k1_plan(int64_t num_q, int64_t num_g, int64_t dim, int k, int dtype,
   // Chunk size: with the queries streamed through L2 as well, 12 MB keeps a chunk's gallery rows AND the
   // live query tiles resident; the resident-query form reads only gallery rows through L2, and longer
   // units mean fewer list hand-overs and query-tile loads (cfg4: 12 / 24 / 48 / 96 MB -> 787 / 765 / 740 / 736 ms).
-  int64_t chunk_mb = p.qres ? 48 : 12;
+  // 64/128-entry lists (top-100) make every list hand-over four to eight times as large: 96 MB chunks there
+  // (cfg4 with K = 100, A/B in one process: 48 MB 830-835 ms, 96 MB 823-827 ms, 144 MB 821-826 ms; top-10: within noise).
+  int64_t chunk_mb = p.qres ? (p.cap >= 64 ? 96 : 48) : 12;
   if (debug_options().k1_chunk_mb > 0) chunk_mb = debug_options().k1_chunk_mb;  // experiments / tests of the chunk hand-over
   int64_t tpc = (chunk_mb << 20) / (tile_bytes > 0 ? tile_bytes : 1);
   if (tpc < 1) tpc = 1;

@@ -769,6 +769,8 @@ def case_l2hints():
     from art_sbir_b200 import ops
     opt = sys.argv[2] if len(sys.argv) > 2 else "k1_l2_hints"
     values = (0, 1, 2, 4, 3, 5, 6, 7, 0, 1, 2, 4, 3, 5, 6, 7) if opt == "k1_l2_hints" else (0, 1, 0, 1)
+    if len(sys.argv) > 3:                      # explicit values, e.g. `l2hints k1_chunk_mb 48,96`: alternated twice
+        values = tuple(int(v) for v in sys.argv[3].split(",")) * 2
     out = []
     for ng, k in ((10_000_000, 10), (1_250_000, 10), (10_000_000, 100)):
         q, g, pos = _clustered(100_000, ng, 512, torch.bfloat16)
