@@ -797,6 +797,33 @@ def case_l2hints():
     return out
 
 
+def case_pairsel():
+    """Wide fp32 rows selected on bf16 copies run the all-shared-memory form (the query tile does not fit tensor memory),
+    which re-reads the query tile for every gallery tile: single-CTA tiles vs CTA pairs (each CTA loads half the gallery tile)."""
+    import torch
+    from art_sbir_b200 import ops
+    out = []
+    for nq, ng, d, k in ((12500, 75000, 2048, 10), (12500, 75000, 2048, 100), (20000, 200000, 1024, 10), (20000, 200000, 2048, 10), (12500, 75000, 2048, 30)):
+        q, g, pos = _clustered(nq, ng, d, torch.float32)
+        base = None
+        for pair in (0, 2, 0, 2):
+            B_set("reset", 0)
+            B_set("k1_pair", pair)
+            r = ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos, return_uncertified=True)
+            torch.cuda.synchronize()
+            us = _graph_us(lambda: ops.pairwise_topk(q, g, k, "euclidean", pos_index=pos), replays=20)
+            k1 = _k1_ms(q, g, k, pos)
+            rec = {"shape": [nq, ng, d, k], "k1_pair": pair, "us": round(us, 1), "k1": k1, "uncertified": int(r[3].item())}
+            if base is None:
+                base = r
+            else:
+                rec["same_result"] = bool(torch.equal(r[0], base[0]) and torch.equal(r[1], base[1]) and torch.equal(r[2], base[2]))
+            out.append(rec)
+        del q, g, pos
+    B_set("reset", 0)
+    return out
+
+
 def case_k100_mainloop():
     """k=100 (cap 128: 3 operand stages) with the epilogue switched off: is it the mainloop?"""
     import torch
